@@ -1,0 +1,295 @@
+// C-ABI convolution entry points: turn a conv description into the tap table / bounding box /
+// output strides of the implicit-GEMM core (conv_igemm.cu), plus the weight/layout pack kernels.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+#include "internal.h"
+
+namespace b200cv {
+
+namespace {
+
+int pick_block_n(int cout, int num_m_tiles) {
+  int bn = 16;
+  while (bn < cout && bn < 256) bn *= 2;
+  // Prefer 128-wide tiles when 256-wide ones leave the last wave mostly empty.
+  if (bn == 256) {
+    const int sms = sm_count();
+    auto waste = [&](int b) {
+      const long long tiles = (long long)num_m_tiles * ((cout + b - 1) / b);
+      const long long waves = (tiles + sms - 1) / sms;
+      return (double)(waves * sms - tiles) / (double)(waves * sms);
+    };
+    if (cout % 256 != 0 && cout % 128 == 0) bn = 128;
+    else if (waste(256) > 0.25 && waste(128) < waste(256)) bn = 128;
+  }
+  return bn;
+}
+
+struct Geometry {
+  // activation tensor the im2col map walks
+  int N, H, W, C;
+  int lower_w, lower_h, upper_w, upper_h, trav_w, trav_h;
+  int OHt, OWt;  // traversal grid (rows of D per image = OHt*OWt)
+};
+
+int run_igemm(const Geometry& g, const void* act, const void* wpk, int64_t w_rows, int64_t w_cols,
+              IgemmParams& p, cudaStream_t stream) {
+  const int kc = kc_for(g.C);
+  p.cblocks = g.C / kc;
+  p.OHW = g.OHt * g.OWt;
+  p.OW = g.OWt;
+  p.M_total = g.N * p.OHW;
+  p.lower_w = g.lower_w;
+  p.lower_h = g.lower_h;
+  p.trav_w = g.trav_w;
+  p.trav_h = g.trav_h;
+  p.num_m_tiles = (p.M_total + 127) / 128;
+  const int bn = pick_block_n(p.Cout, p.num_m_tiles);
+  p.num_n_tiles = (p.Cout + bn - 1) / bn;
+  p.err = device_error_word();
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_im2col_bf16(&tmA, act, g.N, g.H, g.W, g.C, g.C, (int64_t)g.W * g.C,
+                                 (int64_t)g.H * g.W * g.C, g.lower_w, g.lower_h, g.upper_w, g.upper_h,
+                                 g.trav_w, g.trav_h, kc, 128);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tmB, wpk, w_rows, w_cols, w_cols, bn, kc);
+  if (rc) return rc;
+  return launch_igemm(tmA, tmB, p, kc, bn, stream);
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+void fill_epilogue(IgemmParams& p, const b200cv_conv_args* a, int64_t out_off, int64_t res_off,
+                   int64_t mul_h, int64_t mul_w) {
+  const int esz = a->y_dtype == B200CV_DT_F32 ? 4 : 2;
+  p.out = static_cast<char*>(a->y) + out_off * esz;
+  p.out_fp32 = a->y_dtype == B200CV_DT_F32;
+  p.o_sn = a->y_sn;
+  p.o_sh = a->y_sh * mul_h;
+  p.o_sw = a->y_sw * mul_w;
+  p.o_sc = a->y_sc;
+  const int vec = 16 / esz;
+  p.vec_ok = a->y_sc == 1 && aligned16(p.out) && p.o_sn % vec == 0 && p.o_sh % vec == 0 &&
+             p.o_sw % vec == 0;
+  p.res = a->residual ? static_cast<const __nv_bfloat16*>(a->residual) + res_off : nullptr;
+  p.r_sn = a->r_sn;
+  p.r_sh = a->r_sh * mul_h;
+  p.r_sw = a->r_sw * mul_w;
+  p.r_sc = a->r_sc;
+  p.scale = a->scale;
+  p.shift = a->shift;
+  p.act = a->act;
+  p.slope = a->slope;
+  p.stats = a->stats;
+}
+
+int validate_common(const b200cv_conv_args* a) {
+  B200CV_CHECK_ARG(a != nullptr, "conv: null args");
+  B200CV_CHECK_ARG(a->x && a->w && a->y, "conv: null tensor pointer");
+  B200CV_CHECK_ARG(a->N > 0 && a->H > 0 && a->W > 0 && a->Cout > 0, "conv: empty shape");
+  B200CV_CHECK_ARG(a->Cin == pad_channels(a->Cin), "conv: Cin=%d is not a padded channel count", a->Cin);
+  B200CV_CHECK_ARG(a->R >= 1 && a->S >= 1 && a->R * a->S <= kMaxTaps, "conv: filter %dx%d unsupported",
+                   a->R, a->S);
+  B200CV_CHECK_ARG(a->stride >= 1 && a->stride <= 8 && a->dil >= 1 && a->pad >= 0, "conv: bad stride/dil/pad");
+  B200CV_CHECK_ARG(aligned16(a->x) && aligned16(a->w), "conv: x/w must be 16-byte aligned");
+  B200CV_CHECK_ARG(a->y_dtype == B200CV_DT_BF16 || a->y_dtype == B200CV_DT_F32, "conv: bad y_dtype");
+  return 0;
+}
+
+}  // namespace
+}  // namespace b200cv
+
+using namespace b200cv;
+
+extern "C" int b200cv_conv_fwd(const b200cv_conv_args* a, void* stream) {
+  if (int rc = validate_common(a)) return rc;
+  const int OH = (a->H + 2 * a->pad - a->dil * (a->R - 1) - 1) / a->stride + 1;
+  const int OW = (a->W + 2 * a->pad - a->dil * (a->S - 1) - 1) / a->stride + 1;
+  B200CV_CHECK_ARG(OH > 0 && OW > 0, "conv_fwd: empty output");
+  B200CV_CHECK_ARG(a->pad <= 127 && (a->R - 1) * a->dil <= 255, "conv_fwd: pad/dilation out of TMA range");
+  Geometry g;
+  g.N = a->N; g.H = a->H; g.W = a->W; g.C = a->Cin;
+  g.lower_w = -a->pad; g.lower_h = -a->pad;
+  g.upper_w = a->pad - (a->S - 1) * a->dil;
+  g.upper_h = a->pad - (a->R - 1) * a->dil;
+  g.trav_w = a->stride; g.trav_h = a->stride;
+  g.OHt = OH; g.OWt = OW;
+  IgemmParams p{};
+  p.Cout = a->Cout;
+  p.num_taps = a->R * a->S;
+  for (int r = 0; r < a->R; ++r)
+    for (int s = 0; s < a->S; ++s) {
+      const int t = r * a->S + s;
+      p.tap_w[t] = (short)(s * a->dil);
+      p.tap_h[t] = (short)(r * a->dil);
+      p.tap_k[t] = t * a->Cin;
+    }
+  fill_epilogue(p, a, 0, 0, 1, 1);
+  return run_igemm(g, a->x, a->w, a->Cout, (int64_t)a->R * a->S * a->Cin, p,
+                   static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200cv_conv_dgrad(const b200cv_conv_args* a, int out_h, int out_w, void* stream) {
+  if (int rc = validate_common(a)) return rc;
+  B200CV_CHECK_ARG(out_h > 0 && out_w > 0, "conv_dgrad: empty output");
+  const int s = a->stride;
+  B200CV_CHECK_ARG(s == 1 || a->dil == 1, "conv_dgrad: stride>1 with dilation>1 unsupported");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // One launch per output parity class (a single class when stride == 1).
+  for (int pa = 0; pa < s; ++pa) {
+    for (int pb = 0; pb < s; ++pb) {
+      const int OHt = (out_h - pa + s - 1) / s;
+      const int OWt = (out_w - pb + s - 1) / s;
+      if (OHt <= 0 || OWt <= 0) continue;
+      // taps r with (pa + pad - r*dil) divisible by s contribute dY[i + (pa + pad - r*dil)/s]
+      int dr[kMaxTaps], rr[kMaxTaps], nr = 0, dsv[kMaxTaps], ss[kMaxTaps], ns = 0;
+      for (int r = 0; r < a->R; ++r) {
+        const int num = pa + a->pad - r * a->dil;
+        if (((num % s) + s) % s == 0) { dr[nr] = num / s; rr[nr] = r; ++nr; }
+      }
+      for (int q = 0; q < a->S; ++q) {
+        const int num = pb + a->pad - q * a->dil;
+        if (((num % s) + s) % s == 0) { dsv[ns] = num / s; ss[ns] = q; ++ns; }
+      }
+      B200CV_CHECK_ARG(nr > 0 && ns > 0, "conv_dgrad: parity class (%d,%d) has no taps", pa, pb);
+      const int lo_h = *std::min_element(dr, dr + nr);
+      const int lo_w = *std::min_element(dsv, dsv + ns);
+      Geometry g;
+      g.N = a->N; g.H = a->H; g.W = a->W; g.C = a->Cin;
+      g.lower_h = lo_h; g.lower_w = lo_w;
+      g.upper_h = lo_h + OHt - a->H;
+      g.upper_w = lo_w + OWt - a->W;
+      g.trav_h = 1; g.trav_w = 1;
+      g.OHt = OHt; g.OWt = OWt;
+      B200CV_CHECK_ARG(g.lower_h >= -128 && g.lower_h <= 127 && g.upper_h >= -128 && g.upper_h <= 127 &&
+                           g.lower_w >= -128 && g.lower_w <= 127 && g.upper_w >= -128 && g.upper_w <= 127,
+                       "conv_dgrad: bounding box out of TMA range");
+      IgemmParams p{};
+      p.Cout = a->Cout;
+      p.num_taps = nr * ns;
+      int t = 0;
+      for (int i = 0; i < nr; ++i)
+        for (int j = 0; j < ns; ++j, ++t) {
+          p.tap_h[t] = (short)(dr[i] - lo_h);
+          p.tap_w[t] = (short)(dsv[j] - lo_w);
+          p.tap_k[t] = (rr[i] * a->S + ss[j]) * a->Cin;
+        }
+      fill_epilogue(p, a, pa * a->y_sh + pb * a->y_sw, pa * a->r_sh + pb * a->r_sw, s, s);
+      int rc = run_igemm(g, a->x, a->w, a->Cout, (int64_t)a->R * a->S * a->Cin, p, st);
+      if (rc) return rc;
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// layout / packing kernels (bandwidth-trivial next to the convolutions)
+namespace b200cv {
+namespace {
+
+__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                             int C, long long HW, int Cpad, long long total_pix) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_pix;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / HW;
+    const long long hw = i - n * HW;
+    const float* s = src + n * C * HW + hw;
+    __nv_bfloat16* d = dst + i * Cpad;
+    for (int c = 0; c < Cpad; ++c) d[c] = __float2bfloat16_rn(c < C ? s[c * HW] : 0.f);
+  }
+}
+
+__global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst,
+                                             int C, long long HW, int Cpad, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long hw = i % HW;
+    const long long nc = i / HW;
+    const int c = (int)(nc % C);
+    const long long n = nc / C;
+    dst[i] = __bfloat162float(src[(n * HW + hw) * Cpad + c]);
+  }
+}
+
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int O,
+                                    int I, int RS, int Ipad, int Opad, int transpose, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (!transpose) {  // dst[o][t][ip]
+      const int ip = (int)(i % Ipad);
+      const long long r = i / Ipad;
+      const int t = (int)(r % RS);
+      const int o = (int)(r / RS);
+      if (ip < I) v = w[((long long)o * I + ip) * RS + t];
+    } else {  // dst[i][t][op]
+      const int op = (int)(i % Opad);
+      const long long r = i / Opad;
+      const int t = (int)(r % RS);
+      const int ii = (int)(r / RS);
+      if (op < O) v = w[((long long)op * I + ii) * RS + t];
+    }
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __restrict__ dst, int I, int RS,
+                                    int Ipad, long long total) {
+  // dst[o][i][t] = src[o][t][i]
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < total;
+       j += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(j % RS);
+    const long long r = j / RS;
+    const int i = (int)(r % I);
+    const long long o = r / I;
+    dst[j] = src[(o * RS + t) * Ipad + i];
+  }
+}
+
+int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = (long long)sm_count() * 16;
+  return (int)std::max<long long>(1, std::min(g, cap));
+}
+
+}  // namespace
+}  // namespace b200cv
+
+extern "C" int b200cv_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C, int H, int W,
+                                            int Cpad, void* stream) {
+  B200CV_CHECK_ARG(src && dst && N > 0 && C > 0 && H > 0 && W > 0 && Cpad >= C, "nchw->nhwc: bad args");
+  const long long pix = (long long)N * H * W;
+  nchw_f32_to_nhwc_bf16_kernel<<<grid_for(pix, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(dst), C, (long long)H * W, Cpad, pix);
+  return check_launch("nchw_f32_to_nhwc_bf16");
+}
+
+extern "C" int b200cv_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C, int H, int W,
+                                            int Cpad, void* stream) {
+  B200CV_CHECK_ARG(src && dst && N > 0 && C > 0 && H > 0 && W > 0 && Cpad >= C, "nhwc->nchw: bad args");
+  const long long total = (long long)N * C * H * W;
+  nhwc_bf16_to_nchw_f32_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), dst, C, (long long)H * W, Cpad, total);
+  return check_launch("nhwc_bf16_to_nchw_f32");
+}
+
+extern "C" int b200cv_pack_weights(const float* w, void* dst, int O, int I, int R, int S, int Ipad,
+                                   int Opad, int transpose, void* stream) {
+  B200CV_CHECK_ARG(w && dst && O > 0 && I > 0 && R > 0 && S > 0 && Ipad >= I && Opad >= O,
+                   "pack_weights: bad args");
+  const long long total = transpose ? (long long)I * R * S * Opad : (long long)O * R * S * Ipad;
+  pack_weights_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, static_cast<__nv_bfloat16*>(dst), O, I, R * S, Ipad, Opad, transpose, total);
+  return check_launch("pack_weights");
+}
+
+extern "C" int b200cv_unpack_wgrad(const float* src, float* dst, int O, int I, int R, int S, int Ipad,
+                                   void* stream) {
+  B200CV_CHECK_ARG(src && dst && O > 0 && I > 0 && Ipad >= I, "unpack_wgrad: bad args");
+  const long long total = (long long)O * I * R * S;
+  unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, dst, I, R * S, Ipad, total);
+  return check_launch("unpack_wgrad");
+}

@@ -1,0 +1,366 @@
+// Implicit-GEMM convolution core for sm_100a.
+//
+//   D[m, n] = sum_{tap, c} A[pixel(m) + tap][c] * B[n][tap_k[tap] + c]
+//
+// * A (NHWC bf16 activations) is fetched by TMA in im2col mode: one instruction brings the
+//   128 consecutive output pixels of a tile (crossing rows and images, zero-filling the halo)
+//   for one filter tap and one block of KC channels into 128B/64B/32B-swizzled shared memory.
+// * B (packed bf16 weights, K-major) is fetched by a tiled TMA load.
+// * One elected thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16) into a TMEM accumulator;
+//   two accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
+// * Persistent: grid = #SMs, static round-robin tile schedule.
+// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2..5 = epilogue.
+//
+// The same kernel serves forward convolution, stride-1 data-gradient (flipped taps, transposed
+// weights) and the four parity classes of a stride-2 data-gradient; only the tap table, the
+// bounding-box corners and the output strides differ (see conv_api.cu).
+#include <cuda_bf16.h>
+
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace b200cv {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kThreads = 192;
+constexpr int kEpiWarp0 = 2;
+constexpr int kSmemBudget = 200 * 1024;  // pipeline stages only
+
+template <int KC, int BN>
+struct Cfg {
+  static constexpr int kABytes = kBlockM * KC * 2;
+  static constexpr int kBBytes = BN * KC * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : (2 * BN);
+  static constexpr int kRowBytes = KC * 2;               // 32 / 64 / 128
+  static constexpr int kLayout = KC == 64 ? 2 : (KC == 32 ? 4 : 6);
+  static constexpr int kSBO = 8 * kRowBytes;             // 8-row swizzle atom pitch
+  static constexpr int kChunk = BN >= 32 ? 32 : 16;      // epilogue column chunk
+  // extras: barriers (8B each) + tmem ptr + stats[2*BN] + transpose scratch (4 warps x 32 x 33)
+  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kStatBytes = 2 * BN * 4;
+  static constexpr int kScratchBytes = 4 * 32 * 33 * 4;
+  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kBarBytes +
+                                    kStatBytes + kScratchBytes;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  if (act == 1) return v > 0.f ? v : v * slope;
+  if (act == 2) return v > 0.f ? v : 0.f;
+  return v;
+}
+
+template <int KC, int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ IgemmParams p) {
+  using C = Cfg<KC, BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* stage_base = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tfull_bar = empty_bar + C::kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_stats = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + C::kBarBytes);
+  float* s_scratch = s_stats + 2 * BN;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int kiters = p.num_taps * p.cblocks;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    for (int i = 0; i < C::kStages; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tfull_bar[i], 1);
+      ptx::mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
+  }
+  for (int i = threadIdx.x; i < 2 * BN; i += kThreads) s_stats[i] = 0.f;
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile / p.num_n_tiles;
+        const int nt = tile - mt * p.num_n_tiles;
+        const int m0 = mt * kBlockM;
+        const int n_img = m0 / p.OHW;
+        const int rem = m0 - n_img * p.OHW;
+        const int pr = rem / p.OW;
+        const int qc = rem - pr * p.OW;
+        const int cw = p.lower_w + qc * p.trav_w;
+        const int ch = p.lower_h + pr * p.trav_h;
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          const uint16_t ow = static_cast<uint16_t>(p.tap_w[tap]);
+          const uint16_t oh = static_cast<uint16_t>(p.tap_h[tap]);
+          const int kb = p.tap_k[tap];
+          for (int cb = 0; cb < p.cblocks; ++cb) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err, 1);
+            uint8_t* sa = stage_base + stage * C::kStageBytes;
+            uint8_t* sb = sa + C::kABytes;
+            ptx::mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+            ptx::tma_load_im2col_4d(sa, &tmA, &full_bar[stage], cb * KC, cw, ch, n_img, ow, oh);
+            ptx::tma_load_2d(sb, &tmB, &full_bar[stage], kb + cb * KC, nt * BN);
+            if (++stage == C::kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(kBlockM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      if (lane == 0) {
+        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err, 2);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int it = 0; it < kiters; ++it) {
+          ptx::mbar_wait(&full_bar[stage], phase, p.err, 3);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(stage_base + stage * C::kStageBytes);
+          const uint32_t sb = sa + C::kABytes;
+          const uint64_t adesc = ptx::make_smem_desc(sa, 16, C::kSBO, C::kLayout);
+          const uint64_t bdesc = ptx::make_smem_desc(sb, 16, C::kSBO, C::kLayout);
+#pragma unroll
+          for (int k = 0; k < KC / 16; ++k) {
+            // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the >>4 field
+            ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+          }
+          ptx::umma_commit(&empty_bar[stage]);
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        ptx::umma_commit(&tfull_bar[acc]);
+      }
+      __syncwarp();
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    const int et = (warp - kEpiWarp0) * 32 + lane;  // 0..127 among epilogue threads
+    float* scratch = s_scratch + (warp - kEpiWarp0) * 32 * 33;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt = tile / p.num_n_tiles;
+      const int nt = tile - mt * p.num_n_tiles;
+      const int m = mt * kBlockM + quarter * 32 + lane;
+      const bool row_ok = m < p.M_total;
+      long long o_row = 0, r_row = 0;
+      {
+        const int mm = row_ok ? m : 0;
+        const int n_img = mm / p.OHW;
+        const int rem = mm - n_img * p.OHW;
+        const int pr = rem / p.OW;
+        const int qc = rem - pr * p.OW;
+        o_row = n_img * p.o_sn + pr * p.o_sh + qc * p.o_sw;
+        r_row = n_img * p.r_sn + pr * p.r_sh + qc * p.r_sw;
+      }
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase, p.err, 4);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += C::kChunk) {
+        const int n_base = nt * BN + c0;
+        if (n_base >= p.Cout) break;  // warp-uniform
+        float v[C::kChunk];
+        if constexpr (C::kChunk == 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(t_row + c0, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        } else {
+          uint32_t r[16];
+          ptx::tmem_ld_32x16(t_row + c0, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        }
+        // affine + residual + activation, rounded the way it will be stored
+#pragma unroll
+        for (int j = 0; j < C::kChunk; ++j) {
+          const int n = n_base + j;
+          float x = v[j];
+          if (n < p.Cout) {
+            if (p.scale) x *= __ldg(p.scale + n);
+            if (p.shift) x += __ldg(p.shift + n);
+            if (p.res && row_ok) x += __bfloat162float(p.res[r_row + n * p.r_sc]);
+            x = apply_act(x, p.act, p.slope);
+            if (!p.out_fp32) x = __bfloat162float(__float2bfloat16_rn(x));
+          } else {
+            x = 0.f;
+          }
+          v[j] = row_ok ? x : 0.f;
+        }
+        // store
+        if (row_ok) {
+          if (p.out_fp32) {
+            float* o = reinterpret_cast<float*>(p.out) + o_row;
+            if (p.vec_ok && n_base + C::kChunk <= p.Cout) {
+#pragma unroll
+              for (int j = 0; j < C::kChunk; j += 4)
+                *reinterpret_cast<float4*>(o + n_base + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < C::kChunk; ++j)
+                if (n_base + j < p.Cout) o[(n_base + j) * p.o_sc] = v[j];
+            }
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + o_row;
+            if (p.vec_ok && n_base + C::kChunk <= p.Cout) {
+#pragma unroll
+              for (int j = 0; j < C::kChunk; j += 8) {
+                uint4 pk;
+                __nv_bfloat162 b0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+                __nv_bfloat162 b1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+                __nv_bfloat162 b3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&b0);
+                pk.y = *reinterpret_cast<uint32_t*>(&b1);
+                pk.z = *reinterpret_cast<uint32_t*>(&b2);
+                pk.w = *reinterpret_cast<uint32_t*>(&b3);
+                *reinterpret_cast<uint4*>(o + n_base + j) = pk;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < C::kChunk; ++j)
+                if (n_base + j < p.Cout) o[(n_base + j) * p.o_sc] = __float2bfloat16_rn(v[j]);
+            }
+          }
+        }
+        // per-channel sum / sum-of-squares over the 32 rows of this warp (smem transpose)
+        if (p.stats) {
+#pragma unroll
+          for (int j = 0; j < C::kChunk; ++j) scratch[lane * 33 + j] = v[j];
+          __syncwarp();
+          if (lane < C::kChunk) {
+            float s = 0.f, s2 = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              const float x = scratch[r * 33 + lane];
+              s += x;
+              s2 += x * x;
+            }
+            atomicAdd(&s_stats[c0 + lane], s);
+            atomicAdd(&s_stats[BN + c0 + lane], s2);
+          }
+          __syncwarp();
+        }
+      }
+      // accumulator drained: hand the TMEM stage back to the MMA warp
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+      if (p.stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int j = et; j < BN; j += 128) {
+          const int n = nt * BN + j;
+          if (n < p.Cout) {
+            atomicAdd(p.stats + n, s_stats[j]);
+            atomicAdd(p.stats + p.Cout + n, s_stats[BN + j]);
+          }
+          s_stats[j] = 0.f;
+          s_stats[BN + j] = 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+template <int KC, int BN>
+int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p,
+               cudaStream_t stream) {
+  using C = Cfg<KC, BN>;
+  static_assert(C::kStages >= 2, "pipeline too shallow");
+  static bool configured = false;  // benign race: attribute set is idempotent
+  auto kern = igemm_kernel<KC, BN>;
+  if (!configured) {
+    cudaError_t e =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) return set_error(static_cast<int>(e), "igemm smem attr: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  int grid = sm_count();
+  if (grid > tiles) grid = tiles;
+  if (grid < 1) return 0;
+  kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, p);
+  return check_launch("igemm_kernel");
+}
+
+}  // namespace
+
+int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, int kc,
+                 int block_n, cudaStream_t stream) {
+#define B200CV_IGEMM_CASE(KC_, BN_) \
+  if (kc == KC_ && block_n == BN_) return launch_one<KC_, BN_>(tmA, tmB, p, stream);
+  B200CV_IGEMM_CASE(64, 256)
+  B200CV_IGEMM_CASE(64, 128)
+  B200CV_IGEMM_CASE(64, 64)
+  B200CV_IGEMM_CASE(64, 32)
+  B200CV_IGEMM_CASE(64, 16)
+  B200CV_IGEMM_CASE(32, 256)
+  B200CV_IGEMM_CASE(32, 128)
+  B200CV_IGEMM_CASE(32, 64)
+  B200CV_IGEMM_CASE(32, 32)
+  B200CV_IGEMM_CASE(32, 16)
+  B200CV_IGEMM_CASE(16, 256)
+  B200CV_IGEMM_CASE(16, 128)
+  B200CV_IGEMM_CASE(16, 64)
+  B200CV_IGEMM_CASE(16, 32)
+  B200CV_IGEMM_CASE(16, 16)
+#undef B200CV_IGEMM_CASE
+  return set_error(B200CV_ERR_ARG, "igemm: unsupported tile kc=%d block_n=%d", kc, block_n);
+}
+
+}  // namespace b200cv

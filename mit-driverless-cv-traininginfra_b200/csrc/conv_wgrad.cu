@@ -1,0 +1,286 @@
+// Weight-gradient convolution for sm_100a:
+//
+//   dW[o][tap][i] += sum_{pix} dY[pix][o] * X[pix + tap][i]
+//
+// GEMM view per tap: M = output channels (128-row tile), N = input channels (BNW-column tile),
+// K = output pixels.  Both operands are "MN-major" for tcgen05 (the contiguous dimension in
+// memory is the channel, K = pixel is the strided one), which is exactly how TMA lays an
+// NHWC tile down: 64 pixel rows x (<=128 bytes of channels), swizzled.
+//   A = dY tile  : tiled 2-D TMA over [pixels][dy_ld], one or two 64-channel slabs
+//   B = X tile   : im2col TMA (same map family as the forward pass), one per filter tap
+// One dY tile is reused for T taps (T accumulators in TMEM), split-K over the pixel range,
+// fp32 atomics (red.global.add) into the packed gradient.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace b200cv {
+namespace {
+
+constexpr int kWThreads = 192;
+constexpr int kKB = 64;         // pixels per k-block
+constexpr int kMaxWStages = 8;
+
+struct WgradParams {
+  int M_pix, OHW, OW;
+  int lower_w, lower_h, trav_w, trav_h;
+  int Cout, Cin, RS, Ipad;  // Ipad: row pitch of dW in channels (== Cin)
+  int num_o_tiles, num_i_tiles, num_tap_groups, ksplit;
+  int T;         // taps per CTA
+  int a_slabs;   // 1 or 2 64-channel slabs of dY
+  int stages;
+  int kb_total;  // ceil(M_pix / 64)
+  float* dw;
+  int* err;
+  short tap_w[kMaxTaps];
+  short tap_h[kMaxTaps];
+};
+
+// CB: channels per B slab (16/32/64), BNW: N tile (CB, or 128 = two 64-channel slabs)
+template <int CB, int BNW>
+__global__ void __launch_bounds__(kWThreads, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+             const __grid_constant__ WgradParams p) {
+  constexpr int kBSlabs = BNW / CB;            // 1 or 2
+  constexpr int kASlabBytes = kKB * 128;       // 64 pixels x 64 channels bf16
+  constexpr int kBSlabBytes = kKB * CB * 2;
+  constexpr int kBTapBytes = kBSlabs * kBSlabBytes;
+  constexpr int kBRow = CB * 2;
+  constexpr int kBLayout = CB == 64 ? 2 : (CB == 32 ? 4 : 6);
+  constexpr int kChunk = BNW >= 32 ? 32 : 16;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int a_bytes = p.a_slabs * kASlabBytes;
+  const int stage_bytes = 2 * kASlabBytes + p.T * kBTapBytes;  // A region always 2 slabs wide
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + kMaxWStages;
+  uint64_t* done_bar = empty_bar + kMaxWStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile decode: blockIdx.x = (((o_tile * num_i_tiles) + i_tile) * num_tap_groups + tg) * ksplit + ks
+  int b = blockIdx.x;
+  const int ks = b % p.ksplit; b /= p.ksplit;
+  const int tg = b % p.num_tap_groups; b /= p.num_tap_groups;
+  const int it = b % p.num_i_tiles; b /= p.num_i_tiles;
+  const int ot = b;
+  const int kb_per = (p.kb_total + p.ksplit - 1) / p.ksplit;
+  const int kb0 = ks * kb_per;
+  const int kb1 = min(p.kb_total, kb0 + kb_per);
+  const int nkb = kb1 - kb0;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmDY);
+    ptx::prefetch_tmap(&tmX);
+    for (int i = 0; i < p.stages; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], 1);
+    }
+    ptx::mbar_init(done_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (nkb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int m0 = kb * kKB;
+          const int n_img = m0 / p.OHW;
+          const int rem = m0 - n_img * p.OHW;
+          const int pr = rem / p.OW;
+          const int qc = rem - pr * p.OW;
+          const int cw = p.lower_w + qc * p.trav_w;
+          const int ch = p.lower_h + pr * p.trav_h;
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err, 11);
+          uint8_t* sa = smem + stage * stage_bytes;
+          uint8_t* sb = sa + 2 * kASlabBytes;
+          ptx::mbar_expect_tx(&full_bar[stage], a_bytes + p.T * kBTapBytes);
+          for (int s = 0; s < p.a_slabs; ++s)
+            ptx::tma_load_2d(sa + s * kASlabBytes, &tmDY, &full_bar[stage], ot * 128 + s * 64, m0);
+          for (int t = 0; t < p.T; ++t) {
+            const int tap = tg * p.T + t;
+            for (int s = 0; s < kBSlabs; ++s)
+              ptx::tma_load_im2col_4d(sb + t * kBTapBytes + s * kBSlabBytes, &tmX, &full_bar[stage],
+                                      it * BNW + s * CB, cw, ch, n_img,
+                                      static_cast<uint16_t>(p.tap_w[tap]),
+                                      static_cast<uint16_t>(p.tap_h[tap]));
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BNW, 1, 1);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase, p.err, 12);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
+          const uint32_t sb = sa + 2 * kASlabBytes;
+#pragma unroll 1
+          for (int t = 0; t < p.T; ++t) {
+#pragma unroll
+            for (int k = 0; k < kKB / 16; ++k) {
+              // MN-major: LBO = distance between 64-channel slabs, SBO = 8 pixel rows
+              const uint64_t adesc = ptx::make_smem_desc(sa + k * 16 * 128, kASlabBytes, 8 * 128, 2);
+              const uint64_t bdesc = ptx::make_smem_desc(sb + t * kBTapBytes + k * 16 * kBRow,
+                                                         kBSlabBytes, 8 * kBRow, kBLayout);
+              ptx::umma_bf16(tmem_base + t * BNW, adesc, bdesc, idesc, (kb | k) != 0);
+            }
+          }
+          ptx::umma_commit(&empty_bar[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(done_bar);
+      }
+      __syncwarp();
+    } else {
+      const int quarter = warp & 3;
+      const int o = ot * 128 + quarter * 32 + lane;
+      ptx::mbar_wait(done_bar, 0, p.err, 13);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+      for (int t = 0; t < p.T; ++t) {
+        const int tap = tg * p.T + t;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BNW; c0 += kChunk) {
+          float v[kChunk];
+          if constexpr (kChunk == 32) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(t_row + t * BNW + c0, r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          } else {
+            uint32_t r[16];
+            ptx::tmem_ld_32x16(t_row + t * BNW + c0, r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          }
+          const int i0 = it * BNW + c0;
+          if (o < p.Cout && i0 < p.Cin) {
+            float* dst = p.dw + ((long long)o * p.RS + tap) * p.Ipad + i0;
+#pragma unroll
+            for (int j = 0; j < kChunk; j += 4) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]),
+                           "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3])
+                           : "memory");
+            }
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int CB, int BNW>
+int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, WgradParams& p, cudaStream_t stream) {
+  constexpr int kBTapBytes = (BNW / CB) * kKB * CB * 2;
+  const int stage_bytes = 2 * kKB * 128 + p.T * kBTapBytes;
+  p.stages = std::min(kMaxWStages, (196 * 1024) / stage_bytes);
+  if (p.stages < 2) return set_error(B200CV_ERR_ARG, "wgrad: stage too large (%d bytes)", stage_bytes);
+  const int smem = 1024 + p.stages * stage_bytes + (2 * kMaxWStages + 1) * 8 + 16;
+  auto kern = wgrad_kernel<CB, BNW>;
+  static int configured_smem = 0;
+  if (smem > configured_smem) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return set_error((int)e, "wgrad smem attr: %s", cudaGetErrorString(e));
+    configured_smem = 227 * 1024;
+  }
+  const int grid = p.num_o_tiles * p.num_i_tiles * p.num_tap_groups * p.ksplit;
+  kern<<<grid, kWThreads, smem, stream>>>(tmDY, tmX, p);
+  return check_launch("wgrad_kernel");
+}
+
+}  // namespace
+}  // namespace b200cv
+
+using namespace b200cv;
+
+extern "C" int b200cv_conv_wgrad(const void* x, const void* dy, float* dw_packed, int N, int H, int W,
+                                 int Cin, int Cout, int dy_ld, int R, int S, int stride, int pad, int dil,
+                                 void* stream) {
+  B200CV_CHECK_ARG(x && dy && dw_packed, "conv_wgrad: null pointer");
+  B200CV_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cout > 0, "conv_wgrad: empty shape");
+  B200CV_CHECK_ARG(Cin == pad_channels(Cin), "conv_wgrad: Cin=%d is not a padded channel count", Cin);
+  B200CV_CHECK_ARG(dy_ld >= Cout && dy_ld % 8 == 0, "conv_wgrad: dy_ld=%d must be >= Cout and a multiple of 8",
+                   dy_ld);
+  B200CV_CHECK_ARG(R * S <= kMaxTaps && stride >= 1 && stride <= 8 && dil >= 1 && pad >= 0,
+                   "conv_wgrad: unsupported filter");
+  const int OH = (H + 2 * pad - dil * (R - 1) - 1) / stride + 1;
+  const int OW = (W + 2 * pad - dil * (S - 1) - 1) / stride + 1;
+  B200CV_CHECK_ARG(OH > 0 && OW > 0, "conv_wgrad: empty output");
+
+  WgradParams p{};
+  p.OHW = OH * OW;
+  p.OW = OW;
+  p.M_pix = N * p.OHW;
+  p.lower_w = -pad;
+  p.lower_h = -pad;
+  p.trav_w = stride;
+  p.trav_h = stride;
+  p.Cout = Cout;
+  p.Cin = Cin;
+  p.RS = R * S;
+  p.Ipad = Cin;
+  p.dw = dw_packed;
+  p.err = device_error_word();
+  for (int r = 0; r < R; ++r)
+    for (int s = 0; s < S; ++s) {
+      p.tap_w[r * S + s] = (short)(s * dil);
+      p.tap_h[r * S + s] = (short)(r * dil);
+    }
+  const int cb = Cin < 64 ? Cin : 64;
+  const int bnw = Cin < 64 ? Cin : (Cin % 128 == 0 ? 128 : 64);
+  p.num_o_tiles = (Cout + 127) / 128;
+  p.num_i_tiles = Cin / bnw;
+  p.a_slabs = (Cout > 64 && dy_ld > 64) ? 2 : 1;
+  // taps per CTA: the largest divisor of RS whose accumulators fit the 512 TMEM columns
+  int T = 1;
+  for (int t = 1; t <= p.RS; ++t)
+    if (p.RS % t == 0 && t * bnw <= 512 && t <= 9) T = t;
+  if (bnw == 128 && T > 3) T = 3;  // keep >= 3 pipeline stages in shared memory
+  p.T = T;
+  p.num_tap_groups = p.RS / T;
+  p.kb_total = (p.M_pix + kKB - 1) / kKB;
+  const int base_ctas = p.num_o_tiles * p.num_i_tiles * p.num_tap_groups;
+  int ksplit = std::max(1, (2 * sm_count() + base_ctas - 1) / base_ctas);
+  ksplit = std::min(ksplit, std::max(1, p.kb_total / 4));
+  p.ksplit = ksplit;
+
+  CUtensorMap tmDY, tmX;
+  int rc = make_tmap_2d_bf16(&tmDY, dy, p.M_pix, dy_ld, dy_ld, kKB, 64);
+  if (rc) return rc;
+  rc = make_tmap_im2col_bf16(&tmX, x, N, H, W, Cin, Cin, (int64_t)W * Cin, (int64_t)H * W * Cin, -pad, -pad,
+                             pad - (S - 1) * dil, pad - (R - 1) * dil, stride, stride, cb, kKB);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (cb == 64 && bnw == 128) return launch_wgrad<64, 128>(tmDY, tmX, p, st);
+  if (cb == 64 && bnw == 64) return launch_wgrad<64, 64>(tmDY, tmX, p, st);
+  if (cb == 32) return launch_wgrad<32, 32>(tmDY, tmX, p, st);
+  if (cb == 16) return launch_wgrad<16, 16>(tmDY, tmX, p, st);
+  return set_error(B200CV_ERR_ARG, "conv_wgrad: unsupported channel tile");
+}

@@ -1,0 +1,72 @@
+// Internal (non-ABI) declarations shared between the translation units of libb200cv.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200cv.h"
+
+namespace b200cv {
+
+// ---- error plumbing (api.cpp) -------------------------------------------------
+int set_error(int code, const char* fmt, ...);
+int check_launch(const char* what);  // cudaGetLastError() -> error code
+int* device_error_word();            // per-device int the kernels report pipeline timeouts into
+int sm_count();
+
+#define B200CV_CHECK_ARG(cond, ...)                                   \
+  do {                                                                \
+    if (!(cond)) return ::b200cv::set_error(B200CV_ERR_ARG, __VA_ARGS__); \
+  } while (0)
+
+// ---- tensor maps (tmap.cpp) ---------------------------------------------------
+// bf16 NHWC activation, im2col mode. Returns 0 on success.
+int make_tmap_im2col_bf16(CUtensorMap* out, const void* base, int N, int H, int W, int C,
+                          int64_t stride_w_elems, int64_t stride_h_elems, int64_t stride_n_elems,
+                          int lower_w, int lower_h, int upper_w, int upper_h, int trav_w, int trav_h,
+                          int channels_per_pixel, int pixels_per_column);
+// bf16 row-major 2-D matrix [rows][cols] with row pitch `ld` elements; box = [box_rows][box_cols].
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld,
+                      int box_rows, int box_cols);
+
+// ---- implicit-GEMM convolution core (conv_igemm.cu) ----------------------------
+constexpr int kMaxTaps = 64;
+
+struct IgemmParams {
+  // GEMM view: D[m, n] = sum_{tap, c} A_tap[m, c] * B[n, tap_k[tap] + c]
+  int M_total;   // output pixels (rows of D)
+  int OHW, OW;   // pixels per image / per row of the traversal grid
+  int lower_w, lower_h, trav_w, trav_h;
+  int num_taps, cblocks;  // k-iterations = num_taps * cblocks
+  int Cout;               // valid columns of D
+  int num_m_tiles, num_n_tiles;
+  // epilogue: v = acc*scale[n] + shift[n] (+ residual) -> act -> store; stats on the stored value
+  void* out;
+  int out_fp32;  // 0: bf16, 1: fp32
+  int vec_ok;    // 16-byte vector stores allowed (o_sc == 1 and everything 16B aligned)
+  long long o_sn, o_sh, o_sw, o_sc;
+  const __nv_bfloat16* res;
+  long long r_sn, r_sh, r_sw, r_sc;
+  const float* scale;
+  const float* shift;
+  int act;  // 0 none, 1 leaky(slope), 2 relu
+  float slope;
+  float* stats;  // [2*Cout]: sum, sum of squares (atomicAdd), or null
+  int* err;
+  short tap_w[kMaxTaps];
+  short tap_h[kMaxTaps];
+  int tap_k[kMaxTaps];
+};
+
+// A: im2col tensor map over the activation; B: 2-D map over the packed weights.
+// kc = channels per k-block (16/32/64); block_n in {16,32,64,128,256}.
+int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, int kc,
+                 int block_n, cudaStream_t stream);
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+// Channel padding rule for NHWC bf16 activations: 16, 32, or a multiple of 64.
+inline int pad_channels(int c) { return c <= 16 ? 16 : (c <= 32 ? 32 : round_up(c, 64)); }
+inline int kc_for(int cpad) { return cpad < 64 ? cpad : 64; }
+
+}  // namespace b200cv
