@@ -1,0 +1,568 @@
+// Bandwidth-bound NHWC bf16 kernels around the convolutions: training-mode BatchNorm
+// (finalize / apply+activation / backward reductions / backward apply), 2x2 max-pool,
+// nearest x2 upsample, channel-slice copy and accumulate, per-channel column sums.
+// All tensors are [rows = N*H*W][channels] with an explicit row pitch, so a "tensor" may be a
+// channel slice of a wider concat buffer.  Threads move 8 channels (16 bytes) at a time.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+#include "internal.h"
+
+namespace b200cv {
+namespace {
+
+struct bf16x8 {
+  uint4 raw;
+};
+__device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 r;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return r;
+}
+__device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) {
+  return __ldg(reinterpret_cast<const uint4*>(p));
+}
+__device__ __forceinline__ void stg16(__nv_bfloat16* p, const uint4& v) {
+  *reinterpret_cast<uint4*>(p) = v;
+}
+__device__ __forceinline__ float act_fwd(float z, int act, float slope) {
+  if (act == B200CV_ACT_LEAKY) return z > 0.f ? z : z * slope;
+  if (act == B200CV_ACT_RELU) return z > 0.f ? z : 0.f;
+  return z;
+}
+__device__ __forceinline__ float act_grad(float z, int act, float slope) {
+  if (act == B200CV_ACT_LEAKY) return z > 0.f ? 1.f : slope;
+  if (act == B200CV_ACT_RELU) return z > 0.f ? 1.f : 0.f;
+  return 1.f;
+}
+
+int ew_grid(long long work_items, int block) {
+  const long long g = (work_items + block - 1) / block;
+  return (int)std::max<long long>(1, std::min<long long>(g, (long long)sm_count() * 8));
+}
+
+// ------------------------------------------------------------------ BN finalize
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, float count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, const float* __restrict__ conv_bias,
+                                   float eps, float momentum, float* running_mean, float* running_var,
+                                   float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ save_mean, float* __restrict__ save_rstd, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float mean = stats[c] / count;
+  float var = stats[C + c] / count - mean * mean;
+  var = var > 0.f ? var : 0.f;
+  const float rstd = rsqrtf(var + eps);
+  const float g = gamma[c];
+  scale[c] = g * rstd;
+  shift[c] = beta[c] - mean * g * rstd;
+  save_mean[c] = mean;
+  save_rstd[c] = rstd;
+  if (running_mean) {
+    const float m_full = mean + (conv_bias ? conv_bias[c] : 0.f);  // bias is folded out of the conv
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * m_full;
+    const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+  }
+}
+
+// ------------------------------------------------------------------ BN apply (+second branch, +residual)
+//   out = act( y*scale + shift  [+ y2*scale2 + shift2] ) [+ post]
+struct ApplyArgs {
+  const __nv_bfloat16* y; long long y_ld;
+  const float* scale; const float* shift;
+  const __nv_bfloat16* y2; long long y2_ld;
+  const float* scale2; const float* shift2;
+  const __nv_bfloat16* post; long long post_ld;
+  __nv_bfloat16* out; long long out_ld;
+  long long rows; int C; int act; float slope;
+};
+__global__ void bn_apply_kernel(const ApplyArgs a) {
+  const int vpr = a.C >> 3;
+  const long long total = a.rows * vpr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vpr;
+    const int c0 = (int)(i - r * vpr) << 3;
+    float v[8], z[8];
+    unpack8(ldg16(a.y + r * a.y_ld + c0), v);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(a.scale + c0));
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(a.scale + c0 + 4));
+    const float4 h0 = __ldg(reinterpret_cast<const float4*>(a.shift + c0));
+    const float4 h1 = __ldg(reinterpret_cast<const float4*>(a.shift + c0 + 4));
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z[j] = v[j] * sc[j] + sh[j];
+    if (a.y2) {
+      float w[8];
+      unpack8(ldg16(a.y2 + r * a.y2_ld + c0), w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) z[j] += w[j] * __ldg(a.scale2 + c0 + j) + __ldg(a.shift2 + c0 + j);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z[j] = act_fwd(z[j], a.act, a.slope);
+    if (a.post) {
+      float w[8];
+      unpack8(ldg16(a.post + r * a.post_ld + c0), w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) z[j] += w[j];
+    }
+    stg16(a.out + r * a.out_ld + c0, pack8(z));
+  }
+}
+
+// ------------------------------------------------------------------ BN backward, pass 1
+//   dz = da * act'(z);  sums[c] += dz;  sums[C+c] += dz * xhat     (xhat = (y-mean)*rstd)
+// z is recomputed as y*scale+shift (+ second branch); `aout` (the saved activation output) can be
+// given instead when z is not recomputable from one branch alone.
+struct BwdArgs {
+  const __nv_bfloat16* da; long long da_ld;
+  const __nv_bfloat16* y; long long y_ld;
+  const __nv_bfloat16* aout; long long aout_ld;   // optional: sign source for act'
+  const float* scale; const float* shift;         // of this BN (to recompute z when aout == null)
+  const float* mean; const float* rstd;
+  float* sums;                                    // pass 1 out [2C]
+  const float* coef;                              // pass 2 in  [3C]: g, k1, k2
+  __nv_bfloat16* dy; long long dy_ld;             // pass 2 out
+  long long rows; int C; int act; float slope;
+};
+__device__ __forceinline__ void bwd_load(const BwdArgs& a, long long r, int c0, float (&dz)[8], float (&xh)[8]) {
+  float da[8], y[8];
+  unpack8(ldg16(a.da + r * a.da_ld + c0), da);
+  unpack8(ldg16(a.y + r * a.y_ld + c0), y);
+  float zs[8];
+  if (a.aout) {
+    unpack8(ldg16(a.aout + r * a.aout_ld + c0), zs);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) zs[j] = y[j] * __ldg(a.scale + c0 + j) + __ldg(a.shift + c0 + j);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    dz[j] = da[j] * act_grad(zs[j], a.act, a.slope);
+    xh[j] = (y[j] - __ldg(a.mean + c0 + j)) * __ldg(a.rstd + c0 + j);
+  }
+}
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdArgs a) {
+  extern __shared__ float s_acc[];  // [2C]
+  const int C = a.C;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int vpr = C >> 3;                 // <= 256 guaranteed by the host
+  const int rpp = blockDim.x / vpr;       // rows per pass of this block
+  const int cv = threadIdx.x % vpr;
+  const int r0 = threadIdx.x / vpr;
+  const int c0 = cv << 3;
+  float s1[8] = {0}, s2[8] = {0};
+  if (r0 < rpp) {
+    for (long long r = (long long)blockIdx.x * rpp + r0; r < a.rows; r += (long long)gridDim.x * rpp) {
+      float dz[8], xh[8];
+      bwd_load(a, r, c0, dz, xh);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += dz[j];
+        s2[j] += dz[j] * xh[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&s_acc[c0 + j], s1[j]);
+      atomicAdd(&s_acc[C + c0 + j], s2[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(a.sums + i, s_acc[i]);
+}
+
+// coef[c] = gamma*rstd ; coef[C+c] = sum_dz/M ; coef[2C+c] = sum_dz_xhat/M ; also dgamma/dbeta
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ gamma,
+                                       const float* __restrict__ rstd, float count, float* __restrict__ coef,
+                                       float* dgamma, float* dbeta, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  coef[c] = gamma[c] * rstd[c];
+  coef[C + c] = sums[c] / count;
+  coef[2 * C + c] = sums[C + c] / count;
+  if (dbeta) dbeta[c] = sums[c];
+  if (dgamma) dgamma[c] = sums[C + c];
+}
+
+__global__ void bn_bwd_apply_kernel(const BwdArgs a) {
+  const int C = a.C;
+  const int vpr = C >> 3;
+  const long long total = a.rows * vpr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vpr;
+    const int c0 = (int)(i - r * vpr) << 3;
+    float dz[8], xh[8], o[8];
+    bwd_load(a, r, c0, dz, xh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      o[j] = __ldg(a.coef + c0 + j) * (dz[j] - __ldg(a.coef + C + c0 + j) - xh[j] * __ldg(a.coef + 2 * C + c0 + j));
+    stg16(a.dy + r * a.dy_ld + c0, pack8(o));
+  }
+}
+
+// ------------------------------------------------------------------ activation-only backward (no BN)
+//   dz = da * act'(aout)
+__global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ da, long long da_ld,
+                               const __nv_bfloat16* __restrict__ aout, long long aout_ld,
+                               __nv_bfloat16* __restrict__ dz, long long dz_ld, long long rows, int C, int act,
+                               float slope) {
+  const int vpr = C >> 3;
+  const long long total = rows * vpr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vpr;
+    const int c0 = (int)(i - r * vpr) << 3;
+    float g[8], z[8];
+    unpack8(ldg16(da + r * da_ld + c0), g);
+    unpack8(ldg16(aout + r * aout_ld + c0), z);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] *= act_grad(z[j], act, slope);
+    stg16(dz + r * dz_ld + c0, pack8(g));
+  }
+}
+
+// ------------------------------------------------------------------ slice copy / accumulate
+__global__ void copy_slice_kernel(const __nv_bfloat16* __restrict__ src, long long s_ld,
+                                  __nv_bfloat16* __restrict__ dst, long long d_ld, long long rows, int C,
+                                  int accumulate) {
+  const int vpr = C >> 3;
+  const long long total = rows * vpr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vpr;
+    const int c0 = (int)(i - r * vpr) << 3;
+    uint4 v = ldg16(src + r * s_ld + c0);
+    if (accumulate) {
+      float a[8], b[8];
+      unpack8(v, a);
+      unpack8(*reinterpret_cast<const uint4*>(dst + r * d_ld + c0), b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += b[j];
+      v = pack8(a);
+    }
+    stg16(dst + r * d_ld + c0, v);
+  }
+}
+
+// ------------------------------------------------------------------ column sums (conv bias gradient)
+__global__ void __launch_bounds__(256) col_sum_kernel(const __nv_bfloat16* __restrict__ x, long long ld,
+                                                      long long rows, int C, float* __restrict__ out) {
+  extern __shared__ float s_acc[];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int vpr = C >> 3;
+  const int rpp = blockDim.x / vpr;
+  const int cv = threadIdx.x % vpr;
+  const int r0 = threadIdx.x / vpr;
+  if (r0 < rpp) {
+    float s[8] = {0};
+    for (long long r = (long long)blockIdx.x * rpp + r0; r < rows; r += (long long)gridDim.x * rpp) {
+      float v[8];
+      unpack8(ldg16(x + r * ld + (cv << 3)), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[(cv << 3) + j], s[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(out + i, s_acc[i]);
+}
+
+// ------------------------------------------------------------------ 2x2 max-pool (stride 2, or stride 1 with
+// a ZERO pad on the right/bottom edge -- nn.ZeroPad2d((0,1,0,1)) + MaxPool2d(2,1), CVC-YOLOv3/models.py:74-84)
+__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H,
+                                   int W, int C, int stride, int OH, int OW) {
+  const int vpr = C >> 3;
+  const long long total = (long long)N * OH * OW * vpr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % vpr) << 3;
+    long long r = i / vpr;
+    const int ow = (int)(r % OW); r /= OW;
+    const int oh = (int)(r % OH);
+    const long long n = r / OH;
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+#pragma unroll
+    for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+      for (int dw = 0; dw < 2; ++dw) {
+        const int ih = oh * stride + dh, iw = ow * stride + dw;
+        float v[8];
+        if (ih < H && iw < W) unpack8(ldg16(x + ((n * H + ih) * W + iw) * C + c0), v);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = 0.f;  // zero padding takes part in the max
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+      }
+    stg16(y + ((n * OH + oh) * OW + ow) * C + c0, pack8(m));
+  }
+}
+// Gather form: every input pixel sums the gradients of the windows in which it is the FIRST maximum
+// (scan order dh, dw -- the element PyTorch's max_pool2d backward routes to).
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                   __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int stride, int OH,
+                                   int OW) {
+  const int vpr = C >> 3;
+  const long long total = (long long)N * H * W * vpr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % vpr) << 3;
+    long long r = i / vpr;
+    const int iw = (int)(r % W); r /= W;
+    const int ih = (int)(r % H);
+    const long long n = r / H;
+    float g[8] = {0};
+    float me[8];
+    unpack8(ldg16(x + ((n * H + ih) * W + iw) * C + c0), me);
+    for (int oh = (ih - 1 + stride - 1) / stride; oh * stride <= ih; ++oh) {
+      if (oh < 0 || oh >= OH) continue;
+      for (int ow = (iw - 1 + stride - 1) / stride; ow * stride <= iw; ++ow) {
+        if (ow < 0 || ow >= OW) continue;
+        const int my_pos = (ih - oh * stride) * 2 + (iw - ow * stride);
+        bool win[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) win[j] = true;
+#pragma unroll
+        for (int pos = 0; pos < 4; ++pos) {
+          if (pos == my_pos) continue;
+          const int jh = oh * stride + (pos >> 1), jw = ow * stride + (pos & 1);
+          float v[8];
+          if (jh < H && jw < W) unpack8(ldg16(x + ((n * H + jh) * W + jw) * C + c0), v);
+          else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (pos < my_pos ? v[j] >= me[j] : v[j] > me[j]) win[j] = false;
+        }
+        float d[8];
+        unpack8(ldg16(dy + ((n * OH + oh) * OW + ow) * C + c0), d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (win[j]) g[j] += d[j];
+      }
+    }
+    stg16(dx + ((n * H + ih) * W + iw) * C + c0, pack8(g));
+  }
+}
+
+// ------------------------------------------------------------------ nearest x2 upsample
+__global__ void upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                      long long y_ld, int N, int H, int W, int C) {
+  const int vpr = C >> 3;
+  const int OH = 2 * H, OW = 2 * W;
+  const long long total = (long long)N * OH * OW * vpr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % vpr) << 3;
+    long long r = i / vpr;
+    const int ow = (int)(r % OW); r /= OW;
+    const int oh = (int)(r % OH);
+    const long long n = r / OH;
+    stg16(y + ((n * OH + oh) * OW + ow) * y_ld + c0, ldg16(x + ((n * H + (oh >> 1)) * W + (ow >> 1)) * C + c0));
+  }
+}
+__global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_ld,
+                                      __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int accumulate) {
+  const int vpr = C >> 3;
+  const int OH = 2 * H, OW = 2 * W;
+  const long long total = (long long)N * H * W * vpr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % vpr) << 3;
+    long long r = i / vpr;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H);
+    const long long n = r / H;
+    float g[8] = {0};
+#pragma unroll
+    for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+      for (int dw = 0; dw < 2; ++dw) {
+        float v[8];
+        unpack8(ldg16(dy + ((n * OH + 2 * h + dh) * OW + 2 * w + dw) * dy_ld + c0), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] += v[j];
+      }
+    __nv_bfloat16* d = dx + ((n * H + h) * W + w) * C + c0;
+    if (accumulate) {
+      float b[8];
+      unpack8(*reinterpret_cast<const uint4*>(d), b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += b[j];
+    }
+    stg16(d, pack8(g));
+  }
+}
+
+bool ok_vec(const void* p, long long ld, int C) {
+  return p && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && ld % 8 == 0 && C % 8 == 0 && C > 0;
+}
+
+}  // namespace
+}  // namespace b200cv
+
+using namespace b200cv;
+typedef __nv_bfloat16 bf16;
+
+extern "C" int b200cv_bn_finalize(const float* stats, int64_t count, const float* gamma, const float* beta,
+                                  const float* conv_bias, float eps, float momentum, float* running_mean,
+                                  float* running_var, float* scale, float* shift, float* save_mean,
+                                  float* save_rstd, int C, void* stream) {
+  B200CV_CHECK_ARG(stats && gamma && beta && scale && shift && save_mean && save_rstd && C > 0 && count > 0,
+                   "bn_finalize: bad args");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      stats, (float)count, gamma, beta, conv_bias, eps, momentum, running_mean, running_var, scale, shift,
+      save_mean, save_rstd, C);
+  return check_launch("bn_finalize");
+}
+
+extern "C" int b200cv_bn_apply_act(const void* y, int64_t y_ld, const float* scale, const float* shift,
+                                   const void* y2, int64_t y2_ld, const float* scale2, const float* shift2,
+                                   const void* post, int64_t post_ld, void* out, int64_t out_ld, int64_t rows,
+                                   int C, int act, float slope, void* stream) {
+  B200CV_CHECK_ARG(ok_vec(y, y_ld, C) && ok_vec(out, out_ld, C) && scale && shift && rows > 0,
+                   "bn_apply_act: bad args");
+  B200CV_CHECK_ARG(!y2 || (ok_vec(y2, y2_ld, C) && scale2 && shift2), "bn_apply_act: bad second branch");
+  B200CV_CHECK_ARG(!post || ok_vec(post, post_ld, C), "bn_apply_act: bad residual");
+  ApplyArgs a{(const bf16*)y, y_ld, scale, shift, (const bf16*)y2, y2_ld, scale2, shift2,
+              (const bf16*)post, post_ld, (bf16*)out, out_ld, rows, C, act, slope};
+  bn_apply_kernel<<<ew_grid(rows * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  return check_launch("bn_apply_act");
+}
+
+static int fill_bwd(BwdArgs& a, const void* da, int64_t da_ld, const void* y, int64_t y_ld, const void* aout,
+                    int64_t aout_ld, const float* scale, const float* shift, const float* mean, const float* rstd,
+                    int64_t rows, int C, int act, float slope) {
+  B200CV_CHECK_ARG(ok_vec(da, da_ld, C) && ok_vec(y, y_ld, C) && mean && rstd && rows > 0, "bn_bwd: bad args");
+  B200CV_CHECK_ARG(aout ? ok_vec(aout, aout_ld, C) : (scale && shift), "bn_bwd: need aout or scale/shift");
+  B200CV_CHECK_ARG(C <= 2048, "bn_bwd: C=%d too large", C);
+  a = BwdArgs{};
+  a.da = (const bf16*)da; a.da_ld = da_ld; a.y = (const bf16*)y; a.y_ld = y_ld;
+  a.aout = (const bf16*)aout; a.aout_ld = aout_ld; a.scale = scale; a.shift = shift;
+  a.mean = mean; a.rstd = rstd; a.rows = rows; a.C = C; a.act = act; a.slope = slope;
+  return 0;
+}
+
+extern "C" int b200cv_bn_bwd_reduce(const void* da, int64_t da_ld, const void* y, int64_t y_ld, const void* aout,
+                                    int64_t aout_ld, const float* scale, const float* shift, const float* mean,
+                                    const float* rstd, float* sums, int64_t rows, int C, int act, float slope,
+                                    void* stream) {
+  BwdArgs a;
+  if (int rc = fill_bwd(a, da, da_ld, y, y_ld, aout, aout_ld, scale, shift, mean, rstd, rows, C, act, slope))
+    return rc;
+  B200CV_CHECK_ARG(sums != nullptr, "bn_bwd_reduce: null sums");
+  a.sums = sums;
+  const int vpr = C / 8;
+  const int threads = vpr > 256 ? 256 : 256;
+  B200CV_CHECK_ARG(vpr <= 256, "bn_bwd_reduce: C too large");
+  const int rpp = threads / vpr;
+  const long long passes = (rows + rpp - 1) / rpp;
+  const int grid = (int)std::max<long long>(1, std::min<long long>(passes, (long long)sm_count() * 4));
+  bn_bwd_reduce_kernel<<<grid, threads, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(a);
+  return check_launch("bn_bwd_reduce");
+}
+
+extern "C" int b200cv_bn_bwd_finalize(const float* sums, const float* gamma, const float* rstd, int64_t count,
+                                      float* coef, float* dgamma, float* dbeta, int C, void* stream) {
+  B200CV_CHECK_ARG(sums && gamma && rstd && coef && C > 0 && count > 0, "bn_bwd_finalize: bad args");
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      sums, gamma, rstd, (float)count, coef, dgamma, dbeta, C);
+  return check_launch("bn_bwd_finalize");
+}
+
+extern "C" int b200cv_bn_bwd_apply(const void* da, int64_t da_ld, const void* y, int64_t y_ld, const void* aout,
+                                   int64_t aout_ld, const float* scale, const float* shift, const float* mean,
+                                   const float* rstd, const float* coef, void* dy, int64_t dy_ld, int64_t rows,
+                                   int C, int act, float slope, void* stream) {
+  BwdArgs a;
+  if (int rc = fill_bwd(a, da, da_ld, y, y_ld, aout, aout_ld, scale, shift, mean, rstd, rows, C, act, slope))
+    return rc;
+  B200CV_CHECK_ARG(coef && ok_vec(dy, dy_ld, C), "bn_bwd_apply: bad args");
+  a.coef = coef; a.dy = (bf16*)dy; a.dy_ld = dy_ld;
+  bn_bwd_apply_kernel<<<ew_grid(rows * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  return check_launch("bn_bwd_apply");
+}
+
+extern "C" int b200cv_act_bwd(const void* da, int64_t da_ld, const void* aout, int64_t aout_ld, void* dz,
+                              int64_t dz_ld, int64_t rows, int C, int act, float slope, void* stream) {
+  B200CV_CHECK_ARG(ok_vec(da, da_ld, C) && ok_vec(aout, aout_ld, C) && ok_vec(dz, dz_ld, C) && rows > 0,
+                   "act_bwd: bad args");
+  act_bwd_kernel<<<ew_grid(rows * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      (const bf16*)da, da_ld, (const bf16*)aout, aout_ld, (bf16*)dz, dz_ld, rows, C, act, slope);
+  return check_launch("act_bwd");
+}
+
+extern "C" int b200cv_copy_slice(const void* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows, int C,
+                                 int accumulate, void* stream) {
+  B200CV_CHECK_ARG(ok_vec(src, src_ld, C) && ok_vec(dst, dst_ld, C) && rows > 0, "copy_slice: bad args");
+  copy_slice_kernel<<<ew_grid(rows * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      (const bf16*)src, src_ld, (bf16*)dst, dst_ld, rows, C, accumulate);
+  return check_launch("copy_slice");
+}
+
+extern "C" int b200cv_col_sum(const void* x, int64_t ld, int64_t rows, int C, float* out, void* stream) {
+  B200CV_CHECK_ARG(ok_vec(x, ld, C) && out && rows > 0 && C / 8 <= 256, "col_sum: bad args");
+  const int vpr = C / 8;
+  const int rpp = 256 / vpr;
+  const long long passes = (rows + rpp - 1) / rpp;
+  const int grid = (int)std::max<long long>(1, std::min<long long>(passes, (long long)sm_count() * 4));
+  col_sum_kernel<<<grid, 256, C * sizeof(float), static_cast<cudaStream_t>(stream)>>>((const bf16*)x, ld, rows, C, out);
+  return check_launch("col_sum");
+}
+
+extern "C" int b200cv_maxpool2x2_fwd(const void* x, void* y, int N, int H, int W, int C, int stride, void* stream) {
+  B200CV_CHECK_ARG(ok_vec(x, C, C) && ok_vec(y, C, C) && (stride == 1 || stride == 2), "maxpool_fwd: bad args");
+  const int OH = stride == 2 ? H / 2 : H, OW = stride == 2 ? W / 2 : W;
+  maxpool_fwd_kernel<<<ew_grid((long long)N * OH * OW * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      (const bf16*)x, (bf16*)y, N, H, W, C, stride, OH, OW);
+  return check_launch("maxpool_fwd");
+}
+
+extern "C" int b200cv_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C, int stride,
+                                     void* stream) {
+  B200CV_CHECK_ARG(ok_vec(x, C, C) && ok_vec(dy, C, C) && ok_vec(dx, C, C) && (stride == 1 || stride == 2),
+                   "maxpool_bwd: bad args");
+  const int OH = stride == 2 ? H / 2 : H, OW = stride == 2 ? W / 2 : W;
+  maxpool_bwd_kernel<<<ew_grid((long long)N * H * W * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      (const bf16*)x, (const bf16*)dy, (bf16*)dx, N, H, W, C, stride, OH, OW);
+  return check_launch("maxpool_bwd");
+}
+
+extern "C" int b200cv_upsample2x_fwd(const void* x, void* y, int64_t y_ld, int N, int H, int W, int C, void* stream) {
+  B200CV_CHECK_ARG(ok_vec(x, C, C) && ok_vec(y, y_ld, C), "upsample_fwd: bad args");
+  upsample2x_fwd_kernel<<<ew_grid((long long)N * 4 * H * W * (C / 8), 256), 256, 0,
+                          static_cast<cudaStream_t>(stream)>>>((const bf16*)x, (bf16*)y, y_ld, N, H, W, C);
+  return check_launch("upsample_fwd");
+}
+
+extern "C" int b200cv_upsample2x_bwd(const void* dy, int64_t dy_ld, void* dx, int N, int H, int W, int C,
+                                     int accumulate, void* stream) {
+  B200CV_CHECK_ARG(ok_vec(dy, dy_ld, C) && ok_vec(dx, C, C), "upsample_bwd: bad args");
+  upsample2x_bwd_kernel<<<ew_grid((long long)N * H * W * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      (const bf16*)dy, dy_ld, (bf16*)dx, N, H, W, C, accumulate);
+  return check_launch("upsample_bwd");
+}
