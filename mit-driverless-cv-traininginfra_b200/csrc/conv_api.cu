@@ -78,6 +78,7 @@ void fill_epilogue(IgemmParams& p, const b200cv_conv_args* a, int64_t out_off, i
   p.r_sh = a->r_sh * mul_h;
   p.r_sw = a->r_sw * mul_w;
   p.r_sc = a->r_sc;
+  p.res_vec_ok = p.res && a->r_sc == 1 && aligned16(p.res) && p.r_sn % 8 == 0 && p.r_sh % 8 == 0 && p.r_sw % 8 == 0;
   p.scale = a->scale;
   p.shift = a->shift;
   p.act = a->act;

@@ -214,56 +214,86 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
         }
-        // affine + residual + activation, rounded the way it will be stored
+        const bool fast = p.vec_ok && (n_base + C::kChunk <= p.Cout) && (!p.res || p.res_vec_ok);
+        if (fast) {
+          // branch-free per element: the epilogue warps run one per scheduler, every branch costs
+          if (p.scale) {
 #pragma unroll
-        for (int j = 0; j < C::kChunk; ++j) {
-          const int n = n_base + j;
-          float x = v[j];
-          if (n < p.Cout) {
-            if (p.scale) x *= __ldg(p.scale + n);
-            if (p.shift) x += __ldg(p.shift + n);
-            if (p.res && row_ok) x += __bfloat162float(p.res[r_row + n * p.r_sc]);
-            x = apply_act(x, p.act, p.slope);
-            if (!p.out_fp32) x = __bfloat162float(__float2bfloat16_rn(x));
-          } else {
-            x = 0.f;
+            for (int j = 0; j < C::kChunk; j += 4) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + n_base + j));
+              v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
+            }
           }
-          v[j] = row_ok ? x : 0.f;
-        }
-        // store
-        if (row_ok) {
+          if (p.shift) {
+#pragma unroll
+            for (int j = 0; j < C::kChunk; j += 4) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.shift + n_base + j));
+              v[j] += s4.x; v[j + 1] += s4.y; v[j + 2] += s4.z; v[j + 3] += s4.w;
+            }
+          }
+          if (p.res) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res + (row_ok ? r_row : 0) + n_base);
+#pragma unroll
+            for (int j = 0; j < C::kChunk; j += 8) {
+              const uint4 q = __ldg(rp + (j >> 3));
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(h[e]);
+                v[j + 2 * e] += f.x;
+                v[j + 2 * e + 1] += f.y;
+              }
+            }
+          }
+          const float neg = p.act == 1 ? p.slope : (p.act == 2 ? 0.f : 1.f);
+          const float keep = row_ok ? 1.f : 0.f;
+#pragma unroll
+          for (int j = 0; j < C::kChunk; ++j) v[j] = (v[j] > 0.f ? v[j] : v[j] * neg) * keep;
           if (p.out_fp32) {
-            float* o = reinterpret_cast<float*>(p.out) + o_row;
-            if (p.vec_ok && n_base + C::kChunk <= p.Cout) {
+            if (row_ok) {
+              float* o = reinterpret_cast<float*>(p.out) + o_row + n_base;
 #pragma unroll
               for (int j = 0; j < C::kChunk; j += 4)
-                *reinterpret_cast<float4*>(o + n_base + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < C::kChunk; ++j)
-                if (n_base + j < p.Cout) o[(n_base + j) * p.o_sc] = v[j];
+                *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
           } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + o_row;
-            if (p.vec_ok && n_base + C::kChunk <= p.Cout) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + o_row + n_base;
 #pragma unroll
-              for (int j = 0; j < C::kChunk; j += 8) {
-                uint4 pk;
-                __nv_bfloat162 b0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-                __nv_bfloat162 b1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                __nv_bfloat162 b2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-                __nv_bfloat162 b3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                pk.x = *reinterpret_cast<uint32_t*>(&b0);
-                pk.y = *reinterpret_cast<uint32_t*>(&b1);
-                pk.z = *reinterpret_cast<uint32_t*>(&b2);
-                pk.w = *reinterpret_cast<uint32_t*>(&b3);
-                *reinterpret_cast<uint4*>(o + n_base + j) = pk;
+            for (int j = 0; j < C::kChunk; j += 8) {
+              uint4 pk;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                h[e] = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
+                const float2 f = __bfloat1622float2(h[e]);  // statistics see the stored (rounded) value
+                v[j + 2 * e] = f.x;
+                v[j + 2 * e + 1] = f.y;
+              }
+              if (row_ok) *reinterpret_cast<uint4*>(o + j) = pk;
+            }
+          }
+        } else {
+          // generic path: ragged channel tail, strided / unaligned outputs (NCHW heads, odd pitches)
+#pragma unroll 4
+          for (int j = 0; j < C::kChunk; ++j) {
+            const int n = n_base + j;
+            float x = v[j];
+            if (n < p.Cout && row_ok) {
+              if (p.scale) x *= __ldg(p.scale + n);
+              if (p.shift) x += __ldg(p.shift + n);
+              if (p.res) x += __bfloat162float(p.res[r_row + n * p.r_sc]);
+              x = apply_act(x, p.act, p.slope);
+              if (p.out_fp32) {
+                reinterpret_cast<float*>(p.out)[o_row + n * p.o_sc] = x;
+              } else {
+                const __nv_bfloat16 hb = __float2bfloat16_rn(x);
+                reinterpret_cast<__nv_bfloat16*>(p.out)[o_row + n * p.o_sc] = hb;
+                x = __bfloat162float(hb);
               }
             } else {
-#pragma unroll
-              for (int j = 0; j < C::kChunk; ++j)
-                if (n_base + j < p.Cout) o[(n_base + j) * p.o_sc] = __float2bfloat16_rn(v[j]);
+              x = 0.f;
             }
+            v[j] = x;
           }
         }
         // per-channel sum / sum-of-squares over the 32 rows of this warp (smem transpose)

@@ -7,6 +7,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -321,6 +322,89 @@ static void run_wgrad(const Case& c) {
   cudaFree(dx); cudaFree(ddy); cudaFree(ddw);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Timing mode: real Darknet-53 / RektNet layer shapes, CUDA-event timed, no CPU check.
+static void bench_case(const char* name, int N, int H, int W, int Cin_true, int Cout, int R, int stride, int pad,
+                       int dil) {
+  const int Cin = pad_c(Cin_true), Cop = pad_c(Cout);
+  const int OH = (H + 2 * pad - dil * (R - 1) - 1) / stride + 1;
+  const int OW = (W + 2 * pad - dil * (R - 1) - 1) / stride + 1;
+  const size_t nx = (size_t)N * H * W * Cin, ny = (size_t)N * OH * OW * Cop, nw = (size_t)Cop * R * R * Cin;
+  auto* dx = dalloc<__nv_bfloat16>(nx);
+  auto* dy = dalloc<__nv_bfloat16>(ny);
+  auto* dw = dalloc<__nv_bfloat16>(nw);
+  auto* dwt = dalloc<__nv_bfloat16>((size_t)Cin * R * R * Cop);
+  auto* dgw = dalloc<float>(nw);
+  auto* dstats = dalloc<float>(2 * Cout);
+  // non-trivial contents so the power draw is realistic
+  {
+    std::vector<__nv_bfloat16> h(std::max(nx, std::max(ny, nw)));
+    for (auto& v : h) v = __float2bfloat16_rn(frand());
+    CK(cudaMemcpy(dx, h.data(), nx * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dy, h.data(), ny * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dw, h.data(), nw * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dwt, h.data(), nw * 2, cudaMemcpyHostToDevice));
+  }
+  b200cv_conv_args f;
+  memset(&f, 0, sizeof(f));
+  f.N = N; f.H = H; f.W = W; f.Cin = Cin; f.Cout = Cout; f.R = R; f.S = R; f.stride = stride; f.pad = pad; f.dil = dil;
+  f.x = dx; f.w = dw; f.y = dy; f.y_dtype = B200CV_DT_BF16;
+  f.y_sn = (int64_t)OH * OW * Cop; f.y_sh = (int64_t)OW * Cop; f.y_sw = Cop; f.y_sc = 1;
+  f.stats = dstats;
+  b200cv_conv_args g;
+  memset(&g, 0, sizeof(g));
+  g.N = N; g.H = OH; g.W = OW; g.Cin = Cop; g.Cout = Cin_true; g.R = R; g.S = R; g.stride = stride; g.pad = pad; g.dil = dil;
+  g.x = dy; g.w = dwt; g.y = dx; g.y_dtype = B200CV_DT_BF16;
+  g.y_sn = (int64_t)H * W * Cin; g.y_sh = (int64_t)W * Cin; g.y_sw = Cin; g.y_sc = 1;
+  const double flop = 2.0 * N * OH * OW * (double)Cout * R * R * Cin_true;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  float ms[3] = {0, 0, 0};
+  for (int mode = 0; mode < 3; ++mode) {
+    const int iters = 10;
+    int rc = 0;
+    for (int i = 0; i < 3 + iters; ++i) {
+      if (i == 3) CK(cudaEventRecord(e0));
+      if (mode == 0) rc |= b200cv_conv_fwd(&f, nullptr);
+      if (mode == 1) rc |= b200cv_conv_dgrad(&g, H, W, nullptr);
+      if (mode == 2) rc |= b200cv_conv_wgrad(dx, dy, dgw, N, H, W, Cin, Cout, Cop, R, R, stride, pad, dil, nullptr);
+    }
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(&ms[mode], e0, e1));
+    ms[mode] /= iters;
+    if (rc) printf("  rc=%d %s\n", rc, b200cv_last_error());
+  }
+  int derr = b200cv_check_device_error(nullptr);
+  printf("%-28s N%d %dx%d c%d->%d k%d s%d | fwd %.3f ms %.0f TF | dgrad %.3f ms %.0f TF | wgrad %.3f ms %.0f TF | dev=%d\n",
+         name, N, H, W, Cin_true, Cout, R, stride, ms[0], flop / ms[0] * 1e-9, ms[1], flop / ms[1] * 1e-9, ms[2],
+         flop / ms[2] * 1e-9, derr);
+  fflush(stdout);
+  cudaFree(dx); cudaFree(dy); cudaFree(dw); cudaFree(dwt); cudaFree(dgw); cudaFree(dstats);
+}
+
+static int g_only = -1, g_case = 0;
+#define bench_case(...) do { if (g_only < 0 || g_only == g_case) bench_case(__VA_ARGS__); ++g_case; } while (0)
+static void run_bench() {
+  bench_case("dk53 3x3 128->256 @52", 64, 52, 52, 128, 256, 3, 1, 1, 1);
+  bench_case("dk53 3x3 256->512 @26", 64, 26, 26, 256, 512, 3, 1, 1, 1);
+  bench_case("dk53 3x3 512->1024 @13", 64, 13, 13, 512, 1024, 3, 1, 1, 1);
+  bench_case("dk53 3x3 64->128 @104", 64, 104, 104, 64, 128, 3, 1, 1, 1);
+  bench_case("dk53 3x3 32->64 @208", 64, 208, 208, 32, 64, 3, 1, 1, 1);
+  bench_case("dk53 1x1 256->128 @52", 64, 52, 52, 256, 128, 1, 1, 0, 1);
+  bench_case("dk53 1x1 512->256 @26", 64, 26, 26, 512, 256, 1, 1, 0, 1);
+  bench_case("dk53 1x1 1024->512 @13", 64, 13, 13, 1024, 512, 1, 1, 0, 1);
+  bench_case("dk53 3x3 3->32 @416", 64, 416, 416, 3, 32, 3, 1, 1, 1);
+  bench_case("dk53 3x3s2 32->64 @416", 64, 416, 416, 32, 64, 3, 2, 1, 1);
+  bench_case("dk53 3x3s2 128->256 @104", 64, 104, 104, 128, 256, 3, 2, 1, 1);
+  bench_case("dk53 1x1 1024->255 @13", 64, 13, 13, 1024, 255, 1, 1, 0, 1);
+  bench_case("rekt 3x3d2 64->128 @80", 256, 80, 80, 64, 128, 3, 1, 2, 2);
+  bench_case("rekt 3x3 128->128 @80", 256, 80, 80, 128, 128, 3, 1, 1, 1);
+  bench_case("rekt 3x3 16->16 @80", 256, 80, 80, 16, 16, 3, 1, 1, 1);
+  bench_case("rekt 7x7 3->16 @80", 256, 80, 80, 3, 16, 7, 1, 3, 1);
+}
+
 static Case mk(const char* name, int N, int H, int W, int Cin, int Cout, int R, int stride, int pad, int dil) {
   Case c;
   c.name = name; c.N = N; c.H = H; c.W = W; c.Cin_true = Cin; c.Cout = Cout; c.R = R; c.S = R;
@@ -334,6 +418,11 @@ int main(int argc, char** argv) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
   printf("device: %s sm_%d%d, %d SMs\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
+  if (g_filter && strcmp(g_filter, "bench") == 0) {
+    if (argc > 2) g_only = atoi(argv[2]);
+    run_bench();
+    return 0;
+  }
 
   std::vector<Case> fwd;
   fwd.push_back(mk("1x1_c64_o64", 2, 12, 12, 64, 64, 1, 1, 0, 1));
