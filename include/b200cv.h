@@ -75,13 +75,14 @@ typedef struct b200cv_conv_args {
   void* y;
   int32_t y_dtype; /* B200CV_DT_* */
   int64_t y_sn, y_sh, y_sw, y_sc;
-  /* fused epilogue:  y = act(acc*scale[c] + shift[c] + residual)  */
+  /* fused epilogue:  y = act(acc*scale[c] + shift[c] + residual)   (see res_after_act) */
   const float* scale;   /* [Cout] or NULL */
   const float* shift;   /* [Cout] or NULL (conv bias / folded BN) */
   const void* residual; /* bf16 or NULL, addressed like y with its own strides */
   int64_t r_sn, r_sh, r_sw, r_sc;
   int32_t act;
   float slope;
+  int32_t res_after_act; /* 1: y = act(acc*scale+shift) + residual (darknet shortcut after the activation) */
   /* per-channel [sum(y) | sum(y*y)] over N*OH*OW, atomically ADDED into stats[2*Cout]; NULL = off */
   float* stats;
 } b200cv_conv_args;
@@ -101,6 +102,104 @@ int b200cv_conv_dgrad(const b200cv_conv_args* a, int out_h, int out_w, void* str
  * autograd of nn.Conv2d: CVC-YOLOv3/train.py:70, RektNet/train_eval.py:71. */
 int b200cv_conv_wgrad(const void* x, const void* dy, float* dw_packed, int N, int H, int W, int Cin,
                       int Cout, int dy_ld, int R, int S, int stride, int pad, int dil, void* stream);
+
+/* ---- BatchNorm (training mode) + activation, NHWC bf16 rows with explicit pitch -------------- */
+/* From the conv epilogue's [sum | sumsq] produce scale/shift for the apply pass, the saved
+ * mean/rstd for backward, and update running stats (momentum, unbiased var) -- nn.BatchNorm2d in
+ * train(): CVC-YOLOv3/models.py:67, RektNet/keypoint_net.py:19, resnet.py:13,16,20.
+ * conv_bias (optional) is the bias of a conv whose bias was folded out (it cancels in train-mode BN). */
+int b200cv_bn_finalize(const float* stats, int64_t count, const float* gamma, const float* beta,
+                       const float* conv_bias, float eps, float momentum, float* running_mean,
+                       float* running_var, float* scale, float* shift, float* save_mean, float* save_rstd,
+                       int C, void* stream);
+/* out = act(y*scale+shift [+ y2*scale2+shift2]) [+ post]   (LeakyReLU/ReLU: models.py:69-71,
+ * resnet.py:24-26; `post` = darknet shortcut add models.py:325-327). */
+int b200cv_bn_apply_act(const void* y, int64_t y_ld, const float* scale, const float* shift, const void* y2,
+                        int64_t y2_ld, const float* scale2, const float* shift2, const void* post,
+                        int64_t post_ld, void* out, int64_t out_ld, int64_t rows, int C, int act, float slope,
+                        void* stream);
+/* backward pass 1: sums[c] += dz, sums[C+c] += dz*xhat with dz = da*act'(z).  z is recomputed from
+ * y*scale+shift, or its sign taken from `aout` (saved activation output) when given. */
+int b200cv_bn_bwd_reduce(const void* da, int64_t da_ld, const void* y, int64_t y_ld, const void* aout,
+                         int64_t aout_ld, const float* scale, const float* shift, const float* mean,
+                         const float* rstd, float* sums, int64_t rows, int C, int act, float slope, void* stream);
+/* coef = [gamma*rstd | sum_dz/M | sum_dz_xhat/M]; dgamma/dbeta written if non-NULL. */
+int b200cv_bn_bwd_finalize(const float* sums, const float* gamma, const float* rstd, int64_t count, float* coef,
+                           float* dgamma, float* dbeta, int C, void* stream);
+/* backward pass 2: dy = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)). */
+int b200cv_bn_bwd_apply(const void* da, int64_t da_ld, const void* y, int64_t y_ld, const void* aout,
+                        int64_t aout_ld, const float* scale, const float* shift, const float* mean,
+                        const float* rstd, const float* coef, void* dy, int64_t dy_ld, int64_t rows, int C,
+                        int act, float slope, void* stream);
+/* dz = da * act'(aout) for an activation that does not follow a BatchNorm. */
+int b200cv_act_bwd(const void* da, int64_t da_ld, const void* aout, int64_t aout_ld, void* dz, int64_t dz_ld,
+                   int64_t rows, int C, int act, float slope, void* stream);
+/* channel-slice copy (route/concat, models.py:322-324) or accumulate (gradient fan-in). */
+int b200cv_copy_slice(const void* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows, int C,
+                      int accumulate, void* stream);
+/* out[c] += sum over rows (conv bias gradient). */
+int b200cv_col_sum(const void* x, int64_t ld, int64_t rows, int C, float* out, void* stream);
+/* 2x2 max-pool, stride 2, or stride 1 with a ZERO pad right/bottom (models.py:74-84). */
+int b200cv_maxpool2x2_fwd(const void* x, void* y, int N, int H, int W, int C, int stride, void* stream);
+int b200cv_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C, int stride,
+                          void* stream);
+/* nearest x2 upsample (models.py:86-88). */
+int b200cv_upsample2x_fwd(const void* x, void* y, int64_t y_ld, int N, int H, int W, int C, void* stream);
+int b200cv_upsample2x_bwd(const void* dy, int64_t dy_ld, void* dx, int N, int H, int W, int C, int accumulate,
+                          void* stream);
+
+/* ---- YOLO head ------------------------------------------------------------------------------ */
+/* Target assignment (CVC-YOLOv3/utils/utils.py:195-275 build_targets, :163-193 bbox_iou).
+ * targets [B,T,5] = (cls,cx,cy,w,h) normalised, zero rows = padding; anchors_scaled [A,2] = anchor/stride.
+ * Outputs: owner int32 [B,A,Gh,Gw] (winning target index, -1 none), ign u8 [Gh,Gw], rec float [B,T,8]
+ * (gi,gj,best,label as int32 bits; tx,ty,tw,th), counts int32 [2] = (N_mask, N_conf_false). */
+int b200cv_yolo_targets(const float* targets, const float* anchors_scaled, int B, int T, int A, int Gh, int Gw,
+                        float ignore_thres, int32_t* owner, uint8_t* ign, float* rec, int32_t* counts,
+                        void* stream);
+/* Loss sums and/or gradient of the head logits (models.py:150-155,172-211).  logits fp32 addressed by
+ * element strides (channel = a*(5+C)+attr).  sums double[6] (x,y,w,h,obj,noobj un-normalised, atomically
+ * accumulated; NULL = skip).  dlogits (NULL = skip): bf16 or fp32; channel-contiguous layouts get all
+ * d_channels channels written (zeros for class/pad channels), strided fp32 layouts must be zero-filled by
+ * the caller.  gscale: device scalar multiplied into the gradient (upstream grad), NULL = 1. */
+int b200cv_yolo_loss(const float* logits, int64_t z_sb, int64_t z_sy, int64_t z_sx, int64_t z_sc, int B, int A,
+                     int C, int Gh, int Gw, const int32_t* owner, const uint8_t* ign, const float* rec, int T,
+                     const int32_t* counts, float xy_loss, float wh_loss, float obj_loss, float noobj_loss,
+                     double* sums, void* dlogits, int dl_dtype, int64_t d_sb, int64_t d_sy, int64_t d_sx,
+                     int64_t d_sc, int d_channels, const float* gscale, void* stream);
+/* out7[0] += total; out7[1..6] += (x,y,w,h,obj,noobj) -- the tuple order of models.py:211,338. */
+int b200cv_yolo_loss_finalize(const double* sums, const int32_t* counts, float xy_loss, float wh_loss,
+                              float obj_loss, float noobj_loss, float* out7, void* stream);
+/* eval decode (models.py:150-169,213-220) into out[b, row_offset + (a*Gh+gy)*Gw+gx, :5+C]. */
+int b200cv_yolo_decode(const float* logits, int64_t z_sb, int64_t z_sy, int64_t z_sx, int64_t z_sc, int B, int A,
+                       int C, int Gh, int Gw, const float* anchors_scaled, float stride, float* out,
+                       int64_t out_batch_stride, int64_t row_offset, void* stream);
+/* the eight dense tensors build_targets() returns (u8,u8,f32 x5,u8). */
+int b200cv_yolo_targets_dense(const int32_t* owner, const uint8_t* ign, const float* rec, int B, int T, int A,
+                              int C, int Gh, int Gw, uint8_t* mask, uint8_t* conf_mask, float* tx, float* ty,
+                              float* tw, float* th, float* tconf, uint8_t* tcls, void* stream);
+
+/* ---- RektNet head ----------------------------------------------------------------------------- */
+/* flat_softmax + soft_argmax (RektNet/keypoint_net.py:46-56): logits/hm [rows=B*K][H*W] fp32, pts [rows][2];
+ * vx[W], vy[H] are the linspace coordinate tables. */
+int b200cv_kpt_softmax_argmax(const float* logits, const float* vx, const float* vy, float* hm, float* pts,
+                              int rows, int H, int W, void* stream);
+/* CrossRatioLoss.forward (RektNet/cross_ratio_loss.py:20-63).  loss_type 0 l2_softargmax, 1 l2_heatmap,
+ * 2 l1_softargmax.  loss3 = (location, geo, total); ubar float[18] = batch-mean unit vectors (saved for
+ * backward); ws = one double of scratch. */
+int b200cv_kpt_loss(const float* hm, const float* pts, const float* thm, const float* tpts, int B, int K, int HW,
+                    int loss_type, int include_geo, float gamma_h, float gamma_v, double* ws, float* loss3,
+                    float* ubar, void* stream);
+/* Fused backward: loss gradients (g_loc, g_geo device scalars) + optional upstream d_hm/d_pts ->
+ * soft-argmax -> softmax Jacobian -> dlogits as NHWC bf16 [B*H*W][16]. */
+int b200cv_kpt_head_bwd(const float* hm, const float* thm, const float* pts, const float* tpts, const float* ubar,
+                        const float* vx, const float* vy, const float* g_loc, const float* g_geo,
+                        const float* d_hm_up, const float* d_pts_up, int B, int K, int H, int W, int loss_type,
+                        int include_geo, float gamma_h, float gamma_v, void* dlogits, int ld, void* stream);
+/* Un-fused CrossRatioLoss backward for tensors that did not come from KeypointNet: d_pts [B,K,2] and,
+ * if d_hm != NULL, d_hm [B,K,H,W] (= 2 g (hm - thm) / B for l2_heatmap, else 0). */
+int b200cv_kpt_loss_bwd(const float* hm, const float* thm, const float* pts, const float* tpts, const float* ubar,
+                        const float* g_loc, const float* g_geo, int B, int K, int H, int W, int loss_type,
+                        int include_geo, float gamma_h, float gamma_v, float* d_pts, float* d_hm, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,334 @@
+"""Executor of a Darknet cfg on the B200 kernels.
+
+``models.Darknet`` keeps ordinary fp32 ``nn.Conv2d`` / ``nn.BatchNorm2d`` modules (so state_dict,
+``.weights`` I/O and torch.optim work unchanged) but never calls them: forward and backward of the
+whole network are ONE ``torch.autograd.Function`` whose body is a sequence of C-ABI launches over
+NHWC bf16 activations:
+
+  conv (tcgen05 implicit GEMM, epilogue emits per-channel sum/sumsq) -> bn_finalize ->
+  bn_apply + LeakyReLU (+ fused shortcut add) ... -> head conv (fp32 logits) -> yolo targets + loss
+
+and, in reverse, yolo dlogits -> [bn_bwd_reduce, bn_bwd_finalize, bn_bwd_apply, wgrad, dgrad(+fan-in
+residual)] per conv.  Parameter gradients land in one flat fp32 arena (views are returned to
+autograd), which is what the data-parallel all-reduce sends over NCCL.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from . import ops, yolo_ops
+from .lib import require_cuda
+from .parallel import allreduce_gradients
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+class _Layer:
+    __slots__ = ("index", "type", "conv", "bn", "act", "slope", "k", "stride", "pad", "cin", "cout", "inputs",
+                 "post_from", "fused_alias", "yolo", "stats", "scale", "shift", "mean", "rstd", "sums", "coef",
+                 "wpk", "wpk_t", "pool_stride")
+
+    def __init__(self, index, type_):
+        self.index, self.type = index, type_
+        self.conv = self.bn = self.yolo = None
+        self.post_from = None      # conv: index of the tensor added after the activation (fused shortcut)
+        self.fused_alias = False   # shortcut: output is the previous conv's post-add output
+        self.inputs: List[int] = []
+        self.stats = None
+
+
+class DarknetEngine:
+    def __init__(self, model):
+        self.model = model
+        self.layers: List[_Layer] = []
+        slope = float(model.hyperparams["leaky_slope"])
+        n = len(model.module_defs)
+        for i, (d, m) in enumerate(zip(model.module_defs, model.module_list)):
+            L = _Layer(i, d["type"])
+            if L.type == "convolutional":
+                L.conv = m[0]
+                L.bn = m[1] if d["filters"] != "preyolo" else None
+                names = [type(x).__name__ for x in m]
+                L.act = ops.ACT_LEAKY if "LeakyReLU" in names else (ops.ACT_RELU if "ReLU" in names else ops.ACT_NONE)
+                L.slope = slope if L.act == ops.ACT_LEAKY else 0.0
+                L.k, L.stride, L.pad = L.conv.kernel_size[0], L.conv.stride[0], L.conv.padding[0]
+                L.cin, L.cout = L.conv.in_channels, L.conv.out_channels
+                L.inputs = [i - 1]
+            elif L.type == "maxpool":
+                L.pool_stride = int(d["stride"])
+                if int(d["size"]) != 2 or L.pool_stride not in (1, 2):
+                    raise ValueError("only 2x2 max-pool with stride 1 or 2 is supported")
+                L.inputs = [i - 1]
+            elif L.type == "upsample":
+                if int(d["stride"]) != 2:
+                    raise ValueError("only x2 upsample is supported")
+                L.inputs = [i - 1]
+            elif L.type == "route":
+                L.inputs = [(i + v) if v < 0 else v for v in (int(x) for x in d["layers"].split(","))]
+            elif L.type == "shortcut":
+                f = int(d["from"])
+                L.inputs = [i - 1, (i + f) if f < 0 else f]
+            elif L.type == "yolo":
+                L.yolo = m[0]
+                L.inputs = [i - 1]
+            else:
+                raise ValueError(f"unsupported cfg block [{L.type}]")
+            self.layers.append(L)
+        # fuse "conv+bn+act ; shortcut" into the conv's apply pass when nothing else reads the conv output
+        consumers = {i: [] for i in range(-1, n)}
+        for L in self.layers:
+            for j in L.inputs:
+                consumers[j].append(L.index)
+        for L in self.layers:
+            if L.type == "shortcut":
+                prev = self.layers[L.index - 1]
+                if prev.type == "convolutional" and prev.bn is not None and consumers[prev.index] == [L.index]:
+                    prev.post_from = L.inputs[1]
+                    L.fused_alias = True
+        self.params = list(model.parameters())
+        self._offsets = None
+
+    # ------------------------------------------------------------------ helpers
+    def _vec(self, L: _Layer, dev):
+        if L.stats is None or L.stats.device != dev:
+            c = L.cout
+            f = lambda n: torch.empty(n, dtype=torch.float32, device=dev)
+            L.stats, L.scale, L.shift, L.mean, L.rstd = f(2 * c), f(c), f(c), f(c), f(c)
+            L.sums, L.coef = f(2 * c), f(3 * c)
+
+    def _pack(self, need_t: bool):
+        for L in self.layers:
+            if L.type == "convolutional":
+                L.wpk = ops.pack_weights(L.conv.weight, False)
+                L.wpk_t = ops.pack_weights(L.conv.weight, True) if (need_t and L.index > 0) else None
+
+    def _check_input(self, x):
+        require_cuda(x, "Darknet.forward")
+        if x.dim() != 4 or x.shape[1] != self.layers[0].cin:
+            raise ValueError(f"expected input [B,{self.layers[0].cin},H,W], got {tuple(x.shape)}")
+
+    # ------------------------------------------------------------------ forward
+    def _run_forward(self, x, targets, bn_train: bool, want_grad: bool):
+        """Returns (out7 or detections, saved-state)."""
+        model = self.model
+        dev = x.device
+        self._pack(need_t=want_grad)
+        cur = ops.nchw_to_nhwc(x)
+        outs: List[Optional[torch.Tensor]] = [None] * len(self.layers)
+        saved = {}
+        training = targets is not None
+        out7 = torch.zeros(7, dtype=torch.float32, device=dev) if training else None
+        dets, row0 = None, 0
+        if not training:
+            total_rows = 0
+            h = x.shape[2]
+            # rows per head are known only after the head conv ran; collect and concatenate lazily
+            dets = []
+        consts = (model.xy_loss, model.wh_loss, model.object_loss, model.no_object_loss)
+        for L in self.layers:
+            i = L.index
+            if L.type == "convolutional":
+                xin = cur
+                if L.bn is not None:
+                    self._vec(L, dev)
+                    post = outs[L.post_from] if L.post_from is not None else None
+                    if bn_train:
+                        L.stats.zero_()
+                        y = ops.conv_fwd(xin, L.wpk, L.cout, L.k, L.stride, L.pad, stats=L.stats)
+                        count = y.numel() // y.shape[-1]
+                        ops.bn_finalize(L.stats, count, L.bn.weight, L.bn.bias, None, BN_EPS, BN_MOMENTUM,
+                                        L.bn.running_mean, L.bn.running_var, L.scale, L.shift, L.mean, L.rstd)
+                        if L.bn.num_batches_tracked is not None:
+                            L.bn.num_batches_tracked += 1
+                        cur = ops.bn_apply_act(y, L.scale, L.shift, L.act, L.slope, post=post)
+                        saved[i] = (xin, y)
+                    else:
+                        scale = L.bn.weight.detach() * torch.rsqrt(L.bn.running_var + BN_EPS)
+                        shift = L.bn.bias.detach() - L.bn.running_mean * scale
+                        cur = ops.conv_fwd(xin, L.wpk, L.cout, L.k, L.stride, L.pad, scale=scale, shift=shift,
+                                           residual=post, act=L.act, slope=L.slope, res_after_act=True)
+                        if want_grad:
+                            raise RuntimeError("Darknet: backward through eval-mode BatchNorm is not supported; "
+                                               "call model.train() (or wrap the pass in torch.no_grad())")
+                else:  # pre-YOLO conv: bias, linear, fp32 logits
+                    cur = ops.conv_fwd(xin, L.wpk, L.cout, L.k, L.stride, L.pad, out_dtype=torch.float32,
+                                       shift=L.conv.bias.detach())
+                    saved[i] = (xin,)
+            elif L.type == "maxpool":
+                saved[i] = (cur,)
+                cur = ops.maxpool_fwd(cur, L.pool_stride)
+            elif L.type == "upsample":
+                cur = ops.upsample_fwd(cur)
+            elif L.type == "route":
+                if len(L.inputs) == 1:
+                    cur = outs[L.inputs[0]]
+                else:
+                    parts = [outs[j] for j in L.inputs]
+                    b, hh, ww = parts[0].shape[:3]
+                    cur = torch.empty(b, hh, ww, sum(p.shape[-1] for p in parts), dtype=parts[0].dtype, device=dev)
+                    c0 = 0
+                    for p in parts:
+                        ops.copy_slice(p, cur[..., c0:c0 + p.shape[-1]])
+                        c0 += p.shape[-1]
+            elif L.type == "shortcut":
+                if L.fused_alias:
+                    cur = outs[i - 1]
+                else:
+                    cur = outs[L.inputs[0]].clone()
+                    ops.copy_slice(outs[L.inputs[1]], cur, accumulate=True)
+            elif L.type == "yolo":
+                z = cur  # fp32 [B,G,G,Cpad]
+                yl = L.yolo
+                gh, gw = z.shape[1], z.shape[2]
+                stride = yl.image_height / gh
+                sa = yolo_ops.scaled_anchors(yl.anchors, stride, dev)
+                if training:
+                    yt = yolo_ops.yolo_targets(targets, sa, gh, gw, yl.ignore_thres)
+                    sums = torch.zeros(6, dtype=torch.float64, device=dev)
+                    yolo_ops.yolo_loss(z, False, yt, yl.num_classes, consts, sums=sums)
+                    yolo_ops.yolo_loss_finalize(sums, yt, consts, out7)
+                    saved[i] = (z, yt)
+                    cur = None
+                else:
+                    rows = yl.num_anchors * gh * gw
+                    d = torch.empty(z.shape[0], rows, 5 + yl.num_classes, dtype=torch.float32, device=dev)
+                    yolo_ops.yolo_decode(z, False, yl.num_anchors, yl.num_classes, sa, stride, d, 0)
+                    dets.append(d)
+                    cur = d
+            outs[i] = cur
+        if training:
+            return out7, (outs, saved)
+        return torch.cat(dets, 1), None
+
+    # ------------------------------------------------------------------ backward
+    def _grad_views(self, dev):
+        sizes = [p.numel() for p in self.params]
+        arena = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        views, o = [], 0
+        for p, n in zip(self.params, sizes):
+            views.append(arena[o:o + n].view_as(p))
+            o += n
+        return arena, views
+
+    def _run_backward(self, state, g7):
+        outs, saved = state
+        model = self.model
+        dev = g7.device
+        g = g7[0:1].contiguous().float()
+        arena, views = self._grad_views(dev)
+        gview = {id(p): v for p, v in zip(self.params, views)}
+        consts = (model.xy_loss, model.wh_loss, model.object_loss, model.no_object_loss)
+        grads: List[Optional[torch.Tensor]] = [None] * len(self.layers)
+
+        def add_grad(j, t):
+            if j < 0:
+                return
+            if grads[j] is None:
+                grads[j] = t
+            else:
+                ops.copy_slice(t, grads[j], accumulate=True)
+
+        for L in reversed(self.layers):
+            i = L.index
+            if L.type == "yolo":
+                z, yt = saved[i]
+                dl = torch.empty(z.shape, dtype=torch.bfloat16, device=dev)
+                yolo_ops.yolo_loss(z, False, yt, L.yolo.num_classes, consts, dlogits=dl, gscale=g)
+                add_grad(i - 1, dl)
+                continue
+            G = grads[i]
+            if G is None:
+                if L.type == "convolutional":  # parameters that received no gradient
+                    gview[id(L.conv.weight)].zero_()
+                    if L.bn is not None:
+                        gview[id(L.bn.weight)].zero_()
+                        gview[id(L.bn.bias)].zero_()
+                    else:
+                        gview[id(L.conv.bias)].zero_()
+                continue
+            if L.type == "convolutional":
+                if L.bn is not None:
+                    xin, y = saved[i]
+                    count = y.numel() // y.shape[-1]
+                    L.sums.zero_()
+                    ops.bn_bwd_reduce(G, y, None, L.scale, L.shift, L.mean, L.rstd, L.sums, L.act, L.slope)
+                    ops.bn_bwd_finalize(L.sums, L.bn.weight, L.rstd, count, L.coef, gview[id(L.bn.weight)],
+                                        gview[id(L.bn.bias)])
+                    dy = ops.bn_bwd_apply(G, y, None, L.scale, L.shift, L.mean, L.rstd, L.coef, L.act, L.slope)
+                    if L.post_from is not None:
+                        add_grad(L.post_from, G)
+                else:
+                    (xin,) = saved[i]
+                    dy = G
+                    tmp = torch.zeros(dy.shape[-1], dtype=torch.float32, device=dev)
+                    ops.col_sum(dy, tmp)
+                    gview[id(L.conv.bias)].copy_(tmp[:L.cout])
+                dwp = ops.conv_wgrad(xin, dy, L.cout, L.k, L.stride, L.pad)
+                ops.unpack_wgrad(dwp, gview[id(L.conv.weight)])
+                if i > 0:
+                    prev = grads[i - 1]
+                    dx = ops.conv_dgrad(dy, L.wpk_t, L.cin, L.k, L.stride, L.pad, 1, (xin.shape[1], xin.shape[2]),
+                                        out=prev, residual=prev)
+                    grads[i - 1] = dx
+            elif L.type == "maxpool":
+                (xin,) = saved[i]
+                add_grad(i - 1, ops.maxpool_bwd(xin, G, L.pool_stride))
+            elif L.type == "upsample":
+                if grads[i - 1] is None:
+                    grads[i - 1] = ops.upsample_bwd(G)
+                else:
+                    ops.upsample_bwd(G, grads[i - 1], accumulate=True)
+            elif L.type == "route":
+                if len(L.inputs) == 1:
+                    add_grad(L.inputs[0], G)
+                else:
+                    c0 = 0
+                    for j in L.inputs:
+                        c = outs[j].shape[-1]
+                        sl = G[..., c0:c0 + c]
+                        if grads[j] is None:
+                            dst = torch.empty(outs[j].shape, dtype=G.dtype, device=dev)
+                            grads[j] = ops.copy_slice(sl, dst)
+                        else:
+                            ops.copy_slice(sl, grads[j], accumulate=True)
+                        c0 += c
+            elif L.type == "shortcut":
+                if L.fused_alias:
+                    add_grad(i - 1, G)  # the conv adds G to its `post_from` input itself
+                else:
+                    add_grad(L.inputs[0], G)
+                    add_grad(L.inputs[1], G)
+            grads[i] = None
+        allreduce_gradients(arena)
+        return views
+
+    # ------------------------------------------------------------------ public entry points
+    def train_forward(self, x, targets):
+        self._check_input(x)
+        require_cuda(targets, "Darknet.forward(targets)")
+        return _DarknetTrainFn.apply(self, x, targets.float(), self.model.training, *self.params)
+
+    @torch.no_grad()
+    def detect(self, x):
+        self._check_input(x)
+        det, _ = self._run_forward(x.float(), None, bn_train=self.model.training, want_grad=False)
+        return det
+
+
+class _DarknetTrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine, x, targets, bn_train, *params):
+        want_grad = any(ctx.needs_input_grad[4:])
+        out7, state = engine._run_forward(x.float(), targets, bn_train=bn_train, want_grad=want_grad)
+        ctx.engine = engine
+        ctx.state = state
+        return out7
+
+    @staticmethod
+    def backward(ctx, g7):
+        views = ctx.engine._run_backward(ctx.state, g7)
+        ctx.state = None
+        return (None, None, None, None, *views)

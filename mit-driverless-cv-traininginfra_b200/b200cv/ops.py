@@ -1,0 +1,233 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point of include/b200cv.h).
+
+PyTorch supplies device memory (torch.empty), the current stream and nothing else: every function
+here passes raw device pointers / sizes / strides to libb200cv.so.  Activations are NHWC bf16
+tensors of shape [N,H,W,C] (C padded by pad_channels), per-channel vectors are fp32.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from .lib import ACT_LEAKY, ACT_NONE, ACT_RELU, DT_BF16, DT_F32, ConvArgs, lib, ptr, require_cuda, stream_ptr
+
+__all__ = [
+    "ACT_NONE", "ACT_LEAKY", "ACT_RELU", "pad_channels", "conv_out_size", "nchw_to_nhwc", "nhwc_to_nchw",
+    "pack_weights", "unpack_wgrad", "conv_fwd", "conv_dgrad", "conv_wgrad", "bn_finalize", "bn_apply_act",
+    "bn_bwd_reduce", "bn_bwd_finalize", "bn_bwd_apply", "act_bwd", "copy_slice", "col_sum", "maxpool_fwd",
+    "maxpool_bwd", "upsample_fwd", "upsample_bwd", "act_code",
+]
+
+
+def pad_channels(c: int) -> int:
+    return lib().pad_channels(c)
+
+
+def act_code(name: str) -> int:
+    return {"leaky": ACT_LEAKY, "ReLU": ACT_RELU, "relu": ACT_RELU, "linear": ACT_NONE, "none": ACT_NONE}[name]
+
+
+def conv_out_size(h: int, k: int, stride: int, pad: int, dil: int = 1) -> int:
+    return (h + 2 * pad - dil * (k - 1) - 1) // stride + 1
+
+
+def _rows(t: torch.Tensor) -> int:
+    return t.numel() // t.shape[-1]
+
+
+# ------------------------------------------------------------------------------ layout / packing
+def nchw_to_nhwc(x: torch.Tensor, cpad: int | None = None) -> torch.Tensor:
+    """fp32 NCHW -> bf16 NHWC with zero-padded channels."""
+    require_cuda(x, "nchw_to_nhwc")
+    x = x.contiguous().float()
+    n, c, h, w = x.shape
+    cpad = cpad or pad_channels(c)
+    out = torch.empty(n, h, w, cpad, dtype=torch.bfloat16, device=x.device)
+    lib().call("b200cv_nchw_f32_to_nhwc_bf16", ptr(x), ptr(out), n, c, h, w, cpad, stream_ptr())
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor, c: int) -> torch.Tensor:
+    n, h, w, cpad = x.shape
+    out = torch.empty(n, c, h, w, dtype=torch.float32, device=x.device)
+    lib().call("b200cv_nhwc_bf16_to_nchw_f32", ptr(x), ptr(out), n, c, h, w, cpad, stream_ptr())
+    return out
+
+
+def pack_weights(w: torch.Tensor, transpose: bool) -> torch.Tensor:
+    """OIHW fp32 -> bf16 [O][R*S][Ipad] (forward) or [I][R*S][Opad] (data gradient)."""
+    require_cuda(w, "pack_weights")
+    o, i, r, s = w.shape
+    ipad, opad = pad_channels(i), pad_channels(o)
+    shape = (i, r * s, opad) if transpose else (o, r * s, ipad)
+    out = torch.empty(shape, dtype=torch.bfloat16, device=w.device)
+    lib().call("b200cv_pack_weights", ptr(w.detach().contiguous()), ptr(out), o, i, r, s, ipad, opad, int(transpose),
+               stream_ptr())
+    return out
+
+
+def unpack_wgrad(dw_packed: torch.Tensor, out_oihw: torch.Tensor):
+    o, i, r, s = out_oihw.shape
+    lib().call("b200cv_unpack_wgrad", ptr(dw_packed), ptr(out_oihw), o, i, r, s, dw_packed.shape[-1], stream_ptr())
+
+
+# ------------------------------------------------------------------------------ convolution
+def _conv_args(x, wpk, y, cout, k, stride, pad, dil, y_strides, y_dtype, scale, shift, residual, r_strides, act,
+               slope, res_after_act, stats) -> ConvArgs:
+    a = ConvArgs()
+    a.N, a.H, a.W, a.Cin = x.shape
+    a.Cout = cout
+    a.R = a.S = k
+    a.stride, a.pad, a.dil = stride, pad, dil
+    a.x, a.w, a.y = ptr(x), ptr(wpk), ptr(y)
+    a.y_dtype = y_dtype
+    a.y_sn, a.y_sh, a.y_sw, a.y_sc = y_strides
+    a.scale, a.shift, a.residual = ptr(scale), ptr(shift), ptr(residual)
+    if residual is not None:
+        a.r_sn, a.r_sh, a.r_sw, a.r_sc = r_strides
+    a.act, a.slope, a.res_after_act = act, slope, int(res_after_act)
+    a.stats = ptr(stats)
+    return a
+
+
+def conv_fwd(x, wpk, cout, k, stride, pad, dil=1, out=None, out_dtype=torch.bfloat16, out_channels=None, scale=None,
+             shift=None, residual=None, act=ACT_NONE, slope=0.0, res_after_act=False, stats=None,
+             nchw_out=False) -> torch.Tensor:
+    """x NHWC bf16 -> y.  `out` may be a channel slice (a view whose last-dim stride is 1)."""
+    n, h, w, _ = x.shape
+    oh, ow = conv_out_size(h, k, stride, pad, dil), conv_out_size(w, k, stride, pad, dil)
+    if out is None:
+        if nchw_out:
+            out = torch.empty(n, cout, oh, ow, dtype=out_dtype, device=x.device)
+        else:
+            out = torch.empty(n, oh, ow, out_channels or pad_channels(cout), dtype=out_dtype, device=x.device)
+    if nchw_out:
+        ys = (out.stride(0), out.stride(2), out.stride(3), out.stride(1))
+    else:
+        ys = (out.stride(0), out.stride(1), out.stride(2), out.stride(3))
+    rs = None
+    if residual is not None:
+        rs = (residual.stride(0), residual.stride(1), residual.stride(2), residual.stride(3))
+    a = _conv_args(x, wpk, out, cout, k, stride, pad, dil, ys, DT_F32 if out.dtype == torch.float32 else DT_BF16,
+                   scale, shift, residual, rs, act, slope, res_after_act, stats)
+    lib().call("b200cv_conv_fwd", ctypes.byref(a), stream_ptr())
+    return out
+
+
+def conv_dgrad(dy, wpk_t, cin_fwd, k, stride, pad, dil, out_hw, out=None, residual=None) -> torch.Tensor:
+    """dy NHWC bf16 [N,OH,OW,pad(Cout)] -> dx NHWC bf16 [N,H,W,pad(Cin_fwd)] (+ residual)."""
+    n = dy.shape[0]
+    h, w = out_hw
+    if out is None:
+        cpad = pad_channels(cin_fwd)
+        out = torch.empty(n, h, w, cpad, dtype=torch.bfloat16, device=dy.device)
+        if cpad != cin_fwd:
+            out.zero_()
+    ys = (out.stride(0), out.stride(1), out.stride(2), out.stride(3))
+    rs = None
+    if residual is not None:
+        rs = (residual.stride(0), residual.stride(1), residual.stride(2), residual.stride(3))
+    a = _conv_args(dy, wpk_t, out, cin_fwd, k, stride, pad, dil, ys, DT_BF16, None, None, residual, rs, ACT_NONE, 0.0,
+                   False, None)
+    lib().call("b200cv_conv_dgrad", ctypes.byref(a), h, w, stream_ptr())
+    return out
+
+
+def conv_wgrad(x, dy, cout, k, stride, pad, dil=1) -> torch.Tensor:
+    """Returns the packed fp32 gradient [Cout][k*k][Cin_pad]."""
+    n, h, w, cin = x.shape
+    dwp = torch.zeros(cout, k * k, cin, dtype=torch.float32, device=x.device)
+    lib().call("b200cv_conv_wgrad", ptr(x), ptr(dy), ptr(dwp), n, h, w, cin, cout, dy.shape[-1], k, k, stride, pad, dil,
+               stream_ptr())
+    return dwp
+
+
+# ------------------------------------------------------------------------------ batch-norm + activation
+def bn_finalize(stats, count, gamma, beta, conv_bias, eps, momentum, running_mean, running_var, scale, shift, mean,
+                rstd):
+    lib().call("b200cv_bn_finalize", ptr(stats), int(count), ptr(gamma), ptr(beta), ptr(conv_bias), float(eps),
+               float(momentum), ptr(running_mean), ptr(running_var), ptr(scale), ptr(shift), ptr(mean), ptr(rstd),
+               gamma.numel(), stream_ptr())
+
+
+def bn_apply_act(y, scale, shift, act, slope, out=None, y2=None, scale2=None, shift2=None, post=None):
+    c = y.shape[-1]
+    if out is None:
+        out = torch.empty_like(y)
+    lib().call("b200cv_bn_apply_act", ptr(y), y.stride(-2), ptr(scale), ptr(shift), ptr(y2),
+               0 if y2 is None else y2.stride(-2), ptr(scale2), ptr(shift2), ptr(post),
+               0 if post is None else post.stride(-2), ptr(out), out.stride(-2), _rows(y), c, act, float(slope),
+               stream_ptr())
+    return out
+
+
+def bn_bwd_reduce(da, y, aout, scale, shift, mean, rstd, sums, act, slope):
+    lib().call("b200cv_bn_bwd_reduce", ptr(da), da.stride(-2), ptr(y), y.stride(-2), ptr(aout),
+               0 if aout is None else aout.stride(-2), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), ptr(sums),
+               _rows(y), y.shape[-1], act, float(slope), stream_ptr())
+
+
+def bn_bwd_finalize(sums, gamma, rstd, count, coef, dgamma, dbeta):
+    lib().call("b200cv_bn_bwd_finalize", ptr(sums), ptr(gamma), ptr(rstd), int(count), ptr(coef), ptr(dgamma),
+               ptr(dbeta), gamma.numel(), stream_ptr())
+
+
+def bn_bwd_apply(da, y, aout, scale, shift, mean, rstd, coef, act, slope, out=None):
+    if out is None:
+        out = torch.empty_like(y)
+    lib().call("b200cv_bn_bwd_apply", ptr(da), da.stride(-2), ptr(y), y.stride(-2), ptr(aout),
+               0 if aout is None else aout.stride(-2), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), ptr(coef),
+               ptr(out), out.stride(-2), _rows(y), y.shape[-1], act, float(slope), stream_ptr())
+    return out
+
+
+def act_bwd(da, aout, act, slope):
+    out = torch.empty_like(aout)
+    lib().call("b200cv_act_bwd", ptr(da), da.stride(-2), ptr(aout), aout.stride(-2), ptr(out), out.stride(-2),
+               _rows(aout), aout.shape[-1], act, float(slope), stream_ptr())
+    return out
+
+
+def copy_slice(src, dst, accumulate=False):
+    """dst[..., :C] (=|+=) src[..., :C] for NHWC views with unit channel stride."""
+    lib().call("b200cv_copy_slice", ptr(src), src.stride(-2), ptr(dst), dst.stride(-2), _rows(src), src.shape[-1],
+               int(accumulate), stream_ptr())
+    return dst
+
+
+def col_sum(x, out):
+    lib().call("b200cv_col_sum", ptr(x), x.stride(-2), _rows(x), x.shape[-1], ptr(out), stream_ptr())
+    return out
+
+
+def maxpool_fwd(x, stride):
+    n, h, w, c = x.shape
+    oh, ow = (h // 2, w // 2) if stride == 2 else (h, w)
+    y = torch.empty(n, oh, ow, c, dtype=x.dtype, device=x.device)
+    lib().call("b200cv_maxpool2x2_fwd", ptr(x), ptr(y), n, h, w, c, stride, stream_ptr())
+    return y
+
+
+def maxpool_bwd(x, dy, stride):
+    n, h, w, c = x.shape
+    dx = torch.empty_like(x)
+    lib().call("b200cv_maxpool2x2_bwd", ptr(x), ptr(dy), ptr(dx), n, h, w, c, stride, stream_ptr())
+    return dx
+
+
+def upsample_fwd(x, out=None):
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty(n, 2 * h, 2 * w, c, dtype=x.dtype, device=x.device)
+    lib().call("b200cv_upsample2x_fwd", ptr(x), ptr(out), out.stride(-2), n, h, w, c, stream_ptr())
+    return out
+
+
+def upsample_bwd(dy, dx=None, accumulate=False):
+    n, oh, ow, c = dy.shape
+    if dx is None:
+        dx = torch.empty(n, oh // 2, ow // 2, c, dtype=dy.dtype, device=dy.device)
+    lib().call("b200cv_upsample2x_bwd", ptr(dy), dy.stride(-2), ptr(dx), n, oh // 2, ow // 2, c, int(accumulate),
+               stream_ptr())
+    return dx

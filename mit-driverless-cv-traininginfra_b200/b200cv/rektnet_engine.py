@@ -1,0 +1,309 @@
+"""Executor of RektNet's KeypointNet (+ CrossRatioLoss) on the B200 kernels.
+
+``keypoint_net.KeypointNet`` keeps its fp32 nn.Conv2d / nn.BatchNorm2d parameters (same state_dict
+names as the reference) but forward/backward run here: tcgen05 convolutions over NHWC bf16
+(7x7 stem, dilated 3x3, 3x3, 1x1), two-branch BN+ReLU apply for the residual blocks, a head conv that
+writes fp32 NCHW logits, one softmax+soft-argmax kernel, and ONE fused kernel from the loss to the
+head-logit gradient.
+
+Fusion across the module boundary: KeypointNet.forward tags the (hm, pts) it returns with a handle.
+CrossRatioLoss.forward that sees the tag defers its backward to that handle, so the net's backward
+launches a single kernel: loss gradient -> soft-argmax -> softmax Jacobian -> dlogits.  Untagged
+tensors take the un-fused kernels (b200cv_kpt_loss_bwd).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from . import ops
+from .lib import lib, ptr, require_cuda, stream_ptr
+from .parallel import allreduce_gradients
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+LOSS_TYPES = {"l2_softargmax": 0, "l2_sm": 0, "l2_heatmap": 1, "l2_hm": 1, "l1_softargmax": 2, "l1_sm": 2}
+
+
+class _ConvBN:
+    """A conv followed by a train-mode BN; owns the per-channel scratch vectors."""
+
+    def __init__(self, conv, bn):
+        self.conv, self.bn = conv, bn
+        self.k, self.pad, self.dil = conv.kernel_size[0], conv.padding[0], conv.dilation[0]
+        self.cin, self.cout = conv.in_channels, conv.out_channels
+        self.vec_dev = None
+
+    def vecs(self, dev):
+        if self.vec_dev != dev:
+            c = self.cout
+            f = lambda n: torch.empty(n, dtype=torch.float32, device=dev)
+            self.stats, self.scale, self.shift, self.mean, self.rstd = f(2 * c), f(c), f(c), f(c), f(c)
+            self.sums, self.coef = f(2 * c), f(3 * c)
+            self.vec_dev = dev
+
+    def pack(self, need_t):
+        self.wpk = ops.pack_weights(self.conv.weight, False)
+        self.wpk_t = ops.pack_weights(self.conv.weight, True) if need_t else None
+
+    def fwd_train(self, x):
+        self.vecs(x.device)
+        self.stats.zero_()
+        y = ops.conv_fwd(x, self.wpk, self.cout, self.k, 1, self.pad, self.dil, stats=self.stats)
+        count = y.numel() // y.shape[-1]
+        # the conv bias cancels inside a train-mode BN: it is left out of y and only enters running_mean
+        ops.bn_finalize(self.stats, count, self.bn.weight, self.bn.bias, self.conv.bias, BN_EPS, BN_MOMENTUM,
+                        self.bn.running_mean, self.bn.running_var, self.scale, self.shift, self.mean, self.rstd)
+        if self.bn.num_batches_tracked is not None:
+            self.bn.num_batches_tracked += 1
+        return y
+
+    def eval_affine(self):
+        scale = self.bn.weight.detach() * torch.rsqrt(self.bn.running_var + BN_EPS)
+        shift = self.bn.bias.detach() + (self.conv.bias.detach() - self.bn.running_mean) * scale
+        return scale, shift
+
+    def bwd(self, x_in, y, da, aout, act, gview, dx_out=None, want_dx=True):
+        """BN+act backward then wgrad (+ dgrad).  Returns dx (or None)."""
+        count = y.numel() // y.shape[-1]
+        self.sums.zero_()
+        ops.bn_bwd_reduce(da, y, aout, self.scale, self.shift, self.mean, self.rstd, self.sums, act, 0.0)
+        ops.bn_bwd_finalize(self.sums, self.bn.weight, self.rstd, count, self.coef, gview[id(self.bn.weight)],
+                            gview[id(self.bn.bias)])
+        dy = ops.bn_bwd_apply(da, y, aout, self.scale, self.shift, self.mean, self.rstd, self.coef, act, 0.0)
+        dwp = ops.conv_wgrad(x_in, dy, self.cout, self.k, 1, self.pad, self.dil)
+        ops.unpack_wgrad(dwp, gview[id(self.conv.weight)])
+        gview[id(self.conv.bias)].zero_()  # analytically zero under train-mode BN
+        if not want_dx:
+            return None
+        return ops.conv_dgrad(dy, self.wpk_t, self.cin, self.k, 1, self.pad, self.dil, (x_in.shape[1], x_in.shape[2]),
+                              out=dx_out, residual=dx_out)
+
+
+class _HeadHandle:
+    """Links the (hm, pts) returned by KeypointNet.forward with a CrossRatioLoss applied to them."""
+
+    def __init__(self):
+        self.pending = None  # dict set by the fused loss backward
+
+
+class RektNetEngine:
+    def __init__(self, model):
+        self.model = model
+        self.stem = _ConvBN(model.conv, model.bn)
+        self.blocks = []
+        for r in (model.res1, model.res2, model.res3, model.res4):
+            self.blocks.append((_ConvBN(r.conv1, r.bn1), _ConvBN(r.conv2, r.bn2), _ConvBN(r.shortcut_conv, r.shortcut_bn)))
+        self.params = list(model.parameters())
+        self._lin = None
+
+    def _coords(self, dev, h, w):
+        if self._lin is None or self._lin[0].device != dev or self._lin[0].numel() != w or self._lin[1].numel() != h:
+            vy = torch.linspace(0, (h - 1.0) / h, h, dtype=torch.float32, device=dev)  # keypoint_net.py:52-53
+            vx = torch.linspace(0, (w - 1.0) / w, w, dtype=torch.float32, device=dev)
+            self._lin = (vx, vy)
+        return self._lin
+
+    def _all(self):
+        yield self.stem
+        for b in self.blocks:
+            yield from b
+
+    # ------------------------------------------------------------------ forward
+    def _forward(self, x, train: bool, want_grad: bool):
+        m = self.model
+        dev = x.device
+        for c in self._all():
+            c.pack(need_t=want_grad)
+        out_wpk = ops.pack_weights(m.out.weight, False)
+        out_wpk_t = ops.pack_weights(m.out.weight, True) if want_grad else None
+        xin = ops.nchw_to_nhwc(x)
+        saved = {"x": xin, "blocks": [], "out_wpk_t": out_wpk_t}
+        if train:
+            y0 = self.stem.fwd_train(xin)
+            a = ops.bn_apply_act(y0, self.stem.scale, self.stem.shift, ops.ACT_RELU, 0.0)
+            saved["y0"] = y0
+            for c1, c2, cs in self.blocks:
+                y1 = c1.fwd_train(a)
+                a1 = ops.bn_apply_act(y1, c1.scale, c1.shift, ops.ACT_RELU, 0.0)
+                y2 = c2.fwd_train(a1)
+                ys = cs.fwd_train(a)
+                out = ops.bn_apply_act(ys, cs.scale, cs.shift, ops.ACT_RELU, 0.0, y2=y2, scale2=c2.scale,
+                                       shift2=c2.shift)
+                saved["blocks"].append((a, y1, a1, y2, ys, out))
+                a = out
+        else:
+            if want_grad:
+                raise RuntimeError("KeypointNet: backward through eval-mode BatchNorm is not supported; call "
+                                   "model.train() or wrap the pass in torch.no_grad()")
+            sc, sh = self.stem.eval_affine()
+            a = ops.conv_fwd(xin, self.stem.wpk, self.stem.cout, 7, 1, 3, scale=sc, shift=sh, act=ops.ACT_RELU)
+            for c1, c2, cs in self.blocks:
+                sc, sh = c1.eval_affine()
+                a1 = ops.conv_fwd(a, c1.wpk, c1.cout, 3, 1, 2, 2, scale=sc, shift=sh, act=ops.ACT_RELU)
+                sc, sh = cs.eval_affine()
+                t = ops.conv_fwd(a, cs.wpk, cs.cout, 1, 1, 0, scale=sc, shift=sh)
+                sc, sh = c2.eval_affine()
+                a = ops.conv_fwd(a1, c2.wpk, c2.cout, 3, 1, 1, scale=sc, shift=sh, residual=t, act=ops.ACT_RELU)
+        saved["a_last"] = a
+        k = m.out.out_channels
+        logits = ops.conv_fwd(a, out_wpk, k, 1, 1, 0, out_dtype=torch.float32, shift=m.out.bias.detach(), nchw_out=True)
+        return logits, saved
+
+    def _softmax(self, logits):
+        b, k, h, w = logits.shape
+        vx, vy = self._coords(logits.device, h, w)
+        hm = torch.empty_like(logits)
+        pts = torch.empty(b, k, 2, dtype=torch.float32, device=logits.device)
+        lib().call("b200cv_kpt_softmax_argmax", ptr(logits), ptr(vx), ptr(vy), ptr(hm), ptr(pts), b * k, h, w,
+                   stream_ptr())
+        return hm, pts
+
+    # ------------------------------------------------------------------ backward
+    def _grad_views(self, dev):
+        sizes = [p.numel() for p in self.params]
+        arena = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        views, o = [], 0
+        for p, n in zip(self.params, sizes):
+            views.append(arena[o:o + n].view_as(p))
+            o += n
+        return arena, views
+
+    def _backward(self, saved, hm, pts, d_hm, d_pts, handle: Optional[_HeadHandle], logits_grad=None):
+        m = self.model
+        dev = hm.device if hm is not None else logits_grad.device
+        arena, views = self._grad_views(dev)
+        gview = {id(p): v for p, v in zip(self.params, views)}
+        a_last = saved["a_last"]
+        b, h, w = a_last.shape[0], a_last.shape[1], a_last.shape[2]
+        k = m.out.out_channels
+        if logits_grad is not None:  # onnx_mode: gradient of the raw logits (NCHW fp32) given directly
+            dl = ops.nchw_to_nhwc(logits_grad, 16)
+        else:
+            vx, vy = self._coords(dev, h, w)
+            dl = torch.empty(b, h, w, 16, dtype=torch.bfloat16, device=dev)
+            p = handle.pending if handle is not None else None
+            if p is not None:
+                handle.pending = None
+                lib().call("b200cv_kpt_head_bwd", ptr(hm), ptr(p["thm"]), ptr(pts), ptr(p["tpts"]), ptr(p["ubar"]),
+                           ptr(vx), ptr(vy), ptr(p["g_loc"]), ptr(p["g_geo"]), ptr(d_hm), ptr(d_pts), b, k, h, w,
+                           p["loss_type"], int(p["include_geo"]), float(p["gamma_h"]), float(p["gamma_v"]), ptr(dl),
+                           16, stream_ptr())
+            else:
+                zeros = torch.zeros(b, k, 2, dtype=torch.float32, device=dev)
+                lib().call("b200cv_kpt_head_bwd", ptr(hm), None, ptr(pts), ptr(zeros), None, ptr(vx), ptr(vy), None,
+                           None, ptr(d_hm), ptr(d_pts), b, k, h, w, 0, 0, 0.0, 0.0, ptr(dl), 16, stream_ptr())
+        # head conv (bias, linear)
+        tmp = torch.zeros(16, dtype=torch.float32, device=dev)
+        ops.col_sum(dl, tmp)
+        gview[id(m.out.bias)].copy_(tmp[:k])
+        dwp = ops.conv_wgrad(a_last, dl, k, 1, 1, 0)
+        ops.unpack_wgrad(dwp, gview[id(m.out.weight)])
+        g = ops.conv_dgrad(dl, saved["out_wpk_t"], m.out.in_channels, 1, 1, 0, 1, (h, w))
+        for (c1, c2, cs), (a_in, y1, a1, y2, ys, out) in zip(reversed(self.blocks), reversed(saved["blocks"])):
+            # out = relu(bn_s(ys) + bn_2(y2)): both branches see dz = g * relu'(out)
+            g_in = cs.bwd(a_in, ys, g, out, ops.ACT_RELU, gview)
+            g_a1 = c2.bwd(a1, y2, g, out, ops.ACT_RELU, gview)
+            g = c1.bwd(a_in, y1, g_a1, None, ops.ACT_RELU, gview, dx_out=g_in)
+        self.stem.bwd(saved["x"], saved["y0"], g, None, ops.ACT_RELU, gview, want_dx=False)
+        allreduce_gradients(arena)
+        return views
+
+    # ------------------------------------------------------------------ public entry point
+    def run(self, x):
+        require_cuda(x, "KeypointNet.forward")
+        m = self.model
+        if m.onnx_mode:
+            return _KeypointLogitsFn.apply(self, x.float(), m.training, *self.params)
+        handle = _HeadHandle()
+        hm, pts = _KeypointNetFn.apply(self, x.float(), m.training, handle, *self.params)
+        hm._b200cv_head = handle
+        pts._b200cv_head = handle
+        return hm, pts
+
+
+class _KeypointNetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine, x, train, handle, *params):
+        want_grad = any(ctx.needs_input_grad[4:])
+        logits, saved = engine._forward(x, train, want_grad)
+        hm, pts = engine._softmax(logits)
+        ctx.engine, ctx.saved, ctx.handle = engine, saved, handle
+        ctx.save_for_backward(hm, pts)
+        return hm, pts
+
+    @staticmethod
+    def backward(ctx, d_hm, d_pts):
+        hm, pts = ctx.saved_tensors
+        d_hm = d_hm.contiguous().float() if d_hm is not None else None
+        d_pts = d_pts.contiguous().float() if d_pts is not None else None
+        views = ctx.engine._backward(ctx.saved, hm, pts, d_hm, d_pts, ctx.handle)
+        ctx.saved = None
+        return (None, None, None, None, *views)
+
+
+class _KeypointLogitsFn(torch.autograd.Function):
+    """onnx_mode=True: forward returns the raw head logits (keypoint_net.py:65-66)."""
+
+    @staticmethod
+    def forward(ctx, engine, x, train, *params):
+        want_grad = any(ctx.needs_input_grad[3:])
+        logits, saved = engine._forward(x, train, want_grad)
+        ctx.engine, ctx.saved = engine, saved
+        return logits
+
+    @staticmethod
+    def backward(ctx, d_logits):
+        views = ctx.engine._backward(ctx.saved, None, None, None, None, None, logits_grad=d_logits.contiguous().float())
+        ctx.saved = None
+        return (None, None, None, *views)
+
+
+# ---------------------------------------------------------------------------- CrossRatioLoss
+def _loss_forward(hm, pts, thm, tpts, loss_type, include_geo, gamma_h, gamma_v):
+    b, k = pts.shape[0], pts.shape[1]
+    hw = hm.shape[-1] * hm.shape[-2] if hm is not None else 0
+    dev = pts.device
+    loss3 = torch.empty(3, dtype=torch.float32, device=dev)
+    ubar = torch.zeros(18, dtype=torch.float32, device=dev)
+    ws = torch.zeros(1, dtype=torch.float64, device=dev)
+    lib().call("b200cv_kpt_loss", ptr(hm), ptr(pts), ptr(thm), ptr(tpts), b, k, hw, loss_type, int(include_geo),
+               float(gamma_h), float(gamma_v), ptr(ws), ptr(loss3), ptr(ubar), stream_ptr())
+    return loss3, ubar
+
+
+class CrossRatioLossFn(torch.autograd.Function):
+    """(location, geo, total) = f(hm, pts); the backward is fused into KeypointNet's when possible."""
+
+    @staticmethod
+    def forward(ctx, hm, pts, thm, tpts, loss_type, include_geo, gamma_h, gamma_v, handle):
+        require_cuda(pts, "CrossRatioLoss.forward")
+        hm_c, pts_c = hm.contiguous().float(), pts.contiguous().float()
+        thm_c = thm.contiguous().float() if thm is not None else None
+        tpts_c = tpts.contiguous().float()
+        loss3, ubar = _loss_forward(hm_c, pts_c, thm_c, tpts_c, loss_type, include_geo, gamma_h, gamma_v)
+        ctx.save_for_backward(hm_c, pts_c, thm_c, tpts_c, ubar)
+        ctx.cfg = (loss_type, include_geo, gamma_h, gamma_v)
+        ctx.handle = handle
+        return loss3
+
+    @staticmethod
+    def backward(ctx, g3):
+        hm, pts, thm, tpts, ubar = ctx.saved_tensors
+        loss_type, include_geo, gamma_h, gamma_v = ctx.cfg
+        g3 = g3.contiguous().float()
+        g_loc = (g3[0:1] + g3[2:3]).contiguous()  # total = location + geo
+        g_geo = (g3[1:2] + g3[2:3]).contiguous()
+        b, k = pts.shape[0], pts.shape[1]
+        if ctx.handle is not None and ctx.handle.pending is None:
+            # defer: KeypointNet's backward runs the fused kernel.  A zero d_pts keeps autograd flowing.
+            ctx.handle.pending = dict(thm=thm, tpts=tpts, ubar=ubar, g_loc=g_loc, g_geo=g_geo, loss_type=loss_type,
+                                      include_geo=include_geo, gamma_h=gamma_h, gamma_v=gamma_v)
+            return (None, torch.zeros_like(pts), None, None, None, None, None, None, None)
+        d_pts = torch.empty_like(pts)
+        d_hm = torch.empty_like(hm) if (loss_type == 1 and ctx.needs_input_grad[0]) else None
+        lib().call("b200cv_kpt_loss_bwd", ptr(hm), ptr(thm), ptr(pts), ptr(tpts), ptr(ubar), ptr(g_loc), ptr(g_geo), b,
+                   k, hm.shape[-2], hm.shape[-1], loss_type, int(include_geo), float(gamma_h), float(gamma_v),
+                   ptr(d_pts), ptr(d_hm), stream_ptr())
+        return (d_hm, d_pts, None, None, None, None, None, None, None)

@@ -82,6 +82,7 @@ void fill_epilogue(IgemmParams& p, const b200cv_conv_args* a, int64_t out_off, i
   p.scale = a->scale;
   p.shift = a->shift;
   p.act = a->act;
+  p.res_after_act = a->res_after_act;
   p.slope = a->slope;
   p.stats = a->stats;
 }

@@ -231,6 +231,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               v[j] += s4.x; v[j + 1] += s4.y; v[j + 2] += s4.z; v[j + 3] += s4.w;
             }
           }
+          const float neg = p.act == 1 ? p.slope : (p.act == 2 ? 0.f : 1.f);
+          if (p.res_after_act) {
+#pragma unroll
+            for (int j = 0; j < C::kChunk; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * neg;
+          }
           if (p.res) {
             const uint4* rp = reinterpret_cast<const uint4*>(p.res + (row_ok ? r_row : 0) + n_base);
 #pragma unroll
@@ -245,10 +250,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               }
             }
           }
-          const float neg = p.act == 1 ? p.slope : (p.act == 2 ? 0.f : 1.f);
           const float keep = row_ok ? 1.f : 0.f;
+          if (p.res_after_act) {
 #pragma unroll
-          for (int j = 0; j < C::kChunk; ++j) v[j] = (v[j] > 0.f ? v[j] : v[j] * neg) * keep;
+            for (int j = 0; j < C::kChunk; ++j) v[j] *= keep;
+          } else {
+#pragma unroll
+            for (int j = 0; j < C::kChunk; ++j) v[j] = (v[j] > 0.f ? v[j] : v[j] * neg) * keep;
+          }
           if (p.out_fp32) {
             if (row_ok) {
               float* o = reinterpret_cast<float*>(p.out) + o_row + n_base;
@@ -281,8 +290,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (n < p.Cout && row_ok) {
               if (p.scale) x *= __ldg(p.scale + n);
               if (p.shift) x += __ldg(p.shift + n);
-              if (p.res) x += __bfloat162float(p.res[r_row + n * p.r_sc]);
+              if (p.res && !p.res_after_act) x += __bfloat162float(p.res[r_row + n * p.r_sc]);
               x = apply_act(x, p.act, p.slope);
+              if (p.res && p.res_after_act) x += __bfloat162float(p.res[r_row + n * p.r_sc]);
               if (p.out_fp32) {
                 reinterpret_cast<float*>(p.out)[o_row + n * p.o_sc] = x;
               } else {

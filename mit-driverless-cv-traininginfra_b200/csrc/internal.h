@@ -47,6 +47,7 @@ struct IgemmParams {
   int vec_ok;    // 16-byte vector stores allowed (o_sc == 1 and everything 16B aligned)
   long long o_sn, o_sh, o_sw, o_sc;
   const __nv_bfloat16* res;
+  int res_after_act;
   int res_vec_ok;  // residual rows are channel-contiguous and 16B aligned
   long long r_sn, r_sh, r_sw, r_sc;
   const float* scale;

@@ -187,14 +187,10 @@ struct KptBwdArgs {
   float gamma_h, gamma_v;
   __nv_bfloat16* dlogits; int ld;
 };
-__global__ void __launch_bounds__(256) kpt_head_bwd_kernel(const KptBwdArgs a) {
-  __shared__ float s_red[8];
-  __shared__ float s_dp[kKpt * 2];
-  __shared__ float s_s[kKpt];
-  const int b = blockIdx.x;
-  const int K = a.K, HW = a.H * a.W;
-  const float gl = a.g_loc ? *a.g_loc : 0.f;
-  const float gg = a.g_geo ? *a.g_geo : 0.f;
+// d(loss)/d(points) of image b into s_dp[K*2]: location term + collinearity term + upstream gradient.
+// Must be called by the whole block; ends with a __syncthreads().
+__device__ __forceinline__ void point_grads(const KptBwdArgs& a, int b, float gl, float gg, float* s_dp) {
+  const int K = a.K;
   const float invB = 1.f / (float)a.B;
   if (threadIdx.x < K * 2) {
     const int idx = b * K * 2 + threadIdx.x;
@@ -233,6 +229,18 @@ __global__ void __launch_bounds__(256) kpt_head_bwd_kernel(const KptBwdArgs a) {
     }
   }
   __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) kpt_head_bwd_kernel(const KptBwdArgs a) {
+  __shared__ float s_red[8];
+  __shared__ float s_dp[kKpt * 2];
+  __shared__ float s_s[kKpt];
+  const int b = blockIdx.x;
+  const int K = a.K, HW = a.H * a.W;
+  const float gl = a.g_loc ? *a.g_loc : 0.f;
+  const float gg = a.g_geo ? *a.g_geo : 0.f;
+  const float invB = 1.f / (float)a.B;
+  point_grads(a, b, gl, gg, s_dp);
   const float hm_coef = a.loss_type == 1 ? gl * 2.f * invB : 0.f;
   const float* P = a.hm + (long long)b * K * HW;
   const float* Tm = a.thm ? a.thm + (long long)b * K * HW : nullptr;
@@ -275,6 +283,25 @@ __global__ void __launch_bounds__(256) kpt_head_bwd_kernel(const KptBwdArgs a) {
     for (int k = 0; k < 8; ++k) hh[k] = __floats2bfloat162_rn(o[2 * k], o[2 * k + 1]);
     *reinterpret_cast<uint4*>(d) = pk[0];
     *reinterpret_cast<uint4*>(d + 8) = pk[1];
+  }
+}
+
+
+// Un-fused form of the loss backward, for heat-maps / points that did not come from KeypointNet:
+// d_pts [B,K,2] and (l2_heatmap only) d_hm = 2 g (hm - thm) / B.
+__global__ void __launch_bounds__(256) kpt_loss_bwd_kernel(const KptBwdArgs a, float* d_pts, float* d_hm) {
+  __shared__ float s_dp[kKpt * 2 + 2];
+  const int b = blockIdx.x;
+  const float gl = a.g_loc ? *a.g_loc : 0.f;
+  const float gg = a.g_geo ? *a.g_geo : 0.f;
+  point_grads(a, b, gl, gg, s_dp);
+  if (threadIdx.x < a.K * 2) d_pts[b * a.K * 2 + threadIdx.x] = s_dp[threadIdx.x];
+  if (d_hm) {
+    const float coef = a.loss_type == 1 ? gl * 2.f / (float)a.B : 0.f;
+    const long long n = (long long)a.K * a.H * a.W;
+    const float* P = a.hm + b * n;
+    const float* T = a.thm ? a.thm + b * n : nullptr;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) d_hm[b * n + i] = T ? coef * (P[i] - T[i]) : 0.f;
   }
 }
 
@@ -326,4 +353,17 @@ extern "C" int b200cv_kpt_head_bwd(const float* hm, const float* thm, const floa
                gamma_h, gamma_v, static_cast<__nv_bfloat16*>(dlogits), ld};
   kpt_head_bwd_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   return check_launch("kpt_head_bwd");
+}
+
+extern "C" int b200cv_kpt_loss_bwd(const float* hm, const float* thm, const float* pts, const float* tpts,
+                                   const float* ubar, const float* g_loc, const float* g_geo, int B, int K, int H, int W,
+                                   int loss_type, int include_geo, float gamma_h, float gamma_v, float* d_pts,
+                                   float* d_hm, void* stream) {
+  B200CV_CHECK_ARG(pts && tpts && d_pts && B > 0 && K > 0 && K <= kKpt, "kpt_loss_bwd: bad args");
+  B200CV_CHECK_ARG(!d_hm || hm, "kpt_loss_bwd: d_hm needs hm");
+  B200CV_CHECK_ARG(!include_geo || (K == kKpt && ubar), "kpt_loss_bwd: geometric term needs 7 keypoints and ubar");
+  KptBwdArgs a{hm, thm, pts, tpts, ubar, nullptr, nullptr, g_loc, g_geo, nullptr, nullptr, B, K, H, W, loss_type,
+               include_geo, gamma_h, gamma_v, nullptr, 0};
+  kpt_loss_bwd_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, d_pts, d_hm);
+  return check_launch("kpt_loss_bwd");
 }

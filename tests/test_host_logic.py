@@ -1,0 +1,68 @@
+"""Host-side logic: cfg generation/parsing, module construction parity with the reference recipe."""
+import os
+
+import pytest
+import torch
+
+import helpers
+from b200cv import cfg_gen
+from oracle import yolo_oracle as YO
+
+
+@pytest.mark.parametrize("kind,ref_name", [("tiny", "yolo_baseline_tiny.cfg"), ("darknet53", "yolo_baseline.cfg")])
+def test_generated_cfg_equals_reference_cfg(cfg_dir, kind, ref_name):
+    ref = os.path.join(helpers.REF_ROOT, "CVC-YOLOv3", "model_cfg", ref_name)
+    if not os.path.exists(ref):
+        pytest.skip("reference tree not available (GPU box)")
+    from utils.parse_config import parse_model_config
+
+    mine = parse_model_config(cfg_gen.write_cfg(cfg_dir, kind, 800, 800, 80))
+    theirs = YO.parse_cfg(ref)
+    assert len(mine) == len(theirs)
+    for a, b in zip(mine[1:], theirs[1:]):
+        keys = ("type", "filters", "size", "stride", "layers", "from")
+        assert {k: a.get(k) for k in keys} == {k: b.get(k) for k in keys}
+    for k in ("classes", "channels", "yolo_masks", "leaky_slope", "conv_activation", "build_targets_ignore_thresh",
+              "conf_thresh", "nms_thresh", "iou_thresh", "start_weights_dim", "width", "height", "onnx_height"):
+        assert mine[0][k] == theirs[0][k], k
+
+
+def test_parse_config_matches_oracle(cfg_dir):
+    from utils.parse_config import parse_model_config
+
+    path = cfg_gen.write_cfg(cfg_dir, "tiny", 416, 416, 1)
+    assert parse_model_config(path) == YO.parse_cfg(path)
+
+
+@pytest.mark.parametrize("name", ["tiny_128", "full_128", "tiny_128_c80"])
+def test_model_construction_matches_reference(cfg_dir, golden_yolo, name):
+    g = golden_yolo["darknet"][name]
+    model, _ = helpers.make_darknet(cfg_dir, g["cfg"], g["S"], g["C"])
+    helpers.assert_digest(model.named_parameters(), g["digest"])
+    spec = YO.NetSpec(cfg_gen.write_cfg(cfg_dir, helpers.NET_KIND[g["cfg"]], g["S"], g["S"], g["C"]))
+    assert [L["filters"] for L in spec.layers if L["type"] == "convolutional"] == \
+           [m[0].out_channels for d, m in zip(model.module_defs, model.module_list) if d["type"] == "convolutional"]
+
+
+def test_weights_file_roundtrip(cfg_dir, tmp_path):
+    model, _ = helpers.make_darknet(cfg_dir, "yolo_baseline_tiny.cfg", 128, 1)
+    for b in model.buffers():
+        if b.dtype == torch.float32:
+            b.uniform_(0.5, 1.5)
+    path = str(tmp_path / "w.weights")
+    model.save_weights(path, cutoff=len(model.module_list))
+    other, _ = helpers.make_darknet(cfg_dir, "yolo_baseline_tiny.cfg", 128, 1, seed=5)
+    other.load_weights(path, [model.module_list[15][0].out_channels, model.module_list[22][0].out_channels])
+    for (k, a), (_, b) in zip(model.state_dict().items(), other.state_dict().items()):
+        if "num_batches" not in k:
+            assert torch.equal(a, b), k
+
+
+def test_getters(cfg_dir):
+    model, path = helpers.make_darknet(cfg_dir, "yolo_baseline_tiny.cfg", 416, 1)
+    assert model.img_size() == (416, 416)
+    assert model.get_loss_constant() == [2.0, 1.6, 25.0, 0.1]
+    assert model.get_anchors() == cfg_gen.VANILLA_ANCHORS
+    assert model.get_threshs() == (0.8, 0.25, 0.5)
+    assert model.get_num_classes() == 1 and model.get_bw() is False
+    assert model.get_onnx_name() == os.path.basename(path).split(".")[0] + "_416320.onnx"
