@@ -121,12 +121,7 @@ class DarknetEngine:
         saved = {}
         training = targets is not None
         out7 = torch.zeros(7, dtype=torch.float32, device=dev) if training else None
-        dets, row0 = None, 0
-        if not training:
-            total_rows = 0
-            h = x.shape[2]
-            # rows per head are known only after the head conv ran; collect and concatenate lazily
-            dets = []
+        dets = []  # eval: per-head detections, concatenated at the end
         consts = (model.xy_loss, model.wh_loss, model.object_loss, model.no_object_loss)
         for L in self.layers:
             i = L.index
@@ -309,7 +304,7 @@ class DarknetEngine:
     def train_forward(self, x, targets):
         self._check_input(x)
         require_cuda(targets, "Darknet.forward(targets)")
-        return _DarknetTrainFn.apply(self, x, targets.float(), self.model.training, *self.params)
+        return _DarknetTrainFn.apply(self, x, targets.float(), self.model.training, torch.is_grad_enabled(), *self.params)
 
     @torch.no_grad()
     def detect(self, x):
@@ -320,8 +315,8 @@ class DarknetEngine:
 
 class _DarknetTrainFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, engine, x, targets, bn_train, *params):
-        want_grad = any(ctx.needs_input_grad[4:])
+    def forward(ctx, engine, x, targets, bn_train, grad_enabled, *params):
+        want_grad = grad_enabled and any(ctx.needs_input_grad[5:])
         out7, state = engine._run_forward(x.float(), targets, bn_train=bn_train, want_grad=want_grad)
         ctx.engine = engine
         ctx.state = state
@@ -331,4 +326,4 @@ class _DarknetTrainFn(torch.autograd.Function):
     def backward(ctx, g7):
         views = ctx.engine._run_backward(ctx.state, g7)
         ctx.state = None
-        return (None, None, None, None, *views)
+        return (None, None, None, None, None, *views)

@@ -215,9 +215,9 @@ class RektNetEngine:
         require_cuda(x, "KeypointNet.forward")
         m = self.model
         if m.onnx_mode:
-            return _KeypointLogitsFn.apply(self, x.float(), m.training, *self.params)
+            return _KeypointLogitsFn.apply(self, x.float(), m.training, torch.is_grad_enabled(), *self.params)
         handle = _HeadHandle()
-        hm, pts = _KeypointNetFn.apply(self, x.float(), m.training, handle, *self.params)
+        hm, pts = _KeypointNetFn.apply(self, x.float(), m.training, handle, torch.is_grad_enabled(), *self.params)
         hm._b200cv_head = handle
         pts._b200cv_head = handle
         return hm, pts
@@ -225,8 +225,8 @@ class RektNetEngine:
 
 class _KeypointNetFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, engine, x, train, handle, *params):
-        want_grad = any(ctx.needs_input_grad[4:])
+    def forward(ctx, engine, x, train, handle, grad_enabled, *params):
+        want_grad = grad_enabled and any(ctx.needs_input_grad[5:])
         logits, saved = engine._forward(x, train, want_grad)
         hm, pts = engine._softmax(logits)
         ctx.engine, ctx.saved, ctx.handle = engine, saved, handle
@@ -240,15 +240,15 @@ class _KeypointNetFn(torch.autograd.Function):
         d_pts = d_pts.contiguous().float() if d_pts is not None else None
         views = ctx.engine._backward(ctx.saved, hm, pts, d_hm, d_pts, ctx.handle)
         ctx.saved = None
-        return (None, None, None, None, *views)
+        return (None, None, None, None, None, *views)
 
 
 class _KeypointLogitsFn(torch.autograd.Function):
     """onnx_mode=True: forward returns the raw head logits (keypoint_net.py:65-66)."""
 
     @staticmethod
-    def forward(ctx, engine, x, train, *params):
-        want_grad = any(ctx.needs_input_grad[3:])
+    def forward(ctx, engine, x, train, grad_enabled, *params):
+        want_grad = grad_enabled and any(ctx.needs_input_grad[4:])
         logits, saved = engine._forward(x, train, want_grad)
         ctx.engine, ctx.saved = engine, saved
         return logits
@@ -257,7 +257,7 @@ class _KeypointLogitsFn(torch.autograd.Function):
     def backward(ctx, d_logits):
         views = ctx.engine._backward(ctx.saved, None, None, None, None, None, logits_grad=d_logits.contiguous().float())
         ctx.saved = None
-        return (None, None, None, *views)
+        return (None, None, None, None, *views)
 
 
 # ---------------------------------------------------------------------------- CrossRatioLoss

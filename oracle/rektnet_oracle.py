@@ -50,18 +50,33 @@ def init_params(num_kpt: int = 7, seed: int = 0) -> Tuple[Dict[str, torch.Tensor
     return params, buffers
 
 
+class _StoreBf16(torch.autograd.Function):
+    """Straight-through bf16 storage rounding (only for the `emulate_bf16` diagnostic mode)."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.to(torch.bfloat16).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+_ident = lambda t: t
+
+
 def _bn(x, params, buffers, name, training):
     return F.batch_norm(x, buffers[name + ".running_mean"], buffers[name + ".running_var"], params[name + ".weight"],
                         params[name + ".bias"], training=training, momentum=0.1, eps=1e-5)
 
 
-def res_block(x, params, buffers, name, training):
+def res_block(x, params, buffers, name, training, q=_ident):
     """RektNet/resnet.py:22-27: relu(BN(1x1(x)) + BN(3x3(relu(BN(3x3 dil2 pad2 (x))))))."""
-    c1 = F.conv2d(x, params[f"{name}.conv1.weight"], params[f"{name}.conv1.bias"], padding=2, dilation=2)
-    a1 = F.relu(_bn(c1, params, buffers, f"{name}.bn1", training))
-    c2 = F.conv2d(a1, params[f"{name}.conv2.weight"], params[f"{name}.conv2.bias"], padding=1)
-    sc = F.conv2d(x, params[f"{name}.shortcut_conv.weight"], params[f"{name}.shortcut_conv.bias"])
-    return F.relu(_bn(sc, params, buffers, f"{name}.shortcut_bn", training) + _bn(c2, params, buffers, f"{name}.bn2", training))
+    c1 = q(F.conv2d(x, q(params[f"{name}.conv1.weight"]), params[f"{name}.conv1.bias"], padding=2, dilation=2))
+    a1 = q(F.relu(_bn(c1, params, buffers, f"{name}.bn1", training)))
+    c2 = q(F.conv2d(a1, q(params[f"{name}.conv2.weight"]), params[f"{name}.conv2.bias"], padding=1))
+    sc = q(F.conv2d(x, q(params[f"{name}.shortcut_conv.weight"]), params[f"{name}.shortcut_conv.bias"]))
+    return q(F.relu(_bn(sc, params, buffers, f"{name}.shortcut_bn", training) + _bn(c2, params, buffers, f"{name}.bn2", training)))
 
 
 def soft_argmax(hm: torch.Tensor) -> torch.Tensor:
@@ -74,12 +89,17 @@ def soft_argmax(hm: torch.Tensor) -> torch.Tensor:
     return torch.stack([ex, ey], -1)
 
 
-def keypointnet_forward(params, buffers, x, training: bool = True, onnx_mode: bool = False):
-    """RektNet/keypoint_net.py:58-70.  Returns (heat-map [B,K,H,W] softmaxed over H*W, points [B,K,2])."""
-    a = F.relu(_bn(F.conv2d(x, params["conv.weight"], params["conv.bias"], padding=3), params, buffers, "bn", training))
+def keypointnet_forward(params, buffers, x, training: bool = True, onnx_mode: bool = False, emulate_bf16: bool = False):
+    """RektNet/keypoint_net.py:58-70.  Returns (heat-map [B,K,H,W] softmaxed over H*W, points [B,K,2]).
+
+    emulate_bf16=True is NOT the reference algorithm: it also rounds what the B200 path stores in bf16
+    (input, conv weights, conv outputs, activations), to separate kernel errors from storage precision."""
+    q = _StoreBf16.apply if emulate_bf16 else _ident
+    a = q(F.relu(_bn(q(F.conv2d(q(x), q(params["conv.weight"]), params["conv.bias"], padding=3)), params, buffers, "bn",
+                     training)))
     for name, _, _ in BLOCKS:
-        a = res_block(a, params, buffers, name, training)
-    logits = F.conv2d(a, params["out.weight"], params["out.bias"])  # computed twice in the reference (:64,:68)
+        a = res_block(a, params, buffers, name, training, q)
+    logits = F.conv2d(a, q(params["out.weight"]), params["out.bias"])  # computed twice in the reference (:64,:68)
     if onnx_mode:
         return logits
     B, K, H, W = logits.shape

@@ -221,12 +221,30 @@ def yolo_layer(sample: torch.Tensor, targets: Optional[torch.Tensor], anchors, n
 
 
 # --------------------------------------------------------------------------- Darknet interpreter
+class _StoreBf16(torch.autograd.Function):
+    """Straight-through bf16 storage rounding (only used by the `emulate_bf16` diagnostic mode)."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.to(torch.bfloat16).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
 def darknet_forward(spec: NetSpec, params: Dict[str, torch.Tensor], buffers: Dict[str, torch.Tensor],
                     x: torch.Tensor, targets: Optional[torch.Tensor], loss_consts=(2.0, 1.6, 25.0, 0.1),
-                    training: bool = True):
+                    training: bool = True, emulate_bf16: bool = False):
     """CVC-YOLOv3/models.py:312-338 with the module bodies of :59-101 inlined.
-    loss_consts = (xy, wh, no_object, object) -- the constructor order of Darknet (:225)."""
+    loss_consts = (xy, wh, no_object, object) -- the constructor order of Darknet (:225).
+
+    emulate_bf16=True is NOT the reference algorithm: it additionally rounds the tensors the B200 path
+    STORES in bf16 (input image, conv weights, BN'd conv outputs, activations) so that tests can separate
+    kernel errors from the expected effect of bf16 storage.  Parity claims use emulate_bf16=False."""
     xy, wh, noobj, obj = loss_consts
+    q = _StoreBf16.apply if emulate_bf16 else (lambda t: t)
+    x = q(x)
     outs: List[torch.Tensor] = []
     yolo_out = []
     totals = torch.zeros(6)
@@ -234,9 +252,10 @@ def darknet_forward(spec: NetSpec, params: Dict[str, torch.Tensor], buffers: Dic
         i, t = L["index"], L["type"]
         p = f"module_list.{i}."
         if t == "convolutional":
-            x = F.conv2d(x, params[p + f"conv_{i}.weight"], params.get(p + f"conv_{i}.bias"), stride=L["stride"],
+            x = F.conv2d(x, q(params[p + f"conv_{i}.weight"]), params.get(p + f"conv_{i}.bias"), stride=L["stride"],
                          padding=L["pad"])
             if L["bn"]:
+                x = q(x)
                 x = F.batch_norm(x, buffers[p + f"batch_norm_{i}.running_mean"],
                                  buffers[p + f"batch_norm_{i}.running_var"], params[p + f"batch_norm_{i}.weight"],
                                  params[p + f"batch_norm_{i}.bias"], training=training, momentum=0.1, eps=1e-5)
@@ -244,6 +263,8 @@ def darknet_forward(spec: NetSpec, params: Dict[str, torch.Tensor], buffers: Dic
                 x = F.leaky_relu(x, spec.leaky_slope)
             elif L["act"] == "ReLU":
                 x = F.relu(x)
+            if L["bn"]:
+                x = q(x)
         elif t == "maxpool":
             if L["k"] == 2 and L["stride"] == 1:
                 x = F.pad(x, (0, 1, 0, 1))  # ZERO padding, :77-79
@@ -253,7 +274,7 @@ def darknet_forward(spec: NetSpec, params: Dict[str, torch.Tensor], buffers: Dic
         elif t == "route":
             x = torch.cat([outs[j] for j in L["layers"]], 1)  # :323-324
         elif t == "shortcut":
-            x = outs[-1] + outs[L["from"]]  # :326-327
+            x = q(outs[-1] + outs[L["from"]])  # :326-327
         elif t == "yolo":
             if targets is not None:
                 x, parts = yolo_layer(x, targets, L["anchors"], spec.num_classes, spec.height, spec.ignore_thresh, xy,

@@ -1,0 +1,140 @@
+"""tcgen05 convolution kernels (through the C ABI) against torch fp32 on the same bf16-rounded operands."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from b200cv import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+CASES = [  # N, H, W, Cin, Cout, k, stride, pad, dil
+    (2, 13, 13, 64, 128, 3, 1, 1, 1),
+    (3, 26, 26, 128, 256, 3, 1, 1, 1),
+    (2, 16, 16, 32, 64, 3, 2, 1, 1),
+    (2, 13, 13, 64, 64, 3, 2, 1, 1),
+    (2, 20, 20, 16, 16, 3, 1, 2, 2),
+    (2, 20, 20, 3, 16, 7, 1, 3, 1),
+    (2, 13, 13, 256, 18, 1, 1, 0, 1),
+    (2, 13, 13, 1024, 255, 1, 1, 0, 1),
+    (2, 32, 32, 3, 32, 3, 1, 1, 1),
+    (4, 13, 13, 512, 1024, 3, 1, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_conv_fwd_dgrad_wgrad(case):
+    n, h, w, cin, cout, k, s, p, d = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = _bf(torch.randn(n, cin, h, w, generator=g)).requires_grad_(True)
+    wt = _bf(torch.randn(cout, cin, k, k, generator=g) * 0.1).requires_grad_(True)
+    y_ref = F.conv2d(x, wt, None, s, p, d)
+    dy = _bf(torch.randn(y_ref.shape, generator=g))
+    y_ref.backward(dy)
+
+    xd = ops.nchw_to_nhwc(x.detach().to(DEV))
+    wpk = ops.pack_weights(wt.detach().to(DEV), False)
+    wpk_t = ops.pack_weights(wt.detach().to(DEV), True)
+    y = ops.conv_fwd(xd, wpk, cout, k, s, p, d)
+    y_nchw = ops.nhwc_to_nchw(y, cout).cpu()
+    tol = 1.5e-2 * float(y_ref.abs().max())
+    assert float((y_nchw - y_ref.detach()).abs().max()) <= tol
+
+    dyd = ops.nchw_to_nhwc(dy.to(DEV))
+    dx = ops.conv_dgrad(dyd, wpk_t, cin, k, s, p, d, (h, w))
+    dx_nchw = ops.nhwc_to_nchw(dx, cin).cpu()
+    assert float((dx_nchw - x.grad).abs().max()) <= 1.5e-2 * float(x.grad.abs().max())
+
+    dwp = ops.conv_wgrad(xd, dyd, cout, k, s, p, d)
+    dw = torch.empty(cout, cin, k, k, device=DEV)
+    ops.unpack_wgrad(dwp, dw)
+    assert float((dw.cpu() - wt.grad).abs().max()) <= 2e-3 * float(wt.grad.abs().max())
+
+
+def test_conv_epilogue_stats_affine_residual():
+    n, h, w, cin, cout = 4, 13, 13, 64, 128
+    g = torch.Generator().manual_seed(7)
+    x = _bf(torch.randn(n, cin, h, w, generator=g))
+    wt = _bf(torch.randn(cout, cin, 3, 3, generator=g) * 0.1)
+    xd, wpk = ops.nchw_to_nhwc(x.to(DEV)), ops.pack_weights(wt.to(DEV), False)
+    stats = torch.zeros(2 * cout, device=DEV)
+    y = ops.conv_fwd(xd, wpk, cout, 3, 1, 1, stats=stats).float()
+    assert torch.allclose(stats[:cout], y.sum((0, 1, 2)), rtol=1e-3, atol=1e-2)
+    assert torch.allclose(stats[cout:], (y * y).sum((0, 1, 2)), rtol=1e-3, atol=1e-2)
+    scale = torch.rand(cout, device=DEV) + 0.5
+    shift = torch.randn(cout, device=DEV)
+    res = torch.randn(n, h, w, cout, device=DEV).to(torch.bfloat16)
+    ref = F.conv2d(x, wt, None, 1, 1).permute(0, 2, 3, 1).to(DEV)
+    for after in (False, True):
+        out = ops.conv_fwd(xd, wpk, cout, 3, 1, 1, scale=scale, shift=shift, residual=res, act=ops.ACT_LEAKY,
+                           slope=0.1, res_after_act=after).float()
+        z = ref * scale + shift
+        want = F.leaky_relu(z, 0.1) + res.float() if after else F.leaky_relu(z + res.float(), 0.1)
+        assert float((out - want).abs().max()) <= 2e-2 * float(want.abs().max())
+
+
+def test_nchw_fp32_head_output():
+    n, h, w, cin, cout = 2, 20, 20, 128, 7
+    g = torch.Generator().manual_seed(3)
+    x = _bf(torch.randn(n, cin, h, w, generator=g))
+    wt = _bf(torch.randn(cout, cin, 1, 1, generator=g) * 0.1)
+    bias = torch.randn(cout)
+    out = ops.conv_fwd(ops.nchw_to_nhwc(x.to(DEV)), ops.pack_weights(wt.to(DEV), False), cout, 1, 1, 0,
+                       out_dtype=torch.float32, shift=bias.to(DEV), nchw_out=True)
+    assert out.shape == (n, cout, h, w)
+    assert torch.allclose(out.cpu(), F.conv2d(x, wt, bias), rtol=1e-4, atol=1e-4)
+
+
+def test_bn_pool_upsample_against_torch():
+    n, h, w, c = 3, 12, 12, 64
+    g = torch.Generator().manual_seed(11)
+    y = _bf(torch.randn(n, c, h, w, generator=g) * 2 + 0.3)
+    gamma, beta = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g)
+    da = _bf(torch.randn(n, c, h, w, generator=g))
+    yr = y.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm, rv = torch.zeros(c), torch.ones(c)
+    a_ref = F.leaky_relu(F.batch_norm(yr, rm, rv, gr, br, True, 0.1, 1e-5), 0.1)
+    a_ref.backward(da)
+
+    yd = ops.nchw_to_nhwc(y.to(DEV))
+    stats = torch.stack([yd.float().sum((0, 1, 2)), (yd.float() ** 2).sum((0, 1, 2))]).flatten().contiguous()
+    f = lambda k: torch.empty(k, device=DEV)
+    scale, shift, mean, rstd, sums, coef = f(c), f(c), f(c), f(c), torch.zeros(2 * c, device=DEV), f(3 * c)
+    rmd, rvd = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    ops.bn_finalize(stats, n * h * w, gamma.to(DEV), beta.to(DEV), None, 1e-5, 0.1, rmd, rvd, scale, shift, mean, rstd)
+    assert torch.allclose(rmd.cpu(), rm, rtol=1e-4, atol=1e-5) and torch.allclose(rvd.cpu(), rv, rtol=1e-4, atol=1e-5)
+    a = ops.bn_apply_act(yd, scale, shift, ops.ACT_LEAKY, 0.1)
+    assert float((ops.nhwc_to_nchw(a, c).cpu() - a_ref.detach()).abs().max()) < 3e-2
+    dad = ops.nchw_to_nhwc(da.to(DEV))
+    ops.bn_bwd_reduce(dad, yd, None, scale, shift, mean, rstd, sums, ops.ACT_LEAKY, 0.1)
+    dg, db = f(c), f(c)
+    ops.bn_bwd_finalize(sums, gamma.to(DEV), rstd, n * h * w, coef, dg, db)
+    dy = ops.bn_bwd_apply(dad, yd, None, scale, shift, mean, rstd, coef, ops.ACT_LEAKY, 0.1)
+    assert torch.allclose(dg.cpu(), gr.grad, rtol=2e-2, atol=2e-2)
+    assert torch.allclose(db.cpu(), br.grad, rtol=2e-2, atol=2e-2)
+    assert float((ops.nhwc_to_nchw(dy, c).cpu() - yr.grad).abs().max()) < 2e-2 * float(yr.grad.abs().max()) + 1e-3
+
+    # max-pool (both variants) and upsample, forward + backward
+    xp = _bf(torch.randn(n, c, h, w, generator=g)).requires_grad_(True)
+    xd = ops.nchw_to_nhwc(xp.detach().to(DEV))
+    for stride in (2, 1):
+        ref = F.max_pool2d(F.pad(xp, (0, 1, 0, 1)) if stride == 1 else xp, 2, stride)
+        gy = _bf(torch.randn(ref.shape, generator=g))
+        xp.grad = None
+        ref.backward(gy)
+        out = ops.maxpool_fwd(xd, stride)
+        assert torch.equal(ops.nhwc_to_nchw(out, c).cpu(), ref.detach())
+        dx = ops.maxpool_bwd(xd, ops.nchw_to_nhwc(gy.to(DEV)), stride)
+        assert float((ops.nhwc_to_nchw(dx, c).cpu() - xp.grad).abs().max()) < 2e-2
+    up = ops.upsample_fwd(xd)
+    assert torch.equal(ops.nhwc_to_nchw(up, c).cpu(), F.interpolate(xp.detach(), scale_factor=2, mode="nearest"))
+    gu = _bf(torch.randn(n, c, 2 * h, 2 * w, generator=g))
+    dxu = ops.upsample_bwd(ops.nchw_to_nhwc(gu.to(DEV)))
+    want = gu.view(n, c, h, 2, w, 2).sum((3, 5))
+    assert float((ops.nhwc_to_nchw(dxu, c).cpu() - want).abs().max()) < 3e-2
