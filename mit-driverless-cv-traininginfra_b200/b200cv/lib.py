@@ -82,6 +82,7 @@ class _Lib:
         self.cdll = ctypes.CDLL(LIB_PATH)
         self.protos = parse_header()
         self.launches = 0  # kernel-launching ABI calls made (bench.py reports this)
+        self._prof = None
         self._lock = threading.Lock()
         for name, (restype, argtypes) in self.protos.items():
             fn = getattr(self.cdll, name)  # AttributeError => header/library mismatch
@@ -95,10 +96,36 @@ class _Lib:
         return self.cdll.b200cv_last_error().decode()
 
     def call(self, name: str, *args):
+        prof = self._prof
+        if prof is not None:
+            import torch
+
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         rc = getattr(self.cdll, name)(*args)
         self.launches += 1
+        if prof is not None:
+            e1.record()
+            prof.append((name, e0, e1))
         if rc != 0:
             raise B200CVError(f"{name} failed (rc={rc}): {self.last_error()}")
+
+    def profile_step(self, fn):
+        """Run fn() with a CUDA-event pair around every ABI call (on the current stream); returns
+        {entry point: total device milliseconds}.  Measurement aid for bench.py -- not a hot-path feature."""
+        import torch
+
+        torch.cuda.synchronize()
+        self._prof = []
+        try:
+            fn()
+            torch.cuda.synchronize()
+            out = {}
+            for name, e0, e1 in self._prof:
+                out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
+        finally:
+            self._prof = None
+        return out
 
     def pad_channels(self, c: int) -> int:
         return int(self.cdll.b200cv_pad_channels(int(c)))
