@@ -83,8 +83,11 @@ typedef struct b200cv_conv_args {
   int32_t act;
   float slope;
   int32_t res_after_act; /* 1: y = act(acc*scale+shift) + residual (darknet shortcut after the activation) */
-  /* per-channel [sum(y) | sum(y*y)] over N*OH*OW, atomically ADDED into stats[2*Cout]; NULL = off */
+  /* per-channel [sum(y) | sum(y*y)] over N*OH*OW, ADDED into stats[stats_parts][2*Cout] (zero it first;
+   * CTA b adds into row b % stats_parts -- with stats_parts >= #SMs no two CTAs share a row, so the
+   * result is deterministic); NULL = off.  Cout <= 1024 when stats are requested. */
   float* stats;
+  int32_t stats_parts;
 } b200cv_conv_args;
 
 /* y = conv2d(x, w).  nn.Conv2d forward: CVC-YOLOv3/models.py:59-65,320-321;
@@ -108,7 +111,7 @@ int b200cv_conv_wgrad(const void* x, const void* dy, float* dw_packed, int N, in
  * mean/rstd for backward, and update running stats (momentum, unbiased var) -- nn.BatchNorm2d in
  * train(): CVC-YOLOv3/models.py:67, RektNet/keypoint_net.py:19, resnet.py:13,16,20.
  * conv_bias (optional) is the bias of a conv whose bias was folded out (it cancels in train-mode BN). */
-int b200cv_bn_finalize(const float* stats, int64_t count, const float* gamma, const float* beta,
+int b200cv_bn_finalize(const float* stats, int stats_parts, int64_t count, const float* gamma, const float* beta,
                        const float* conv_bias, float eps, float momentum, float* running_mean,
                        float* running_var, float* scale, float* shift, float* save_mean, float* save_rstd,
                        int C, void* stream);
@@ -118,13 +121,16 @@ int b200cv_bn_apply_act(const void* y, int64_t y_ld, const float* scale, const f
                         int64_t y2_ld, const float* scale2, const float* shift2, const void* post,
                         int64_t post_ld, void* out, int64_t out_ld, int64_t rows, int C, int act, float slope,
                         void* stream);
-/* backward pass 1: sums[c] += dz, sums[C+c] += dz*xhat with dz = da*act'(z).  z is recomputed from
+/* backward pass 1: partials[p][c] = sum dz, partials[p][C+c] = sum dz*xhat over the rows block p owns
+ * (p < nparts, every row of partials is written), with dz = da*act'(z).  z is recomputed from
  * y*scale+shift, or its sign taken from `aout` (saved activation output) when given. */
 int b200cv_bn_bwd_reduce(const void* da, int64_t da_ld, const void* y, int64_t y_ld, const void* aout,
                          int64_t aout_ld, const float* scale, const float* shift, const float* mean,
-                         const float* rstd, float* sums, int64_t rows, int C, int act, float slope, void* stream);
-/* coef = [gamma*rstd | sum_dz/M | sum_dz_xhat/M]; dgamma/dbeta written if non-NULL. */
-int b200cv_bn_bwd_finalize(const float* sums, const float* gamma, const float* rstd, int64_t count, float* coef,
+                         const float* rstd, float* partials, int nparts, int64_t rows, int C, int act, float slope,
+                         void* stream);
+/* coef = [gamma*rstd | sum_dz/M | sum_dz_xhat/M] from the nparts partial rows; dgamma/dbeta written if non-NULL. */
+int b200cv_bn_bwd_finalize(const float* partials, int nparts, const float* gamma, const float* rstd, int64_t count,
+                           float* coef,
                            float* dgamma, float* dbeta, int C, void* stream);
 /* backward pass 2: dy = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)). */
 int b200cv_bn_bwd_apply(const void* da, int64_t da_ld, const void* y, int64_t y_ld, const void* aout,

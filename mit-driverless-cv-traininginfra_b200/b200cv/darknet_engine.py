@@ -96,8 +96,8 @@ class DarknetEngine:
         if L.stats is None or L.stats.device != dev:
             c = L.cout
             f = lambda n: torch.empty(n, dtype=torch.float32, device=dev)
-            L.stats, L.scale, L.shift, L.mean, L.rstd = f(2 * c), f(c), f(c), f(c), f(c)
-            L.sums, L.coef = f(2 * c), f(3 * c)
+            L.stats = ops.stats_buffer(c, dev)
+            L.scale, L.shift, L.mean, L.rstd, L.coef = f(c), f(c), f(c), f(c), f(3 * c)
 
     def _pack(self, need_t: bool):
         for L in self.layers:
@@ -248,9 +248,8 @@ class DarknetEngine:
                 if L.bn is not None:
                     xin, y = saved[i]
                     count = y.numel() // y.shape[-1]
-                    L.sums.zero_()
-                    ops.bn_bwd_reduce(G, y, None, L.scale, L.shift, L.mean, L.rstd, L.sums, L.act, L.slope)
-                    ops.bn_bwd_finalize(L.sums, L.bn.weight, L.rstd, count, L.coef, gview[id(L.bn.weight)],
+                    parts = ops.bn_bwd_reduce(G, y, None, L.scale, L.shift, L.mean, L.rstd, L.act, L.slope)
+                    ops.bn_bwd_finalize(parts, L.bn.weight, L.rstd, count, L.coef, gview[id(L.bn.weight)],
                                         gview[id(L.bn.bias)])
                     dy = ops.bn_bwd_apply(G, y, None, L.scale, L.shift, L.mean, L.rstd, L.coef, L.act, L.slope)
                     if L.post_from is not None:

@@ -35,7 +35,7 @@ class ConvArgs(ctypes.Structure):
         ("scale", ctypes.c_void_p), ("shift", ctypes.c_void_p), ("residual", ctypes.c_void_p),
         ("r_sn", ctypes.c_int64), ("r_sh", ctypes.c_int64), ("r_sw", ctypes.c_int64), ("r_sc", ctypes.c_int64),
         ("act", ctypes.c_int32), ("slope", ctypes.c_float), ("res_after_act", ctypes.c_int32),
-        ("stats", ctypes.c_void_p),
+        ("stats", ctypes.c_void_p), ("stats_parts", ctypes.c_int32),
     ]
 
 

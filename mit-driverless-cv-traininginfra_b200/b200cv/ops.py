@@ -16,7 +16,7 @@ __all__ = [
     "ACT_NONE", "ACT_LEAKY", "ACT_RELU", "pad_channels", "conv_out_size", "nchw_to_nhwc", "nhwc_to_nchw",
     "pack_weights", "unpack_wgrad", "conv_fwd", "conv_dgrad", "conv_wgrad", "bn_finalize", "bn_apply_act",
     "bn_bwd_reduce", "bn_bwd_finalize", "bn_bwd_apply", "act_bwd", "copy_slice", "col_sum", "maxpool_fwd",
-    "maxpool_bwd", "upsample_fwd", "upsample_bwd", "act_code",
+    "maxpool_bwd", "upsample_fwd", "upsample_bwd", "act_code", "sm_count", "stats_buffer",
 ]
 
 
@@ -88,6 +88,7 @@ def _conv_args(x, wpk, y, cout, k, stride, pad, dil, y_strides, y_dtype, scale, 
         a.r_sn, a.r_sh, a.r_sw, a.r_sc = r_strides
     a.act, a.slope, a.res_after_act = act, slope, int(res_after_act)
     a.stats = ptr(stats)
+    a.stats_parts = stats.shape[0] if stats is not None and stats.dim() == 2 else 1
     return a
 
 
@@ -144,9 +145,19 @@ def conv_wgrad(x, dy, cout, k, stride, pad, dil=1) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------ batch-norm + activation
+def sm_count(device=None) -> int:
+    return torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device()).multi_processor_count
+
+
+def stats_buffer(cout: int, device) -> torch.Tensor:
+    """Zeroed [#SMs][2*Cout] partial-statistics matrix for conv_fwd(stats=...): one row per CTA."""
+    return torch.zeros(sm_count(device), 2 * cout, dtype=torch.float32, device=device)
+
+
 def bn_finalize(stats, count, gamma, beta, conv_bias, eps, momentum, running_mean, running_var, scale, shift, mean,
                 rstd):
-    lib().call("b200cv_bn_finalize", ptr(stats), int(count), ptr(gamma), ptr(beta), ptr(conv_bias), float(eps),
+    parts = stats.shape[0] if stats.dim() == 2 else 1
+    lib().call("b200cv_bn_finalize", ptr(stats), parts, int(count), ptr(gamma), ptr(beta), ptr(conv_bias), float(eps),
                float(momentum), ptr(running_mean), ptr(running_var), ptr(scale), ptr(shift), ptr(mean), ptr(rstd),
                gamma.numel(), stream_ptr())
 
@@ -162,15 +173,22 @@ def bn_apply_act(y, scale, shift, act, slope, out=None, y2=None, scale2=None, sh
     return out
 
 
-def bn_bwd_reduce(da, y, aout, scale, shift, mean, rstd, sums, act, slope):
+def bn_bwd_reduce(da, y, aout, scale, shift, mean, rstd, act, slope, partials=None):
+    """Returns the [nparts][2C] partial sums (every row written by the kernel)."""
+    rows, c = _rows(y), y.shape[-1]
+    if partials is None:
+        rows_per_block = (256 // (c // 8)) * 4
+        nparts = max(1, min(2 * sm_count(y.device), (rows + rows_per_block - 1) // rows_per_block))
+        partials = torch.empty(nparts, 2 * c, dtype=torch.float32, device=y.device)
     lib().call("b200cv_bn_bwd_reduce", ptr(da), da.stride(-2), ptr(y), y.stride(-2), ptr(aout),
-               0 if aout is None else aout.stride(-2), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), ptr(sums),
-               _rows(y), y.shape[-1], act, float(slope), stream_ptr())
+               0 if aout is None else aout.stride(-2), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), ptr(partials),
+               partials.shape[0], rows, c, act, float(slope), stream_ptr())
+    return partials
 
 
-def bn_bwd_finalize(sums, gamma, rstd, count, coef, dgamma, dbeta):
-    lib().call("b200cv_bn_bwd_finalize", ptr(sums), ptr(gamma), ptr(rstd), int(count), ptr(coef), ptr(dgamma),
-               ptr(dbeta), gamma.numel(), stream_ptr())
+def bn_bwd_finalize(partials, gamma, rstd, count, coef, dgamma, dbeta):
+    lib().call("b200cv_bn_bwd_finalize", ptr(partials), partials.shape[0], ptr(gamma), ptr(rstd), int(count),
+               ptr(coef), ptr(dgamma), ptr(dbeta), gamma.numel(), stream_ptr())
 
 
 def bn_bwd_apply(da, y, aout, scale, shift, mean, rstd, coef, act, slope, out=None):

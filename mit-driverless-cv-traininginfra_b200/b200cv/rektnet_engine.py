@@ -39,8 +39,8 @@ class _ConvBN:
         if self.vec_dev != dev:
             c = self.cout
             f = lambda n: torch.empty(n, dtype=torch.float32, device=dev)
-            self.stats, self.scale, self.shift, self.mean, self.rstd = f(2 * c), f(c), f(c), f(c), f(c)
-            self.sums, self.coef = f(2 * c), f(3 * c)
+            self.stats = ops.stats_buffer(c, dev)
+            self.scale, self.shift, self.mean, self.rstd, self.coef = f(c), f(c), f(c), f(c), f(3 * c)
             self.vec_dev = dev
 
     def pack(self, need_t):
@@ -67,9 +67,8 @@ class _ConvBN:
     def bwd(self, x_in, y, da, aout, act, gview, dx_out=None, want_dx=True):
         """BN+act backward then wgrad (+ dgrad).  Returns dx (or None)."""
         count = y.numel() // y.shape[-1]
-        self.sums.zero_()
-        ops.bn_bwd_reduce(da, y, aout, self.scale, self.shift, self.mean, self.rstd, self.sums, act, 0.0)
-        ops.bn_bwd_finalize(self.sums, self.bn.weight, self.rstd, count, self.coef, gview[id(self.bn.weight)],
+        parts = ops.bn_bwd_reduce(da, y, aout, self.scale, self.shift, self.mean, self.rstd, act, 0.0)
+        ops.bn_bwd_finalize(parts, self.bn.weight, self.rstd, count, self.coef, gview[id(self.bn.weight)],
                             gview[id(self.bn.bias)])
         dy = ops.bn_bwd_apply(da, y, aout, self.scale, self.shift, self.mean, self.rstd, self.coef, act, 0.0)
         dwp = ops.conv_wgrad(x_in, dy, self.cout, self.k, 1, self.pad, self.dil)

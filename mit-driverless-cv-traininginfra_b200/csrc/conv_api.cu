@@ -85,6 +85,7 @@ void fill_epilogue(IgemmParams& p, const b200cv_conv_args* a, int64_t out_off, i
   p.res_after_act = a->res_after_act;
   p.slope = a->slope;
   p.stats = a->stats;
+  p.stats_parts = a->stats_parts > 0 ? a->stats_parts : 1;
 }
 
 int validate_common(const b200cv_conv_args* a) {
@@ -97,6 +98,7 @@ int validate_common(const b200cv_conv_args* a) {
   B200CV_CHECK_ARG(a->stride >= 1 && a->stride <= 8 && a->dil >= 1 && a->pad >= 0, "conv: bad stride/dil/pad");
   B200CV_CHECK_ARG(aligned16(a->x) && aligned16(a->w), "conv: x/w must be 16-byte aligned");
   B200CV_CHECK_ARG(a->y_dtype == B200CV_DT_BF16 || a->y_dtype == B200CV_DT_F32, "conv: bad y_dtype");
+  B200CV_CHECK_ARG(!a->stats || a->Cout <= 1024, "conv: statistics support at most 1024 output channels");
   return 0;
 }
 
@@ -191,6 +193,8 @@ extern "C" int b200cv_conv_dgrad(const b200cv_conv_args* a, int out_h, int out_w
 namespace b200cv {
 namespace {
 
+// one thread per pixel: C coalesced plane reads (consecutive threads = consecutive pixels), then the
+// pixel's Cpad bf16 channels go out as 16-byte stores
 __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                              int C, long long HW, int Cpad, long long total_pix) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_pix;
@@ -199,7 +203,16 @@ __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ src, __nv
     const long long hw = i - n * HW;
     const float* s = src + n * C * HW + hw;
     __nv_bfloat16* d = dst + i * Cpad;
-    for (int c = 0; c < Cpad; ++c) d[c] = __float2bfloat16_rn(c < C ? s[c * HW] : 0.f);
+    for (int c0 = 0; c0 < Cpad; c0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (c0 + j) < C ? __ldg(s + (long long)(c0 + j) * HW) : 0.f;
+      uint4 pk;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      *reinterpret_cast<uint4*>(d + c0) = pk;
+    }
   }
 }
 

@@ -26,7 +26,8 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kThreads = 192;
 constexpr int kEpiWarp0 = 2;
-constexpr int kSmemBudget = 200 * 1024;  // pipeline stages only
+constexpr int kSmemBudget = 196 * 1024;  // pipeline stages only
+constexpr int kMaxStatC = 1024;
 
 template <int KC, int BN>
 struct Cfg {
@@ -42,7 +43,7 @@ struct Cfg {
   static constexpr int kChunk = BN >= 32 ? 32 : 16;      // epilogue column chunk
   // extras: barriers (8B each) + tmem ptr + stats[2*BN] + transpose scratch (4 warps x 32 x 33)
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kStatBytes = 2 * BN * 4;
+  static constexpr int kStatBytes = 2 * kMaxStatC * 4;  // per-CTA [sum | sumsq] for every output channel
   static constexpr int kScratchBytes = 4 * 32 * 33 * 4;
   static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kBarBytes +
                                     kStatBytes + kScratchBytes;
@@ -60,8 +61,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
              const __grid_constant__ IgemmParams p) {
   using C = Cfg<KC, BN>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // align to 1024 B (128B-swizzle atom) by pointer arithmetic so the shared state space stays provable
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage_base = smem;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
   uint64_t* empty_bar = full_bar + C::kStages;
@@ -69,7 +70,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* s_stats = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + C::kBarBytes);
-  float* s_scratch = s_stats + 2 * BN;
+  float* s_scratch = s_stats + 2 * kMaxStatC;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -92,7 +93,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 1) {
     ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
   }
-  for (int i = threadIdx.x; i < 2 * BN; i += kThreads) s_stats[i] = 0.f;
+  if (p.stats)
+    for (int i = threadIdx.x; i < 2 * kMaxStatC; i += kThreads) s_stats[i] = 0.f;
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -283,7 +285,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         } else {
           // generic path: ragged channel tail, strided / unaligned outputs (NCHW heads, odd pitches)
-#pragma unroll 4
+#pragma unroll
           for (int j = 0; j < C::kChunk; ++j) {
             const int n = n_base + j;
             float x = v[j];
@@ -319,8 +321,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               s += x;
               s2 += x * x;
             }
-            atomicAdd(&s_stats[c0 + lane], s);
-            atomicAdd(&s_stats[BN + c0 + lane], s2);
+            atomicAdd(&s_stats[n_base + lane], s);
+            atomicAdd(&s_stats[kMaxStatC + n_base + lane], s2);
           }
           __syncwarp();
         }
@@ -333,18 +335,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         acc = 0;
         acc_phase ^= 1;
       }
-      if (p.stats) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int j = et; j < BN; j += 128) {
-          const int n = nt * BN + j;
-          if (n < p.Cout) {
-            atomicAdd(p.stats + n, s_stats[j]);
-            atomicAdd(p.stats + p.Cout + n, s_stats[BN + j]);
-          }
-          s_stats[j] = 0.f;
-          s_stats[BN + j] = 0.f;
+    }
+    if (p.stats) {
+      // one flush per CTA lifetime: the per-channel partials of all its tiles go to row blockIdx % parts
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float* dst = p.stats + static_cast<long long>(blockIdx.x % p.stats_parts) * 2 * p.Cout;
+      for (int n = et; n < p.Cout; n += 128) {
+        const float s = s_stats[n], s2 = s_stats[kMaxStatC + n];
+        if (s != 0.f || s2 != 0.f) {
+          atomicAdd(dst + n, s);
+          atomicAdd(dst + p.Cout + n, s2);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
     }
   }

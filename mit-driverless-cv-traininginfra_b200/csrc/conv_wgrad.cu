@@ -53,8 +53,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
   constexpr int kChunk = BNW >= 32 ? 32 : 16;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // align to 1024 B (128B-swizzle atom) by pointer arithmetic so the shared state space stays provable
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int a_bytes = p.a_slabs * kASlabBytes;
   const int stage_bytes = 2 * kASlabBytes + p.T * kBTapBytes;  // A region always 2 slabs wide
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);

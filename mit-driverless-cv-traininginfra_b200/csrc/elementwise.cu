@@ -54,15 +54,31 @@ int ew_grid(long long work_items, int block) {
 }
 
 // ------------------------------------------------------------------ BN finalize
-__global__ void bn_finalize_kernel(const float* __restrict__ stats, float count, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, const float* __restrict__ conv_bias,
-                                   float eps, float momentum, float* running_mean, float* running_var,
-                                   float* __restrict__ scale, float* __restrict__ shift,
-                                   float* __restrict__ save_mean, float* __restrict__ save_rstd, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const float mean = stats[c] / count;
-  float var = stats[C + c] / count - mean * mean;
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const float* __restrict__ stats, int parts, float count, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, const float* __restrict__ conv_bias, float eps, float momentum,
+                   float* running_mean, float* running_var, float* __restrict__ scale, float* __restrict__ shift,
+                   float* __restrict__ save_mean, float* __restrict__ save_rstd, int C) {
+  __shared__ float sh1[8][33], sh2[8][33];
+  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float s1 = 0.f, s2 = 0.f;
+  if (c < C)
+    for (int p = py; p < parts; p += 8) {  // fixed order: deterministic statistics
+      s1 += stats[(long long)p * 2 * C + c];
+      s2 += stats[(long long)p * 2 * C + C + c];
+    }
+  sh1[py][cx] = s1;
+  sh2[py][cx] = s2;
+  __syncthreads();
+  if (py != 0 || c >= C) return;
+#pragma unroll
+  for (int q = 1; q < 8; ++q) {
+    s1 += sh1[q][cx];
+    s2 += sh2[q][cx];
+  }
+  const float mean = s1 / count;
+  float var = s2 / count - mean * mean;
   var = var > 0.f ? var : 0.f;
   const float rstd = rsqrtf(var + eps);
   const float g = gamma[c];
@@ -89,38 +105,72 @@ struct ApplyArgs {
   __nv_bfloat16* out; long long out_ld;
   long long rows; int C; int act; float slope;
 };
-__global__ void bn_apply_kernel(const ApplyArgs a) {
+__device__ __forceinline__ uint4 ldg_stream_fwd(const __nv_bfloat16* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void load8f(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+constexpr int kApplyUnroll = 4;
+// a thread owns 8 fixed channels (scale/shift in registers) and streams rows, kApplyUnroll rows in flight
+__global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyArgs a) {
   const int vpr = a.C >> 3;
-  const long long total = a.rows * vpr;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / vpr;
-    const int c0 = (int)(i - r * vpr) << 3;
-    float v[8], z[8];
-    unpack8(ldg16(a.y + r * a.y_ld + c0), v);
-    const float4 s0 = __ldg(reinterpret_cast<const float4*>(a.scale + c0));
-    const float4 s1 = __ldg(reinterpret_cast<const float4*>(a.scale + c0 + 4));
-    const float4 h0 = __ldg(reinterpret_cast<const float4*>(a.shift + c0));
-    const float4 h1 = __ldg(reinterpret_cast<const float4*>(a.shift + c0 + 4));
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+  const int rpp = blockDim.x / vpr;
+  const int cv = threadIdx.x % vpr;
+  const int r0 = threadIdx.x / vpr;
+  const int c0 = cv << 3;
+  if (r0 >= rpp) return;
+  float sc[8], sh[8], sc2[8], sh2[8];
+  load8f(a.scale + c0, sc);
+  load8f(a.shift + c0, sh);
+  if (a.y2) {
+    load8f(a.scale2 + c0, sc2);
+    load8f(a.shift2 + c0, sh2);
+  }
+  const float neg = a.act == B200CV_ACT_LEAKY ? a.slope : (a.act == B200CV_ACT_RELU ? 0.f : 1.f);
+  const long long stride = (long long)gridDim.x * rpp;
+  for (long long r = (long long)blockIdx.x * rpp + r0; r < a.rows; r += stride * kApplyUnroll) {
+    uint4 qy[kApplyUnroll], q2[kApplyUnroll], qp[kApplyUnroll];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) z[j] = v[j] * sc[j] + sh[j];
-    if (a.y2) {
-      float w[8];
-      unpack8(ldg16(a.y2 + r * a.y2_ld + c0), w);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) z[j] += w[j] * __ldg(a.scale2 + c0 + j) + __ldg(a.shift2 + c0 + j);
+    for (int u = 0; u < kApplyUnroll; ++u) {
+      const long long rr = r + u * stride;
+      if (rr < a.rows) {
+        qy[u] = ldg_stream_fwd(a.y + rr * a.y_ld + c0);
+        if (a.y2) q2[u] = ldg_stream_fwd(a.y2 + rr * a.y2_ld + c0);
+        if (a.post) qp[u] = ldg_stream_fwd(a.post + rr * a.post_ld + c0);
+      }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) z[j] = act_fwd(z[j], a.act, a.slope);
-    if (a.post) {
-      float w[8];
-      unpack8(ldg16(a.post + r * a.post_ld + c0), w);
+    for (int u = 0; u < kApplyUnroll; ++u) {
+      const long long rr = r + u * stride;
+      if (rr < a.rows) {
+        float v[8], z[8];
+        unpack8(qy[u], v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) z[j] += w[j];
+        for (int j = 0; j < 8; ++j) z[j] = v[j] * sc[j] + sh[j];
+        if (a.y2) {
+          float w[8];
+          unpack8(q2[u], w);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) z[j] += w[j] * sc2[j] + sh2[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[j] = z[j] > 0.f ? z[j] : z[j] * neg;
+        if (a.post) {
+          float w[8];
+          unpack8(qp[u], w);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) z[j] += w[j];
+        }
+        stg16(a.out + rr * a.out_ld + c0, pack8(z));
+      }
     }
-    stg16(a.out + r * a.out_ld + c0, pack8(z));
   }
 }
 
@@ -139,23 +189,52 @@ struct BwdArgs {
   __nv_bfloat16* dy; long long dy_ld;             // pass 2 out
   long long rows; int C; int act; float slope;
 };
-__device__ __forceinline__ void bwd_load(const BwdArgs& a, long long r, int c0, float (&dz)[8], float (&xh)[8]) {
-  float da[8], y[8];
-  unpack8(ldg16(a.da + r * a.da_ld + c0), da);
-  unpack8(ldg16(a.y + r * a.y_ld + c0), y);
-  float zs[8];
+// Per-thread channel constants: a thread owns 8 fixed channels and walks over rows, so the per-channel
+// vectors are loaded once (the kernels are pure streaming: 16-byte loads, several rows in flight).
+struct ChanConsts {
+  float scale[8], shift[8], mean[8], rstd[8];
+};
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load_consts(const BwdArgs& a, int c0, ChanConsts& k) {
+  if (a.aout == nullptr) {
+    load8(a.scale + c0, k.scale);
+    load8(a.shift + c0, k.shift);
+  }
+  load8(a.mean + c0, k.mean);
+  load8(a.rstd + c0, k.rstd);
+}
+__device__ __forceinline__ uint4 ldg_stream(const __nv_bfloat16* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void bwd_math(const BwdArgs& a, const ChanConsts& k, const uint4& qda, const uint4& qy,
+                                         const uint4& qa, float (&dz)[8], float (&xh)[8]) {
+  float da[8], y[8], zs[8];
+  unpack8(qda, da);
+  unpack8(qy, y);
   if (a.aout) {
-    unpack8(ldg16(a.aout + r * a.aout_ld + c0), zs);
+    unpack8(qa, zs);
   } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) zs[j] = y[j] * __ldg(a.scale + c0 + j) + __ldg(a.shift + c0 + j);
+    for (int j = 0; j < 8; ++j) zs[j] = y[j] * k.scale[j] + k.shift[j];
   }
+  const float neg = a.act == B200CV_ACT_LEAKY ? a.slope : (a.act == B200CV_ACT_RELU ? 0.f : 1.f);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    dz[j] = da[j] * act_grad(zs[j], a.act, a.slope);
-    xh[j] = (y[j] - __ldg(a.mean + c0 + j)) * __ldg(a.rstd + c0 + j);
+    dz[j] = da[j] * (zs[j] > 0.f ? 1.f : neg);
+    xh[j] = (y[j] - k.mean[j]) * k.rstd[j];
   }
 }
+
+constexpr int kBwdUnroll = 4;
+
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdArgs a) {
   extern __shared__ float s_acc[];  // [2C]
   const int C = a.C;
@@ -166,15 +245,33 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdArgs a) {
   const int cv = threadIdx.x % vpr;
   const int r0 = threadIdx.x / vpr;
   const int c0 = cv << 3;
-  float s1[8] = {0}, s2[8] = {0};
+  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (r0 < rpp) {
-    for (long long r = (long long)blockIdx.x * rpp + r0; r < a.rows; r += (long long)gridDim.x * rpp) {
-      float dz[8], xh[8];
-      bwd_load(a, r, c0, dz, xh);
+    ChanConsts k;
+    load_consts(a, c0, k);
+    const long long stride = (long long)gridDim.x * rpp;
+    for (long long r = (long long)blockIdx.x * rpp + r0; r < a.rows; r += stride * kBwdUnroll) {
+      uint4 qda[kBwdUnroll], qy[kBwdUnroll], qa[kBwdUnroll];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s1[j] += dz[j];
-        s2[j] += dz[j] * xh[j];
+      for (int u = 0; u < kBwdUnroll; ++u) {
+        const long long rr = r + u * stride;
+        if (rr < a.rows) {
+          qda[u] = ldg_stream(a.da + rr * a.da_ld + c0);
+          qy[u] = ldg_stream(a.y + rr * a.y_ld + c0);
+          if (a.aout) qa[u] = ldg_stream(a.aout + rr * a.aout_ld + c0);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kBwdUnroll; ++u) {
+        if (r + u * stride < a.rows) {
+          float dz[8], xh[8];
+          bwd_math(a, k, qda[u], qy[u], qa[u], dz, xh);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            s1[j] += dz[j];
+            s2[j] += dz[j] * xh[j];
+          }
+        }
       }
     }
 #pragma unroll
@@ -184,36 +281,79 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdArgs a) {
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(a.sums + i, s_acc[i]);
+  float* row = a.sums + (long long)blockIdx.x * 2 * C;  // this block's row of the partials matrix
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) row[i] = s_acc[i];
 }
 
 // coef[c] = gamma*rstd ; coef[C+c] = sum_dz/M ; coef[2C+c] = sum_dz_xhat/M ; also dgamma/dbeta
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ gamma,
-                                       const float* __restrict__ rstd, float count, float* __restrict__ coef,
-                                       float* dgamma, float* dbeta, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  coef[c] = gamma[c] * rstd[c];
-  coef[C + c] = sums[c] / count;
-  coef[2 * C + c] = sums[C + c] / count;
-  if (dbeta) dbeta[c] = sums[c];
-  if (dgamma) dgamma[c] = sums[C + c];
+// block = 32 channels x 8 part-lanes: partial rows are summed 8 at a time, then folded through shared memory
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, const float* __restrict__ gamma,
+                       const float* __restrict__ rstd, float count, float* __restrict__ coef, float* dgamma,
+                       float* dbeta, int C) {
+  __shared__ float sh1[8][33], sh2[8][33];
+  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float s1 = 0.f, s2 = 0.f;
+  if (c < C)
+    for (int p = py; p < nparts; p += 8) {
+      s1 += partials[(long long)p * 2 * C + c];
+      s2 += partials[(long long)p * 2 * C + C + c];
+    }
+  sh1[py][cx] = s1;
+  sh2[py][cx] = s2;
+  __syncthreads();
+  if (py == 0 && c < C) {
+#pragma unroll
+    for (int q = 1; q < 8; ++q) {
+      s1 += sh1[q][cx];
+      s2 += sh2[q][cx];
+    }
+    coef[c] = gamma[c] * rstd[c];
+    coef[C + c] = s1 / count;
+    coef[2 * C + c] = s2 / count;
+    if (dbeta) dbeta[c] = s1;
+    if (dgamma) dgamma[c] = s2;
+  }
 }
 
-__global__ void bn_bwd_apply_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdArgs a) {
   const int C = a.C;
   const int vpr = C >> 3;
-  const long long total = a.rows * vpr;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / vpr;
-    const int c0 = (int)(i - r * vpr) << 3;
-    float dz[8], xh[8], o[8];
-    bwd_load(a, r, c0, dz, xh);
+  const int rpp = blockDim.x / vpr;
+  const int cv = threadIdx.x % vpr;
+  const int r0 = threadIdx.x / vpr;
+  const int c0 = cv << 3;
+  if (r0 >= rpp) return;
+  ChanConsts k;
+  load_consts(a, c0, k);
+  float g[8], k1[8], k2[8];
+  load8(a.coef + c0, g);
+  load8(a.coef + C + c0, k1);
+  load8(a.coef + 2 * C + c0, k2);
+  const long long stride = (long long)gridDim.x * rpp;
+  for (long long r = (long long)blockIdx.x * rpp + r0; r < a.rows; r += stride * kBwdUnroll) {
+    uint4 qda[kBwdUnroll], qy[kBwdUnroll], qa[kBwdUnroll];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      o[j] = __ldg(a.coef + c0 + j) * (dz[j] - __ldg(a.coef + C + c0 + j) - xh[j] * __ldg(a.coef + 2 * C + c0 + j));
-    stg16(a.dy + r * a.dy_ld + c0, pack8(o));
+    for (int u = 0; u < kBwdUnroll; ++u) {
+      const long long rr = r + u * stride;
+      if (rr < a.rows) {
+        qda[u] = ldg_stream(a.da + rr * a.da_ld + c0);
+        qy[u] = ldg_stream(a.y + rr * a.y_ld + c0);
+        if (a.aout) qa[u] = ldg_stream(a.aout + rr * a.aout_ld + c0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kBwdUnroll; ++u) {
+      const long long rr = r + u * stride;
+      if (rr < a.rows) {
+        float dz[8], xh[8], o[8];
+        bwd_math(a, k, qda[u], qy[u], qa[u], dz, xh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = g[j] * (dz[j] - k1[j] - xh[j] * k2[j]);
+        stg16(a.dy + rr * a.dy_ld + c0, pack8(o));
+      }
+    }
   }
 }
 
@@ -428,14 +568,15 @@ bool ok_vec(const void* p, long long ld, int C) {
 using namespace b200cv;
 typedef __nv_bfloat16 bf16;
 
-extern "C" int b200cv_bn_finalize(const float* stats, int64_t count, const float* gamma, const float* beta,
+extern "C" int b200cv_bn_finalize(const float* stats, int stats_parts, int64_t count, const float* gamma, const float* beta,
                                   const float* conv_bias, float eps, float momentum, float* running_mean,
                                   float* running_var, float* scale, float* shift, float* save_mean,
                                   float* save_rstd, int C, void* stream) {
-  B200CV_CHECK_ARG(stats && gamma && beta && scale && shift && save_mean && save_rstd && C > 0 && count > 0,
+  B200CV_CHECK_ARG(stats && gamma && beta && scale && shift && save_mean && save_rstd && C > 0 && count > 0 &&
+                       stats_parts > 0,
                    "bn_finalize: bad args");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      stats, (float)count, gamma, beta, conv_bias, eps, momentum, running_mean, running_var, scale, shift,
+  bn_finalize_kernel<<<(C + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      stats, stats_parts, (float)count, gamma, beta, conv_bias, eps, momentum, running_mean, running_var, scale, shift,
       save_mean, save_rstd, C);
   return check_launch("bn_finalize");
 }
@@ -450,7 +591,13 @@ extern "C" int b200cv_bn_apply_act(const void* y, int64_t y_ld, const float* sca
   B200CV_CHECK_ARG(!post || ok_vec(post, post_ld, C), "bn_apply_act: bad residual");
   ApplyArgs a{(const bf16*)y, y_ld, scale, shift, (const bf16*)y2, y2_ld, scale2, shift2,
               (const bf16*)post, post_ld, (bf16*)out, out_ld, rows, C, act, slope};
-  bn_apply_kernel<<<ew_grid(rows * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  B200CV_CHECK_ARG(C / 8 <= 256, "bn_apply_act: C too large");
+  {
+    const int rpp = 256 / (C / 8);
+    const long long passes = (rows + (long long)rpp * kApplyUnroll - 1) / ((long long)rpp * kApplyUnroll);
+    const int grid = (int)std::max<long long>(1, std::min<long long>(passes, (long long)sm_count() * 8));
+    bn_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  }
   return check_launch("bn_apply_act");
 }
 
@@ -469,28 +616,26 @@ static int fill_bwd(BwdArgs& a, const void* da, int64_t da_ld, const void* y, in
 
 extern "C" int b200cv_bn_bwd_reduce(const void* da, int64_t da_ld, const void* y, int64_t y_ld, const void* aout,
                                     int64_t aout_ld, const float* scale, const float* shift, const float* mean,
-                                    const float* rstd, float* sums, int64_t rows, int C, int act, float slope,
-                                    void* stream) {
+                                    const float* rstd, float* partials, int nparts, int64_t rows, int C, int act,
+                                    float slope, void* stream) {
   BwdArgs a;
   if (int rc = fill_bwd(a, da, da_ld, y, y_ld, aout, aout_ld, scale, shift, mean, rstd, rows, C, act, slope))
     return rc;
-  B200CV_CHECK_ARG(sums != nullptr, "bn_bwd_reduce: null sums");
-  a.sums = sums;
+  B200CV_CHECK_ARG(partials != nullptr && nparts > 0, "bn_bwd_reduce: null partials");
+  a.sums = partials;
   const int vpr = C / 8;
   const int threads = vpr > 256 ? 256 : 256;
   B200CV_CHECK_ARG(vpr <= 256, "bn_bwd_reduce: C too large");
-  const int rpp = threads / vpr;
-  const long long passes = (rows + rpp - 1) / rpp;
-  const int grid = (int)std::max<long long>(1, std::min<long long>(passes, (long long)sm_count() * 4));
+  const int grid = nparts;  // block p writes row p of the partials (blocks without rows write zeros)
   bn_bwd_reduce_kernel<<<grid, threads, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(a);
   return check_launch("bn_bwd_reduce");
 }
 
-extern "C" int b200cv_bn_bwd_finalize(const float* sums, const float* gamma, const float* rstd, int64_t count,
-                                      float* coef, float* dgamma, float* dbeta, int C, void* stream) {
-  B200CV_CHECK_ARG(sums && gamma && rstd && coef && C > 0 && count > 0, "bn_bwd_finalize: bad args");
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      sums, gamma, rstd, (float)count, coef, dgamma, dbeta, C);
+extern "C" int b200cv_bn_bwd_finalize(const float* partials, int nparts, const float* gamma, const float* rstd,
+                                      int64_t count, float* coef, float* dgamma, float* dbeta, int C, void* stream) {
+  B200CV_CHECK_ARG(partials && nparts > 0 && gamma && rstd && coef && C > 0 && count > 0, "bn_bwd_finalize: bad args");
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      partials, nparts, gamma, rstd, (float)count, coef, dgamma, dbeta, C);
   return check_launch("bn_bwd_finalize");
 }
 
@@ -503,7 +648,13 @@ extern "C" int b200cv_bn_bwd_apply(const void* da, int64_t da_ld, const void* y,
     return rc;
   B200CV_CHECK_ARG(coef && ok_vec(dy, dy_ld, C), "bn_bwd_apply: bad args");
   a.coef = coef; a.dy = (bf16*)dy; a.dy_ld = dy_ld;
-  bn_bwd_apply_kernel<<<ew_grid(rows * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  B200CV_CHECK_ARG(C / 8 <= 256, "bn_bwd_apply: C too large");
+  {
+    const int rpp = 256 / (C / 8);
+    const long long passes = (rows + (long long)rpp * kBwdUnroll - 1) / ((long long)rpp * kBwdUnroll);
+    const int grid = (int)std::max<long long>(1, std::min<long long>(passes, (long long)sm_count() * 8));
+    bn_bwd_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  }
   return check_launch("bn_bwd_apply");
 }
 

@@ -54,7 +54,8 @@ struct IgemmParams {
   const float* shift;
   int act;  // 0 none, 1 leaky(slope), 2 relu
   float slope;
-  float* stats;  // [2*Cout]: sum, sum of squares (atomicAdd), or null
+  float* stats;  // [stats_parts][2*Cout]: sum, sum of squares (added), or null
+  int stats_parts;
   int* err;
   short tap_w[kMaxTaps];
   short tap_h[kMaxTaps];

@@ -62,10 +62,14 @@ def test_conv_epilogue_stats_affine_residual():
     x = _bf(torch.randn(n, cin, h, w, generator=g))
     wt = _bf(torch.randn(cout, cin, 3, 3, generator=g) * 0.1)
     xd, wpk = ops.nchw_to_nhwc(x.to(DEV)), ops.pack_weights(wt.to(DEV), False)
-    stats = torch.zeros(2 * cout, device=DEV)
+    stats = ops.stats_buffer(cout, DEV)
     y = ops.conv_fwd(xd, wpk, cout, 3, 1, 1, stats=stats).float()
-    assert torch.allclose(stats[:cout], y.sum((0, 1, 2)), rtol=1e-3, atol=1e-2)
-    assert torch.allclose(stats[cout:], (y * y).sum((0, 1, 2)), rtol=1e-3, atol=1e-2)
+    tot = stats.sum(0)
+    assert torch.allclose(tot[:cout], y.sum((0, 1, 2)), rtol=1e-3, atol=1e-2)
+    assert torch.allclose(tot[cout:], (y * y).sum((0, 1, 2)), rtol=1e-3, atol=1e-2)
+    again = ops.stats_buffer(cout, DEV)
+    ops.conv_fwd(xd, wpk, cout, 3, 1, 1, stats=again)
+    assert torch.equal(stats, again)  # per-CTA rows: bit-reproducible statistics
     scale = torch.rand(cout, device=DEV) + 0.5
     shift = torch.randn(cout, device=DEV)
     res = torch.randn(n, h, w, cout, device=DEV).to(torch.bfloat16)
@@ -105,14 +109,14 @@ def test_bn_pool_upsample_against_torch():
     yd = ops.nchw_to_nhwc(y.to(DEV))
     stats = torch.stack([yd.float().sum((0, 1, 2)), (yd.float() ** 2).sum((0, 1, 2))]).flatten().contiguous()
     f = lambda k: torch.empty(k, device=DEV)
-    scale, shift, mean, rstd, sums, coef = f(c), f(c), f(c), f(c), torch.zeros(2 * c, device=DEV), f(3 * c)
+    scale, shift, mean, rstd, coef = f(c), f(c), f(c), f(c), f(3 * c)
     rmd, rvd = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
     ops.bn_finalize(stats, n * h * w, gamma.to(DEV), beta.to(DEV), None, 1e-5, 0.1, rmd, rvd, scale, shift, mean, rstd)
     assert torch.allclose(rmd.cpu(), rm, rtol=1e-4, atol=1e-5) and torch.allclose(rvd.cpu(), rv, rtol=1e-4, atol=1e-5)
     a = ops.bn_apply_act(yd, scale, shift, ops.ACT_LEAKY, 0.1)
     assert float((ops.nhwc_to_nchw(a, c).cpu() - a_ref.detach()).abs().max()) < 3e-2
     dad = ops.nchw_to_nhwc(da.to(DEV))
-    ops.bn_bwd_reduce(dad, yd, None, scale, shift, mean, rstd, sums, ops.ACT_LEAKY, 0.1)
+    sums = ops.bn_bwd_reduce(dad, yd, None, scale, shift, mean, rstd, ops.ACT_LEAKY, 0.1)
     dg, db = f(c), f(c)
     ops.bn_bwd_finalize(sums, gamma.to(DEV), rstd, n * h * w, coef, dg, db)
     dy = ops.bn_bwd_apply(dad, yd, None, scale, shift, mean, rstd, coef, ops.ACT_LEAKY, 0.1)

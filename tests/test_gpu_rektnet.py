@@ -75,7 +75,7 @@ def test_unfused_loss_backward_equals_fused(golden_rekt):
         grads.append({k: p.grad.clone() for k, p in net.named_parameters() if "weight" in k})
     for k in grads[0]:
         assert _cos(grads[0][k], grads[1][k]) > 0.99, k
-        assert abs(float(grads[0][k].norm() / grads[1][k].norm()) - 1) < 0.03, k
+        assert abs(float(grads[0][k].norm() / grads[1][k].norm()) - 1) < 0.08, k
 
 
 def test_rektnet_eval_and_onnx_mode(golden_rekt):
