@@ -249,12 +249,13 @@ def main():
     e2e_value = world * BATCH * steps / (ms_e2e / 1e3)
 
     out = None
+    # roofline of the dominant kernels: event-time every conv launch of one more step (every rank runs the
+    # step -- it contains the gradient all-reduce -- rank 0 reports)
+    prof = lib().profile_step(lambda: step(imgs_d, tg_d))
     if rank == 0:
-        # roofline of the dominant kernels: event-time every conv launch of one more step
         spec = YO.NetSpec(cfg)
         fwd_f, tot_f = conv_flops_per_image(spec.layers, IMG)
         pk = peaks()
-        prof = lib().profile_step(lambda: step(imgs_d, tg_d))
         conv_ms = sum(v for k, v in prof.items() if k in ("b200cv_conv_fwd", "b200cv_conv_dgrad", "b200cv_conv_wgrad"))
         step_ms = sum(prof.values())
         achieved = tot_f * BATCH / (conv_ms / 1e3) / 1e12
