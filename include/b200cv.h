@@ -63,6 +63,17 @@ int b200cv_pack_weights(const float* w_oihw, void* dst, int O, int I, int R, int
 int b200cv_unpack_wgrad(const float* dw_packed, float* dw_oihw, int O, int I, int R, int S,
                         int Ipad, void* stream);
 
+/* Multi-tensor forms: one launch packs (or un-packs) every conv weight of a network.  `table_dev` is a
+ * DEVICE array of n entries; pack: src = OIHW fp32 weight, dst = packed bf16; unpack: src = packed fp32
+ * gradient [O][R*S][Ipad], dst = OIHW fp32 gradient (transpose/Opad ignored). */
+typedef struct b200cv_pack_entry {
+  const float* src;
+  void* dst;
+  int32_t O, I, RS, Ipad, Opad, transpose;
+} b200cv_pack_entry;
+int b200cv_pack_weights_multi(const void* table_dev, int n, void* stream);
+int b200cv_unpack_wgrad_multi(const void* table_dev, int n, void* stream);
+
 /* ---- convolution (tcgen05 implicit GEMM) ------------------------------------------------- */
 typedef struct b200cv_conv_args {
   /* input activation: NHWC bf16 [N,H,W,Cin], Cin == b200cv_pad_channels(true Cin) */
@@ -84,8 +95,8 @@ typedef struct b200cv_conv_args {
   float slope;
   int32_t res_after_act; /* 1: y = act(acc*scale+shift) + residual (darknet shortcut after the activation) */
   /* per-channel [sum(y) | sum(y*y)] over N*OH*OW, ADDED into stats[stats_parts][2*Cout] (zero it first;
-   * CTA b adds into row b % stats_parts -- with stats_parts >= #SMs no two CTAs share a row, so the
-   * result is deterministic); NULL = off.  Cout <= 1024 when stats are requested. */
+   * CTA b adds into row b % stats_parts -- with stats_parts >= #SMs no two CTAs share a row, i.e. no
+   * contended global atomics); NULL = off.  Cout <= 1024 when stats are requested. */
   float* stats;
   int32_t stats_parts;
 } b200cv_conv_args;

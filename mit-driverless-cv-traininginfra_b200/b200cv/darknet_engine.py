@@ -20,6 +20,7 @@ import torch
 
 from . import ops, yolo_ops
 from .lib import require_cuda
+from .packing import ConvPackSet, GradArena
 from .parallel import allreduce_gradients
 
 BN_EPS = 1e-5
@@ -89,7 +90,8 @@ class DarknetEngine:
                     prev.post_from = L.inputs[1]
                     L.fused_alias = True
         self.params = list(model.parameters())
-        self._offsets = None
+        self._arena = None
+        self._packs = None
 
     # ------------------------------------------------------------------ helpers
     def _vec(self, L: _Layer, dev):
@@ -99,11 +101,17 @@ class DarknetEngine:
             L.stats = ops.stats_buffer(c, dev)
             L.scale, L.shift, L.mean, L.rstd, L.coef = f(c), f(c), f(c), f(c), f(3 * c)
 
+    def _setup(self, dev):
+        if self._arena is None or self._arena.flat.device != dev:
+            self._arena = GradArena(self.params, dev)
+            convs = [(L.conv, L.index > 0) for L in self.layers if L.type == "convolutional"]
+            self._packs = ConvPackSet(convs, dev, self._arena)
+            for L in self.layers:
+                if L.type == "convolutional":
+                    L.wpk, L.wpk_t = self._packs.wpk[id(L.conv)], self._packs.wpk_t[id(L.conv)]
+
     def _pack(self, need_t: bool):
-        for L in self.layers:
-            if L.type == "convolutional":
-                L.wpk = ops.pack_weights(L.conv.weight, False)
-                L.wpk_t = ops.pack_weights(L.conv.weight, True) if (need_t and L.index > 0) else None
+        self._packs.pack_all(need_t)
 
     def _check_input(self, x):
         require_cuda(x, "Darknet.forward")
@@ -115,6 +123,7 @@ class DarknetEngine:
         """Returns (out7 or detections, saved-state)."""
         model = self.model
         dev = x.device
+        self._setup(dev)
         self._pack(need_t=want_grad)
         cur = ops.nchw_to_nhwc(x)
         outs: List[Optional[torch.Tensor]] = [None] * len(self.layers)
@@ -199,22 +208,21 @@ class DarknetEngine:
         return torch.cat(dets, 1), None
 
     # ------------------------------------------------------------------ backward
-    def _grad_views(self, dev):
-        sizes = [p.numel() for p in self.params]
-        arena = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
-        views, o = [], 0
-        for p, n in zip(self.params, sizes):
-            views.append(arena[o:o + n].view_as(p))
-            o += n
-        return arena, views
-
     def _run_backward(self, state, g7):
         outs, saved = state
         model = self.model
         dev = g7.device
         g = g7[0:1].contiguous().float()
-        arena, views = self._grad_views(dev)
-        gview = {id(p): v for p, v in zip(self.params, views)}
+        arena = self._arena
+        if arena.aliased_by_param_grads():
+            # param.grad still aliases the arena (zero_grad(set_to_none=False)): use a private arena for this
+            # backward so autograd's in-place accumulation stays correct
+            arena = GradArena(self.params, dev)
+            packs = ConvPackSet([(L.conv, L.index > 0) for L in self.layers if L.type == "convolutional"], dev, arena)
+        else:
+            packs = self._packs
+        packs.zero_grads()
+        views, gview = arena.views, arena.view_of
         consts = (model.xy_loss, model.wh_loss, model.object_loss, model.no_object_loss)
         grads: List[Optional[torch.Tensor]] = [None] * len(self.layers)
 
@@ -260,8 +268,7 @@ class DarknetEngine:
                     tmp = torch.zeros(dy.shape[-1], dtype=torch.float32, device=dev)
                     ops.col_sum(dy, tmp)
                     gview[id(L.conv.bias)].copy_(tmp[:L.cout])
-                dwp = ops.conv_wgrad(xin, dy, L.cout, L.k, L.stride, L.pad)
-                ops.unpack_wgrad(dwp, gview[id(L.conv.weight)])
+                ops.conv_wgrad(xin, dy, L.cout, L.k, L.stride, L.pad, out=packs.dwp[id(L.conv)])
                 if i > 0:
                     prev = grads[i - 1]
                     dx = ops.conv_dgrad(dy, L.wpk_t, L.cin, L.k, L.stride, L.pad, 1, (xin.shape[1], xin.shape[2]),
@@ -296,7 +303,8 @@ class DarknetEngine:
                     add_grad(L.inputs[0], G)
                     add_grad(L.inputs[1], G)
             grads[i] = None
-        allreduce_gradients(arena)
+        packs.unpack_all()
+        allreduce_gradients(arena.flat)
         return views
 
     # ------------------------------------------------------------------ public entry points

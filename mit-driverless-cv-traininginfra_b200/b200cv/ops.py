@@ -135,10 +135,10 @@ def conv_dgrad(dy, wpk_t, cin_fwd, k, stride, pad, dil, out_hw, out=None, residu
     return out
 
 
-def conv_wgrad(x, dy, cout, k, stride, pad, dil=1) -> torch.Tensor:
-    """Returns the packed fp32 gradient [Cout][k*k][Cin_pad]."""
+def conv_wgrad(x, dy, cout, k, stride, pad, dil=1, out=None) -> torch.Tensor:
+    """Accumulates into (and returns) the packed fp32 gradient [Cout][k*k][Cin_pad]; `out` must be zeroed."""
     n, h, w, cin = x.shape
-    dwp = torch.zeros(cout, k * k, cin, dtype=torch.float32, device=x.device)
+    dwp = out if out is not None else torch.zeros(cout, k * k, cin, dtype=torch.float32, device=x.device)
     lib().call("b200cv_conv_wgrad", ptr(x), ptr(dy), ptr(dwp), n, h, w, cin, cout, dy.shape[-1], k, k, stride, pad, dil,
                stream_ptr())
     return dwp

@@ -1,0 +1,113 @@
+"""Per-network weight staging: every conv weight is re-packed (OIHW fp32 -> bf16 operand layouts) with ONE
+multi-tensor launch per step, weight gradients are accumulated in one flat packed fp32 arena (one memset) and
+un-packed into the OIHW gradient arena with one more launch."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from .lib import lib, stream_ptr
+from .ops import pad_channels
+
+_ENTRY = np.dtype([("src", np.uint64), ("dst", np.uint64), ("O", np.int32), ("I", np.int32), ("RS", np.int32),
+                   ("Ipad", np.int32), ("Opad", np.int32), ("transpose", np.int32)])
+assert _ENTRY.itemsize == 40
+
+
+class GradArena:
+    """Flat fp32 gradient arena with one view per parameter (what the data-parallel all-reduce sends)."""
+
+    def __init__(self, params, device):
+        self.params = params
+        sizes = [p.numel() for p in params]
+        self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=device)
+        self.views, o = [], 0
+        for p, n in zip(params, sizes):
+            self.views.append(self.flat[o:o + n].view_as(p))
+            o += n
+        self.view_of = {id(p): v for p, v in zip(params, self.views)}
+
+    def aliased_by_param_grads(self) -> bool:
+        """True if some param.grad still IS a view of this arena (zero_grad(set_to_none=False) style loops):
+        writing the arena in place would then corrupt autograd's accumulation."""
+        lo = self.flat.data_ptr()
+        hi = lo + self.flat.numel() * 4
+        return any(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in self.params)
+
+
+class ConvPackSet:
+    def __init__(self, convs, device, grad_arena: GradArena):
+        """convs: list of (nn.Conv2d, need_transposed_pack)."""
+        self.convs = [c for c, _ in convs]
+        self.device = device
+        fwd_sizes, t_sizes, g_sizes = [], [], []
+        for conv, need_t in convs:
+            o, i, r, s = conv.weight.shape
+            fwd_sizes.append(o * r * s * pad_channels(i))
+            t_sizes.append(i * r * s * pad_channels(o) if need_t else 0)
+            g_sizes.append(o * r * s * pad_channels(i))
+        al = lambda n: (n + 127) // 128 * 128  # keep every view 256-byte aligned
+        self._wpk = torch.empty(sum(al(n) for n in fwd_sizes), dtype=torch.bfloat16, device=device)
+        self._wpk_t = torch.empty(max(1, sum(al(n) for n in t_sizes)), dtype=torch.bfloat16, device=device)
+        self.dwp_flat = torch.zeros(sum(al(n) for n in g_sizes), dtype=torch.float32, device=device)
+        self.wpk, self.wpk_t, self.dwp = {}, {}, {}
+        of = ot = og = 0
+        for (conv, need_t), nf, nt, ng in zip(convs, fwd_sizes, t_sizes, g_sizes):
+            o, i, r, s = conv.weight.shape
+            self.wpk[id(conv)] = self._wpk[of:of + nf].view(o, r * s, pad_channels(i))
+            of += al(nf)
+            if need_t:
+                self.wpk_t[id(conv)] = self._wpk_t[ot:ot + nt].view(i, r * s, pad_channels(o))
+                ot += al(nt)
+            else:
+                self.wpk_t[id(conv)] = None
+            self.dwp[id(conv)] = self.dwp_flat[og:og + ng].view(o, r * s, pad_channels(i))
+            og += al(ng)
+        self._need_t = [t for _, t in convs]
+        self._ptrs = None
+        self._pack_table = self._pack_table_fwd = None
+        self._n_pack = self._n_fwd = 0
+        # gradient un-pack table (static: packed arena -> OIHW views of the gradient arena)
+        rows = []
+        for conv in self.convs:
+            o, i, r, s = conv.weight.shape
+            rows.append((self.dwp[id(conv)].data_ptr(), grad_arena.view_of[id(conv.weight)].data_ptr(), o, i, r * s,
+                         pad_channels(i), 0, 0))
+        self._unpack_table = self._to_device(rows)
+        self._n_unpack = len(rows)
+
+    def _to_device(self, rows):
+        arr = np.array(rows, dtype=_ENTRY)
+        return torch.from_numpy(arr.view(np.uint8).copy()).to(self.device)
+
+    def _refresh_tables(self):
+        ptrs = tuple(c.weight.data_ptr() for c in self.convs)
+        if ptrs == self._ptrs:
+            return
+        self._ptrs = ptrs
+        fwd, both = [], []
+        for conv, need_t in zip(self.convs, self._need_t):
+            o, i, r, s = conv.weight.shape
+            e = (conv.weight.data_ptr(), self.wpk[id(conv)].data_ptr(), o, i, r * s, pad_channels(i), pad_channels(o), 0)
+            fwd.append(e)
+            both.append(e)
+            if need_t:
+                both.append((conv.weight.data_ptr(), self.wpk_t[id(conv)].data_ptr(), o, i, r * s, pad_channels(i),
+                             pad_channels(o), 1))
+        self._pack_table_fwd, self._n_fwd = self._to_device(fwd), len(fwd)
+        self._pack_table, self._n_pack = self._to_device(both), len(both)
+
+    def pack_all(self, need_t: bool):
+        self._refresh_tables()
+        if need_t:
+            lib().call("b200cv_pack_weights_multi", self._pack_table.data_ptr(), self._n_pack, stream_ptr())
+        else:
+            lib().call("b200cv_pack_weights_multi", self._pack_table_fwd.data_ptr(), self._n_fwd, stream_ptr())
+
+    def zero_grads(self):
+        self.dwp_flat.zero_()
+
+    def unpack_all(self):
+        lib().call("b200cv_unpack_wgrad_multi", self._unpack_table.data_ptr(), self._n_unpack, stream_ptr())

@@ -19,6 +19,7 @@ import torch
 
 from . import ops
 from .lib import lib, ptr, require_cuda, stream_ptr
+from .packing import ConvPackSet, GradArena
 from .parallel import allreduce_gradients
 
 BN_EPS = 1e-5
@@ -43,10 +44,6 @@ class _ConvBN:
             self.scale, self.shift, self.mean, self.rstd, self.coef = f(c), f(c), f(c), f(c), f(3 * c)
             self.vec_dev = dev
 
-    def pack(self, need_t):
-        self.wpk = ops.pack_weights(self.conv.weight, False)
-        self.wpk_t = ops.pack_weights(self.conv.weight, True) if need_t else None
-
     def fwd_train(self, x):
         self.vecs(x.device)
         self.stats.zero_()
@@ -64,15 +61,14 @@ class _ConvBN:
         shift = self.bn.bias.detach() + (self.conv.bias.detach() - self.bn.running_mean) * scale
         return scale, shift
 
-    def bwd(self, x_in, y, da, aout, act, gview, dx_out=None, want_dx=True):
+    def bwd(self, x_in, y, da, aout, act, gview, packs, dx_out=None, want_dx=True):
         """BN+act backward then wgrad (+ dgrad).  Returns dx (or None)."""
         count = y.numel() // y.shape[-1]
         parts = ops.bn_bwd_reduce(da, y, aout, self.scale, self.shift, self.mean, self.rstd, act, 0.0)
         ops.bn_bwd_finalize(parts, self.bn.weight, self.rstd, count, self.coef, gview[id(self.bn.weight)],
                             gview[id(self.bn.bias)])
         dy = ops.bn_bwd_apply(da, y, aout, self.scale, self.shift, self.mean, self.rstd, self.coef, act, 0.0)
-        dwp = ops.conv_wgrad(x_in, dy, self.cout, self.k, 1, self.pad, self.dil)
-        ops.unpack_wgrad(dwp, gview[id(self.conv.weight)])
+        ops.conv_wgrad(x_in, dy, self.cout, self.k, 1, self.pad, self.dil, out=packs.dwp[id(self.conv)])
         gview[id(self.conv.bias)].zero_()  # analytically zero under train-mode BN
         if not want_dx:
             return None
@@ -96,6 +92,22 @@ class RektNetEngine:
             self.blocks.append((_ConvBN(r.conv1, r.bn1), _ConvBN(r.conv2, r.bn2), _ConvBN(r.shortcut_conv, r.shortcut_bn)))
         self.params = list(model.parameters())
         self._lin = None
+        self._arena = None
+        self._packs = None
+
+    def _conv_list(self):
+        convs = [(self.stem.conv, False)]
+        for b in self.blocks:
+            convs += [(c.conv, True) for c in b]
+        convs.append((self.model.out, True))
+        return convs
+
+    def _setup(self, dev):
+        if self._arena is None or self._arena.flat.device != dev:
+            self._arena = GradArena(self.params, dev)
+            self._packs = ConvPackSet(self._conv_list(), dev, self._arena)
+            for c in self._all():
+                c.wpk, c.wpk_t = self._packs.wpk[id(c.conv)], self._packs.wpk_t[id(c.conv)]
 
     def _coords(self, dev, h, w):
         if self._lin is None or self._lin[0].device != dev or self._lin[0].numel() != w or self._lin[1].numel() != h:
@@ -113,10 +125,9 @@ class RektNetEngine:
     def _forward(self, x, train: bool, want_grad: bool):
         m = self.model
         dev = x.device
-        for c in self._all():
-            c.pack(need_t=want_grad)
-        out_wpk = ops.pack_weights(m.out.weight, False)
-        out_wpk_t = ops.pack_weights(m.out.weight, True) if want_grad else None
+        self._setup(dev)
+        self._packs.pack_all(want_grad)
+        out_wpk, out_wpk_t = self._packs.wpk[id(m.out)], self._packs.wpk_t[id(m.out)]
         xin = ops.nchw_to_nhwc(x)
         saved = {"x": xin, "blocks": [], "out_wpk_t": out_wpk_t}
         if train:
@@ -160,20 +171,17 @@ class RektNetEngine:
         return hm, pts
 
     # ------------------------------------------------------------------ backward
-    def _grad_views(self, dev):
-        sizes = [p.numel() for p in self.params]
-        arena = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
-        views, o = [], 0
-        for p, n in zip(self.params, sizes):
-            views.append(arena[o:o + n].view_as(p))
-            o += n
-        return arena, views
-
     def _backward(self, saved, hm, pts, d_hm, d_pts, handle: Optional[_HeadHandle], logits_grad=None):
         m = self.model
         dev = hm.device if hm is not None else logits_grad.device
-        arena, views = self._grad_views(dev)
-        gview = {id(p): v for p, v in zip(self.params, views)}
+        arena = self._arena
+        if arena.aliased_by_param_grads():
+            arena = GradArena(self.params, dev)
+            packs = ConvPackSet(self._conv_list(), dev, arena)
+        else:
+            packs = self._packs
+        packs.zero_grads()
+        views, gview = arena.views, arena.view_of
         a_last = saved["a_last"]
         b, h, w = a_last.shape[0], a_last.shape[1], a_last.shape[2]
         k = m.out.out_channels
@@ -197,16 +205,16 @@ class RektNetEngine:
         tmp = torch.zeros(16, dtype=torch.float32, device=dev)
         ops.col_sum(dl, tmp)
         gview[id(m.out.bias)].copy_(tmp[:k])
-        dwp = ops.conv_wgrad(a_last, dl, k, 1, 1, 0)
-        ops.unpack_wgrad(dwp, gview[id(m.out.weight)])
+        ops.conv_wgrad(a_last, dl, k, 1, 1, 0, out=packs.dwp[id(m.out)])
         g = ops.conv_dgrad(dl, saved["out_wpk_t"], m.out.in_channels, 1, 1, 0, 1, (h, w))
         for (c1, c2, cs), (a_in, y1, a1, y2, ys, out) in zip(reversed(self.blocks), reversed(saved["blocks"])):
             # out = relu(bn_s(ys) + bn_2(y2)): both branches see dz = g * relu'(out)
-            g_in = cs.bwd(a_in, ys, g, out, ops.ACT_RELU, gview)
-            g_a1 = c2.bwd(a1, y2, g, out, ops.ACT_RELU, gview)
-            g = c1.bwd(a_in, y1, g_a1, None, ops.ACT_RELU, gview, dx_out=g_in)
-        self.stem.bwd(saved["x"], saved["y0"], g, None, ops.ACT_RELU, gview, want_dx=False)
-        allreduce_gradients(arena)
+            g_in = cs.bwd(a_in, ys, g, out, ops.ACT_RELU, gview, packs)
+            g_a1 = c2.bwd(a1, y2, g, out, ops.ACT_RELU, gview, packs)
+            g = c1.bwd(a_in, y1, g_a1, None, ops.ACT_RELU, gview, packs, dx_out=g_in)
+        self.stem.bwd(saved["x"], saved["y0"], g, None, ops.ACT_RELU, gview, packs, want_dx=False)
+        packs.unpack_all()
+        allreduce_gradients(arena.flat)
         return views
 
     # ------------------------------------------------------------------ public entry point

@@ -263,6 +263,50 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __rest
   }
 }
 
+
+// ---- multi-tensor variants: one launch for every conv of a network (grid.y = table entry) ----------
+struct PackEntry {          // mirrors b200cv_pack_entry (include/b200cv.h)
+  const float* src;         // OIHW fp32 (pack) / packed fp32 gradient (unpack)
+  void* dst;                // packed bf16 (pack) / OIHW fp32 gradient (unpack)
+  int O, I, RS, Ipad, Opad, transpose;
+};
+__global__ void pack_weights_multi_kernel(const PackEntry* __restrict__ table) {
+  const PackEntry e = table[blockIdx.y];
+  const long long total = e.transpose ? (long long)e.I * e.RS * e.Opad : (long long)e.O * e.RS * e.Ipad;
+  __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(e.dst);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (!e.transpose) {
+      const int ip = (int)(i % e.Ipad);
+      const long long r = i / e.Ipad;
+      const int t = (int)(r % e.RS);
+      const int o = (int)(r / e.RS);
+      if (ip < e.I) v = e.src[((long long)o * e.I + ip) * e.RS + t];
+    } else {
+      const int op = (int)(i % e.Opad);
+      const long long r = i / e.Opad;
+      const int t = (int)(r % e.RS);
+      const int ii = (int)(r / e.RS);
+      if (op < e.O) v = e.src[((long long)op * e.I + ii) * e.RS + t];
+    }
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+__global__ void unpack_wgrad_multi_kernel(const PackEntry* __restrict__ table) {
+  const PackEntry e = table[blockIdx.y];
+  const long long total = (long long)e.O * e.I * e.RS;
+  float* dst = static_cast<float*>(e.dst);
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < total;
+       j += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(j % e.RS);
+    const long long r = j / e.RS;
+    const int i = (int)(r % e.I);
+    const long long o = r / e.I;
+    dst[j] = e.src[(o * e.RS + t) * e.Ipad + i];
+  }
+}
+
 int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = (long long)sm_count() * 16;
@@ -307,4 +351,19 @@ extern "C" int b200cv_unpack_wgrad(const float* src, float* dst, int O, int I, i
   unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, dst, I, R * S, Ipad, total);
   return check_launch("unpack_wgrad");
+}
+
+extern "C" int b200cv_pack_weights_multi(const void* table_dev, int n, void* stream) {
+  B200CV_CHECK_ARG(table_dev && n > 0 && n <= 65535, "pack_weights_multi: bad args");
+  static_assert(sizeof(PackEntry) == sizeof(b200cv_pack_entry), "pack entry ABI mismatch");
+  pack_weights_multi_kernel<<<dim3(64, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const PackEntry*>(table_dev));
+  return check_launch("pack_weights_multi");
+}
+
+extern "C" int b200cv_unpack_wgrad_multi(const void* table_dev, int n, void* stream) {
+  B200CV_CHECK_ARG(table_dev && n > 0 && n <= 65535, "unpack_wgrad_multi: bad args");
+  unpack_wgrad_multi_kernel<<<dim3(64, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const PackEntry*>(table_dev));
+  return check_launch("unpack_wgrad_multi");
 }
