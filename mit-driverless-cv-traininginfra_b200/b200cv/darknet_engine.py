@@ -25,6 +25,13 @@ from .parallel import allreduce_gradients
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
+GRAPH_WARMUP_CALLS = 2  # eager steps with a given input shape before the step is captured as CUDA graphs
+
+
+def _graphs_enabled() -> bool:
+    import os
+
+    return os.environ.get("B200CV_CUDA_GRAPH", "1") != "0"
 
 
 class _Layer:
@@ -92,6 +99,8 @@ class DarknetEngine:
         self.params = list(model.parameters())
         self._arena = None
         self._packs = None
+        self._anchor_cache = {}
+        self._graphs = {}       # (shapes) -> _GraphedStep | int (eager warm-up calls seen so far)
 
     # ------------------------------------------------------------------ helpers
     def _vec(self, L: _Layer, dev):
@@ -112,6 +121,12 @@ class DarknetEngine:
 
     def _pack(self, need_t: bool):
         self._packs.pack_all(need_t)
+
+    def _anchors(self, L, gh, dev):
+        key = (L.index, gh, str(dev))
+        if key not in self._anchor_cache:
+            self._anchor_cache[key] = yolo_ops.scaled_anchors(L.yolo.anchors, L.yolo.image_height / gh, dev)
+        return self._anchor_cache[key]
 
     def _check_input(self, x):
         require_cuda(x, "Darknet.forward")
@@ -188,7 +203,7 @@ class DarknetEngine:
                 yl = L.yolo
                 gh, gw = z.shape[1], z.shape[2]
                 stride = yl.image_height / gh
-                sa = yolo_ops.scaled_anchors(yl.anchors, stride, dev)
+                sa = self._anchors(L, gh, dev)
                 if training:
                     yt = yolo_ops.yolo_targets(targets, sa, gh, gw, yl.ignore_thres)
                     sums = torch.zeros(6, dtype=torch.float64, device=dev)
@@ -208,13 +223,13 @@ class DarknetEngine:
         return torch.cat(dets, 1), None
 
     # ------------------------------------------------------------------ backward
-    def _run_backward(self, state, g7):
+    def _run_backward(self, state, g7, force_persistent_arena=False, do_allreduce=True):
         outs, saved = state
         model = self.model
         dev = g7.device
         g = g7[0:1].contiguous().float()
         arena = self._arena
-        if arena.aliased_by_param_grads():
+        if not force_persistent_arena and arena.aliased_by_param_grads():
             # param.grad still aliases the arena (zero_grad(set_to_none=False)): use a private arena for this
             # backward so autograd's in-place accumulation stays correct
             arena = GradArena(self.params, dev)
@@ -304,14 +319,35 @@ class DarknetEngine:
                     add_grad(L.inputs[1], G)
             grads[i] = None
         packs.unpack_all()
-        allreduce_gradients(arena.flat)
+        if do_allreduce:
+            allreduce_gradients(arena.flat)
         return views
 
     # ------------------------------------------------------------------ public entry points
     def train_forward(self, x, targets):
         self._check_input(x)
         require_cuda(targets, "Darknet.forward(targets)")
-        return _DarknetTrainFn.apply(self, x, targets.float(), self.model.training, torch.is_grad_enabled(), *self.params)
+        targets = targets.float()
+        grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.params)
+        if grad and self.model.training and _graphs_enabled() and not torch.cuda.is_current_stream_capturing():
+            key = (tuple(x.shape), tuple(targets.shape), str(x.device))
+            entry = self._graphs.get(key, 0)
+            if isinstance(entry, _GraphedStep):
+                if entry.usable():
+                    return _DarknetGraphFn.apply(entry, x, targets, *self.params)
+            elif entry >= GRAPH_WARMUP_CALLS:
+                try:
+                    self._graphs[key] = _GraphedStep(self, x, targets)
+                    return _DarknetGraphFn.apply(self._graphs[key], x, targets, *self.params)
+                except Exception as e:  # capture is an optimisation: fall back to the eager launches, loudly
+                    import warnings
+
+                    warnings.warn(f"b200cv: CUDA-graph capture failed ({e}); staying on eager launches")
+                    self._graphs[key] = -(10 ** 9)
+                    torch.cuda.synchronize()
+            else:
+                self._graphs[key] = entry + 1
+        return _DarknetTrainFn.apply(self, x, targets, self.model.training, torch.is_grad_enabled(), *self.params)
 
     @torch.no_grad()
     def detect(self, x):
@@ -334,3 +370,52 @@ class _DarknetTrainFn(torch.autograd.Function):
         views = ctx.engine._run_backward(ctx.state, g7)
         ctx.state = None
         return (None, None, None, None, None, *views)
+
+
+class _GraphedStep:
+    """One training step (fixed shapes) captured as two CUDA graphs -- forward+loss and backward -- sharing a
+    memory pool, so the ~1200 launches of a Darknet-53 step cost two graph launches on the host.  Inputs are
+    copied into static buffers; the gradient all-reduce stays outside the graph."""
+
+    def __init__(self, engine, x, targets):
+        self.engine = engine
+        dev = x.device
+        self.static_x = x.detach().float().clone()
+        self.static_t = targets.detach().clone()
+        self.static_g = torch.zeros(7, dtype=torch.float32, device=dev)
+        self.static_g[0] = 1.0
+        engine._setup(dev)
+        self.weight_ptrs = tuple(p.data_ptr() for p in engine.params)
+        torch.cuda.synchronize()
+        self.pool = torch.cuda.graph_pool_handle()
+        self.fwd_graph, self.bwd_graph = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.no_grad():
+            with torch.cuda.graph(self.fwd_graph, pool=self.pool):
+                self.out7, self.state = engine._run_forward(self.static_x, self.static_t, bn_train=True, want_grad=True)
+            with torch.cuda.graph(self.bwd_graph, pool=self.pool):
+                self.views = engine._run_backward(self.state, self.static_g, force_persistent_arena=True,
+                                                  do_allreduce=False)
+        torch.cuda.synchronize()
+
+    def usable(self) -> bool:
+        e = self.engine
+        return (tuple(p.data_ptr() for p in e.params) == self.weight_ptrs and e._arena is not None
+                and not e._arena.aliased_by_param_grads())
+
+
+class _DarknetGraphFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, step, x, targets, *params):
+        step.static_x.copy_(x, non_blocking=True)
+        step.static_t.copy_(targets, non_blocking=True)
+        step.fwd_graph.replay()
+        ctx.step = step
+        return step.out7.clone()
+
+    @staticmethod
+    def backward(ctx, g7):
+        step = ctx.step
+        step.static_g.copy_(g7)
+        step.bwd_graph.replay()
+        allreduce_gradients(step.engine._arena.flat)
+        return (None, None, None, *step.views)

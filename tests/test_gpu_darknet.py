@@ -166,7 +166,9 @@ def test_every_backward_op_in_context(cfg_dir, cfg_name, S, B):
         xh = (yf - mean) * rstd
         m = yf.numel() // c
         k1, k2 = dz.sum((0, 1, 2)) / m, (dz * xh).sum((0, 1, 2)) / m
-        errs.append(("bn_bwd_k", tuple(y.shape), max(rel(coef[c:2 * c], k1), rel(coef[2 * c:], k2))))
+        rms = float(dz.pow(2).mean().sqrt()) + 1e-20  # the means are near-cancelling sums: scale by rms(dz)
+        errs.append(("bn_bwd_k", tuple(y.shape), max(float((coef[c:2 * c] - k1).abs().max()),
+                                                     float((coef[2 * c:] - k2).abs().max())) / rms))
         errs.append(("bn_bwd_apply", tuple(y.shape), rel(o.float(), coef[:c] * (dz - k1 - xh * k2))))
         return o
 
@@ -180,6 +182,42 @@ def test_every_backward_op_in_context(cfg_dir, cfg_name, S, B):
     finally:
         ops.conv_wgrad, ops.conv_dgrad, ops.bn_bwd_apply = orig
     assert len(errs) > 30
-    tol = {"wgrad": 2e-3, "dgrad": 6e-3, "bn_bwd_apply": 6e-3, "bn_bwd_k": 2e-3}  # outputs are bf16 (2^-9) or fp32
+    tol = {"wgrad": 2e-3, "dgrad": 6e-3, "bn_bwd_apply": 1.2e-2, "bn_bwd_k": 2e-3}  # outputs are bf16 (2^-9) or fp32
     bad = [e for e in errs if not e[2] < tol[e[0]]]
     assert not bad, bad[:5]
+
+
+def test_cuda_graph_step_matches_eager(cfg_dir):
+    """After two eager calls a training step is replayed from CUDA graphs: same losses, same weights after
+    several optimizer steps, BN running statistics keep advancing, and new inputs are honoured."""
+    import os
+
+    res = {}
+    for mode in ("0", "1"):
+        os.environ["B200CV_CUDA_GRAPH"] = mode
+        model, _ = helpers.make_darknet(cfg_dir, "yolo_baseline_tiny.cfg", 128, 1)
+        model = model.to(DEV).train()
+        opt = torch.optim.SGD(model.parameters(), lr=1e-3)
+        hist = []
+        for it in range(5):
+            x = YO.synth_images(2, 128, 128, seed=it).to(DEV)
+            tg = YO.synth_targets(2, 16, seed=10 + it).to(DEV)
+            opt.zero_grad()
+            losses = model(x, tg)
+            losses[0].sum().backward()
+            opt.step()
+            hist.append(torch.stack([l.detach() for l in losses]).cpu())
+        res[mode] = (hist, {k: v.detach().cpu().clone() for k, v in model.state_dict().items()})
+        if mode == "1":
+            from b200cv.darknet_engine import _GraphedStep
+
+            assert any(isinstance(v, _GraphedStep) for v in model.engine()._graphs.values())
+    os.environ["B200CV_CUDA_GRAPH"] = "1"
+    for a, b in zip(res["0"][0], res["1"][0]):
+        assert torch.allclose(a, b, rtol=2e-2, atol=1e-4), (a, b)
+    for k, v in res["0"][1].items():
+        w = res["1"][1][k]
+        if v.dtype.is_floating_point:
+            assert float((v - w).abs().max()) <= 5e-2 * float(v.abs().max()) + 1e-5, k
+        else:
+            assert torch.equal(v, w), k  # num_batches_tracked advanced identically
