@@ -251,7 +251,9 @@ def main():
     out = None
     # roofline of the dominant kernels: event-time every conv launch of one more step (every rank runs the
     # step -- it contains the gradient all-reduce -- rank 0 reports)
+    os.environ["B200CV_CUDA_GRAPH"] = "0"  # per-launch events need the eager launches, not the captured graph
     prof = lib().profile_step(lambda: step(imgs_d, tg_d))
+    os.environ["B200CV_CUDA_GRAPH"] = "1"
     if rank == 0:
         spec = YO.NetSpec(cfg)
         fwd_f, tot_f = conv_flops_per_image(spec.layers, IMG)

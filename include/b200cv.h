@@ -53,6 +53,11 @@ int b200cv_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C, int 
 /* NHWC bf16 [N,H,W,Cpad] (first C channels) -> NCHW fp32 [N,C,H,W]. */
 int b200cv_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C, int H, int W, int Cpad,
                                  void* stream);
+/* Explicit im2col for few-channel inputs (the 3-channel image layers: CVC-YOLOv3/models.py conv_0,
+ * RektNet/keypoint_net.py:17): NCHW fp32 x -> bf16 patch matrix [N*OH*OW][Kp], k = (r*S+s)*C + c, zero padded.
+ * The convolution then runs as a 1x1 conv over the patch matrix (Cin = Kp). */
+int b200cv_im2col_nchw_f32(const float* x, void* patches, int N, int C, int H, int W, int R, int S, int stride,
+                           int pad, int dil, int Kp, void* stream);
 /* OIHW fp32 conv weight -> packed bf16.
  *   transpose == 0: [O][R*S][Ipad]      (forward operand;  K index = tap*Ipad + i)
  *   transpose == 1: [I][R*S][Opad]      (data-gradient operand; K index = tap*Opad + o)
@@ -71,6 +76,8 @@ typedef struct b200cv_pack_entry {
   void* dst;
   int32_t O, I, RS, Ipad, Opad, transpose;
 } b200cv_pack_entry;
+/* entry.transpose == 2 selects the FLAT layout used with b200cv_im2col_nchw_f32: packed row = [Ipad] with
+ * k = tap*I + i (Ipad >= R*S*I); the matching gradient row is un-packed the same way. */
 int b200cv_pack_weights_multi(const void* table_dev, int n, void* stream);
 int b200cv_unpack_wgrad_multi(const void* table_dev, int n, void* stream);
 

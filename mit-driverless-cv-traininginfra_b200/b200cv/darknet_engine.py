@@ -114,10 +114,14 @@ class DarknetEngine:
         if self._arena is None or self._arena.flat.device != dev:
             self._arena = GradArena(self.params, dev)
             convs = [(L.conv, L.index > 0) for L in self.layers if L.type == "convolutional"]
-            self._packs = ConvPackSet(convs, dev, self._arena)
+            self._packs = ConvPackSet(convs, dev, self._arena, flat=self._flat_convs())
             for L in self.layers:
                 if L.type == "convolutional":
                     L.wpk, L.wpk_t = self._packs.wpk[id(L.conv)], self._packs.wpk_t[id(L.conv)]
+
+    def _flat_convs(self):
+        L0 = self.layers[0]
+        return [L0.conv] if (L0.type == "convolutional" and ops.use_flat_path(L0.cin, L0.k)) else []
 
     def _pack(self, need_t: bool):
         self._packs.pack_all(need_t)
@@ -140,7 +144,9 @@ class DarknetEngine:
         dev = x.device
         self._setup(dev)
         self._pack(need_t=want_grad)
-        cur = ops.nchw_to_nhwc(x)
+        flat0 = bool(self._flat_convs())
+        cur = ops.im2col_nchw(x, self.layers[0].k, self.layers[0].stride, self.layers[0].pad) if flat0 \
+            else ops.nchw_to_nhwc(x)
         outs: List[Optional[torch.Tensor]] = [None] * len(self.layers)
         saved = {}
         training = targets is not None
@@ -151,12 +157,13 @@ class DarknetEngine:
             i = L.index
             if L.type == "convolutional":
                 xin = cur
+                k_, st_, pd_ = (1, 1, 0) if (flat0 and i == 0) else (L.k, L.stride, L.pad)
                 if L.bn is not None:
                     self._vec(L, dev)
                     post = outs[L.post_from] if L.post_from is not None else None
                     if bn_train:
                         L.stats.zero_()
-                        y = ops.conv_fwd(xin, L.wpk, L.cout, L.k, L.stride, L.pad, stats=L.stats)
+                        y = ops.conv_fwd(xin, L.wpk, L.cout, k_, st_, pd_, stats=L.stats)
                         count = y.numel() // y.shape[-1]
                         ops.bn_finalize(L.stats, count, L.bn.weight, L.bn.bias, None, BN_EPS, BN_MOMENTUM,
                                         L.bn.running_mean, L.bn.running_var, L.scale, L.shift, L.mean, L.rstd)
@@ -167,13 +174,13 @@ class DarknetEngine:
                     else:
                         scale = L.bn.weight.detach() * torch.rsqrt(L.bn.running_var + BN_EPS)
                         shift = L.bn.bias.detach() - L.bn.running_mean * scale
-                        cur = ops.conv_fwd(xin, L.wpk, L.cout, L.k, L.stride, L.pad, scale=scale, shift=shift,
+                        cur = ops.conv_fwd(xin, L.wpk, L.cout, k_, st_, pd_, scale=scale, shift=shift,
                                            residual=post, act=L.act, slope=L.slope, res_after_act=True)
                         if want_grad:
                             raise RuntimeError("Darknet: backward through eval-mode BatchNorm is not supported; "
                                                "call model.train() (or wrap the pass in torch.no_grad())")
                 else:  # pre-YOLO conv: bias, linear, fp32 logits
-                    cur = ops.conv_fwd(xin, L.wpk, L.cout, L.k, L.stride, L.pad, out_dtype=torch.float32,
+                    cur = ops.conv_fwd(xin, L.wpk, L.cout, k_, st_, pd_, out_dtype=torch.float32,
                                        shift=L.conv.bias.detach())
                     saved[i] = (xin,)
             elif L.type == "maxpool":
@@ -233,7 +240,8 @@ class DarknetEngine:
             # param.grad still aliases the arena (zero_grad(set_to_none=False)): use a private arena for this
             # backward so autograd's in-place accumulation stays correct
             arena = GradArena(self.params, dev)
-            packs = ConvPackSet([(L.conv, L.index > 0) for L in self.layers if L.type == "convolutional"], dev, arena)
+            packs = ConvPackSet([(L.conv, L.index > 0) for L in self.layers if L.type == "convolutional"], dev, arena,
+                                flat=self._flat_convs())
         else:
             packs = self._packs
         packs.zero_grads()
@@ -283,7 +291,10 @@ class DarknetEngine:
                     tmp = torch.zeros(dy.shape[-1], dtype=torch.float32, device=dev)
                     ops.col_sum(dy, tmp)
                     gview[id(L.conv.bias)].copy_(tmp[:L.cout])
-                ops.conv_wgrad(xin, dy, L.cout, L.k, L.stride, L.pad, out=packs.dwp[id(L.conv)])
+                if i == 0 and self._flat_convs():
+                    ops.conv_wgrad(xin, dy, L.cout, 1, 1, 0, out=packs.dwp[id(L.conv)])  # xin = im2col patches
+                else:
+                    ops.conv_wgrad(xin, dy, L.cout, L.k, L.stride, L.pad, out=packs.dwp[id(L.conv)])
                 if i > 0:
                     prev = grads[i - 1]
                     dx = ops.conv_dgrad(dy, L.wpk_t, L.cin, L.k, L.stride, L.pad, 1, (xin.shape[1], xin.shape[2]),

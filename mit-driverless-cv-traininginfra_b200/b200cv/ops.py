@@ -16,7 +16,8 @@ __all__ = [
     "ACT_NONE", "ACT_LEAKY", "ACT_RELU", "pad_channels", "conv_out_size", "nchw_to_nhwc", "nhwc_to_nchw",
     "pack_weights", "unpack_wgrad", "conv_fwd", "conv_dgrad", "conv_wgrad", "bn_finalize", "bn_apply_act",
     "bn_bwd_reduce", "bn_bwd_finalize", "bn_bwd_apply", "act_bwd", "copy_slice", "col_sum", "maxpool_fwd",
-    "maxpool_bwd", "upsample_fwd", "upsample_bwd", "act_code", "sm_count", "stats_buffer",
+    "maxpool_bwd", "upsample_fwd", "upsample_bwd", "act_code", "sm_count", "stats_buffer", "im2col_nchw",
+    "use_flat_path", "flat_k",
 ]
 
 
@@ -52,6 +53,29 @@ def nhwc_to_nchw(x: torch.Tensor, c: int) -> torch.Tensor:
     n, h, w, cpad = x.shape
     out = torch.empty(n, c, h, w, dtype=torch.float32, device=x.device)
     lib().call("b200cv_nhwc_bf16_to_nchw_f32", ptr(x), ptr(out), n, c, h, w, cpad, stream_ptr())
+    return out
+
+
+def flat_k(cin: int, k: int) -> int:
+    """Padded K of the flat (explicit-im2col) layout of a k x k conv over cin channels."""
+    return pad_channels(cin * k * k)
+
+
+def use_flat_path(cin: int, k: int) -> bool:
+    """Few-channel image layers run as explicit im2col + 1x1 conv (one TMA tile per output tile instead of
+    k*k nearly-empty 16-channel tiles)."""
+    return cin <= 4 and cin * k * k <= 256
+
+
+def im2col_nchw(x: torch.Tensor, k: int, stride: int, pad: int, dil: int = 1) -> torch.Tensor:
+    """NCHW fp32 image -> bf16 patches [N,OH,OW,Kp] (k index = (r*k+s)*C + c)."""
+    require_cuda(x, "im2col_nchw")
+    x = x.contiguous().float()
+    n, c, h, w = x.shape
+    oh, ow = conv_out_size(h, k, stride, pad, dil), conv_out_size(w, k, stride, pad, dil)
+    kp = flat_k(c, k)
+    out = torch.empty(n, oh, ow, kp, dtype=torch.bfloat16, device=x.device)
+    lib().call("b200cv_im2col_nchw_f32", ptr(x), ptr(out), n, c, h, w, k, k, stride, pad, dil, kp, stream_ptr())
     return out
 
 

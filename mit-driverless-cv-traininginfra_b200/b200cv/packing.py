@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from .lib import lib, stream_ptr
-from .ops import pad_channels
+from .ops import flat_k, pad_channels
 
 _ENTRY = np.dtype([("src", np.uint64), ("dst", np.uint64), ("O", np.int32), ("I", np.int32), ("RS", np.int32),
                    ("Ipad", np.int32), ("Opad", np.int32), ("transpose", np.int32)])
@@ -38,16 +38,19 @@ class GradArena:
 
 
 class ConvPackSet:
-    def __init__(self, convs, device, grad_arena: GradArena):
-        """convs: list of (nn.Conv2d, need_transposed_pack)."""
+    def __init__(self, convs, device, grad_arena: GradArena, flat=()):
+        """convs: list of (nn.Conv2d, need_transposed_pack); `flat`: convs that use the explicit-im2col
+        layout [O][1][Kp] (k = tap*I + i) instead of [O][taps][Ipad]."""
         self.convs = [c for c, _ in convs]
         self.device = device
+        self._flat = {id(c) for c in flat}
         fwd_sizes, t_sizes, g_sizes = [], [], []
         for conv, need_t in convs:
             o, i, r, s = conv.weight.shape
-            fwd_sizes.append(o * r * s * pad_channels(i))
+            n_fwd = o * flat_k(i, r) if id(conv) in self._flat else o * r * s * pad_channels(i)
+            fwd_sizes.append(n_fwd)
             t_sizes.append(i * r * s * pad_channels(o) if need_t else 0)
-            g_sizes.append(o * r * s * pad_channels(i))
+            g_sizes.append(n_fwd)
         al = lambda n: (n + 127) // 128 * 128  # keep every view 256-byte aligned
         self._wpk = torch.empty(sum(al(n) for n in fwd_sizes), dtype=torch.bfloat16, device=device)
         self._wpk_t = torch.empty(max(1, sum(al(n) for n in t_sizes)), dtype=torch.bfloat16, device=device)
@@ -56,14 +59,15 @@ class ConvPackSet:
         of = ot = og = 0
         for (conv, need_t), nf, nt, ng in zip(convs, fwd_sizes, t_sizes, g_sizes):
             o, i, r, s = conv.weight.shape
-            self.wpk[id(conv)] = self._wpk[of:of + nf].view(o, r * s, pad_channels(i))
+            shape = (o, 1, flat_k(i, r)) if id(conv) in self._flat else (o, r * s, pad_channels(i))
+            self.wpk[id(conv)] = self._wpk[of:of + nf].view(shape)
             of += al(nf)
             if need_t:
                 self.wpk_t[id(conv)] = self._wpk_t[ot:ot + nt].view(i, r * s, pad_channels(o))
                 ot += al(nt)
             else:
                 self.wpk_t[id(conv)] = None
-            self.dwp[id(conv)] = self.dwp_flat[og:og + ng].view(o, r * s, pad_channels(i))
+            self.dwp[id(conv)] = self.dwp_flat[og:og + ng].view(shape)
             og += al(ng)
         self._need_t = [t for _, t in convs]
         self._ptrs = None
@@ -73,8 +77,9 @@ class ConvPackSet:
         rows = []
         for conv in self.convs:
             o, i, r, s = conv.weight.shape
+            fl = id(conv) in self._flat
             rows.append((self.dwp[id(conv)].data_ptr(), grad_arena.view_of[id(conv.weight)].data_ptr(), o, i, r * s,
-                         pad_channels(i), 0, 0))
+                         flat_k(i, r) if fl else pad_channels(i), 0, 2 if fl else 0))
         self._unpack_table = self._to_device(rows)
         self._n_unpack = len(rows)
 
@@ -90,7 +95,9 @@ class ConvPackSet:
         fwd, both = [], []
         for conv, need_t in zip(self.convs, self._need_t):
             o, i, r, s = conv.weight.shape
-            e = (conv.weight.data_ptr(), self.wpk[id(conv)].data_ptr(), o, i, r * s, pad_channels(i), pad_channels(o), 0)
+            fl = id(conv) in self._flat
+            e = (conv.weight.data_ptr(), self.wpk[id(conv)].data_ptr(), o, i, r * s,
+                 flat_k(i, r) if fl else pad_channels(i), pad_channels(o), 2 if fl else 0)
             fwd.append(e)
             both.append(e)
             if need_t:

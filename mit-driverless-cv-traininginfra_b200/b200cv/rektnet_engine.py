@@ -87,6 +87,7 @@ class RektNetEngine:
     def __init__(self, model):
         self.model = model
         self.stem = _ConvBN(model.conv, model.bn)
+        self.stem.k, self.stem.pad, self.stem.dil = 1, 0, 1  # explicit-im2col stem: a 1x1 conv over the patches
         self.blocks = []
         for r in (model.res1, model.res2, model.res3, model.res4):
             self.blocks.append((_ConvBN(r.conv1, r.bn1), _ConvBN(r.conv2, r.bn2), _ConvBN(r.shortcut_conv, r.shortcut_bn)))
@@ -105,7 +106,7 @@ class RektNetEngine:
     def _setup(self, dev):
         if self._arena is None or self._arena.flat.device != dev:
             self._arena = GradArena(self.params, dev)
-            self._packs = ConvPackSet(self._conv_list(), dev, self._arena)
+            self._packs = ConvPackSet(self._conv_list(), dev, self._arena, flat=[self.stem.conv])
             for c in self._all():
                 c.wpk, c.wpk_t = self._packs.wpk[id(c.conv)], self._packs.wpk_t[id(c.conv)]
 
@@ -128,7 +129,7 @@ class RektNetEngine:
         self._setup(dev)
         self._packs.pack_all(want_grad)
         out_wpk, out_wpk_t = self._packs.wpk[id(m.out)], self._packs.wpk_t[id(m.out)]
-        xin = ops.nchw_to_nhwc(x)
+        xin = ops.im2col_nchw(x, 7, 1, 3)  # stem runs as explicit im2col + 1x1 conv over [.., 192] patches
         saved = {"x": xin, "blocks": [], "out_wpk_t": out_wpk_t}
         if train:
             y0 = self.stem.fwd_train(xin)
@@ -148,7 +149,7 @@ class RektNetEngine:
                 raise RuntimeError("KeypointNet: backward through eval-mode BatchNorm is not supported; call "
                                    "model.train() or wrap the pass in torch.no_grad()")
             sc, sh = self.stem.eval_affine()
-            a = ops.conv_fwd(xin, self.stem.wpk, self.stem.cout, 7, 1, 3, scale=sc, shift=sh, act=ops.ACT_RELU)
+            a = ops.conv_fwd(xin, self.stem.wpk, self.stem.cout, 1, 1, 0, scale=sc, shift=sh, act=ops.ACT_RELU)
             for c1, c2, cs in self.blocks:
                 sc, sh = c1.eval_affine()
                 a1 = ops.conv_fwd(a, c1.wpk, c1.cout, 3, 1, 2, 2, scale=sc, shift=sh, act=ops.ACT_RELU)
@@ -177,7 +178,7 @@ class RektNetEngine:
         arena = self._arena
         if arena.aliased_by_param_grads():
             arena = GradArena(self.params, dev)
-            packs = ConvPackSet(self._conv_list(), dev, arena)
+            packs = ConvPackSet(self._conv_list(), dev, arena, flat=[self.stem.conv])
         else:
             packs = self._packs
         packs.zero_grads()

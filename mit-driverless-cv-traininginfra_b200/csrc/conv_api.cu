@@ -272,12 +272,18 @@ struct PackEntry {          // mirrors b200cv_pack_entry (include/b200cv.h)
 };
 __global__ void pack_weights_multi_kernel(const PackEntry* __restrict__ table) {
   const PackEntry e = table[blockIdx.y];
-  const long long total = e.transpose ? (long long)e.I * e.RS * e.Opad : (long long)e.O * e.RS * e.Ipad;
+  // transpose == 2: "flat" pack [O][Ipad] with k = tap*I + i (whole filter in one padded K run)
+  const long long total = e.transpose == 2 ? (long long)e.O * e.Ipad
+                          : (e.transpose ? (long long)e.I * e.RS * e.Opad : (long long)e.O * e.RS * e.Ipad);
   __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(e.dst);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     float v = 0.f;
-    if (!e.transpose) {
+    if (e.transpose == 2) {
+      const int k = (int)(i % e.Ipad);
+      const int o = (int)(i / e.Ipad);
+      if (k < e.RS * e.I) v = e.src[((long long)o * e.I + (k % e.I)) * e.RS + (k / e.I)];
+    } else if (!e.transpose) {
       const int ip = (int)(i % e.Ipad);
       const long long r = i / e.Ipad;
       const int t = (int)(r % e.RS);
@@ -303,7 +309,76 @@ __global__ void unpack_wgrad_multi_kernel(const PackEntry* __restrict__ table) {
     const long long r = j / e.RS;
     const int i = (int)(r % e.I);
     const long long o = r / e.I;
-    dst[j] = e.src[(o * e.RS + t) * e.Ipad + i];
+    dst[j] = e.transpose == 2 ? e.src[o * e.Ipad + t * e.I + i] : e.src[(o * e.RS + t) * e.Ipad + i];
+  }
+}
+
+// explicit im2col for the 3-channel input layers: NCHW fp32 image -> bf16 patch matrix [N*OH*OW][Kp],
+// k = (r*S+s)*C + c.  One thread per output pixel (plane reads coalesce across threads); R,S,C are
+// compile-time so the patch lives in registers and goes out as 16-byte stores.
+template <int R, int S, int C>
+__global__ void __launch_bounds__(256)
+im2col_nchw_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H, int W, int stride,
+                   int pad, int dil, int OH, int OW, int Kp) {
+  constexpr int K = R * S * C;
+  constexpr int K8 = (K + 7) / 8 * 8;
+  const long long total = (long long)N * OH * OW;
+  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < total;
+       m += (long long)gridDim.x * blockDim.x) {
+    const int ow = (int)(m % OW);
+    const long long t = m / OW;
+    const int oh = (int)(t % OH);
+    const long long n = t / OH;
+    const float* xn = x + n * C * H * W;
+    __nv_bfloat16* o = out + m * Kp;
+    float v[K8];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int ih = oh * stride - pad + r * dil;
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const int iw = ow * stride - pad + s * dil;
+        const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
+#pragma unroll
+        for (int c = 0; c < C; ++c) v[(r * S + s) * C + c] = ok ? __ldg(xn + ((long long)c * H + ih) * W + iw) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int k = K; k < K8; ++k) v[k] = 0.f;
+#pragma unroll
+    for (int k0 = 0; k0 < K8; k0 += 8) {
+      uint4 pk;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[k0 + 2 * j], v[k0 + 2 * j + 1]);
+      *reinterpret_cast<uint4*>(o + k0) = pk;
+    }
+    for (int k0 = K8; k0 < Kp; k0 += 8) *reinterpret_cast<uint4*>(o + k0) = make_uint4(0, 0, 0, 0);
+  }
+}
+// generic fallback (any R,S,C)
+__global__ void im2col_nchw_generic_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int C,
+                                           int H, int W, int R, int S, int stride, int pad, int dil, int OH, int OW,
+                                           int Kp) {
+  const long long total = (long long)N * OH * OW;
+  const int K = R * S * C;
+  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < total;
+       m += (long long)gridDim.x * blockDim.x) {
+    const int ow = (int)(m % OW);
+    const long long t = m / OW;
+    const int oh = (int)(t % OH);
+    const long long n = t / OH;
+    const float* xn = x + n * C * H * W;
+    __nv_bfloat16* o = out + m * Kp;
+    for (int k = 0; k < Kp; ++k) {
+      float val = 0.f;
+      if (k < K) {
+        const int c = k % C, rs = k / C;
+        const int ih = oh * stride - pad + (rs / S) * dil, iw = ow * stride - pad + (rs % S) * dil;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) val = __ldg(xn + ((long long)c * H + ih) * W + iw);
+      }
+      o[k] = __float2bfloat16_rn(val);
+    }
   }
 }
 
@@ -366,4 +441,27 @@ extern "C" int b200cv_unpack_wgrad_multi(const void* table_dev, int n, void* str
   unpack_wgrad_multi_kernel<<<dim3(64, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const PackEntry*>(table_dev));
   return check_launch("unpack_wgrad_multi");
+}
+
+extern "C" int b200cv_im2col_nchw_f32(const float* x, void* patches, int N, int C, int H, int W, int R, int S,
+                                      int stride, int pad, int dil, int Kp, void* stream) {
+  B200CV_CHECK_ARG(x && patches && N > 0 && C > 0 && H > 0 && W > 0 && R > 0 && S > 0 && stride > 0 && dil > 0,
+                   "im2col: bad args");
+  B200CV_CHECK_ARG(Kp >= R * S * C && Kp % 8 == 0, "im2col: Kp=%d must be a multiple of 8 and >= R*S*C", Kp);
+  const int OH = (H + 2 * pad - dil * (R - 1) - 1) / stride + 1;
+  const int OW = (W + 2 * pad - dil * (S - 1) - 1) / stride + 1;
+  B200CV_CHECK_ARG(OH > 0 && OW > 0, "im2col: empty output");
+  const long long total = (long long)N * OH * OW;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(patches);
+  const int grid = grid_for(total, 256);
+  if (R == 3 && S == 3 && C == 3)
+    im2col_nchw_kernel<3, 3, 3><<<grid, 256, 0, st>>>(x, o, N, H, W, stride, pad, dil, OH, OW, Kp);
+  else if (R == 7 && S == 7 && C == 3)
+    im2col_nchw_kernel<7, 7, 3><<<grid, 256, 0, st>>>(x, o, N, H, W, stride, pad, dil, OH, OW, Kp);
+  else if (R == 3 && S == 3 && C == 1)
+    im2col_nchw_kernel<3, 3, 1><<<grid, 256, 0, st>>>(x, o, N, H, W, stride, pad, dil, OH, OW, Kp);
+  else
+    im2col_nchw_generic_kernel<<<grid, 256, 0, st>>>(x, o, N, C, H, W, R, S, stride, pad, dil, OH, OW, Kp);
+  return check_launch("im2col_nchw");
 }

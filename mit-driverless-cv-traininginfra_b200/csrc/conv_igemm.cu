@@ -34,7 +34,11 @@ struct Cfg {
   static constexpr int kABytes = kBlockM * KC * 2;
   static constexpr int kBBytes = BN * KC * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+  // Small stages (<= 16 KB: the 16/32-channel layers) are latency- not bandwidth-bound per k-iteration:
+  // run two CTAs per SM (each with a shallower ring) so their TMA / mbarrier round trips overlap.
+  static constexpr int kCtasPerSm = kStageBytes <= 16 * 1024 ? 2 : 1;
+  static constexpr int kBudget = kCtasPerSm == 2 ? 80 * 1024 : kSmemBudget;
+  static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : (2 * BN);
   static constexpr int kRowBytes = KC * 2;               // 32 / 64 / 128
@@ -56,7 +60,7 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
 }
 
 template <int KC, int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, Cfg<KC, BN>::kCtasPerSm)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ IgemmParams p) {
   using C = Cfg<KC, BN>;
@@ -372,7 +376,7 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams
     configured = true;
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
-  int grid = sm_count();
+  int grid = sm_count() * C::kCtasPerSm;
   if (grid > tiles) grid = tiles;
   if (grid < 1) return 0;
   kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, p);
