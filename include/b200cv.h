@@ -190,6 +190,16 @@ int b200cv_yolo_loss(const float* logits, int64_t z_sb, int64_t z_sy, int64_t z_
                      const int32_t* counts, float xy_loss, float wh_loss, float obj_loss, float noobj_loss,
                      double* sums, void* dlogits, int dl_dtype, int64_t d_sb, int64_t d_sy, int64_t d_sx,
                      int64_t d_sc, int d_channels, const float* gscale, void* stream);
+/* Engine form of the same loss/gradient in two kernels: b200cv_yolo_loss_cells runs one thread per anchor
+ * cell and writes compact fp32 cell gradients dcell[pixel][cell_ld] (index a*5+attr, every cell written);
+ * b200cv_yolo_expand_dlogits streams them into the dense NHWC head gradient (exact zeros for class/pad
+ * channels).  sums / gscale as in b200cv_yolo_loss. */
+int b200cv_yolo_loss_cells(const float* logits, int64_t z_sb, int64_t z_sy, int64_t z_sx, int64_t z_sc, int B, int A,
+                           int C, int Gh, int Gw, const int32_t* owner, const uint8_t* ign, const float* rec, int T,
+                           const int32_t* counts, float xy_loss, float wh_loss, float obj_loss, float noobj_loss,
+                           double* sums, float* dcell, int cell_ld, const float* gscale, void* stream);
+int b200cv_yolo_expand_dlogits(const float* dcell, int cell_ld, void* dlogits, int dl_dtype, int64_t d_ld,
+                               int d_channels, int64_t npix, int A, int C, void* stream);
 /* out7[0] += total; out7[1..6] += (x,y,w,h,obj,noobj) -- the tuple order of models.py:211,338. */
 int b200cv_yolo_loss_finalize(const double* sums, const int32_t* counts, float xy_loss, float wh_loss,
                               float obj_loss, float noobj_loss, float* out7, void* stream);

@@ -214,7 +214,7 @@ class DarknetEngine:
                 if training:
                     yt = yolo_ops.yolo_targets(targets, sa, gh, gw, yl.ignore_thres)
                     sums = torch.zeros(6, dtype=torch.float64, device=dev)
-                    yolo_ops.yolo_loss(z, False, yt, yl.num_classes, consts, sums=sums)
+                    yolo_ops.yolo_loss_cells(z, False, yt, yl.num_classes, consts, sums=sums)
                     yolo_ops.yolo_loss_finalize(sums, yt, consts, out7)
                     saved[i] = (z, yt)
                     cur = None
@@ -261,8 +261,7 @@ class DarknetEngine:
             i = L.index
             if L.type == "yolo":
                 z, yt = saved[i]
-                dl = torch.empty(z.shape, dtype=torch.bfloat16, device=dev)
-                yolo_ops.yolo_loss(z, False, yt, L.yolo.num_classes, consts, dlogits=dl, gscale=g)
+                dl = yolo_ops.yolo_head_grad(z, yt, L.yolo.num_classes, consts, g)
                 add_grad(i - 1, dl)
                 continue
             G = grads[i]

@@ -78,6 +78,33 @@ def yolo_loss(z, nchw, yt: YoloTargets, num_classes, consts, sums=None, dlogits=
                ptr(dlogits), ddt, *ds, dch, ptr(gscale), stream_ptr())
 
 
+def yolo_loss_cells(z, nchw, yt: YoloTargets, num_classes, consts, sums=None, dcell=None, gscale=None):
+    """One thread per anchor cell: loss sums and/or compact cell gradients dcell [B*Gh*Gw, >=5A] fp32."""
+    xy, wh, obj, noobj = consts
+    lib().call("b200cv_yolo_loss_cells", ptr(z), *_head_strides(z, nchw), yt.B, yt.A, num_classes, yt.Gh, yt.Gw,
+               ptr(yt.owner), ptr(yt.ign), ptr(yt.rec), yt.T, ptr(yt.counts), float(xy), float(wh), float(obj),
+               float(noobj), ptr(sums), ptr(dcell), 0 if dcell is None else dcell.shape[-1], ptr(gscale), stream_ptr())
+
+
+def yolo_expand_dlogits(dcell, dlogits, num_anchors, num_classes):
+    """Compact cell gradients -> dense NHWC head gradient [B,G,G,Cpad] (zeros for class / pad channels)."""
+    npix = dlogits.numel() // dlogits.shape[-1]
+    lib().call("b200cv_yolo_expand_dlogits", ptr(dcell), dcell.shape[-1], ptr(dlogits),
+               DT_F32 if dlogits.dtype == torch.float32 else DT_BF16, dlogits.stride(-2), dlogits.shape[-1], npix,
+               num_anchors, num_classes, stream_ptr())
+
+
+def yolo_head_grad(z, yt: YoloTargets, num_classes, consts, gscale, out_dtype=torch.bfloat16):
+    """dlogits (NHWC, same shape as z) of the YOLO loss: cell kernel + streaming expansion."""
+    npix = z.shape[0] * z.shape[1] * z.shape[2]
+    cell_ld = (5 * yt.A + 3) // 4 * 4
+    dcell = torch.empty(npix, cell_ld, dtype=torch.float32, device=z.device)
+    yolo_loss_cells(z, False, yt, num_classes, consts, dcell=dcell, gscale=gscale)
+    dl = torch.empty(z.shape, dtype=out_dtype, device=z.device)
+    yolo_expand_dlogits(dcell, dl, yt.A, num_classes)
+    return dl
+
+
 def yolo_loss_finalize(sums, yt: YoloTargets, consts, out7):
     xy, wh, obj, noobj = consts
     lib().call("b200cv_yolo_loss_finalize", ptr(sums), ptr(yt.counts), float(xy), float(wh), float(obj), float(noobj),

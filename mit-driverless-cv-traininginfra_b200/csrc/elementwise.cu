@@ -64,7 +64,8 @@ bn_finalize_kernel(const float* __restrict__ stats, int parts, float count, cons
   const int c = blockIdx.x * 32 + cx;
   float s1 = 0.f, s2 = 0.f;
   if (c < C)
-    for (int p = py; p < parts; p += 8) {  // fixed order: deterministic statistics
+#pragma unroll 8
+    for (int p = py; p < parts; p += 8) {  // fixed order
       s1 += stats[(long long)p * 2 * C + c];
       s2 += stats[(long long)p * 2 * C + C + c];
     }
@@ -296,6 +297,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, const flo
   const int c = blockIdx.x * 32 + cx;
   float s1 = 0.f, s2 = 0.f;
   if (c < C)
+#pragma unroll 8
     for (int p = py; p < nparts; p += 8) {
       s1 += partials[(long long)p * 2 * C + c];
       s2 += partials[(long long)p * 2 * C + C + c];

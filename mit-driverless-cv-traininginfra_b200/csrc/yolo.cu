@@ -192,53 +192,65 @@ yolo_loss_nhwc_kernel(const float* __restrict__ z, long long z_ld, OutT* __restr
                       int B, int A, int C, int Gh, int Gw, const int* __restrict__ owner,
                       const unsigned char* __restrict__ ign, const YoloRec* __restrict__ rec, int T,
                       const int* __restrict__ counts, LossConsts k, double* sums, const float* gscale) {
+  // The grid is sized so that (threads per block) % vpp == 0: a thread keeps the SAME 8 channels for its whole
+  // life, classifies them once, and only walks over pixels -- no per-item divisions by (5+C), and the threads
+  // that own nothing but class/pad channels just stream zeros.
   const int nattr = 5 + C;
   const int nch = A * nattr;
   const int vpp = d_ch >> 3;
-  const long long total = (long long)B * Gh * Gw * vpp;
-  const float g = gscale ? *gscale : 1.f;
-  const float inv_nm = 1.f / (float)counts[0];
-  const float inv_nf = 1.f / (float)counts[1];
+  const int tpb = (blockDim.x / vpp) * vpp;  // active threads per block
   float acc[6] = {0, 0, 0, 0, 0, 0};
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long pix = i / vpp;
-    const int c0 = (int)(i - pix * vpp) << 3;
-    const int gx = (int)(pix % Gw);
-    const long long r = pix / Gw;
-    const int gy = (int)(r % Gh);
-    const int b = (int)(r / Gh);
-    float out[8];
-    int a_cached = -1;
-    CellInfo cell;
+  if ((int)threadIdx.x < tpb) {
+    const int v = threadIdx.x % vpp;
+    const int c0 = v << 3;
+    int an[8], at[8];
+    bool any = false;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int ch = c0 + j;
-      float d = 0.f;
-      if (ch < nch) {
-        const int a = ch / nattr;
-        const int attr = ch - a * nattr;
-        if (attr < 5) {
-          if (a != a_cached) {
-            cell = load_cell(owner, ign, rec, T, b, a, gy, gx, A, Gh, Gw);
-            a_cached = a;
+      an[j] = ch < nch ? ch / nattr : -1;
+      at[j] = ch < nch ? ch - an[j] * nattr : 99;
+      any |= at[j] < 5;
+    }
+    const int pix_per_block = tpb / vpp;
+    const int npix = B * Gh * Gw;
+    const float g = gscale ? *gscale : 1.f;
+    const float inv_nm = 1.f / (float)counts[0];
+    const float inv_nf = 1.f / (float)counts[1];
+    const int GG = Gh * Gw;
+    for (int pix = blockIdx.x * pix_per_block + threadIdx.x / vpp; pix < npix; pix += gridDim.x * pix_per_block) {
+      float out[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (any) {
+        const int b = pix / GG;
+        const int rem = pix - b * GG;
+        const int gy = rem / Gw;
+        const int gx = rem - gy * Gw;
+        int a_cached = -1;
+        CellInfo cell;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (at[j] < 5) {
+            if (an[j] != a_cached) {
+              cell = load_cell(owner, ign, rec, T, b, an[j], gy, gx, A, Gh, Gw);
+              a_cached = an[j];
+            }
+            if (cell.m || (at[j] == 4 && cell.cf))
+              out[j] = g * attr_term(at[j], __ldg(z + (long long)pix * z_ld + c0 + j), cell, k, inv_nm, inv_nf, acc);
           }
-          if (cell.m || (attr == 4 && cell.cf)) d = attr_term(attr, __ldg(z + pix * z_ld + ch), cell, k, inv_nm, inv_nf, acc);
         }
       }
-      out[j] = d * g;
-    }
-    if (dl) {
-      OutT* o = dl + pix * d_ld + c0;
-      if constexpr (sizeof(OutT) == 2) {
-        uint4 pk;
-        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+      if (dl) {
+        OutT* o = dl + (long long)pix * d_ld + c0;
+        if constexpr (sizeof(OutT) == 2) {
+          uint4 pk;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(out[2 * j], out[2 * j + 1]);
-        *reinterpret_cast<uint4*>(o) = pk;
-      } else {
-        *reinterpret_cast<float4*>(o) = make_float4(out[0], out[1], out[2], out[3]);
-        *reinterpret_cast<float4*>(o + 4) = make_float4(out[4], out[5], out[6], out[7]);
+          for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(out[2 * j], out[2 * j + 1]);
+          *reinterpret_cast<uint4*>(o) = pk;
+        } else {
+          *reinterpret_cast<float4*>(o) = make_float4(out[0], out[1], out[2], out[3]);
+          *reinterpret_cast<float4*>(o + 4) = make_float4(out[4], out[5], out[6], out[7]);
+        }
       }
     }
   }
@@ -249,8 +261,8 @@ yolo_loss_nhwc_kernel(const float* __restrict__ z, long long z_ld, OutT* __restr
 // writes only the five non-zero gradient channels (the caller zero-fills dlogits first).
 __global__ void __launch_bounds__(256)
 yolo_loss_strided_kernel(const float* __restrict__ z, long long z_sb, long long z_sy, long long z_sx, long long z_sc,
-                         float* __restrict__ dl, long long d_sb, long long d_sy, long long d_sx, long long d_sc, int B,
-                         int A, int C, int Gh, int Gw, const int* __restrict__ owner,
+                         float* __restrict__ dl, long long d_sb, long long d_sy, long long d_sx, long long d_sc,
+                         long long d_sa, int B, int A, int C, int Gh, int Gw, const int* __restrict__ owner,
                          const unsigned char* __restrict__ ign, const YoloRec* __restrict__ rec, int T,
                          const int* __restrict__ counts, LossConsts k, double* sums, const float* gscale) {
   const int nattr = 5 + C;
@@ -267,15 +279,65 @@ yolo_loss_strided_kernel(const float* __restrict__ z, long long z_sb, long long 
     const int a = (int)(r % A);
     const int b = (int)(r / A);
     const CellInfo cell = load_cell(owner, ign, rec, T, b, a, gy, gx, A, Gh, Gw);
-    if (!cell.m && !cell.cf) continue;
+    if (!cell.m && !cell.cf) {
+      if (dl && d_sa == 5)  // compact cell gradients are not pre-zeroed by the caller
+        for (int attr = 0; attr < 5; ++attr) dl[b * d_sb + gy * d_sy + gx * d_sx + (long long)a * 5 + attr] = 0.f;
+      continue;
+    }
     const long long zoff = b * z_sb + gy * z_sy + gx * z_sx + (long long)a * nattr * z_sc;
-    const long long doff = b * d_sb + gy * d_sy + gx * d_sx + (long long)a * nattr * d_sc;
+    const long long doff = b * d_sb + gy * d_sy + gx * d_sx + (long long)a * d_sa;
+    if (!cell.m && dl && d_sa == 5)
+      for (int attr = 0; attr < 4; ++attr) dl[doff + attr] = 0.f;
     for (int attr = cell.m ? 0 : 4; attr < 5; ++attr) {
       const float d = attr_term(attr, z[zoff + attr * z_sc], cell, k, inv_nm, inv_nf, acc);
       if (dl) dl[doff + attr * d_sc] = d * g;
     }
   }
   if (sums) block_accumulate(acc, sums);
+}
+
+// Dense head gradient from the compact per-cell gradients: row = pixel, d_ch channels, channel a*(5+C)+attr takes
+// dcell[pix][a*5+attr] for attr < 5 and an exact zero otherwise.  Pure streaming: a thread owns 8 fixed channels.
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+yolo_expand_kernel(const float* __restrict__ dcell, int cell_ld, OutT* __restrict__ dl, long long d_ld, int d_ch,
+                   int npix, int A, int C) {
+  const int nattr = 5 + C;
+  const int nch = A * nattr;
+  const int vpp = d_ch >> 3;
+  const int tpb = (blockDim.x / vpp) * vpp;
+  if ((int)threadIdx.x >= tpb) return;
+  const int c0 = (threadIdx.x % vpp) << 3;
+  int src[8];
+  bool any = false;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = c0 + j;
+    const int a = ch < nch ? ch / nattr : 0;
+    const int attr = ch < nch ? ch - a * nattr : 99;
+    src[j] = attr < 5 ? a * 5 + attr : -1;
+    any |= src[j] >= 0;
+  }
+  const int pix_per_block = tpb / vpp;
+  for (int pix = blockIdx.x * pix_per_block + threadIdx.x / vpp; pix < npix; pix += gridDim.x * pix_per_block) {
+    float out[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (any) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (src[j] >= 0) out[j] = __ldg(dcell + (long long)pix * cell_ld + src[j]);
+    }
+    OutT* o = dl + (long long)pix * d_ld + c0;
+    if constexpr (sizeof(OutT) == 2) {
+      uint4 pk;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(out[2 * j], out[2 * j + 1]);
+      *reinterpret_cast<uint4*>(o) = pk;
+    } else {
+      *reinterpret_cast<float4*>(o) = make_float4(out[0], out[1], out[2], out[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(out[4], out[5], out[6], out[7]);
+    }
+  }
 }
 
 // out7[0] += total, out7[1..6] += (x, y, w, h, obj, noobj)  -- the order of models.py:211
@@ -400,6 +462,7 @@ extern "C" int b200cv_yolo_loss(const float* logits, int64_t z_sb, int64_t z_sy,
                                    (reinterpret_cast<uintptr_t>(dlogits) & 15) == 0 && d_sx % 8 == 0);
   if (z_nhwc && d_nhwc) {
     const int dch = dlogits ? d_channels : round_up(nch, 8);
+    B200CV_CHECK_ARG(dch / 8 <= 256, "yolo_loss: more than 2048 head channels");
     const long long work = (long long)B * Gh * Gw * (dch / 8);
     if (!dlogits || dl_dtype == B200CV_DT_BF16)
       yolo_loss_nhwc_kernel<__nv_bfloat16><<<grid1d(work, 256), 256, 0, st>>>(
@@ -413,9 +476,45 @@ extern "C" int b200cv_yolo_loss(const float* logits, int64_t z_sb, int64_t z_sy,
   }
   B200CV_CHECK_ARG(!dlogits || dl_dtype == B200CV_DT_F32, "yolo_loss: strided dlogits must be fp32 (zero-filled)");
   yolo_loss_strided_kernel<<<grid1d((long long)B * A * Gh * Gw, 256), 256, 0, st>>>(
-      logits, z_sb, z_sy, z_sx, z_sc, static_cast<float*>(dlogits), d_sb, d_sy, d_sx, d_sc, B, A, C, Gh, Gw, owner,
-      ign, r, T, counts, k, sums, gscale);
+      logits, z_sb, z_sy, z_sx, z_sc, static_cast<float*>(dlogits), d_sb, d_sy, d_sx, d_sc, (long long)(5 + C) * d_sc,
+      B, A, C, Gh, Gw, owner, ign, r, T, counts, k, sums, gscale);
   return check_launch("yolo_loss_strided");
+}
+
+// Two-kernel form of the head gradient used by the engine: (1) one thread per anchor cell (massively parallel,
+// hides the owner -> record -> logit load chain) writes compact fp32 cell gradients [pixels][cell_ld >= 5A];
+// (2) a streaming kernel expands them into the dense NHWC dlogits rows the head conv's dgrad/wgrad read.
+extern "C" int b200cv_yolo_loss_cells(const float* logits, int64_t z_sb, int64_t z_sy, int64_t z_sx, int64_t z_sc,
+                                      int B, int A, int C, int Gh, int Gw, const int32_t* owner, const uint8_t* ign,
+                                      const float* rec, int T, const int32_t* counts, float xy_loss, float wh_loss,
+                                      float obj_loss, float noobj_loss, double* sums, float* dcell, int cell_ld,
+                                      const float* gscale, void* stream) {
+  B200CV_CHECK_ARG(logits && owner && ign && rec && counts && (sums || dcell), "yolo_loss_cells: null pointer");
+  B200CV_CHECK_ARG(B > 0 && A > 0 && C >= 0 && Gh > 0 && Gw > 0 && T > 0 && (!dcell || cell_ld >= 5 * A),
+                   "yolo_loss_cells: bad shape");
+  const LossConsts k{xy_loss, wh_loss, obj_loss, noobj_loss};
+  yolo_loss_strided_kernel<<<grid1d((long long)B * A * Gh * Gw, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, z_sb, z_sy, z_sx, z_sc, dcell, (long long)Gh * Gw * cell_ld, (long long)Gw * cell_ld, cell_ld, 1, 5, B,
+      A, C, Gh, Gw, owner, ign, reinterpret_cast<const YoloRec*>(rec), T, counts, k, sums, gscale);
+  return check_launch("yolo_loss_cells");
+}
+
+extern "C" int b200cv_yolo_expand_dlogits(const float* dcell, int cell_ld, void* dlogits, int dl_dtype, int64_t d_ld,
+                                          int d_channels, int64_t npix, int A, int C, void* stream) {
+  B200CV_CHECK_ARG(dcell && dlogits && npix > 0 && npix < (1ll << 31) && A > 0 && cell_ld >= 5 * A,
+                   "yolo_expand_dlogits: bad args");
+  B200CV_CHECK_ARG(d_channels % 8 == 0 && d_channels >= A * (5 + C) && d_channels <= d_ld && d_channels / 8 <= 256 &&
+                       (reinterpret_cast<uintptr_t>(dlogits) & 15) == 0 && d_ld % 8 == 0,
+                   "yolo_expand_dlogits: bad dlogits layout");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = grid1d(npix * (d_channels / 8), 256);
+  if (dl_dtype == B200CV_DT_BF16)
+    yolo_expand_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(dcell, cell_ld, static_cast<__nv_bfloat16*>(dlogits), d_ld,
+                                                            d_channels, (int)npix, A, C);
+  else
+    yolo_expand_kernel<float><<<grid, 256, 0, st>>>(dcell, cell_ld, static_cast<float*>(dlogits), d_ld, d_channels,
+                                                    (int)npix, A, C);
+  return check_launch("yolo_expand_dlogits");
 }
 
 extern "C" int b200cv_yolo_loss_finalize(const double* sums, const int32_t* counts, float xy_loss, float wh_loss,

@@ -87,6 +87,11 @@ def test_yolo_loss_nhwc_bf16_engine_layout_matches_strided():
     yolo_ops.yolo_loss(z_nchw, True, yt, C, consts, sums=s1, dlogits=d1, gscale=gs)
     yolo_ops.yolo_loss(z_nhwc, False, yt, C, consts, sums=s2, dlogits=d2, gscale=gs)
     assert torch.allclose(s1, s2, rtol=1e-5)
+    # the engine's two-kernel form (cell kernel + streaming expansion) gives the same dense gradient
+    s3 = torch.zeros(6, dtype=torch.float64, device=DEV)
+    yolo_ops.yolo_loss_cells(z_nhwc, False, yt, C, consts, sums=s3)
+    d3 = yolo_ops.yolo_head_grad(z_nhwc, yt, C, consts, gs)
+    assert torch.allclose(s1, s3, rtol=1e-5) and torch.equal(d3, d2)
     assert float(d2[..., nch:].float().abs().max()) == 0.0
     want = d1.permute(0, 2, 3, 1)
     assert torch.allclose(d2[..., :nch].float(), want, rtol=1e-2, atol=1e-7)
