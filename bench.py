@@ -167,6 +167,9 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--ncu-window", action="store_true",
+                    help="after warm-up run ONE eager step between cudaProfilerStart/Stop and exit "
+                         "(for `ncu --profile-from-start off`; prints no bench line)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -228,8 +231,17 @@ def main():
             ms = float(t)
         return ms, lib().launches - l0
 
+    if args.ncu_window:
+        os.environ["B200CV_CUDA_GRAPH"] = "0"
     for _ in range(warmup):
         step(imgs_d, tg_d)
+    if args.ncu_window:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step(imgs_d, tg_d)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     sampler = ClockSampler(local) if rank == 0 else None
     ms, launches = timed(lambda: step(imgs_d, tg_d), steps)
     clocks = sampler.stop() if sampler else None

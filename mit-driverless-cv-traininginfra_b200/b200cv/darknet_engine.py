@@ -36,8 +36,8 @@ def _graphs_enabled() -> bool:
 
 class _Layer:
     __slots__ = ("index", "type", "conv", "bn", "act", "slope", "k", "stride", "pad", "cin", "cout", "inputs",
-                 "post_from", "fused_alias", "yolo", "stats", "scale", "shift", "mean", "rstd", "sums", "coef",
-                 "wpk", "wpk_t", "pool_stride")
+                 "post_from", "fused_alias", "yolo", "stats", "bstats", "scale", "shift", "mean", "rstd", "sums",
+                 "coef", "wpk", "wpk_t", "pool_stride")
 
     def __init__(self, index, type_):
         self.index, self.type = index, type_
@@ -103,15 +103,24 @@ class DarknetEngine:
         self._graphs = {}       # (shapes) -> _GraphedStep | int (eager warm-up calls seen so far)
 
     # ------------------------------------------------------------------ helpers
-    def _vec(self, L: _Layer, dev):
-        if L.stats is None or L.stats.device != dev:
-            c = L.cout
-            f = lambda n: torch.empty(n, dtype=torch.float32, device=dev)
-            L.stats = ops.stats_buffer(c, dev)
-            L.scale, L.shift, L.mean, L.rstd, L.coef = f(c), f(c), f(c), f(c), f(3 * c)
-
     def _setup(self, dev):
         if self._arena is None or self._arena.flat.device != dev:
+            # per-channel vectors of every BN layer; the partial-statistics matrices (forward: sum / sum of squares
+            # from the conv epilogue, backward: sum dz / sum dz*xhat) live in two flat arenas so that one memset
+            # per pass clears all of them
+            bn_layers = [L for L in self.layers if L.type == "convolutional" and L.bn is not None]
+            per = [ops.STAT_PARTS * 2 * L.cout for L in bn_layers]
+            self._fstat_arena = torch.zeros(sum(per), dtype=torch.float32, device=dev)
+            self._bstat_arena = torch.zeros(sum(per), dtype=torch.float32, device=dev)
+            off = 0
+            f = lambda n: torch.empty(n, dtype=torch.float32, device=dev)
+            for L, n in zip(bn_layers, per):
+                c = L.cout
+                L.stats = self._fstat_arena[off:off + n].view(ops.STAT_PARTS, 2 * c)
+                L.bstats = self._bstat_arena[off:off + n].view(ops.STAT_PARTS, 2 * c)
+                L.scale, L.shift, L.mean, L.rstd, L.coef = f(c), f(c), f(c), f(c), f(3 * c)
+                off += n
+            self._nbt = [L.bn.num_batches_tracked for L in bn_layers if L.bn.num_batches_tracked is not None]
             self._arena = GradArena(self.params, dev)
             convs = [(L.conv, L.index > 0) for L in self.layers if L.type == "convolutional"]
             self._packs = ConvPackSet(convs, dev, self._arena, flat=self._flat_convs())
@@ -151,6 +160,10 @@ class DarknetEngine:
         saved = {}
         training = targets is not None
         out7 = torch.zeros(7, dtype=torch.float32, device=dev) if training else None
+        if bn_train:
+            self._fstat_arena.zero_()
+            if self._nbt:
+                torch._foreach_add_(self._nbt, 1)
         dets = []  # eval: per-head detections, concatenated at the end
         consts = (model.xy_loss, model.wh_loss, model.object_loss, model.no_object_loss)
         for L in self.layers:
@@ -159,16 +172,12 @@ class DarknetEngine:
                 xin = cur
                 k_, st_, pd_ = (1, 1, 0) if (flat0 and i == 0) else (L.k, L.stride, L.pad)
                 if L.bn is not None:
-                    self._vec(L, dev)
                     post = outs[L.post_from] if L.post_from is not None else None
                     if bn_train:
-                        L.stats.zero_()
                         y = ops.conv_fwd(xin, L.wpk, L.cout, k_, st_, pd_, stats=L.stats)
                         count = y.numel() // y.shape[-1]
                         ops.bn_finalize(L.stats, count, L.bn.weight, L.bn.bias, None, BN_EPS, BN_MOMENTUM,
                                         L.bn.running_mean, L.bn.running_var, L.scale, L.shift, L.mean, L.rstd)
-                        if L.bn.num_batches_tracked is not None:
-                            L.bn.num_batches_tracked += 1
                         cur = ops.bn_apply_act(y, L.scale, L.shift, L.act, L.slope, post=post)
                         saved[i] = (xin, y)
                     else:
@@ -245,6 +254,7 @@ class DarknetEngine:
         else:
             packs = self._packs
         packs.zero_grads()
+        self._bstat_arena.zero_()
         views, gview = arena.views, arena.view_of
         consts = (model.xy_loss, model.wh_loss, model.object_loss, model.no_object_loss)
         grads: List[Optional[torch.Tensor]] = [None] * len(self.layers)
@@ -278,7 +288,8 @@ class DarknetEngine:
                 if L.bn is not None:
                     xin, y = saved[i]
                     count = y.numel() // y.shape[-1]
-                    parts = ops.bn_bwd_reduce(G, y, None, L.scale, L.shift, L.mean, L.rstd, L.act, L.slope)
+                    parts = ops.bn_bwd_reduce(G, y, None, L.scale, L.shift, L.mean, L.rstd, L.act, L.slope,
+                                              partials=L.bstats)
                     ops.bn_bwd_finalize(parts, L.bn.weight, L.rstd, count, L.coef, gview[id(L.bn.weight)],
                                         gview[id(L.bn.bias)])
                     dy = ops.bn_bwd_apply(G, y, None, L.scale, L.shift, L.mean, L.rstd, L.coef, L.act, L.slope)
@@ -382,6 +393,12 @@ class _DarknetTrainFn(torch.autograd.Function):
         return (None, None, None, None, None, *views)
 
 
+def _count_launches(n: int):
+    from .lib import lib
+
+    lib().launches += n
+
+
 class _GraphedStep:
     """One training step (fixed shapes) captured as two CUDA graphs -- forward+loss and backward -- sharing a
     memory pool, so the ~1200 launches of a Darknet-53 step cost two graph launches on the host.  Inputs are
@@ -399,12 +416,18 @@ class _GraphedStep:
         torch.cuda.synchronize()
         self.pool = torch.cuda.graph_pool_handle()
         self.fwd_graph, self.bwd_graph = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        from .lib import lib
+
+        n0 = lib().launches
         with torch.no_grad():
             with torch.cuda.graph(self.fwd_graph, pool=self.pool):
                 self.out7, self.state = engine._run_forward(self.static_x, self.static_t, bn_train=True, want_grad=True)
+            n1 = lib().launches
             with torch.cuda.graph(self.bwd_graph, pool=self.pool):
                 self.views = engine._run_backward(self.state, self.static_g, force_persistent_arena=True,
                                                   do_allreduce=False)
+        # kernel-launching ABI calls recorded in each graph: a replay launches that many of our kernels
+        self.fwd_launches, self.bwd_launches = n1 - n0, lib().launches - n1
         torch.cuda.synchronize()
 
     def usable(self) -> bool:
@@ -419,6 +442,7 @@ class _DarknetGraphFn(torch.autograd.Function):
         step.static_x.copy_(x, non_blocking=True)
         step.static_t.copy_(targets, non_blocking=True)
         step.fwd_graph.replay()
+        _count_launches(step.fwd_launches)
         ctx.step = step
         return step.out7.clone()
 
@@ -427,5 +451,6 @@ class _DarknetGraphFn(torch.autograd.Function):
         step = ctx.step
         step.static_g.copy_(g7)
         step.bwd_graph.replay()
+        _count_launches(step.bwd_launches)
         allreduce_gradients(step.engine._arena.flat)
         return (None, None, None, *step.views)

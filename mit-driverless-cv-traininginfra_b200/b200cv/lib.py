@@ -95,7 +95,7 @@ class _Lib:
     def last_error(self) -> str:
         return self.cdll.b200cv_last_error().decode()
 
-    def call(self, name: str, *args):
+    def call(self, name: str, *args, tag=None):
         prof = self._prof
         if prof is not None:
             import torch
@@ -106,11 +106,11 @@ class _Lib:
         self.launches += 1
         if prof is not None:
             e1.record()
-            prof.append((name, e0, e1))
+            prof.append((name, e0, e1, tag))
         if rc != 0:
             raise B200CVError(f"{name} failed (rc={rc}): {self.last_error()}")
 
-    def profile_step(self, fn):
+    def profile_step(self, fn, detail=False):
         """Run fn() with a CUDA-event pair around every ABI call (on the current stream); returns
         {entry point: total device milliseconds}.  Measurement aid for bench.py -- not a hot-path feature."""
         import torch
@@ -120,8 +120,10 @@ class _Lib:
         try:
             fn()
             torch.cuda.synchronize()
+            if detail:  # every call in launch order: (entry point, tag, ms)
+                return [(name, tag, e0.elapsed_time(e1)) for name, e0, e1, tag in self._prof]
             out = {}
-            for name, e0, e1 in self._prof:
+            for name, e0, e1, _ in self._prof:
                 out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
         finally:
             self._prof = None

@@ -136,7 +136,7 @@ def conv_fwd(x, wpk, cout, k, stride, pad, dil=1, out=None, out_dtype=torch.bflo
         rs = (residual.stride(0), residual.stride(1), residual.stride(2), residual.stride(3))
     a = _conv_args(x, wpk, out, cout, k, stride, pad, dil, ys, DT_F32 if out.dtype == torch.float32 else DT_BF16,
                    scale, shift, residual, rs, act, slope, res_after_act, stats)
-    lib().call("b200cv_conv_fwd", ctypes.byref(a), stream_ptr())
+    lib().call("b200cv_conv_fwd", ctypes.byref(a), stream_ptr(), tag=(x.shape[-1], cout, k, stride, n, oh, ow))
     return out
 
 
@@ -155,7 +155,8 @@ def conv_dgrad(dy, wpk_t, cin_fwd, k, stride, pad, dil, out_hw, out=None, residu
         rs = (residual.stride(0), residual.stride(1), residual.stride(2), residual.stride(3))
     a = _conv_args(dy, wpk_t, out, cin_fwd, k, stride, pad, dil, ys, DT_BF16, None, None, residual, rs, ACT_NONE, 0.0,
                    False, None)
-    lib().call("b200cv_conv_dgrad", ctypes.byref(a), h, w, stream_ptr())
+    lib().call("b200cv_conv_dgrad", ctypes.byref(a), h, w, stream_ptr(),
+               tag=(cin_fwd, dy.shape[-1], k, stride, n, dy.shape[1], dy.shape[2]))
     return out
 
 
@@ -164,7 +165,7 @@ def conv_wgrad(x, dy, cout, k, stride, pad, dil=1, out=None) -> torch.Tensor:
     n, h, w, cin = x.shape
     dwp = out if out is not None else torch.zeros(cout, k * k, cin, dtype=torch.float32, device=x.device)
     lib().call("b200cv_conv_wgrad", ptr(x), ptr(dy), ptr(dwp), n, h, w, cin, cout, dy.shape[-1], k, k, stride, pad, dil,
-               stream_ptr())
+               stream_ptr(), tag=(cin, cout, k, stride, n, dy.shape[1], dy.shape[2]))
     return dwp
 
 
@@ -173,9 +174,13 @@ def sm_count(device=None) -> int:
     return torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device()).multi_processor_count
 
 
+STAT_PARTS = 32  # rows of a partial-statistics matrix: CTA / block b adds into row b % STAT_PARTS
+
+
 def stats_buffer(cout: int, device) -> torch.Tensor:
-    """Zeroed [#SMs][2*Cout] partial-statistics matrix for conv_fwd(stats=...): one row per CTA."""
-    return torch.zeros(sm_count(device), 2 * cout, dtype=torch.float32, device=device)
+    """Zeroed [STAT_PARTS][2*Cout] partial-statistics matrix for conv_fwd(stats=...) / bn_bwd_reduce(partials=...):
+    the kernels ADD into it (a few CTAs per row, once per CTA lifetime), the finalize kernels sum the rows."""
+    return torch.zeros(STAT_PARTS, 2 * cout, dtype=torch.float32, device=device)
 
 
 def bn_finalize(stats, count, gamma, beta, conv_bias, eps, momentum, running_mean, running_var, scale, shift, mean,
@@ -193,20 +198,18 @@ def bn_apply_act(y, scale, shift, act, slope, out=None, y2=None, scale2=None, sh
     lib().call("b200cv_bn_apply_act", ptr(y), y.stride(-2), ptr(scale), ptr(shift), ptr(y2),
                0 if y2 is None else y2.stride(-2), ptr(scale2), ptr(shift2), ptr(post),
                0 if post is None else post.stride(-2), ptr(out), out.stride(-2), _rows(y), c, act, float(slope),
-               stream_ptr())
+               stream_ptr(), tag=(_rows(y), c))
     return out
 
 
 def bn_bwd_reduce(da, y, aout, scale, shift, mean, rstd, act, slope, partials=None):
-    """Returns the [nparts][2C] partial sums (every row written by the kernel)."""
+    """Adds the per-block sums into `partials` ([nparts][2C], zeroed by the caller; allocated if None)."""
     rows, c = _rows(y), y.shape[-1]
     if partials is None:
-        rows_per_block = (256 // (c // 8)) * 4
-        nparts = max(1, min(2 * sm_count(y.device), (rows + rows_per_block - 1) // rows_per_block))
-        partials = torch.empty(nparts, 2 * c, dtype=torch.float32, device=y.device)
+        partials = stats_buffer(c, y.device)
     lib().call("b200cv_bn_bwd_reduce", ptr(da), da.stride(-2), ptr(y), y.stride(-2), ptr(aout),
                0 if aout is None else aout.stride(-2), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), ptr(partials),
-               partials.shape[0], rows, c, act, float(slope), stream_ptr())
+               partials.shape[0], rows, c, act, float(slope), stream_ptr(), tag=(rows, c))
     return partials
 
 
@@ -220,7 +223,8 @@ def bn_bwd_apply(da, y, aout, scale, shift, mean, rstd, coef, act, slope, out=No
         out = torch.empty_like(y)
     lib().call("b200cv_bn_bwd_apply", ptr(da), da.stride(-2), ptr(y), y.stride(-2), ptr(aout),
                0 if aout is None else aout.stride(-2), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), ptr(coef),
-               ptr(out), out.stride(-2), _rows(y), y.shape[-1], act, float(slope), stream_ptr())
+               ptr(out), out.stride(-2), _rows(y), y.shape[-1], act, float(slope), stream_ptr(),
+               tag=(_rows(y), y.shape[-1]))
     return out
 
 
@@ -234,7 +238,7 @@ def act_bwd(da, aout, act, slope):
 def copy_slice(src, dst, accumulate=False):
     """dst[..., :C] (=|+=) src[..., :C] for NHWC views with unit channel stride."""
     lib().call("b200cv_copy_slice", ptr(src), src.stride(-2), ptr(dst), dst.stride(-2), _rows(src), src.shape[-1],
-               int(accumulate), stream_ptr())
+               int(accumulate), stream_ptr(), tag=(_rows(src), src.shape[-1]))
     return dst
 
 

@@ -9,7 +9,12 @@
 // * One elected thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16) into a TMEM accumulator;
 //   two accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
 // * Persistent: grid = #SMs, static round-robin tile schedule.
-// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2..5 = epilogue.
+// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2..9 = epilogue
+//   (two warps per TMEM lane quarter, each taking every other 32-column chunk of the accumulator:
+//   with one warp per scheduler every latency of the epilogue was exposed and short-K layers were
+//   epilogue-bound).  Per-channel BatchNorm statistics are column sums over the 32 rows of a warp
+//   (shared-memory transpose, 16 columns at a time) accumulated in a warp-private shared row for the
+//   whole CTA lifetime -- no shared-memory atomics -- and flushed to global once.
 //
 // The same kernel serves forward convolution, stride-1 data-gradient (flipped taps, transposed
 // weights) and the four parity classes of a stride-2 data-gradient; only the tap table, the
@@ -24,10 +29,12 @@ namespace b200cv {
 namespace {
 
 constexpr int kBlockM = 128;
-constexpr int kThreads = 192;
 constexpr int kEpiWarp0 = 2;
-constexpr int kSmemBudget = 196 * 1024;  // pipeline stages only
-constexpr int kMaxStatC = 1024;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);  // 320
+constexpr int kSmemMax = 227 * 1024;                    // dynamic shared memory of one CTA alone on an SM
+constexpr int kSmemMax2 = 113 * 1024;                   // ... of each of two co-resident CTAs
+constexpr int kScratchLd = 17;                          // [32 rows][16 columns + 1] fp32 transpose tile
 
 template <int KC, int BN>
 struct Cfg {
@@ -37,20 +44,23 @@ struct Cfg {
   // Small stages (<= 16 KB: the 16/32-channel layers) are latency- not bandwidth-bound per k-iteration:
   // run two CTAs per SM (each with a shallower ring) so their TMA / mbarrier round trips overlap.
   static constexpr int kCtasPerSm = kStageBytes <= 16 * 1024 ? 2 : 1;
-  static constexpr int kBudget = kCtasPerSm == 2 ? 80 * 1024 : kSmemBudget;
-  static constexpr int kStagesRaw = kBudget / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : (2 * BN);
   static constexpr int kRowBytes = KC * 2;               // 32 / 64 / 128
   static constexpr int kLayout = KC == 64 ? 2 : (KC == 32 ? 4 : 6);
   static constexpr int kSBO = 8 * kRowBytes;             // 8-row swizzle atom pitch
   static constexpr int kChunk = BN >= 32 ? 32 : 16;      // epilogue column chunk
-  // extras: barriers (8B each) + tmem ptr + stats[2*BN] + transpose scratch (4 warps x 32 x 33)
-  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kStatBytes = 2 * kMaxStatC * 4;  // per-CTA [sum | sumsq] for every output channel
-  static constexpr int kScratchBytes = 4 * 32 * 33 * 4;
-  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kBarBytes +
-                                    kStatBytes + kScratchBytes;
+  static constexpr int kNumChunks = BN / kChunk;         // 1..8
+  static constexpr int kChunksPerWarp = (kNumChunks + 1) / 2;
+  static constexpr int kAccPerWarp = kChunksPerWarp * kChunk;  // columns a warp keeps statistics for
+  // extras: barriers (8B each, up to 8 stages) + tmem ptr | per-warp [sum | sumsq] rows | transpose scratch
+  static constexpr int kBarBytes = (2 * 8 + 4) * 8 + 16;
+  static constexpr int kStatBytes = kEpiWarps * 2 * kAccPerWarp * 4;
+  static constexpr int kScratchBytes = kEpiWarps * 32 * kScratchLd * 4;
+  static constexpr int kExtraBytes = 1024 /*align slack*/ + kBarBytes + kStatBytes + kScratchBytes;
+  static constexpr int kBudget = (kCtasPerSm == 2 ? kSmemMax2 : kSmemMax) - kExtraBytes;
+  static constexpr int kStagesRaw = kBudget / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kSmemBytes = kExtraBytes + kStages * kStageBytes;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
@@ -74,7 +84,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* s_stats = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + C::kBarBytes);
-  float* s_scratch = s_stats + 2 * kMaxStatC;
+  float* s_scratch = s_stats + kEpiWarps * 2 * C::kAccPerWarp;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -90,7 +100,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
-      ptx::mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+      ptx::mbar_init(&tempty_bar[i], kEpiWarps);  // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
   }
@@ -98,7 +108,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
   }
   if (p.stats)
-    for (int i = threadIdx.x; i < 2 * kMaxStatC; i += kThreads) s_stats[i] = 0.f;
+    for (int i = threadIdx.x; i < kEpiWarps * 2 * C::kAccPerWarp; i += kThreads) s_stats[i] = 0.f;
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -177,15 +187,39 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    const int ew = warp - kEpiWarp0;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may read
-    const int et = (warp - kEpiWarp0) * 32 + lane;  // 0..127 among epilogue threads
-    float* scratch = s_scratch + (warp - kEpiWarp0) * 32 * 33;
+    const int half = ew >> 2;      // which chunks of the accumulator: half, half + 2, ...
+    float* scratch = s_scratch + ew * 32 * kScratchLd;
+    float* my_sum = s_stats + ew * 2 * C::kAccPerWarp;  // [kAccPerWarp sums | kAccPerWarp sums of squares]
+    float* my_sq = my_sum + C::kAccPerWarp;
+    float* stats_row = p.stats ? p.stats + static_cast<long long>(blockIdx.x % p.stats_parts) * 2 * p.Cout : nullptr;
+    int stat_nt = -1;  // n-tile the warp-private statistics belong to
+    // adds the warp-private partial sums of n-tile `nt` to this CTA's row of the global partials and clears them
+    auto flush_stats = [&](int nt) {
+      for (int i = lane; i < C::kAccPerWarp; i += 32) {
+        const int ci = i / C::kChunk;
+        const int n = nt * BN + (half + 2 * ci) * C::kChunk + (i - ci * C::kChunk);
+        const float s1 = my_sum[i], s2 = my_sq[i];
+        if (n < p.Cout && (s1 != 0.f || s2 != 0.f)) {
+          atomicAdd(stats_row + n, s1);
+          atomicAdd(stats_row + p.Cout + n, s2);
+        }
+        my_sum[i] = 0.f;
+        my_sq[i] = 0.f;
+      }
+      __syncwarp();
+    };
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile / p.num_n_tiles;
       const int nt = tile - mt * p.num_n_tiles;
+      if (p.stats && nt != stat_nt) {
+        if (stat_nt >= 0) flush_stats(stat_nt);
+        stat_nt = nt;
+      }
       const int m = mt * kBlockM + quarter * 32 + lane;
       const bool row_ok = m < p.M_total;
       long long o_row = 0, r_row = 0;
@@ -203,9 +237,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
 
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += C::kChunk) {
+      for (int ci = 0; ci < C::kChunksPerWarp; ++ci) {
+        const int c0 = (half + 2 * ci) * C::kChunk;
         const int n_base = nt * BN + c0;
-        if (n_base >= p.Cout) break;  // warp-uniform
+        if (c0 >= BN || n_base >= p.Cout) break;  // warp-uniform
         float v[C::kChunk];
         if constexpr (C::kChunk == 32) {
           uint32_t r[32];
@@ -222,7 +257,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         const bool fast = p.vec_ok && (n_base + C::kChunk <= p.Cout) && (!p.res || p.res_vec_ok);
         if (fast) {
-          // branch-free per element: the epilogue warps run one per scheduler, every branch costs
+          // branch-free per element: every branch costs an exposed latency in these warps
           if (p.scale) {
 #pragma unroll
             for (int j = 0; j < C::kChunk; j += 4) {
@@ -238,11 +273,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
           }
           const float neg = p.act == 1 ? p.slope : (p.act == 2 ? 0.f : 1.f);
-          if (p.res_after_act) {
-#pragma unroll
-            for (int j = 0; j < C::kChunk; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * neg;
-          }
           if (p.res) {
+            if (p.res_after_act) {
+#pragma unroll
+              for (int j = 0; j < C::kChunk; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * neg;
+            }
             const uint4* rp = reinterpret_cast<const uint4*>(p.res + (row_ok ? r_row : 0) + n_base);
 #pragma unroll
             for (int j = 0; j < C::kChunk; j += 8) {
@@ -255,14 +290,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 v[j + 2 * e + 1] += f.y;
               }
             }
+            if (!p.res_after_act && p.act != 0) {
+#pragma unroll
+              for (int j = 0; j < C::kChunk; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * neg;
+            }
+          } else if (p.act != 0) {
+#pragma unroll
+            for (int j = 0; j < C::kChunk; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * neg;
           }
-          const float keep = row_ok ? 1.f : 0.f;
-          if (p.res_after_act) {
+          if (!row_ok) {  // rows past M_total: nothing stored, nothing counted
 #pragma unroll
-            for (int j = 0; j < C::kChunk; ++j) v[j] *= keep;
-          } else {
-#pragma unroll
-            for (int j = 0; j < C::kChunk; ++j) v[j] = (v[j] > 0.f ? v[j] : v[j] * neg) * keep;
+            for (int j = 0; j < C::kChunk; ++j) v[j] = 0.f;
           }
           if (p.out_fp32) {
             if (row_ok) {
@@ -312,23 +350,35 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             v[j] = x;
           }
         }
-        // per-channel sum / sum-of-squares over the 32 rows of this warp (smem transpose)
+        // per-channel sum / sum of squares over the 32 rows of this warp: transpose 16 columns at a time
+        // through shared memory; lane l sums column (l & 15) over rows 16*(l >> 4) .. +15 with independent
+        // partial sums, the two half-warps are combined with one shuffle
         if (p.stats) {
 #pragma unroll
-          for (int j = 0; j < C::kChunk; ++j) scratch[lane * 33 + j] = v[j];
-          __syncwarp();
-          if (lane < C::kChunk) {
-            float s = 0.f, s2 = 0.f;
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
-              const float x = scratch[r * 33 + lane];
-              s += x;
-              s2 += x * x;
+          for (int hh = 0; hh < C::kChunk / 16; ++hh) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) scratch[lane * kScratchLd + j] = v[hh * 16 + j];
+            __syncwarp();
+            const float* col = scratch + (lane >> 4) * 16 * kScratchLd + (lane & 15);
+            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+            for (int r = 0; r < 16; r += 2) {
+              const float x0 = col[r * kScratchLd], x1 = col[(r + 1) * kScratchLd];
+              a0 += x0;
+              a1 += x1;
+              b0 = fmaf(x0, x0, b0);
+              b1 = fmaf(x1, x1, b1);
             }
-            atomicAdd(&s_stats[n_base + lane], s);
-            atomicAdd(&s_stats[kMaxStatC + n_base + lane], s2);
+            float s1 = a0 + a1, s2 = b0 + b1;
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+            if (lane < 16) {
+              const int i = ci * C::kChunk + hh * 16 + lane;
+              my_sum[i] += s1;
+              my_sq[i] += s2;
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
       // accumulator drained: hand the TMEM stage back to the MMA warp
@@ -340,18 +390,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         acc_phase ^= 1;
       }
     }
-    if (p.stats) {
-      // one flush per CTA lifetime: the per-channel partials of all its tiles go to row blockIdx % parts
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      float* dst = p.stats + static_cast<long long>(blockIdx.x % p.stats_parts) * 2 * p.Cout;
-      for (int n = et; n < p.Cout; n += 128) {
-        const float s = s_stats[n], s2 = s_stats[kMaxStatC + n];
-        if (s != 0.f || s2 != 0.f) {
-          atomicAdd(dst + n, s);
-          atomicAdd(dst + p.Cout + n, s2);
-        }
-      }
-    }
+    if (p.stats && stat_nt >= 0) flush_stats(stat_nt);
   }
 
   ptx::tc_fence_before();

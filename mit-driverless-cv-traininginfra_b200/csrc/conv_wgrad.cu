@@ -267,7 +267,9 @@ extern "C" int b200cv_conv_wgrad(const void* x, const void* dy, float* dw_packed
   p.num_tap_groups = p.RS / T;
   p.kb_total = (p.M_pix + kKB - 1) / kKB;
   const int base_ctas = p.num_o_tiles * p.num_i_tiles * p.num_tap_groups;
-  int ksplit = std::max(1, (2 * sm_count() + base_ctas - 1) / base_ctas);
+  // split-K so that the grid fills (at most) two full waves of one CTA per SM: rounding the split UP left a
+  // third, nearly empty wave (e.g. 312 CTAs on 148 SMs)
+  int ksplit = std::max(1, (2 * sm_count()) / base_ctas);
   ksplit = std::min(ksplit, std::max(1, p.kb_total / 4));
   p.ksplit = ksplit;
 

@@ -95,6 +95,44 @@ bn_finalize_kernel(const float* __restrict__ stats, int parts, float count, cons
   }
 }
 
+// ------------------------------------------------------------------ streaming helpers (4 channels / thread)
+// The BN passes are pure streaming kernels.  A thread owns FOUR fixed channels (8-byte accesses; a warp still
+// moves 256 contiguous bytes per instruction) so that the per-channel constants fit in few registers and
+// 5-6 blocks of 256 threads stay resident per SM: the 8-channel version needed 112-146 registers, ran one or
+// two blocks per SM and was latency-bound at ~3.5 TB/s.
+__device__ __forceinline__ uint2 ldg_stream8(const __nv_bfloat16* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg8(__nv_bfloat16* p, const uint2& v) { *reinterpret_cast<uint2*>(p) = v; }
+__device__ __forceinline__ void unpack4(const uint2& r, float (&f)[4]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+  const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+}
+__device__ __forceinline__ uint2 pack4(const float (&f)[4]) {
+  uint2 r;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+  h[0] = __floats2bfloat162_rn(f[0], f[1]);
+  h[1] = __floats2bfloat162_rn(f[2], f[3]);
+  return r;
+}
+__device__ __forceinline__ void load4f(const float* p, float (&v)[4]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+constexpr int kEwThreads = 256;
+constexpr int kEwUnroll = 4;      // rows in flight per thread
+constexpr int kEwBlocksPerSm = 6;
+
+// grid of a row-streaming kernel: blocks walk rows with stride gridDim * rows_per_pass
+int stream_grid(long long rows, int C) {
+  const int rpp = kEwThreads / (C / 4);
+  const long long passes = (rows + (long long)rpp * kEwUnroll - 1) / ((long long)rpp * kEwUnroll);
+  return (int)std::max<long long>(1, std::min<long long>(passes, (long long)sm_count() * kEwBlocksPerSm));
+}
+
 // ------------------------------------------------------------------ BN apply (+second branch, +residual)
 //   out = act( y*scale + shift  [+ y2*scale2 + shift2] ) [+ post]
 struct ApplyArgs {
@@ -106,184 +144,147 @@ struct ApplyArgs {
   __nv_bfloat16* out; long long out_ld;
   long long rows; int C; int act; float slope;
 };
-__device__ __forceinline__ uint4 ldg_stream_fwd(const __nv_bfloat16* p) {
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p));
-  return r;
-}
-__device__ __forceinline__ void load8f(const float* p, float (&v)[8]) {
-  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-  const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-constexpr int kApplyUnroll = 4;
-// a thread owns 8 fixed channels (scale/shift in registers) and streams rows, kApplyUnroll rows in flight
-__global__ void __launch_bounds__(256) bn_apply_kernel(const ApplyArgs a) {
-  const int vpr = a.C >> 3;
-  const int rpp = blockDim.x / vpr;
+template <bool kTwo, bool kPost>
+__global__ void __launch_bounds__(kEwThreads, 4) bn_apply_kernel(const ApplyArgs a) {
+  const int vpr = a.C >> 2;
+  const int rpp = kEwThreads / vpr;
   const int cv = threadIdx.x % vpr;
   const int r0 = threadIdx.x / vpr;
-  const int c0 = cv << 3;
+  const int c0 = cv << 2;
   if (r0 >= rpp) return;
-  float sc[8], sh[8], sc2[8], sh2[8];
-  load8f(a.scale + c0, sc);
-  load8f(a.shift + c0, sh);
-  if (a.y2) {
-    load8f(a.scale2 + c0, sc2);
-    load8f(a.shift2 + c0, sh2);
+  float sc[4], sh[4], sc2[4], sh2[4];
+  load4f(a.scale + c0, sc);
+  load4f(a.shift + c0, sh);
+  if (kTwo) {
+    load4f(a.scale2 + c0, sc2);
+    load4f(a.shift2 + c0, sh2);
   }
   const float neg = a.act == B200CV_ACT_LEAKY ? a.slope : (a.act == B200CV_ACT_RELU ? 0.f : 1.f);
   const long long stride = (long long)gridDim.x * rpp;
-  for (long long r = (long long)blockIdx.x * rpp + r0; r < a.rows; r += stride * kApplyUnroll) {
-    uint4 qy[kApplyUnroll], q2[kApplyUnroll], qp[kApplyUnroll];
+  for (long long r = (long long)blockIdx.x * rpp + r0; r < a.rows; r += stride * kEwUnroll) {
+    uint2 qy[kEwUnroll], q2[kEwUnroll], qp[kEwUnroll];
 #pragma unroll
-    for (int u = 0; u < kApplyUnroll; ++u) {
+    for (int u = 0; u < kEwUnroll; ++u) {
       const long long rr = r + u * stride;
       if (rr < a.rows) {
-        qy[u] = ldg_stream_fwd(a.y + rr * a.y_ld + c0);
-        if (a.y2) q2[u] = ldg_stream_fwd(a.y2 + rr * a.y2_ld + c0);
-        if (a.post) qp[u] = ldg_stream_fwd(a.post + rr * a.post_ld + c0);
+        qy[u] = ldg_stream8(a.y + rr * a.y_ld + c0);
+        if (kTwo) q2[u] = ldg_stream8(a.y2 + rr * a.y2_ld + c0);
+        if (kPost) qp[u] = ldg_stream8(a.post + rr * a.post_ld + c0);
       }
     }
 #pragma unroll
-    for (int u = 0; u < kApplyUnroll; ++u) {
+    for (int u = 0; u < kEwUnroll; ++u) {
       const long long rr = r + u * stride;
       if (rr < a.rows) {
-        float v[8], z[8];
-        unpack8(qy[u], v);
+        float v[4], z[4];
+        unpack4(qy[u], v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) z[j] = v[j] * sc[j] + sh[j];
-        if (a.y2) {
-          float w[8];
-          unpack8(q2[u], w);
+        for (int j = 0; j < 4; ++j) z[j] = v[j] * sc[j] + sh[j];
+        if (kTwo) {
+          float w[4];
+          unpack4(q2[u], w);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) z[j] += w[j] * sc2[j] + sh2[j];
+          for (int j = 0; j < 4; ++j) z[j] += w[j] * sc2[j] + sh2[j];
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) z[j] = z[j] > 0.f ? z[j] : z[j] * neg;
-        if (a.post) {
-          float w[8];
-          unpack8(qp[u], w);
+        for (int j = 0; j < 4; ++j) z[j] = z[j] > 0.f ? z[j] : z[j] * neg;
+        if (kPost) {
+          float w[4];
+          unpack4(qp[u], w);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) z[j] += w[j];
+          for (int j = 0; j < 4; ++j) z[j] += w[j];
         }
-        stg16(a.out + rr * a.out_ld + c0, pack8(z));
+        stg8(a.out + rr * a.out_ld + c0, pack4(z));
       }
     }
   }
 }
 
-// ------------------------------------------------------------------ BN backward, pass 1
-//   dz = da * act'(z);  sums[c] += dz;  sums[C+c] += dz * xhat     (xhat = (y-mean)*rstd)
-// z is recomputed as y*scale+shift (+ second branch); `aout` (the saved activation output) can be
-// given instead when z is not recomputable from one branch alone.
+// ------------------------------------------------------------------ BN backward
+//   dz = da * act'(z);  pass 1: sums[c] += dz, sums[C+c] += dz * xhat  (xhat = (y-mean)*rstd)
+//   pass 2: dy = g * (dz - k1 - xhat*k2)   with coef = [g | k1 | k2]
+// z is recomputed as y*scale+shift; `aout` (the saved activation output) can be given instead when z is
+// not recomputable from one branch alone (only its sign is used).
 struct BwdArgs {
   const __nv_bfloat16* da; long long da_ld;
   const __nv_bfloat16* y; long long y_ld;
   const __nv_bfloat16* aout; long long aout_ld;   // optional: sign source for act'
   const float* scale; const float* shift;         // of this BN (to recompute z when aout == null)
   const float* mean; const float* rstd;
-  float* sums;                                    // pass 1 out [2C]
+  float* sums;                                    // pass 1 out: [nparts][2C], ADDED to (caller zeroes)
+  int nparts;
   const float* coef;                              // pass 2 in  [3C]: g, k1, k2
   __nv_bfloat16* dy; long long dy_ld;             // pass 2 out
   long long rows; int C; int act; float slope;
 };
-// Per-thread channel constants: a thread owns 8 fixed channels and walks over rows, so the per-channel
-// vectors are loaded once (the kernels are pure streaming: 16-byte loads, several rows in flight).
-struct ChanConsts {
-  float scale[8], shift[8], mean[8], rstd[8];
-};
-__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
-  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-  const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-__device__ __forceinline__ void load_consts(const BwdArgs& a, int c0, ChanConsts& k) {
-  if (a.aout == nullptr) {
-    load8(a.scale + c0, k.scale);
-    load8(a.shift + c0, k.shift);
-  }
-  load8(a.mean + c0, k.mean);
-  load8(a.rstd + c0, k.rstd);
-}
-__device__ __forceinline__ uint4 ldg_stream(const __nv_bfloat16* p) {
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p));
-  return r;
-}
-__device__ __forceinline__ void bwd_math(const BwdArgs& a, const ChanConsts& k, const uint4& qda, const uint4& qy,
-                                         const uint4& qa, float (&dz)[8], float (&xh)[8]) {
-  float da[8], y[8], zs[8];
-  unpack8(qda, da);
-  unpack8(qy, y);
-  if (a.aout) {
-    unpack8(qa, zs);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) zs[j] = y[j] * k.scale[j] + k.shift[j];
-  }
-  const float neg = a.act == B200CV_ACT_LEAKY ? a.slope : (a.act == B200CV_ACT_RELU ? 0.f : 1.f);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    dz[j] = da[j] * (zs[j] > 0.f ? 1.f : neg);
-    xh[j] = (y[j] - k.mean[j]) * k.rstd[j];
-  }
-}
 
-constexpr int kBwdUnroll = 4;
-
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BwdArgs a) {
+template <bool kAout>
+__global__ void __launch_bounds__(kEwThreads, 4) bn_bwd_reduce_kernel(const BwdArgs a) {
   extern __shared__ float s_acc[];  // [2C]
   const int C = a.C;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
-  const int vpr = C >> 3;                 // <= 256 guaranteed by the host
-  const int rpp = blockDim.x / vpr;       // rows per pass of this block
+  const int vpr = C >> 2;
+  const int rpp = kEwThreads / vpr;
   const int cv = threadIdx.x % vpr;
   const int r0 = threadIdx.x / vpr;
-  const int c0 = cv << 3;
-  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int c0 = cv << 2;
   if (r0 < rpp) {
-    ChanConsts k;
-    load_consts(a, c0, k);
+    float sc[4], sh[4], mean[4];
+    if (!kAout) {
+      load4f(a.scale + c0, sc);
+      load4f(a.shift + c0, sh);
+    }
+    load4f(a.mean + c0, mean);
+    const float neg = a.act == B200CV_ACT_LEAKY ? a.slope : (a.act == B200CV_ACT_RELU ? 0.f : 1.f);
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
     const long long stride = (long long)gridDim.x * rpp;
-    for (long long r = (long long)blockIdx.x * rpp + r0; r < a.rows; r += stride * kBwdUnroll) {
-      uint4 qda[kBwdUnroll], qy[kBwdUnroll], qa[kBwdUnroll];
+    for (long long r = (long long)blockIdx.x * rpp + r0; r < a.rows; r += stride * kEwUnroll) {
+      uint2 qda[kEwUnroll], qy[kEwUnroll], qa[kEwUnroll];
 #pragma unroll
-      for (int u = 0; u < kBwdUnroll; ++u) {
+      for (int u = 0; u < kEwUnroll; ++u) {
         const long long rr = r + u * stride;
         if (rr < a.rows) {
-          qda[u] = ldg_stream(a.da + rr * a.da_ld + c0);
-          qy[u] = ldg_stream(a.y + rr * a.y_ld + c0);
-          if (a.aout) qa[u] = ldg_stream(a.aout + rr * a.aout_ld + c0);
+          qda[u] = ldg_stream8(a.da + rr * a.da_ld + c0);
+          qy[u] = ldg_stream8(a.y + rr * a.y_ld + c0);
+          if (kAout) qa[u] = ldg_stream8(a.aout + rr * a.aout_ld + c0);
         }
       }
 #pragma unroll
-      for (int u = 0; u < kBwdUnroll; ++u) {
+      for (int u = 0; u < kEwUnroll; ++u) {
         if (r + u * stride < a.rows) {
-          float dz[8], xh[8];
-          bwd_math(a, k, qda[u], qy[u], qa[u], dz, xh);
+          float da[4], y[4], zs[4];
+          unpack4(qda[u], da);
+          unpack4(qy[u], y);
+          if (kAout) {
+            unpack4(qa[u], zs);
+          } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            s1[j] += dz[j];
-            s2[j] += dz[j] * xh[j];
+            for (int j = 0; j < 4; ++j) zs[j] = y[j] * sc[j] + sh[j];
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float dz = da[j] * (zs[j] > 0.f ? 1.f : neg);
+            s1[j] += dz;
+            s2[j] = fmaf(dz, y[j] - mean[j], s2[j]);
           }
         }
       }
     }
+    float rstd[4];
+    load4f(a.rstd + c0, rstd);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 4; ++j) {
       atomicAdd(&s_acc[c0 + j], s1[j]);
-      atomicAdd(&s_acc[C + c0 + j], s2[j]);
+      atomicAdd(&s_acc[C + c0 + j], s2[j] * rstd[j]);
     }
   }
   __syncthreads();
-  float* row = a.sums + (long long)blockIdx.x * 2 * C;  // this block's row of the partials matrix
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) row[i] = s_acc[i];
+  float* row = a.sums + (long long)(blockIdx.x % a.nparts) * 2 * C;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    const float v = s_acc[i];
+    if (v != 0.f) atomicAdd(row + i, v);
+  }
 }
 
 // coef[c] = gamma*rstd ; coef[C+c] = sum_dz/M ; coef[2C+c] = sum_dz_xhat/M ; also dgamma/dbeta
@@ -319,41 +320,66 @@ bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, const flo
   }
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdArgs a) {
+//   dy = g*(dz - k1 - xhat*k2) = g*dz + A*y + B   with A = -g*k2*rstd, B = -g*k1 - A*mean
+template <bool kAout>
+__global__ void __launch_bounds__(kEwThreads, 4) bn_bwd_apply_kernel(const BwdArgs a) {
   const int C = a.C;
-  const int vpr = C >> 3;
-  const int rpp = blockDim.x / vpr;
+  const int vpr = C >> 2;
+  const int rpp = kEwThreads / vpr;
   const int cv = threadIdx.x % vpr;
   const int r0 = threadIdx.x / vpr;
-  const int c0 = cv << 3;
+  const int c0 = cv << 2;
   if (r0 >= rpp) return;
-  ChanConsts k;
-  load_consts(a, c0, k);
-  float g[8], k1[8], k2[8];
-  load8(a.coef + c0, g);
-  load8(a.coef + C + c0, k1);
-  load8(a.coef + 2 * C + c0, k2);
-  const long long stride = (long long)gridDim.x * rpp;
-  for (long long r = (long long)blockIdx.x * rpp + r0; r < a.rows; r += stride * kBwdUnroll) {
-    uint4 qda[kBwdUnroll], qy[kBwdUnroll], qa[kBwdUnroll];
+  float sc[4], sh[4], g[4], A[4], B[4];
+  if (!kAout) {
+    load4f(a.scale + c0, sc);
+    load4f(a.shift + c0, sh);
+  }
+  {
+    float k1[4], k2[4], mean[4], rstd[4];
+    load4f(a.coef + c0, g);
+    load4f(a.coef + C + c0, k1);
+    load4f(a.coef + 2 * C + c0, k2);
+    load4f(a.mean + c0, mean);
+    load4f(a.rstd + c0, rstd);
 #pragma unroll
-    for (int u = 0; u < kBwdUnroll; ++u) {
+    for (int j = 0; j < 4; ++j) {
+      A[j] = -g[j] * k2[j] * rstd[j];
+      B[j] = -g[j] * k1[j] - A[j] * mean[j];
+    }
+  }
+  const float neg = a.act == B200CV_ACT_LEAKY ? a.slope : (a.act == B200CV_ACT_RELU ? 0.f : 1.f);
+  const long long stride = (long long)gridDim.x * rpp;
+  for (long long r = (long long)blockIdx.x * rpp + r0; r < a.rows; r += stride * kEwUnroll) {
+    uint2 qda[kEwUnroll], qy[kEwUnroll], qa[kEwUnroll];
+#pragma unroll
+    for (int u = 0; u < kEwUnroll; ++u) {
       const long long rr = r + u * stride;
       if (rr < a.rows) {
-        qda[u] = ldg_stream(a.da + rr * a.da_ld + c0);
-        qy[u] = ldg_stream(a.y + rr * a.y_ld + c0);
-        if (a.aout) qa[u] = ldg_stream(a.aout + rr * a.aout_ld + c0);
+        qda[u] = ldg_stream8(a.da + rr * a.da_ld + c0);
+        qy[u] = ldg_stream8(a.y + rr * a.y_ld + c0);
+        if (kAout) qa[u] = ldg_stream8(a.aout + rr * a.aout_ld + c0);
       }
     }
 #pragma unroll
-    for (int u = 0; u < kBwdUnroll; ++u) {
+    for (int u = 0; u < kEwUnroll; ++u) {
       const long long rr = r + u * stride;
       if (rr < a.rows) {
-        float dz[8], xh[8], o[8];
-        bwd_math(a, k, qda[u], qy[u], qa[u], dz, xh);
+        float da[4], y[4], zs[4], o[4];
+        unpack4(qda[u], da);
+        unpack4(qy[u], y);
+        if (kAout) {
+          unpack4(qa[u], zs);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = g[j] * (dz[j] - k1[j] - xh[j] * k2[j]);
-        stg16(a.dy + rr * a.dy_ld + c0, pack8(o));
+          for (int j = 0; j < 4; ++j) zs[j] = y[j] * sc[j] + sh[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float dz = da[j] * (zs[j] > 0.f ? 1.f : neg);
+          o[j] = fmaf(g[j], dz, fmaf(A[j], y[j], B[j]));
+        }
+        stg8(a.dy + rr * a.dy_ld + c0, pack4(o));
       }
     }
   }
@@ -593,12 +619,14 @@ extern "C" int b200cv_bn_apply_act(const void* y, int64_t y_ld, const float* sca
   B200CV_CHECK_ARG(!post || ok_vec(post, post_ld, C), "bn_apply_act: bad residual");
   ApplyArgs a{(const bf16*)y, y_ld, scale, shift, (const bf16*)y2, y2_ld, scale2, shift2,
               (const bf16*)post, post_ld, (bf16*)out, out_ld, rows, C, act, slope};
-  B200CV_CHECK_ARG(C / 8 <= 256, "bn_apply_act: C too large");
+  B200CV_CHECK_ARG(C / 4 <= kEwThreads, "bn_apply_act: C too large");
   {
-    const int rpp = 256 / (C / 8);
-    const long long passes = (rows + (long long)rpp * kApplyUnroll - 1) / ((long long)rpp * kApplyUnroll);
-    const int grid = (int)std::max<long long>(1, std::min<long long>(passes, (long long)sm_count() * 8));
-    bn_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    const int grid = stream_grid(rows, C);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (y2 && post) bn_apply_kernel<true, true><<<grid, kEwThreads, 0, st>>>(a);
+    else if (y2) bn_apply_kernel<true, false><<<grid, kEwThreads, 0, st>>>(a);
+    else if (post) bn_apply_kernel<false, true><<<grid, kEwThreads, 0, st>>>(a);
+    else bn_apply_kernel<false, false><<<grid, kEwThreads, 0, st>>>(a);
   }
   return check_launch("bn_apply_act");
 }
@@ -608,7 +636,7 @@ static int fill_bwd(BwdArgs& a, const void* da, int64_t da_ld, const void* y, in
                     int64_t rows, int C, int act, float slope) {
   B200CV_CHECK_ARG(ok_vec(da, da_ld, C) && ok_vec(y, y_ld, C) && mean && rstd && rows > 0, "bn_bwd: bad args");
   B200CV_CHECK_ARG(aout ? ok_vec(aout, aout_ld, C) : (scale && shift), "bn_bwd: need aout or scale/shift");
-  B200CV_CHECK_ARG(C <= 2048, "bn_bwd: C=%d too large", C);
+  B200CV_CHECK_ARG(C / 4 <= kEwThreads, "bn_bwd: C=%d too large", C);
   a = BwdArgs{};
   a.da = (const bf16*)da; a.da_ld = da_ld; a.y = (const bf16*)y; a.y_ld = y_ld;
   a.aout = (const bf16*)aout; a.aout_ld = aout_ld; a.scale = scale; a.shift = shift;
@@ -624,12 +652,12 @@ extern "C" int b200cv_bn_bwd_reduce(const void* da, int64_t da_ld, const void* y
   if (int rc = fill_bwd(a, da, da_ld, y, y_ld, aout, aout_ld, scale, shift, mean, rstd, rows, C, act, slope))
     return rc;
   B200CV_CHECK_ARG(partials != nullptr && nparts > 0, "bn_bwd_reduce: null partials");
-  a.sums = partials;
-  const int vpr = C / 8;
-  const int threads = vpr > 256 ? 256 : 256;
-  B200CV_CHECK_ARG(vpr <= 256, "bn_bwd_reduce: C too large");
-  const int grid = nparts;  // block p writes row p of the partials (blocks without rows write zeros)
-  bn_bwd_reduce_kernel<<<grid, threads, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(a);
+  a.sums = partials;  // [nparts][2C], zeroed by the caller: block b ADDS its sums to row b % nparts
+  a.nparts = nparts;
+  const int grid = stream_grid(rows, C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (aout) bn_bwd_reduce_kernel<true><<<grid, kEwThreads, 2 * C * sizeof(float), st>>>(a);
+  else bn_bwd_reduce_kernel<false><<<grid, kEwThreads, 2 * C * sizeof(float), st>>>(a);
   return check_launch("bn_bwd_reduce");
 }
 
@@ -650,12 +678,11 @@ extern "C" int b200cv_bn_bwd_apply(const void* da, int64_t da_ld, const void* y,
     return rc;
   B200CV_CHECK_ARG(coef && ok_vec(dy, dy_ld, C), "bn_bwd_apply: bad args");
   a.coef = coef; a.dy = (bf16*)dy; a.dy_ld = dy_ld;
-  B200CV_CHECK_ARG(C / 8 <= 256, "bn_bwd_apply: C too large");
   {
-    const int rpp = 256 / (C / 8);
-    const long long passes = (rows + (long long)rpp * kBwdUnroll - 1) / ((long long)rpp * kBwdUnroll);
-    const int grid = (int)std::max<long long>(1, std::min<long long>(passes, (long long)sm_count() * 8));
-    bn_bwd_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    const int grid = stream_grid(rows, C);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (aout) bn_bwd_apply_kernel<true><<<grid, kEwThreads, 0, st>>>(a);
+    else bn_bwd_apply_kernel<false><<<grid, kEwThreads, 0, st>>>(a);
   }
   return check_launch("bn_bwd_apply");
 }
