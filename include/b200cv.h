@@ -155,6 +155,21 @@ int b200cv_bn_bwd_apply(const void* da, int64_t da_ld, const void* y, int64_t y_
                         int64_t aout_ld, const float* scale, const float* shift, const float* mean,
                         const float* rstd, const float* coef, void* dy, int64_t dy_ld, int64_t rows, int C,
                         int act, float slope, void* stream);
+/* Fused forms used by the Darknet engine (one launch instead of finalize + apply): every block first folds the
+ * [parts][2C] partial statistics into the per-channel constants in shared memory, block 0 also publishes them
+ * (scale/shift/save_mean/save_rstd, running statistics; dgamma/dbeta/coef) exactly like b200cv_bn_finalize /
+ * b200cv_bn_bwd_finalize, then the block streams its rows like b200cv_bn_apply_act / b200cv_bn_bwd_apply. */
+int b200cv_bn_stats_apply_act(const float* stats, int stats_parts, int64_t count, const float* gamma,
+                              const float* beta, const float* conv_bias, float eps, float momentum,
+                              float* running_mean, float* running_var, float* scale, float* shift,
+                              float* save_mean, float* save_rstd, const void* y, int64_t y_ld, const void* post,
+                              int64_t post_ld, void* out, int64_t out_ld, int64_t rows, int C, int act,
+                              float slope, void* stream);
+int b200cv_bn_bwd_stats_apply(const float* partials, int nparts, int64_t count, const float* gamma, float* coef,
+                              float* dgamma, float* dbeta, const void* da, int64_t da_ld, const void* y,
+                              int64_t y_ld, const float* scale, const float* shift, const float* mean,
+                              const float* rstd, void* dy, int64_t dy_ld, int64_t rows, int C, int act,
+                              float slope, void* stream);
 /* dz = da * act'(aout) for an activation that does not follow a BatchNorm. */
 int b200cv_act_bwd(const void* da, int64_t da_ld, const void* aout, int64_t aout_ld, void* dz, int64_t dz_ld,
                    int64_t rows, int C, int act, float slope, void* stream);

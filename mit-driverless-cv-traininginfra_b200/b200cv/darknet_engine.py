@@ -176,9 +176,9 @@ class DarknetEngine:
                     if bn_train:
                         y = ops.conv_fwd(xin, L.wpk, L.cout, k_, st_, pd_, stats=L.stats)
                         count = y.numel() // y.shape[-1]
-                        ops.bn_finalize(L.stats, count, L.bn.weight, L.bn.bias, None, BN_EPS, BN_MOMENTUM,
-                                        L.bn.running_mean, L.bn.running_var, L.scale, L.shift, L.mean, L.rstd)
-                        cur = ops.bn_apply_act(y, L.scale, L.shift, L.act, L.slope, post=post)
+                        cur = ops.bn_stats_apply_act(L.stats, count, L.bn.weight, L.bn.bias, None, BN_EPS, BN_MOMENTUM,
+                                                     L.bn.running_mean, L.bn.running_var, L.scale, L.shift, L.mean,
+                                                     L.rstd, y, L.act, L.slope, post=post)
                         saved[i] = (xin, y)
                     else:
                         scale = L.bn.weight.detach() * torch.rsqrt(L.bn.running_var + BN_EPS)
@@ -290,9 +290,9 @@ class DarknetEngine:
                     count = y.numel() // y.shape[-1]
                     parts = ops.bn_bwd_reduce(G, y, None, L.scale, L.shift, L.mean, L.rstd, L.act, L.slope,
                                               partials=L.bstats)
-                    ops.bn_bwd_finalize(parts, L.bn.weight, L.rstd, count, L.coef, gview[id(L.bn.weight)],
-                                        gview[id(L.bn.bias)])
-                    dy = ops.bn_bwd_apply(G, y, None, L.scale, L.shift, L.mean, L.rstd, L.coef, L.act, L.slope)
+                    dy = ops.bn_bwd_stats_apply(parts, count, L.bn.weight, L.coef, gview[id(L.bn.weight)],
+                                                gview[id(L.bn.bias)], G, y, L.scale, L.shift, L.mean, L.rstd, L.act,
+                                                L.slope)
                     if L.post_from is not None:
                         add_grad(L.post_from, G)
                 else:

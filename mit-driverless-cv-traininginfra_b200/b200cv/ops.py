@@ -15,7 +15,7 @@ from .lib import ACT_LEAKY, ACT_NONE, ACT_RELU, DT_BF16, DT_F32, ConvArgs, lib, 
 __all__ = [
     "ACT_NONE", "ACT_LEAKY", "ACT_RELU", "pad_channels", "conv_out_size", "nchw_to_nhwc", "nhwc_to_nchw",
     "pack_weights", "unpack_wgrad", "conv_fwd", "conv_dgrad", "conv_wgrad", "bn_finalize", "bn_apply_act",
-    "bn_bwd_reduce", "bn_bwd_finalize", "bn_bwd_apply", "act_bwd", "copy_slice", "col_sum", "maxpool_fwd",
+    "bn_bwd_reduce", "bn_bwd_finalize", "bn_bwd_apply", "bn_stats_apply_act", "bn_bwd_stats_apply", "act_bwd", "copy_slice", "col_sum", "maxpool_fwd",
     "maxpool_bwd", "upsample_fwd", "upsample_bwd", "act_code", "sm_count", "stats_buffer", "im2col_nchw",
     "use_flat_path", "flat_k",
 ]
@@ -174,7 +174,7 @@ def sm_count(device=None) -> int:
     return torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device()).multi_processor_count
 
 
-STAT_PARTS = 32  # rows of a partial-statistics matrix: CTA / block b adds into row b % STAT_PARTS
+STAT_PARTS = 8  # rows of a partial-statistics matrix: CTA / block b adds into row b % STAT_PARTS
 
 
 def stats_buffer(cout: int, device) -> torch.Tensor:
@@ -199,6 +199,32 @@ def bn_apply_act(y, scale, shift, act, slope, out=None, y2=None, scale2=None, sh
                0 if y2 is None else y2.stride(-2), ptr(scale2), ptr(shift2), ptr(post),
                0 if post is None else post.stride(-2), ptr(out), out.stride(-2), _rows(y), c, act, float(slope),
                stream_ptr(), tag=(_rows(y), c))
+    return out
+
+
+def bn_stats_apply_act(stats, count, gamma, beta, conv_bias, eps, momentum, running_mean, running_var, scale, shift,
+                       mean, rstd, y, act, slope, out=None, post=None):
+    """bn_finalize + bn_apply_act in ONE launch (every block folds the partial statistics itself)."""
+    c = y.shape[-1]
+    if out is None:
+        out = torch.empty_like(y)
+    parts = stats.shape[0] if stats.dim() == 2 else 1
+    lib().call("b200cv_bn_stats_apply_act", ptr(stats), parts, int(count), ptr(gamma), ptr(beta), ptr(conv_bias),
+               float(eps), float(momentum), ptr(running_mean), ptr(running_var), ptr(scale), ptr(shift), ptr(mean),
+               ptr(rstd), ptr(y), y.stride(-2), ptr(post), 0 if post is None else post.stride(-2), ptr(out),
+               out.stride(-2), _rows(y), c, act, float(slope), stream_ptr(), tag=(_rows(y), c))
+    return out
+
+
+def bn_bwd_stats_apply(partials, count, gamma, coef, dgamma, dbeta, da, y, scale, shift, mean, rstd, act, slope,
+                       out=None):
+    """bn_bwd_finalize + bn_bwd_apply in ONE launch."""
+    if out is None:
+        out = torch.empty_like(y)
+    lib().call("b200cv_bn_bwd_stats_apply", ptr(partials), partials.shape[0], int(count), ptr(gamma), ptr(coef),
+               ptr(dgamma), ptr(dbeta), ptr(da), da.stride(-2), ptr(y), y.stride(-2), ptr(scale), ptr(shift),
+               ptr(mean), ptr(rstd), ptr(out), out.stride(-2), _rows(y), y.shape[-1], act, float(slope),
+               stream_ptr(), tag=(_rows(y), y.shape[-1]))
     return out
 
 

@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "internal.h"
 
@@ -49,6 +50,10 @@ int run_igemm(const Geometry& g, const void* act, const void* wpk, int64_t w_row
   const int bn = pick_block_n(p.Cout, p.num_m_tiles);
   p.num_n_tiles = (p.Cout + bn - 1) / bn;
   p.err = device_error_word();
+  {
+    static const int dbg = getenv("B200CV_DBG") ? atoi(getenv("B200CV_DBG")) : 0;
+    p.dbg = dbg;
+  }
   CUtensorMap tmA, tmB;
   int rc = make_tmap_im2col_bf16(&tmA, act, g.N, g.H, g.W, g.C, g.C, (int64_t)g.W * g.C,
                                  (int64_t)g.H * g.W * g.C, g.lower_w, g.lower_h, g.upper_w, g.upper_h,
@@ -56,7 +61,20 @@ int run_igemm(const Geometry& g, const void* act, const void* wpk, int64_t w_row
   if (rc) return rc;
   rc = make_tmap_2d_bf16(&tmB, wpk, w_rows, w_cols, w_cols, bn, kc);
   if (rc) return rc;
-  return launch_igemm(tmA, tmB, p, kc, bn, stream);
+  // Staged TMA-store epilogue when the output is a plain row-major bf16 matrix [M][ld] (forward convs and
+  // stride-1 data gradients); strided (parity scatter, NCHW), fp32 or unaligned outputs take the generic one.
+  const long long ld = p.o_sw;
+  static const bool no_tma_store = getenv("B200CV_NO_TMA_STORE") != nullptr;
+  const bool tma_out = !no_tma_store && !p.out_fp32 && p.vec_ok && p.o_sc == 1 && ld >= p.Cout && ld % 8 == 0 &&
+                       p.o_sh == (long long)p.OW * ld && p.o_sn == (long long)p.OHW * ld && p.Cout % 8 == 0 &&
+                       (!p.res || p.res_vec_ok);
+  if (tma_out) {
+    CUtensorMap tmO;
+    rc = make_tmap_2d_bf16(&tmO, p.out, p.M_total, p.Cout, ld, 32, bn >= 32 ? 32 : 16);
+    if (rc) return rc;
+    return launch_igemm(tmA, tmB, &tmO, p, kc, bn, stream);
+  }
+  return launch_igemm(tmA, tmB, nullptr, p, kc, bn, stream);
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

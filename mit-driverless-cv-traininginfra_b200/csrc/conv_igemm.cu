@@ -36,15 +36,18 @@ constexpr int kSmemMax = 227 * 1024;                    // dynamic shared memory
 constexpr int kSmemMax2 = 113 * 1024;                   // ... of each of two co-resident CTAs
 constexpr int kScratchLd = 17;                          // [32 rows][16 columns + 1] fp32 transpose tile
 
-template <int KC, int BN>
+// kTma: the output is a plain row-major bf16 matrix [M][ld] -> the epilogue stages 32x32 (or 32x16) bf16 tiles in
+// swizzled shared memory and writes them with TMA bulk stores; BN statistics are read back from the staged
+// tile.  Otherwise ("generic": fp32 / strided / ragged outputs) rows are stored directly from registers.
+template <int KC, int BN, bool kTma>
 struct Cfg {
   static constexpr int kABytes = kBlockM * KC * 2;
   static constexpr int kBBytes = BN * KC * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   // Small stages (<= 16 KB: the 16/32-channel layers) are latency- not bandwidth-bound per k-iteration:
   // run two CTAs per SM (each with a shallower ring) so their TMA / mbarrier round trips overlap.
-  static constexpr int kCtasPerSm = kStageBytes <= 16 * 1024 ? 2 : 1;
   static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : (2 * BN);
+  static constexpr int kCtasPerSm = (kStageBytes <= 16 * 1024 && kTmemCols <= 256) ? 2 : 1;
   static constexpr int kRowBytes = KC * 2;               // 32 / 64 / 128
   static constexpr int kLayout = KC == 64 ? 2 : (KC == 32 ? 4 : 6);
   static constexpr int kSBO = 8 * kRowBytes;             // 8-row swizzle atom pitch
@@ -52,15 +55,17 @@ struct Cfg {
   static constexpr int kNumChunks = BN / kChunk;         // 1..8
   static constexpr int kChunksPerWarp = (kNumChunks + 1) / 2;
   static constexpr int kAccPerWarp = kChunksPerWarp * kChunk;  // columns a warp keeps statistics for
-  // extras: barriers (8B each, up to 8 stages) + tmem ptr | per-warp [sum | sumsq] rows | transpose scratch
-  static constexpr int kBarBytes = (2 * 8 + 4) * 8 + 16;
-  static constexpr int kStatBytes = kEpiWarps * 2 * kAccPerWarp * 4;
-  static constexpr int kScratchBytes = kEpiWarps * 32 * kScratchLd * 4;
-  static constexpr int kExtraBytes = 1024 /*align slack*/ + kBarBytes + kStatBytes + kScratchBytes;
+  static constexpr int kBarBytes = (2 * 8 + 4) * 8 + 16;       // barriers (8 B each, up to 8 stages) + tmem ptr
+  // generic: per-warp [sum | sumsq] rows + fp32 transpose scratch; TMA: one 1 KB-aligned staging tile per warp
+  static constexpr int kStatBytes = kTma ? 0 : kEpiWarps * 2 * kAccPerWarp * 4;
+  static constexpr int kScratchBytes = kTma ? kEpiWarps * 2048 : kEpiWarps * 32 * kScratchLd * 4;
+  static constexpr int kExtraBytes = 1024 /*align slack*/ + 2048 /*barrier block + align*/ + kStatBytes + kScratchBytes;
   static constexpr int kBudget = (kCtasPerSm == 2 ? kSmemMax2 : kSmemMax) - kExtraBytes;
   static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kSmemBytes = kExtraBytes + kStages * kStageBytes;
+  static_assert(kBarBytes <= 1024, "barrier block");
+  static_assert(kStageBytes % 256 == 0, "stage alignment");
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
@@ -69,11 +74,25 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   return v;
 }
 
-template <int KC, int BN>
-__global__ void __launch_bounds__(kThreads, Cfg<KC, BN>::kCtasPerSm)
+// One step of the keep-half butterfly: lanes whose BIT is set keep s[N..2N) and give s[0..N) away (and vice
+// versa); after the steps N = 4, 2, 1 every lane of the 8-lane group holds the group total of ONE column.
+template <int N, int BIT>
+__device__ __forceinline__ void keep_half_step(float (&s)[8], float (&t)[8], int lane) {
+  const bool up = (lane & BIT) != 0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const float send_s = up ? s[k] : s[k + N], keep_s = up ? s[k + N] : s[k];
+    const float send_t = up ? t[k] : t[k + N], keep_t = up ? t[k + N] : t[k];
+    s[k] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, BIT);
+    t[k] = keep_t + __shfl_xor_sync(0xffffffffu, send_t, BIT);
+  }
+}
+
+template <int KC, int BN, bool kTma>
+__global__ void __launch_bounds__(kThreads, Cfg<KC, BN, kTma>::kCtasPerSm)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-             const __grid_constant__ IgemmParams p) {
-  using C = Cfg<KC, BN>;
+             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ IgemmParams p) {
+  using C = Cfg<KC, BN, kTma>;
   extern __shared__ uint8_t smem_raw[];
   // align to 1024 B (128B-swizzle atom) by pointer arithmetic so the shared state space stays provable
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -83,7 +102,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tfull_bar = empty_bar + C::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* s_stats = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + C::kBarBytes);
+  // stage ring (multiple of 1 KB) | 1 KB barrier block | staging tiles (TMA) or stats rows + scratch (generic)
+  uint8_t* s_extra = reinterpret_cast<uint8_t*>(full_bar) + C::kBarBytes;
+  s_extra += (1024u - (ptx::smem_u32(s_extra) & 1023u)) & 1023u;  // staging tiles: swizzle-atom aligned
+  float* s_stats = reinterpret_cast<float*>(s_extra);
   float* s_scratch = s_stats + kEpiWarps * 2 * C::kAccPerWarp;
 
   const int warp = threadIdx.x >> 5;
@@ -94,6 +116,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
+    if (kTma) ptx::prefetch_tmap(&tmO);
     for (int i = 0; i < C::kStages; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
       ptx::mbar_init(&empty_bar[i], 1);
@@ -107,7 +130,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 1) {
     ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
   }
-  if (p.stats)
+  if (!kTma && p.stats)
     for (int i = threadIdx.x; i < kEpiWarps * 2 * C::kAccPerWarp; i += kThreads) s_stats[i] = 0.f;
   ptx::tc_fence_before();
   __syncthreads();
@@ -191,6 +214,206 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int ew = warp - kEpiWarp0;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may read
     const int half = ew >> 2;      // which chunks of the accumulator: half, half + 2, ...
+    if constexpr (kTma) {
+      // ---- staged epilogue: registers -> swizzled smem tile -> TMA bulk store; statistics from the staged tile
+      constexpr int RB = C::kChunk * 2;  // bytes per staged row: 64 (SWIZZLE_64B) or 32 (SWIZZLE_32B)
+      constexpr int NJ = RB / 16;        // 16-byte pieces per row
+      uint8_t* stg = s_extra + ew * 2048;
+      const int sw_w = RB == 64 ? ((lane >> 1) & 3) : ((lane >> 2) & 1);  // writer: row = lane
+      // reader of the statistics: lane = (q: 16-byte piece, g: row group); rows g + (32/NR)*i, piece q
+      constexpr int NR = RB == 64 ? 4 : 2;                // rows per reader lane
+      const int rq = RB == 64 ? (lane & 3) : (lane & 1);
+      const int rg = RB == 64 ? (lane >> 2) : (lane >> 1);
+      const int sw_r = RB == 64 ? ((rg >> 1) & 3) : ((rg >> 2) & 1);
+      const uint8_t* rd0 = stg + rg * RB + ((rq ^ sw_r) * 16);
+      const int my_col = RB == 64 ? (8 * rq + rg) : (8 * rq + (rg >> 1));  // column this lane ends up owning
+      const bool col_owner = RB == 64 ? true : ((lane & 2) == 0);
+      float acc_s[C::kChunksPerWarp], acc_t[C::kChunksPerWarp];
+#pragma unroll
+      for (int i = 0; i < C::kChunksPerWarp; ++i) acc_s[i] = acc_t[i] = 0.f;
+      float* stats_row =
+          p.stats ? p.stats + static_cast<long long>(blockIdx.x % p.stats_parts) * 2 * p.Cout : nullptr;
+      int stat_nt = -1;
+      bool store_pending = false;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile / p.num_n_tiles;
+        const int nt = tile - mt * p.num_n_tiles;
+        if (p.stats && nt != stat_nt) {
+          if (stat_nt >= 0) {
+#pragma unroll
+            for (int ci = 0; ci < C::kChunksPerWarp; ++ci) {
+              const int n = stat_nt * BN + (half + 2 * ci) * C::kChunk + my_col;
+              if (col_owner && (half + 2 * ci) < C::kNumChunks && n < p.Cout) {
+                atomicAdd(stats_row + n, acc_s[ci]);
+                atomicAdd(stats_row + p.Cout + n, acc_t[ci]);
+              }
+              acc_s[ci] = acc_t[ci] = 0.f;
+            }
+          }
+          stat_nt = nt;
+        }
+        const int m_warp = mt * kBlockM + quarter * 32;  // first output row of this warp
+        const int m = m_warp + lane;
+        const bool row_ok = m < p.M_total;
+        long long r_row = 0;
+        if (p.res) {
+          const int mm = row_ok ? m : 0;
+          const int n_img = mm / p.OHW;
+          const int rem = mm - n_img * p.OHW;
+          const int pr = rem / p.OW;
+          const int qc = rem - pr * p.OW;
+          r_row = n_img * p.r_sn + pr * p.r_sh + qc * p.r_sw;
+        }
+        ptx::mbar_wait(&tfull_bar[acc], acc_phase, p.err, 4);
+        ptx::tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+
+#pragma unroll
+        for (int ci = 0; ci < C::kChunksPerWarp; ++ci) {
+          const int c0 = (half + 2 * ci) * C::kChunk;
+          const int n_base = nt * BN + c0;
+          if (c0 >= BN || n_base >= p.Cout || (p.dbg & 4)) break;  // warp-uniform
+          float v[C::kChunk];
+          if constexpr (C::kChunk == 32) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(t_row + c0, r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          } else {
+            uint32_t r[16];
+            ptx::tmem_ld_32x16(t_row + c0, r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          }
+          // columns >= Cout of a ragged last chunk are clipped by the TMA store; keep their loads in bounds
+          const bool full = n_base + C::kChunk <= p.Cout;
+          if (p.scale) {
+#pragma unroll
+            for (int j = 0; j < C::kChunk; j += 4) {
+              if (full || n_base + j + 4 <= p.Cout) {
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + n_base + j));
+                v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
+              }
+            }
+          }
+          if (p.shift) {
+#pragma unroll
+            for (int j = 0; j < C::kChunk; j += 4) {
+              if (full || n_base + j + 4 <= p.Cout) {
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.shift + n_base + j));
+                v[j] += s4.x; v[j + 1] += s4.y; v[j + 2] += s4.z; v[j + 3] += s4.w;
+              }
+            }
+          }
+          const float neg = p.act == 1 ? p.slope : (p.act == 2 ? 0.f : 1.f);
+          if (p.res) {
+            if (p.res_after_act) {
+#pragma unroll
+              for (int j = 0; j < C::kChunk; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * neg;
+            }
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res + r_row + n_base);
+#pragma unroll
+            for (int j = 0; j < C::kChunk; j += 8) {
+              if (full || n_base + j + 8 <= p.Cout) {
+                const uint4 q = __ldg(rp + (j >> 3));
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __bfloat1622float2(h[e]);
+                  v[j + 2 * e] += f.x;
+                  v[j + 2 * e + 1] += f.y;
+                }
+              }
+            }
+            if (!p.res_after_act && p.act != 0) {
+#pragma unroll
+              for (int j = 0; j < C::kChunk; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * neg;
+            }
+          } else if (p.act != 0) {
+#pragma unroll
+            for (int j = 0; j < C::kChunk; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * neg;
+          }
+          if (!row_ok) {  // rows past M_total are clipped by the store and must not be counted
+#pragma unroll
+            for (int j = 0; j < C::kChunk; ++j) v[j] = 0.f;
+          }
+          // the previous bulk store of this warp must have finished READING the staging tile
+          if (store_pending) {
+            if (lane == 0) ptx::tma_store_wait_read<0>();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            uint4 pk;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+            *reinterpret_cast<uint4*>(stg + lane * RB + ((j ^ sw_w) * 16)) = pk;
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && !(p.dbg & 1)) {
+            ptx::tma_store_2d(&tmO, stg, n_base, m_warp);
+            ptx::tma_store_commit();
+          }
+          store_pending = true;
+          if (p.stats && !(p.dbg & 2)) {
+            // column sums of the STORED (bf16-rounded) tile: each lane adds NR rows of one 16-byte piece, a
+            // keep-half butterfly over the row-group lanes leaves one column per lane
+            float s[8], t[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s[k] = t[k] = 0.f;
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+              const uint4 u = *reinterpret_cast<const uint4*>(rd0 + i * (32 / NR) * RB);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(h[e]);
+                s[2 * e] += f.x;
+                s[2 * e + 1] += f.y;
+                t[2 * e] = fmaf(f.x, f.x, t[2 * e]);
+                t[2 * e + 1] = fmaf(f.y, f.y, t[2 * e + 1]);
+              }
+            }
+            keep_half_step<4, 16>(s, t, lane);
+            keep_half_step<2, 8>(s, t, lane);
+            keep_half_step<1, 4>(s, t, lane);
+            if (RB == 32) {  // 16 row-group lanes: one more (full) step
+              s[0] += __shfl_xor_sync(0xffffffffu, s[0], 2);
+              t[0] += __shfl_xor_sync(0xffffffffu, t[0], 2);
+            }
+            acc_s[ci] += s[0];
+            acc_t[ci] += t[0];
+            __syncwarp();  // all lanes are done reading before the tile is overwritten
+          }
+        }
+        // accumulator drained: hand the TMEM stage back to the MMA warp
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+      if (p.stats && stat_nt >= 0) {
+#pragma unroll
+        for (int ci = 0; ci < C::kChunksPerWarp; ++ci) {
+          const int n = stat_nt * BN + (half + 2 * ci) * C::kChunk + my_col;
+          if (col_owner && (half + 2 * ci) < C::kNumChunks && n < p.Cout) {
+            atomicAdd(stats_row + n, acc_s[ci]);
+            atomicAdd(stats_row + p.Cout + n, acc_t[ci]);
+          }
+        }
+      }
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
+      __syncwarp();
+    } else {
     float* scratch = s_scratch + ew * 32 * kScratchLd;
     float* my_sum = s_stats + ew * 2 * C::kAccPerWarp;  // [kAccPerWarp sums | kAccPerWarp sums of squares]
     float* my_sq = my_sum + C::kAccPerWarp;
@@ -241,6 +464,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int c0 = (half + 2 * ci) * C::kChunk;
         const int n_base = nt * BN + c0;
         if (c0 >= BN || n_base >= p.Cout) break;  // warp-uniform
+        if (p.dbg & 4) continue;
         float v[C::kChunk];
         if constexpr (C::kChunk == 32) {
           uint32_t r[32];
@@ -322,7 +546,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 v[j + 2 * e] = f.x;
                 v[j + 2 * e + 1] = f.y;
               }
-              if (row_ok) *reinterpret_cast<uint4*>(o + j) = pk;
+              if (row_ok && !(p.dbg & 1)) *reinterpret_cast<uint4*>(o + j) = pk;
             }
           }
         } else {
@@ -353,7 +577,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // per-channel sum / sum of squares over the 32 rows of this warp: transpose 16 columns at a time
         // through shared memory; lane l sums column (l & 15) over rows 16*(l >> 4) .. +15 with independent
         // partial sums, the two half-warps are combined with one shuffle
-        if (p.stats) {
+        if (p.stats && !(p.dbg & 2)) {
 #pragma unroll
           for (int hh = 0; hh < C::kChunk / 16; ++hh) {
 #pragma unroll
@@ -391,6 +615,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
     if (p.stats && stat_nt >= 0) flush_stats(stat_nt);
+    }
   }
 
   ptx::tc_fence_before();
@@ -401,13 +626,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 }
 
-template <int KC, int BN>
-int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p,
+template <int KC, int BN, bool kTma>
+int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const IgemmParams& p,
                cudaStream_t stream) {
-  using C = Cfg<KC, BN>;
+  using C = Cfg<KC, BN, kTma>;
   static_assert(C::kStages >= 2, "pipeline too shallow");
   static bool configured = false;  // benign race: attribute set is idempotent
-  auto kern = igemm_kernel<KC, BN>;
+  auto kern = igemm_kernel<KC, BN, kTma>;
   if (!configured) {
     cudaError_t e =
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
@@ -418,16 +643,18 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams
   int grid = sm_count() * C::kCtasPerSm;
   if (grid > tiles) grid = tiles;
   if (grid < 1) return 0;
-  kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, p);
+  kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, tmO, p);
   return check_launch("igemm_kernel");
 }
 
 }  // namespace
 
-int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, int kc,
-                 int block_n, cudaStream_t stream) {
-#define B200CV_IGEMM_CASE(KC_, BN_) \
-  if (kc == KC_ && block_n == BN_) return launch_one<KC_, BN_>(tmA, tmB, p, stream);
+int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmO, const IgemmParams& p,
+                 int kc, int block_n, cudaStream_t stream) {
+#define B200CV_IGEMM_CASE(KC_, BN_)                                                        \
+  if (kc == KC_ && block_n == BN_)                                                         \
+    return tmO ? launch_one<KC_, BN_, true>(tmA, tmB, *tmO, p, stream)                     \
+               : launch_one<KC_, BN_, false>(tmA, tmB, tmA, p, stream);
   B200CV_IGEMM_CASE(64, 256)
   B200CV_IGEMM_CASE(64, 128)
   B200CV_IGEMM_CASE(64, 64)

@@ -8,8 +8,12 @@
 // NHWC tile down: 64 pixel rows x (<=128 bytes of channels), swizzled.
 //   A = dY tile  : tiled 2-D TMA over [pixels][dy_ld], one or two 64-channel slabs
 //   B = X tile   : im2col TMA (same map family as the forward pass), one per filter tap
-// One dY tile is reused for T taps (T accumulators in TMEM), split-K over the pixel range,
-// fp32 atomics (red.global.add) into the packed gradient.
+// One dY tile is reused for T taps (T accumulators in TMEM), split-K over the pixel range; the epilogue
+// stages 32x32 fp32 tiles in swizzled shared memory and lets the TMA unit reduce-add them into the packed
+// gradient (cp.reduce.async.bulk.tensor .add): the per-thread red.global.add.v4 version spent ~40 LSU cycles
+// per warp instruction (32 rows = 32 lines) in a non-overlapped tail of every CTA.  CTAs that share a pixel
+// range (all output-channel tiles / tap groups of one k-split) are adjacent in the grid so that range is
+// fetched from HBM once and served from L2 to the others.
 #include <cuda_bf16.h>
 
 #include <algorithm>
@@ -43,7 +47,7 @@ struct WgradParams {
 template <int CB, int BNW>
 __global__ void __launch_bounds__(kWThreads, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
-             const __grid_constant__ WgradParams p) {
+             const __grid_constant__ CUtensorMap tmDW, const __grid_constant__ WgradParams p) {
   constexpr int kBSlabs = BNW / CB;            // 1 or 2
   constexpr int kASlabBytes = kKB * 128;       // 64 pixels x 64 channels bf16
   constexpr int kBSlabBytes = kKB * CB * 2;
@@ -61,16 +65,19 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
   uint64_t* empty_bar = full_bar + kMaxWStages;
   uint64_t* done_bar = empty_bar + kMaxWStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+  // per-epilogue-warp staging tile [32 rows][kChunk fp32], 1 KB aligned (swizzle atom)
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(tmem_slot + 4);
+  s_stage += (1024u - (ptx::smem_u32(s_stage) & 1023u)) & 1023u;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // tile decode: blockIdx.x = (((o_tile * num_i_tiles) + i_tile) * num_tap_groups + tg) * ksplit + ks
+  // tile decode (k-split major): blockIdx.x = ((ks * num_o_tiles + o_tile) * num_i_tiles + i_tile) * num_tap_groups + tg
   int b = blockIdx.x;
-  const int ks = b % p.ksplit; b /= p.ksplit;
   const int tg = b % p.num_tap_groups; b /= p.num_tap_groups;
   const int it = b % p.num_i_tiles; b /= p.num_i_tiles;
-  const int ot = b;
+  const int ot = b % p.num_o_tiles; b /= p.num_o_tiles;
+  const int ks = b;
   const int kb_per = (p.kb_total + p.ksplit - 1) / p.ksplit;
   const int kb0 = ks * kb_per;
   const int kb1 = min(p.kb_total, kb0 + kb_per);
@@ -151,10 +158,15 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
       __syncwarp();
     } else {
       const int quarter = warp & 3;
-      const int o = ot * 128 + quarter * 32 + lane;
+      constexpr int RB = kChunk * 4;  // bytes per staged row: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
+      constexpr int NJ = RB / 16;
+      uint8_t* stg = s_stage + (warp - 2) * 4096;
+      const int sw = RB == 128 ? (lane & 7) : ((lane >> 1) & 3);
+      const int o_row = ot * 128 + quarter * 32;
       ptx::mbar_wait(done_bar, 0, p.err, 13);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+      bool pending = false;
       for (int t = 0; t < p.T; ++t) {
         const int tap = tg * p.T + t;
 #pragma unroll 1
@@ -174,17 +186,27 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
             for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
           }
           const int i0 = it * BNW + c0;
-          if (o < p.Cout && i0 < p.Cin) {
-            float* dst = p.dw + ((long long)o * p.RS + tap) * p.Ipad + i0;
-#pragma unroll
-            for (int j = 0; j < kChunk; j += 4) {
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]),
-                           "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3])
-                           : "memory");
+          if (o_row < p.Cout && i0 < p.Cin) {  // warp-uniform
+            if (pending) {  // the previous reduce of this warp must have finished reading the staging tile
+              if (lane == 0) ptx::tma_store_wait_read<0>();
+              __syncwarp();
             }
+#pragma unroll
+            for (int j = 0; j < NJ; ++j)
+              *reinterpret_cast<float4*>(stg + lane * RB + ((j ^ sw) * 16)) =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_reduce_add_2d(&tmDW, stg, tap * p.Ipad + i0, o_row);  // rows >= Cout are clipped
+              ptx::tma_store_commit();
+            }
+            pending = true;
           }
         }
       }
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      __syncwarp();
     }
   }
 
@@ -197,12 +219,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
 }
 
 template <int CB, int BNW>
-int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, WgradParams& p, cudaStream_t stream) {
+int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const CUtensorMap& tmDW, WgradParams& p,
+                 cudaStream_t stream) {
   constexpr int kBTapBytes = (BNW / CB) * kKB * CB * 2;
   const int stage_bytes = 2 * kKB * 128 + p.T * kBTapBytes;
-  p.stages = std::min(kMaxWStages, (196 * 1024) / stage_bytes);
+  p.stages = std::min(kMaxWStages, (204 * 1024) / stage_bytes);
   if (p.stages < 2) return set_error(B200CV_ERR_ARG, "wgrad: stage too large (%d bytes)", stage_bytes);
-  const int smem = 1024 + p.stages * stage_bytes + (2 * kMaxWStages + 1) * 8 + 16;
+  // align slack | stage ring | barriers + tmem slot | align slack + 4 staging tiles of 4 KB
+  const int smem = 1024 + p.stages * stage_bytes + (2 * kMaxWStages + 1) * 8 + 32 + 1024 + 4 * 4096;
   auto kern = wgrad_kernel<CB, BNW>;
   static int configured_smem = 0;
   if (smem > configured_smem) {
@@ -211,7 +235,7 @@ int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, WgradParams& p
     configured_smem = 227 * 1024;
   }
   const int grid = p.num_o_tiles * p.num_i_tiles * p.num_tap_groups * p.ksplit;
-  kern<<<grid, kWThreads, smem, stream>>>(tmDY, tmX, p);
+  kern<<<grid, kWThreads, smem, stream>>>(tmDY, tmX, tmDW, p);
   return check_launch("wgrad_kernel");
 }
 
@@ -279,10 +303,14 @@ extern "C" int b200cv_conv_wgrad(const void* x, const void* dy, float* dw_packed
   rc = make_tmap_im2col_bf16(&tmX, x, N, H, W, Cin, Cin, (int64_t)W * Cin, (int64_t)H * W * Cin, -pad, -pad,
                              pad - (S - 1) * dil, pad - (R - 1) * dil, stride, stride, cb, kKB);
   if (rc) return rc;
+  CUtensorMap tmDW;
+  rc = make_tmap_2d_f32(&tmDW, dw_packed, Cout, (int64_t)p.RS * p.Ipad, (int64_t)p.RS * p.Ipad, 32,
+                        bnw >= 32 ? 32 : 16);
+  if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (cb == 64 && bnw == 128) return launch_wgrad<64, 128>(tmDY, tmX, p, st);
-  if (cb == 64 && bnw == 64) return launch_wgrad<64, 64>(tmDY, tmX, p, st);
-  if (cb == 32) return launch_wgrad<32, 32>(tmDY, tmX, p, st);
-  if (cb == 16) return launch_wgrad<16, 16>(tmDY, tmX, p, st);
+  if (cb == 64 && bnw == 128) return launch_wgrad<64, 128>(tmDY, tmX, tmDW, p, st);
+  if (cb == 64 && bnw == 64) return launch_wgrad<64, 64>(tmDY, tmX, tmDW, p, st);
+  if (cb == 32) return launch_wgrad<32, 32>(tmDY, tmX, tmDW, p, st);
+  if (cb == 16) return launch_wgrad<16, 16>(tmDY, tmX, tmDW, p, st);
   return set_error(B200CV_ERR_ARG, "conv_wgrad: unsupported channel tile");
 }

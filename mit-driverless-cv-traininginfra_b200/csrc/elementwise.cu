@@ -200,6 +200,92 @@ __global__ void __launch_bounds__(kEwThreads, 4) bn_apply_kernel(const ApplyArgs
   }
 }
 
+// ---- fused: fold the partial statistics (bn_finalize) in the prologue of every block, then apply
+struct FusedFwdArgs {
+  const float* stats; int parts; float count;
+  const float* gamma; const float* beta; const float* conv_bias; float eps, momentum;
+  float* running_mean; float* running_var;
+  float* scale; float* shift; float* save_mean; float* save_rstd;
+};
+template <bool kPost>
+__global__ void __launch_bounds__(kEwThreads, 4) bn_stats_apply_kernel(const FusedFwdArgs f, const ApplyArgs a) {
+  extern __shared__ float s_ss[];  // [scale | shift]
+  const int C = a.C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int p = 0; p < f.parts; ++p) {
+      s1 += __ldg(f.stats + (long long)p * 2 * C + c);
+      s2 += __ldg(f.stats + (long long)p * 2 * C + C + c);
+    }
+    const float mean = s1 / f.count;
+    float var = s2 / f.count - mean * mean;
+    var = var > 0.f ? var : 0.f;
+    const float rstd = rsqrtf(var + f.eps);
+    const float g = f.gamma[c];
+    const float sc = g * rstd, sh = f.beta[c] - mean * g * rstd;
+    s_ss[c] = sc;
+    s_ss[C + c] = sh;
+    if (blockIdx.x == 0) {
+      f.scale[c] = sc;
+      f.shift[c] = sh;
+      f.save_mean[c] = mean;
+      f.save_rstd[c] = rstd;
+      if (f.running_mean) {
+        const float m_full = mean + (f.conv_bias ? f.conv_bias[c] : 0.f);
+        f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * m_full;
+        const float unbiased = f.count > 1.f ? var * f.count / (f.count - 1.f) : var;
+        f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * unbiased;
+      }
+    }
+  }
+  __syncthreads();
+  const int vpr = C >> 2;
+  const int rpp = kEwThreads / vpr;
+  const int cv = threadIdx.x % vpr;
+  const int r0 = threadIdx.x / vpr;
+  const int c0 = cv << 2;
+  if (r0 >= rpp) return;
+  float sc[4], sh[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sc[j] = s_ss[c0 + j];
+    sh[j] = s_ss[C + c0 + j];
+  }
+  const float neg = a.act == B200CV_ACT_LEAKY ? a.slope : (a.act == B200CV_ACT_RELU ? 0.f : 1.f);
+  const long long stride = (long long)gridDim.x * rpp;
+  for (long long r = (long long)blockIdx.x * rpp + r0; r < a.rows; r += stride * kEwUnroll) {
+    uint2 qy[kEwUnroll], qp[kEwUnroll];
+#pragma unroll
+    for (int u = 0; u < kEwUnroll; ++u) {
+      const long long rr = r + u * stride;
+      if (rr < a.rows) {
+        qy[u] = ldg_stream8(a.y + rr * a.y_ld + c0);
+        if (kPost) qp[u] = ldg_stream8(a.post + rr * a.post_ld + c0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kEwUnroll; ++u) {
+      const long long rr = r + u * stride;
+      if (rr < a.rows) {
+        float v[4], z[4];
+        unpack4(qy[u], v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          z[j] = v[j] * sc[j] + sh[j];
+          z[j] = z[j] > 0.f ? z[j] : z[j] * neg;
+        }
+        if (kPost) {
+          float w[4];
+          unpack4(qp[u], w);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) z[j] += w[j];
+        }
+        stg8(a.out + rr * a.out_ld + c0, pack4(z));
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ BN backward
 //   dz = da * act'(z);  pass 1: sums[c] += dz, sums[C+c] += dz * xhat  (xhat = (y-mean)*rstd)
 //   pass 2: dy = g * (dz - k1 - xhat*k2)   with coef = [g | k1 | k2]
@@ -377,6 +463,84 @@ __global__ void __launch_bounds__(kEwThreads, 4) bn_bwd_apply_kernel(const BwdAr
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float dz = da[j] * (zs[j] > 0.f ? 1.f : neg);
+          o[j] = fmaf(g[j], dz, fmaf(A[j], y[j], B[j]));
+        }
+        stg8(a.dy + rr * a.dy_ld + c0, pack4(o));
+      }
+    }
+  }
+}
+
+// ---- fused: fold the backward partial sums (bn_bwd_finalize) in the prologue of every block, then apply
+struct FusedBwdArgs {
+  const float* partials; int nparts; float count;
+  const float* gamma; float* coef; float* dgamma; float* dbeta;
+};
+__global__ void __launch_bounds__(kEwThreads, 4) bn_bwd_stats_apply_kernel(const FusedBwdArgs f, const BwdArgs a) {
+  extern __shared__ float s_gab[];  // [g | A | B]
+  const int C = a.C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int p = 0; p < f.nparts; ++p) {
+      s1 += __ldg(f.partials + (long long)p * 2 * C + c);
+      s2 += __ldg(f.partials + (long long)p * 2 * C + C + c);
+    }
+    const float rstd = a.rstd[c], mean = a.mean[c];
+    const float g = f.gamma[c] * rstd;
+    const float k1 = s1 / f.count, k2 = s2 / f.count;
+    const float A = -g * k2 * rstd;
+    s_gab[c] = g;
+    s_gab[C + c] = A;
+    s_gab[2 * C + c] = -g * k1 - A * mean;
+    if (blockIdx.x == 0) {
+      if (f.coef) {
+        f.coef[c] = g;
+        f.coef[C + c] = k1;
+        f.coef[2 * C + c] = k2;
+      }
+      if (f.dbeta) f.dbeta[c] = s1;
+      if (f.dgamma) f.dgamma[c] = s2;
+    }
+  }
+  __syncthreads();
+  const int vpr = C >> 2;
+  const int rpp = kEwThreads / vpr;
+  const int cv = threadIdx.x % vpr;
+  const int r0 = threadIdx.x / vpr;
+  const int c0 = cv << 2;
+  if (r0 >= rpp) return;
+  float sc[4], sh[4], g[4], A[4], B[4];
+  load4f(a.scale + c0, sc);
+  load4f(a.shift + c0, sh);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    g[j] = s_gab[c0 + j];
+    A[j] = s_gab[C + c0 + j];
+    B[j] = s_gab[2 * C + c0 + j];
+  }
+  const float neg = a.act == B200CV_ACT_LEAKY ? a.slope : (a.act == B200CV_ACT_RELU ? 0.f : 1.f);
+  const long long stride = (long long)gridDim.x * rpp;
+  for (long long r = (long long)blockIdx.x * rpp + r0; r < a.rows; r += stride * kEwUnroll) {
+    uint2 qda[kEwUnroll], qy[kEwUnroll];
+#pragma unroll
+    for (int u = 0; u < kEwUnroll; ++u) {
+      const long long rr = r + u * stride;
+      if (rr < a.rows) {
+        qda[u] = ldg_stream8(a.da + rr * a.da_ld + c0);
+        qy[u] = ldg_stream8(a.y + rr * a.y_ld + c0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kEwUnroll; ++u) {
+      const long long rr = r + u * stride;
+      if (rr < a.rows) {
+        float da[4], y[4], o[4];
+        unpack4(qda[u], da);
+        unpack4(qy[u], y);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float z = y[j] * sc[j] + sh[j];
+          const float dz = da[j] * (z > 0.f ? 1.f : neg);
           o[j] = fmaf(g[j], dz, fmaf(A[j], y[j], B[j]));
         }
         stg8(a.dy + rr * a.dy_ld + c0, pack4(o));
@@ -685,6 +849,46 @@ extern "C" int b200cv_bn_bwd_apply(const void* da, int64_t da_ld, const void* y,
     else bn_bwd_apply_kernel<false><<<grid, kEwThreads, 0, st>>>(a);
   }
   return check_launch("bn_bwd_apply");
+}
+
+extern "C" int b200cv_bn_stats_apply_act(const float* stats, int stats_parts, int64_t count, const float* gamma,
+                                         const float* beta, const float* conv_bias, float eps, float momentum,
+                                         float* running_mean, float* running_var, float* scale, float* shift,
+                                         float* save_mean, float* save_rstd, const void* y, int64_t y_ld,
+                                         const void* post, int64_t post_ld, void* out, int64_t out_ld, int64_t rows,
+                                         int C, int act, float slope, void* stream) {
+  B200CV_CHECK_ARG(stats && gamma && beta && scale && shift && save_mean && save_rstd && C > 0 && count > 0 &&
+                       stats_parts > 0,
+                   "bn_stats_apply_act: bad statistics args");
+  B200CV_CHECK_ARG(ok_vec(y, y_ld, C) && ok_vec(out, out_ld, C) && rows > 0, "bn_stats_apply_act: bad args");
+  B200CV_CHECK_ARG(!post || ok_vec(post, post_ld, C), "bn_stats_apply_act: bad residual");
+  B200CV_CHECK_ARG(C / 4 <= kEwThreads, "bn_stats_apply_act: C too large");
+  FusedFwdArgs f{stats, stats_parts, (float)count, gamma, beta, conv_bias, eps, momentum, running_mean, running_var,
+                 scale, shift, save_mean, save_rstd};
+  ApplyArgs a{(const bf16*)y, y_ld, nullptr, nullptr, nullptr, 0, nullptr, nullptr,
+              (const bf16*)post, post_ld, (bf16*)out, out_ld, rows, C, act, slope};
+  const int grid = stream_grid(rows, C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t smem = 2 * (size_t)C * sizeof(float);
+  if (post) bn_stats_apply_kernel<true><<<grid, kEwThreads, smem, st>>>(f, a);
+  else bn_stats_apply_kernel<false><<<grid, kEwThreads, smem, st>>>(f, a);
+  return check_launch("bn_stats_apply_act");
+}
+
+extern "C" int b200cv_bn_bwd_stats_apply(const float* partials, int nparts, int64_t count, const float* gamma,
+                                         float* coef, float* dgamma, float* dbeta, const void* da, int64_t da_ld,
+                                         const void* y, int64_t y_ld, const float* scale, const float* shift,
+                                         const float* mean, const float* rstd, void* dy, int64_t dy_ld,
+                                         int64_t rows, int C, int act, float slope, void* stream) {
+  BwdArgs a;
+  if (int rc = fill_bwd(a, da, da_ld, y, y_ld, nullptr, 0, scale, shift, mean, rstd, rows, C, act, slope)) return rc;
+  B200CV_CHECK_ARG(partials && nparts > 0 && gamma && count > 0 && ok_vec(dy, dy_ld, C),
+                   "bn_bwd_stats_apply: bad args");
+  a.dy = (bf16*)dy; a.dy_ld = dy_ld;
+  FusedBwdArgs f{partials, nparts, (float)count, gamma, coef, dgamma, dbeta};
+  const int grid = stream_grid(rows, C);
+  bn_bwd_stats_apply_kernel<<<grid, kEwThreads, 3 * (size_t)C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(f, a);
+  return check_launch("bn_bwd_stats_apply");
 }
 
 extern "C" int b200cv_act_bwd(const void* da, int64_t da_ld, const void* aout, int64_t aout_ld, void* dz,

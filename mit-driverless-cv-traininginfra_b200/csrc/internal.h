@@ -30,6 +30,10 @@ int make_tmap_im2col_bf16(CUtensorMap* out, const void* base, int N, int H, int 
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld,
                       int box_rows, int box_cols);
 
+// fp32 row-major 2-D matrix (the packed weight gradient): box = [box_rows][box_cols], swizzle = box row bytes.
+int make_tmap_2d_f32(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                     int box_cols);
+
 // ---- implicit-GEMM convolution core (conv_igemm.cu) ----------------------------
 constexpr int kMaxTaps = 64;
 
@@ -57,6 +61,7 @@ struct IgemmParams {
   float* stats;  // [stats_parts][2*Cout]: sum, sum of squares (added), or null
   int stats_parts;
   int* err;
+  int dbg;  // B200CV_DBG bits (bring-up timing experiments only): 1 no stores, 2 no stats, 4 no TMEM read
   short tap_w[kMaxTaps];
   short tap_h[kMaxTaps];
   int tap_k[kMaxTaps];
@@ -64,8 +69,10 @@ struct IgemmParams {
 
 // A: im2col tensor map over the activation; B: 2-D map over the packed weights.
 // kc = channels per k-block (16/32/64); block_n in {16,32,64,128,256}.
-int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, int kc,
-                 int block_n, cudaStream_t stream);
+// tmO: 2-D map over a row-major bf16 output [M][Cout] with box {epilogue chunk, 32 rows} (staged TMA-store
+// epilogue), or null for the generic (direct-store) epilogue.
+int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmO, const IgemmParams& p,
+                 int kc, int block_n, cudaStream_t stream);
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 // Channel padding rule for NHWC bf16 activations: 16, 32, or a multiple of 64.

@@ -96,4 +96,21 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t 
   return 0;
 }
 
+int make_tmap_2d_f32(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                     int box_cols) {
+  std::call_once(g_once, resolve);
+  if (!g_tiled) return set_error(B200CV_ERR_DRIVER, "cuTensorMapEncodeTiled not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_tiled(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box,
+                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(box_cols * 4),
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(B200CV_ERR_DRIVER, "cuTensorMapEncodeTiled(f32) failed (%d): rows%lld cols%lld ld%lld box(%d,%d)",
+                     (int)r, (long long)rows, (long long)cols, (long long)ld, box_rows, box_cols);
+  return 0;
+}
+
 }  // namespace b200cv
