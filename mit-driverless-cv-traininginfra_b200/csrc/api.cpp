@@ -14,6 +14,7 @@ thread_local char g_err[512] = "";
 std::mutex g_mu;
 int g_sm_count[64] = {0};
 int* g_err_word[64] = {nullptr};
+void* g_identity[64] = {nullptr};
 }  // namespace
 
 int set_error(int code, const char* fmt, ...) {
@@ -55,6 +56,23 @@ int* device_error_word() {
     g_err_word[dev] = p;
   }
   return g_err_word[dev];
+}
+
+const void* device_identity128() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_identity[dev]) {
+    // 32 KB of library-owned immutable state per device: the A operand of the "residual by tensor core" trick
+    static unsigned short host[128 * 128];
+    for (int i = 0; i < 128 * 128; ++i) host[i] = (i / 128 == i % 128) ? 0x3F80 : 0;  // bf16 1.0
+    void* p = nullptr;
+    if (cudaMalloc(&p, sizeof(host)) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(p, host, sizeof(host), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+    g_identity[dev] = p;
+  }
+  return g_identity[dev];
 }
 
 }  // namespace b200cv

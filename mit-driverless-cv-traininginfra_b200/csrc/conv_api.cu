@@ -61,6 +61,27 @@ int run_igemm(const Geometry& g, const void* act, const void* wpk, int64_t w_row
   if (rc) return rc;
   rc = make_tmap_2d_bf16(&tmB, wpk, w_rows, w_cols, w_cols, bn, kc);
   if (rc) return rc;
+  // Residual added by the tensor core (D += I * R as extra k-iterations) when the epilogue is a pure "+ residual":
+  // no scale / activation, the residual a row-major bf16 matrix [M][ld] walked exactly like the output rows.
+  CUtensorMap tmI, tmR;
+  const CUtensorMap* pI = nullptr;
+  const CUtensorMap* pR = nullptr;
+  static const bool no_res_mma = getenv("B200CV_NO_RES_MMA") != nullptr;
+  if (p.res && !no_res_mma && bn % 64 == 0 && !p.scale && p.act == 0 && p.res_vec_ok && p.r_sc == 1 &&
+      p.r_sw % 8 == 0 && p.r_sh == (long long)p.OW * p.r_sw && p.r_sn == (long long)p.OHW * p.r_sw) {
+    const void* ident = device_identity128();
+    if (!ident) return set_error(B200CV_ERR_DEVICE, "igemm: identity matrix allocation failed");
+    rc = make_tmap_2d_bf16(&tmI, ident, 128, 128, 128, 128, kc);
+    if (rc) return rc;
+    // residual columns past the tensor are zero-filled by TMA (the residual has >= Cout channels)
+    const long long res_cols = std::min<long long>(p.r_sw, (p.Cout + 7) / 8 * 8);
+    rc = make_tmap_2d_bf16(&tmR, p.res, p.M_total, res_cols, p.r_sw, kc, 64);
+    if (rc) return rc;
+    pI = &tmI;
+    pR = &tmR;
+    p.res_iters = 128 / kc;
+    p.res = nullptr;  // nothing left for the epilogue to add
+  }
   // Staged TMA-store epilogue when the output is a plain row-major bf16 matrix [M][ld] (forward convs and
   // stride-1 data gradients); strided (parity scatter, NCHW), fp32 or unaligned outputs take the generic one.
   const long long ld = p.o_sw;
@@ -72,9 +93,9 @@ int run_igemm(const Geometry& g, const void* act, const void* wpk, int64_t w_row
     CUtensorMap tmO;
     rc = make_tmap_2d_bf16(&tmO, p.out, p.M_total, p.Cout, ld, 32, bn >= 32 ? 32 : 16);
     if (rc) return rc;
-    return launch_igemm(tmA, tmB, &tmO, p, kc, bn, stream);
+    return launch_igemm(tmA, tmB, &tmO, pI, pR, p, kc, bn, stream);
   }
-  return launch_igemm(tmA, tmB, nullptr, p, kc, bn, stream);
+  return launch_igemm(tmA, tmB, nullptr, pI, pR, p, kc, bn, stream);
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

@@ -91,7 +91,8 @@ __device__ __forceinline__ void keep_half_step(float (&s)[8], float (&t)[8], int
 template <int KC, int BN, bool kTma>
 __global__ void __launch_bounds__(kThreads, Cfg<KC, BN, kTma>::kCtasPerSm)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ IgemmParams p) {
+             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmI,
+             const __grid_constant__ CUtensorMap tmR, const __grid_constant__ IgemmParams p) {
   using C = Cfg<KC, BN, kTma>;
   extern __shared__ uint8_t smem_raw[];
   // align to 1024 B (128B-swizzle atom) by pointer arithmetic so the shared state space stays provable
@@ -117,6 +118,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     if (kTma) ptx::prefetch_tmap(&tmO);
+    if (p.res_iters) {
+      ptx::prefetch_tmap(&tmI);
+      ptx::prefetch_tmap(&tmR);
+    }
     for (int i = 0; i < C::kStages; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
       ptx::mbar_init(&empty_bar[i], 1);
@@ -169,6 +174,24 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
           }
         }
+        // residual by tensor core: D += I[:, j*KC .. +KC) * R[m0 + j*KC .. +KC, n-tile]; the residual rows land
+        // as an MN-major B operand, 64 channels (128 bytes) per slab
+        if constexpr (BN % 64 == 0) {
+          for (int j = 0; j < p.res_iters; ++j) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err, 1);
+            uint8_t* sa = stage_base + stage * C::kStageBytes;
+            uint8_t* sb = sa + C::kABytes;
+            ptx::mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+            ptx::tma_load_2d(sa, &tmI, &full_bar[stage], j * KC, 0);
+#pragma unroll
+            for (int sl = 0; sl < BN / 64; ++sl)
+              ptx::tma_load_2d(sb + sl * KC * 128, &tmR, &full_bar[stage], nt * BN + sl * 64, m0 + j * KC);
+            if (++stage == C::kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -199,6 +222,27 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1;
+          }
+        }
+        if constexpr (BN % 64 == 0) {
+          constexpr uint32_t idesc_res = ptx::make_idesc_bf16(kBlockM, BN, 0, 1);  // B = residual rows, MN-major
+          for (int j = 0; j < p.res_iters; ++j) {
+            ptx::mbar_wait(&full_bar[stage], phase, p.err, 3);
+            ptx::tc_fence_after();
+            const uint32_t sa = ptx::smem_u32(stage_base + stage * C::kStageBytes);
+            const uint32_t sb = sa + C::kABytes;
+            const uint64_t adesc = ptx::make_smem_desc(sa, 16, C::kSBO, C::kLayout);
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k) {
+              // MN-major B: LBO = distance between 64-channel slabs, SBO = 8 rows of 128 bytes
+              const uint64_t bdesc = ptx::make_smem_desc(sb + k * 16 * 128, KC * 128, 8 * 128, 2);
+              ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc, idesc_res, 1u);
+            }
+            ptx::umma_commit(&empty_bar[stage]);
+            if (++stage == C::kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
         ptx::umma_commit(&tfull_bar[acc]);
@@ -627,8 +671,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 }
 
 template <int KC, int BN, bool kTma>
-int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const IgemmParams& p,
-               cudaStream_t stream) {
+int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmI,
+               const CUtensorMap& tmR, const IgemmParams& p, cudaStream_t stream) {
   using C = Cfg<KC, BN, kTma>;
   static_assert(C::kStages >= 2, "pipeline too shallow");
   static bool configured = false;  // benign race: attribute set is idempotent
@@ -643,18 +687,22 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
   int grid = sm_count() * C::kCtasPerSm;
   if (grid > tiles) grid = tiles;
   if (grid < 1) return 0;
-  kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, tmO, p);
+  kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, tmO, tmI, tmR, p);
   return check_launch("igemm_kernel");
 }
 
 }  // namespace
 
-int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmO, const IgemmParams& p,
-                 int kc, int block_n, cudaStream_t stream) {
+int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmO, const CUtensorMap* tmI,
+                 const CUtensorMap* tmR, const IgemmParams& p, int kc, int block_n, cudaStream_t stream) {
+  if (p.res_iters && (!tmI || !tmR || block_n % 64 != 0))
+    return set_error(B200CV_ERR_ARG, "igemm: tensor-core residual needs identity/residual maps and block_n %% 64 == 0");
+  const CUtensorMap& mI = tmI ? *tmI : tmA;  // unused copies when the feature is off
+  const CUtensorMap& mR = tmR ? *tmR : tmA;
 #define B200CV_IGEMM_CASE(KC_, BN_)                                                        \
   if (kc == KC_ && block_n == BN_)                                                         \
-    return tmO ? launch_one<KC_, BN_, true>(tmA, tmB, *tmO, p, stream)                     \
-               : launch_one<KC_, BN_, false>(tmA, tmB, tmA, p, stream);
+    return tmO ? launch_one<KC_, BN_, true>(tmA, tmB, *tmO, mI, mR, p, stream)             \
+               : launch_one<KC_, BN_, false>(tmA, tmB, tmA, mI, mR, p, stream);
   B200CV_IGEMM_CASE(64, 256)
   B200CV_IGEMM_CASE(64, 128)
   B200CV_IGEMM_CASE(64, 64)

@@ -61,6 +61,7 @@ struct IgemmParams {
   float* stats;  // [stats_parts][2*Cout]: sum, sum of squares (added), or null
   int stats_parts;
   int* err;
+  int res_iters;  // residual added by the tensor core: extra k-iterations D += I[:, k-slice] * R[k-slice rows, :] (0 = off)
   int dbg;  // B200CV_DBG bits (bring-up timing experiments only): 1 no stores, 2 no stats, 4 no TMEM read
   short tap_w[kMaxTaps];
   short tap_h[kMaxTaps];
@@ -71,8 +72,10 @@ struct IgemmParams {
 // kc = channels per k-block (16/32/64); block_n in {16,32,64,128,256}.
 // tmO: 2-D map over a row-major bf16 output [M][Cout] with box {epilogue chunk, 32 rows} (staged TMA-store
 // epilogue), or null for the generic (direct-store) epilogue.
-int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmO, const IgemmParams& p,
-                 int kc, int block_n, cudaStream_t stream);
+// tmI / tmR (both or neither): 128x128 bf16 identity and the row-major residual [M][ld] for p.res_iters > 0.
+int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmO, const CUtensorMap* tmI,
+                 const CUtensorMap* tmR, const IgemmParams& p, int kc, int block_n, cudaStream_t stream);
+const void* device_identity128();    // bf16 [128][128] identity matrix (library-owned, per device)
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 // Channel padding rule for NHWC bf16 activations: 16, 32, or a multiple of 64.
