@@ -106,6 +106,22 @@ typedef struct b200cv_conv_args {
    * contended global atomics); NULL = off.  Cout <= 1024 when stats are requested. */
   float* stats;
   int32_t stats_parts;
+  /* b200cv_conv_dgrad only -- fused first pass of the BatchNorm backward of the layer that PRODUCED the
+   * activation whose gradient this call writes (b200cv_bn_bwd_reduce folded into the epilogue): with
+   * G = the stored output (bf16), z = bn_y*bn_scale+bn_shift, dz = G*act'(z) the epilogue ADDS
+   * [sum dz | sum dz*(bn_y-bn_mean)*bn_rstd] per channel into bn_sums[bn_parts][2*Cout] (zero it first).
+   * bn_y: NHWC bf16 rows with pitch bn_y_ld laid out like the output.  Needs the row-major bf16 output form
+   * (stride-1 gradients); otherwise the call fails with B200CV_ERR_ARG.  bn_sums == NULL = off. */
+  float* bn_sums;
+  int32_t bn_parts;
+  const void* bn_y;
+  int64_t bn_y_ld;
+  const float* bn_scale;
+  const float* bn_shift;
+  const float* bn_mean;
+  const float* bn_rstd;
+  int32_t bn_act;
+  float bn_slope;
 } b200cv_conv_args;
 
 /* y = conv2d(x, w).  nn.Conv2d forward: CVC-YOLOv3/models.py:59-65,320-321;

@@ -28,6 +28,12 @@ BN_MOMENTUM = 0.1
 GRAPH_WARMUP_CALLS = 2  # eager steps with a given input shape before the step is captured as CUDA graphs
 
 
+def _fuse_bn_reduce() -> bool:
+    import os
+
+    return os.environ.get("B200CV_FUSE_BN_REDUCE", "1") != "0"
+
+
 def _graphs_enabled() -> bool:
     import os
 
@@ -109,6 +115,10 @@ class DarknetEngine:
             # from the conv epilogue, backward: sum dz / sum dz*xhat) live in two flat arenas so that one memset
             # per pass clears all of them
             bn_layers = [L for L in self.layers if L.type == "convolutional" and L.bn is not None]
+            for L in bn_layers:
+                if ops.pad_channels(L.cout) != L.cout:
+                    raise ValueError(f"BatchNorm over {L.cout} channels: the B200 layout needs 16, 32 or a multiple "
+                                     "of 64 channels in every normalised layer")
             per = [ops.STAT_PARTS * 2 * L.cout for L in bn_layers]
             self._fstat_arena = torch.zeros(sum(per), dtype=torch.float32, device=dev)
             self._bstat_arena = torch.zeros(sum(per), dtype=torch.float32, device=dev)
@@ -127,6 +137,18 @@ class DarknetEngine:
             for L in self.layers:
                 if L.type == "convolutional":
                     L.wpk, L.wpk_t = self._packs.wpk[id(L.conv)], self._packs.wpk_t[id(L.conv)]
+
+    def _bn_owner(self, j: int):
+        """Index of the conv+BN layer whose activation output IS tensor outs[j] (so that the gradient written into
+        grads[j] is that layer's dL/da), or None."""
+        if j < 0:
+            return None
+        Lj = self.layers[j]
+        if Lj.type == "convolutional" and Lj.bn is not None and Lj.post_from is None:
+            return j
+        if Lj.type == "shortcut" and Lj.fused_alias:
+            return j - 1
+        return None
 
     def _flat_convs(self):
         L0 = self.layers[0]
@@ -258,6 +280,8 @@ class DarknetEngine:
         views, gview = arena.views, arena.view_of
         consts = (model.xy_loss, model.wh_loss, model.object_loss, model.no_object_loss)
         grads: List[Optional[torch.Tensor]] = [None] * len(self.layers)
+        reduced = set()  # BN layers whose backward sums were already produced by a dgrad epilogue
+        fuse = _fuse_bn_reduce()
 
         def add_grad(j, t):
             if j < 0:
@@ -288,8 +312,9 @@ class DarknetEngine:
                 if L.bn is not None:
                     xin, y = saved[i]
                     count = y.numel() // y.shape[-1]
-                    parts = ops.bn_bwd_reduce(G, y, None, L.scale, L.shift, L.mean, L.rstd, L.act, L.slope,
-                                              partials=L.bstats)
+                    parts = L.bstats
+                    if i not in reduced:
+                        ops.bn_bwd_reduce(G, y, None, L.scale, L.shift, L.mean, L.rstd, L.act, L.slope, partials=parts)
                     dy = ops.bn_bwd_stats_apply(parts, count, L.bn.weight, L.coef, gview[id(L.bn.weight)],
                                                 gview[id(L.bn.bias)], G, y, L.scale, L.shift, L.mean, L.rstd, L.act,
                                                 L.slope)
@@ -307,8 +332,18 @@ class DarknetEngine:
                     ops.conv_wgrad(xin, dy, L.cout, L.k, L.stride, L.pad, out=packs.dwp[id(L.conv)])
                 if i > 0:
                     prev = grads[i - 1]
+                    # this dgrad completes grads[i-1]; when that is the activation gradient of a conv+BN layer the
+                    # first pass of its BN backward (sum dz, sum dz*xhat) is folded into the epilogue
+                    # (3x3 gradients only: the 1x1 ones are HBM-bound and the extra y stream costs them more than the
+                    # separate reduce pass -- measured 91 us fused vs 36 + 45 us for 256->128 @52x52)
+                    owner = self._bn_owner(i - 1) if (fuse and L.stride == 1 and L.k > 1) else None
+                    bn_red = None
+                    if owner is not None:
+                        T = self.layers[owner]
+                        bn_red = (saved[owner][1], T.scale, T.shift, T.mean, T.rstd, T.act, T.slope, T.bstats)
+                        reduced.add(owner)
                     dx = ops.conv_dgrad(dy, L.wpk_t, L.cin, L.k, L.stride, L.pad, 1, (xin.shape[1], xin.shape[2]),
-                                        out=prev, residual=prev)
+                                        out=prev, residual=prev, bn_reduce=bn_red)
                     grads[i - 1] = dx
             elif L.type == "maxpool":
                 (xin,) = saved[i]

@@ -36,6 +36,10 @@ class ConvArgs(ctypes.Structure):
         ("r_sn", ctypes.c_int64), ("r_sh", ctypes.c_int64), ("r_sw", ctypes.c_int64), ("r_sc", ctypes.c_int64),
         ("act", ctypes.c_int32), ("slope", ctypes.c_float), ("res_after_act", ctypes.c_int32),
         ("stats", ctypes.c_void_p), ("stats_parts", ctypes.c_int32),
+        ("bn_sums", ctypes.c_void_p), ("bn_parts", ctypes.c_int32), ("bn_y", ctypes.c_void_p),
+        ("bn_y_ld", ctypes.c_int64), ("bn_scale", ctypes.c_void_p), ("bn_shift", ctypes.c_void_p),
+        ("bn_mean", ctypes.c_void_p), ("bn_rstd", ctypes.c_void_p), ("bn_act", ctypes.c_int32),
+        ("bn_slope", ctypes.c_float),
     ]
 
 

@@ -140,8 +140,10 @@ def conv_fwd(x, wpk, cout, k, stride, pad, dil=1, out=None, out_dtype=torch.bflo
     return out
 
 
-def conv_dgrad(dy, wpk_t, cin_fwd, k, stride, pad, dil, out_hw, out=None, residual=None) -> torch.Tensor:
-    """dy NHWC bf16 [N,OH,OW,pad(Cout)] -> dx NHWC bf16 [N,H,W,pad(Cin_fwd)] (+ residual)."""
+def conv_dgrad(dy, wpk_t, cin_fwd, k, stride, pad, dil, out_hw, out=None, residual=None, bn_reduce=None) -> torch.Tensor:
+    """dy NHWC bf16 [N,OH,OW,pad(Cout)] -> dx NHWC bf16 [N,H,W,pad(Cin_fwd)] (+ residual).
+    bn_reduce = (y, scale, shift, mean, rstd, act, slope, sums): also accumulate the BN-backward sums of the layer
+    whose activation gradient dx is (stride-1 only), see b200cv_conv_args.bn_sums."""
     n = dy.shape[0]
     h, w = out_hw
     if out is None:
@@ -155,6 +157,12 @@ def conv_dgrad(dy, wpk_t, cin_fwd, k, stride, pad, dil, out_hw, out=None, residu
         rs = (residual.stride(0), residual.stride(1), residual.stride(2), residual.stride(3))
     a = _conv_args(dy, wpk_t, out, cin_fwd, k, stride, pad, dil, ys, DT_BF16, None, None, residual, rs, ACT_NONE, 0.0,
                    False, None)
+    if bn_reduce is not None:
+        by, bsc, bsh, bmean, brstd, bact, bslope, bsums = bn_reduce
+        a.bn_sums, a.bn_parts = ptr(bsums), bsums.shape[0]
+        a.bn_y, a.bn_y_ld = ptr(by), by.stride(-2)
+        a.bn_scale, a.bn_shift, a.bn_mean, a.bn_rstd = ptr(bsc), ptr(bsh), ptr(bmean), ptr(brstd)
+        a.bn_act, a.bn_slope = bact, float(bslope)
     lib().call("b200cv_conv_dgrad", ctypes.byref(a), h, w, stream_ptr(),
                tag=(cin_fwd, dy.shape[-1], k, stride, n, dy.shape[1], dy.shape[2]))
     return out

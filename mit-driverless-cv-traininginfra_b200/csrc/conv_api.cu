@@ -36,7 +36,7 @@ struct Geometry {
 };
 
 int run_igemm(const Geometry& g, const void* act, const void* wpk, int64_t w_rows, int64_t w_cols,
-              IgemmParams& p, cudaStream_t stream) {
+              IgemmParams& p, cudaStream_t stream, const void* bn_y = nullptr, int64_t bn_y_ld = 0) {
   const int kc = kc_for(g.C);
   p.cblocks = g.C / kc;
   p.OHW = g.OHt * g.OWt;
@@ -90,12 +90,18 @@ int run_igemm(const Geometry& g, const void* act, const void* wpk, int64_t w_row
                        p.o_sh == (long long)p.OW * ld && p.o_sn == (long long)p.OHW * ld && p.Cout % 8 == 0 &&
                        (!p.res || p.res_vec_ok);
   if (tma_out) {
-    CUtensorMap tmO;
+    CUtensorMap tmO, tmY;
     rc = make_tmap_2d_bf16(&tmO, p.out, p.M_total, p.Cout, ld, 32, bn >= 32 ? 32 : 16);
     if (rc) return rc;
-    return launch_igemm(tmA, tmB, &tmO, pI, pR, p, kc, bn, stream);
+    if (p.bn_sums) {
+      rc = make_tmap_2d_bf16(&tmY, bn_y, p.M_total, p.Cout, bn_y_ld, 32, bn >= 32 ? 32 : 16);
+      if (rc) return rc;
+    }
+    return launch_igemm(tmA, tmB, &tmO, pI, pR, p.bn_sums ? &tmY : nullptr, p, kc, bn, stream);
   }
-  return launch_igemm(tmA, tmB, nullptr, pI, pR, p, kc, bn, stream);
+  if (p.bn_sums)
+    return set_error(B200CV_ERR_ARG, "conv_dgrad: the fused BN-backward reduction needs a row-major bf16 output");
+  return launch_igemm(tmA, tmB, nullptr, pI, pR, nullptr, p, kc, bn, stream);
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -220,7 +226,20 @@ extern "C" int b200cv_conv_dgrad(const b200cv_conv_args* a, int out_h, int out_w
           p.tap_k[t] = (rr[i] * a->S + ss[j]) * a->Cin;
         }
       fill_epilogue(p, a, pa * a->y_sh + pb * a->y_sw, pa * a->r_sh + pb * a->r_sw, s, s);
-      int rc = run_igemm(g, a->x, a->w, a->Cout, (int64_t)a->R * a->S * a->Cin, p, st);
+      if (a->bn_sums) {
+        B200CV_CHECK_ARG(s == 1, "conv_dgrad: the fused BN-backward reduction needs stride 1");
+        B200CV_CHECK_ARG(a->bn_y && a->bn_scale && a->bn_shift && a->bn_mean && a->bn_rstd && a->bn_parts > 0 &&
+                             a->bn_y_ld % 8 == 0 && aligned16(a->bn_y),
+                         "conv_dgrad: incomplete bn_* arguments");
+        p.bn_sums = a->bn_sums;
+        p.bn_parts = a->bn_parts;
+        p.bn_scale = a->bn_scale;
+        p.bn_shift = a->bn_shift;
+        p.bn_mean = a->bn_mean;
+        p.bn_rstd = a->bn_rstd;
+        p.bn_neg = a->bn_act == B200CV_ACT_LEAKY ? a->bn_slope : (a->bn_act == B200CV_ACT_RELU ? 0.f : 1.f);
+      }
+      int rc = run_igemm(g, a->x, a->w, a->Cout, (int64_t)a->R * a->S * a->Cin, p, st, a->bn_y, a->bn_y_ld);
       if (rc) return rc;
     }
   }

@@ -35,12 +35,17 @@ constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);  // 320
 constexpr int kSmemMax = 227 * 1024;                    // dynamic shared memory of one CTA alone on an SM
 constexpr int kSmemMax2 = 113 * 1024;                   // ... of each of two co-resident CTAs
 constexpr int kScratchLd = 17;                          // [32 rows][16 columns + 1] fp32 transpose tile
+constexpr int kMaxStages = 8;
+constexpr int kMaxYSlots = 4;
 
 // kTma: the output is a plain row-major bf16 matrix [M][ld] -> the epilogue stages 32x32 (or 32x16) bf16 tiles in
 // swizzled shared memory and writes them with TMA bulk stores; BN statistics are read back from the staged
 // tile.  Otherwise ("generic": fp32 / strided / ragged outputs) rows are stored directly from registers.
-template <int KC, int BN, bool kTma>
+// kMode 2 = kTma plus the fused BN-backward reduction (a 2-deep ring of TMA-loaded y tiles per epilogue warp).
+template <int KC, int BN, int kMode>
 struct Cfg {
+  static constexpr bool kTma = kMode >= 1;
+  static constexpr bool kBnRed = kMode == 2;
   static constexpr int kABytes = kBlockM * KC * 2;
   static constexpr int kBBytes = BN * KC * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -55,15 +60,21 @@ struct Cfg {
   static constexpr int kNumChunks = BN / kChunk;         // 1..8
   static constexpr int kChunksPerWarp = (kNumChunks + 1) / 2;
   static constexpr int kAccPerWarp = kChunksPerWarp * kChunk;  // columns a warp keeps statistics for
-  static constexpr int kBarBytes = (2 * 8 + 4) * 8 + 16;       // barriers (8 B each, up to 8 stages) + tmem ptr
+  // barriers (8 B each): full/empty (8 stages max), tfull/tempty, kMaxYSlots per epilogue warp for the y ring; + tmem ptr
+  static constexpr int kBarBytes = (2 * kMaxStages + 4 + kMaxYSlots * kEpiWarps) * 8 + 16;
   // generic: per-warp [sum | sumsq] rows + fp32 transpose scratch; TMA: one 1 KB-aligned staging tile per warp
   static constexpr int kStatBytes = kTma ? 0 : kEpiWarps * 2 * kAccPerWarp * 4;
   static constexpr int kScratchBytes = kTma ? kEpiWarps * 2048 : kEpiWarps * 32 * kScratchLd * 4;
-  static constexpr int kExtraBytes = 1024 /*align slack*/ + 2048 /*barrier block + align*/ + kStatBytes + kScratchBytes;
-  static constexpr int kBudget = (kCtasPerSm == 2 ? kSmemMax2 : kSmemMax) - kExtraBytes;
-  static constexpr int kStagesRaw = kBudget / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kSmemBytes = kExtraBytes + kStages * kStageBytes;
+  // shared memory of a launch with `y_slots` y tiles per epilogue warp (0 unless kBnRed); the pipeline gets
+  // whatever is left (stages are a RUN-TIME parameter: short-K layers trade stages for a deeper y ring)
+  static constexpr int extra_bytes(int y_slots) {
+    return 1024 /*align slack*/ + 2048 /*barrier block + align*/ + kStatBytes + kScratchBytes +
+           kEpiWarps * y_slots * 2048;
+  }
+  static constexpr int stages_for(int y_slots) {
+    const int n = ((kCtasPerSm == 2 ? kSmemMax2 : kSmemMax) - extra_bytes(y_slots)) / kStageBytes;
+    return n > kMaxStages ? kMaxStages : n;
+  }
   static_assert(kBarBytes <= 1024, "barrier block");
   static_assert(kStageBytes % 256 == 0, "stage alignment");
 };
@@ -88,21 +99,26 @@ __device__ __forceinline__ void keep_half_step(float (&s)[8], float (&t)[8], int
   }
 }
 
-template <int KC, int BN, bool kTma>
-__global__ void __launch_bounds__(kThreads, Cfg<KC, BN, kTma>::kCtasPerSm)
+template <int KC, int BN, int kMode>
+__global__ void __launch_bounds__(kThreads, Cfg<KC, BN, kMode>::kCtasPerSm)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmI,
-             const __grid_constant__ CUtensorMap tmR, const __grid_constant__ IgemmParams p) {
-  using C = Cfg<KC, BN, kTma>;
+             const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmY,
+             const __grid_constant__ IgemmParams p) {
+  using C = Cfg<KC, BN, kMode>;
+  constexpr bool kTma = C::kTma;
+  constexpr bool kBnRed = C::kBnRed;
   extern __shared__ uint8_t smem_raw[];
   // align to 1024 B (128B-swizzle atom) by pointer arithmetic so the shared state space stays provable
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage_base = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
-  uint64_t* empty_bar = full_bar + C::kStages;
-  uint64_t* tfull_bar = empty_bar + C::kStages;
+  const int nstages = p.stages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + nstages * C::kStageBytes);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* y_bar = tempty_bar + 2;  // [kEpiWarps][kMaxYSlots]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_bar + kMaxYSlots * kEpiWarps);
   // stage ring (multiple of 1 KB) | 1 KB barrier block | staging tiles (TMA) or stats rows + scratch (generic)
   uint8_t* s_extra = reinterpret_cast<uint8_t*>(full_bar) + C::kBarBytes;
   s_extra += (1024u - (ptx::smem_u32(s_extra) & 1023u)) & 1023u;  // staging tiles: swizzle-atom aligned
@@ -122,13 +138,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       ptx::prefetch_tmap(&tmI);
       ptx::prefetch_tmap(&tmR);
     }
-    for (int i = 0; i < C::kStages; ++i) {
+    for (int i = 0; i < nstages; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
       ptx::mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
       ptx::mbar_init(&tempty_bar[i], kEpiWarps);  // one arrive per epilogue warp
+    }
+    if (kBnRed) {
+      ptx::prefetch_tmap(&tmY);
+      for (int i = 0; i < kMaxYSlots * kEpiWarps; ++i) ptx::mbar_init(&y_bar[i], 1);
     }
     ptx::fence_barrier_init();
   }
@@ -168,7 +188,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             ptx::mbar_expect_tx(&full_bar[stage], C::kStageBytes);
             ptx::tma_load_im2col_4d(sa, &tmA, &full_bar[stage], cb * KC, cw, ch, n_img, ow, oh);
             ptx::tma_load_2d(sb, &tmB, &full_bar[stage], kb + cb * KC, nt * BN);
-            if (++stage == C::kStages) {
+            if (++stage == nstages) {
               stage = 0;
               phase ^= 1;
             }
@@ -186,7 +206,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int sl = 0; sl < BN / 64; ++sl)
               ptx::tma_load_2d(sb + sl * KC * 128, &tmR, &full_bar[stage], nt * BN + sl * 64, m0 + j * KC);
-            if (++stage == C::kStages) {
+            if (++stage == nstages) {
               stage = 0;
               phase ^= 1;
             }
@@ -219,7 +239,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
           }
           ptx::umma_commit(&empty_bar[stage]);
-          if (++stage == C::kStages) {
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
@@ -239,7 +259,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc, idesc_res, 1u);
             }
             ptx::umma_commit(&empty_bar[stage]);
-            if (++stage == C::kStages) {
+            if (++stage == nstages) {
               stage = 0;
               phase ^= 1;
             }
@@ -275,8 +295,46 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       float acc_s[C::kChunksPerWarp], acc_t[C::kChunksPerWarp];
 #pragma unroll
       for (int i = 0; i < C::kChunksPerWarp; ++i) acc_s[i] = acc_t[i] = 0.f;
+      // statistics target: forward [sum | sumsq] (p.stats) or, fused BN backward, [sum dz | sum dz*xhat] (p.bn_sums)
+      float* const stat_base = kBnRed ? p.bn_sums : p.stats;
+      const int stat_parts = kBnRed ? p.bn_parts : p.stats_parts;
       float* stats_row =
-          p.stats ? p.stats + static_cast<long long>(blockIdx.x % p.stats_parts) * 2 * p.Cout : nullptr;
+          stat_base ? stat_base + static_cast<long long>(blockIdx.x % stat_parts) * 2 * p.Cout : nullptr;
+      // ---- fused BN backward: ring of two TMA-loaded y tiles, one chunk ahead of the one being processed
+      const int yslots = p.y_slots, ylog = p.y_slots_log2;  // power of two
+      uint8_t* const ybuf = s_extra + kEpiWarps * 2048 + ew * yslots * 2048;
+      uint64_t* const ybar = y_bar + kMaxYSlots * ew;
+      const uint32_t y_off = static_cast<uint32_t>(rd0 - stg);  // same (row, piece) as in the staging tile
+      auto chunk_valid = [&](int tile, int ci) {
+        const int c0 = (half + 2 * ci) * C::kChunk;
+        return ci < C::kChunksPerWarp && c0 < BN && (tile % p.num_n_tiles) * BN + c0 < p.Cout;
+      };
+      auto next_chunk = [&](int& tile, int& ci) {  // in processing order; tile >= num_tiles = none left
+        do {
+          if (++ci >= C::kChunksPerWarp) {
+            ci = 0;
+            tile += gridDim.x;
+          }
+        } while (tile < num_tiles && !chunk_valid(tile, ci));
+      };
+      auto issue_y = [&](int tile, int ci, int slot) {
+        if (lane == 0) {
+          const int mt = tile / p.num_n_tiles;
+          const int nt = tile - mt * p.num_n_tiles;
+          ptx::mbar_expect_tx(&ybar[slot], 32 * RB);
+          ptx::tma_load_2d(ybuf + slot * 2048, &tmY, &ybar[slot], nt * BN + (half + 2 * ci) * C::kChunk,
+                           mt * kBlockM + quarter * 32);
+        }
+      };
+      uint32_t ycount = 0;  // chunks processed by this warp: slot = ycount % yslots, phase = (ycount / yslots) & 1
+      int pf_tile = blockIdx.x, pf_ci = 0;  // next chunk whose y tile has not been requested yet
+      if (kBnRed) {
+        if (pf_tile < num_tiles && !chunk_valid(pf_tile, pf_ci)) next_chunk(pf_tile, pf_ci);
+        for (int d = 0; d < yslots && pf_tile < num_tiles; ++d) {
+          issue_y(pf_tile, pf_ci, d);
+          next_chunk(pf_tile, pf_ci);
+        }
+      }
       int stat_nt = -1;
       bool store_pending = false;
       int acc = 0;
@@ -284,14 +342,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mt = tile / p.num_n_tiles;
         const int nt = tile - mt * p.num_n_tiles;
-        if (p.stats && nt != stat_nt) {
+        if (stat_base && nt != stat_nt) {
           if (stat_nt >= 0) {
 #pragma unroll
             for (int ci = 0; ci < C::kChunksPerWarp; ++ci) {
               const int n = stat_nt * BN + (half + 2 * ci) * C::kChunk + my_col;
               if (col_owner && (half + 2 * ci) < C::kNumChunks && n < p.Cout) {
                 atomicAdd(stats_row + n, acc_s[ci]);
-                atomicAdd(stats_row + p.Cout + n, acc_t[ci]);
+                atomicAdd(stats_row + p.Cout + n, kBnRed ? acc_t[ci] * __ldg(p.bn_rstd + n) : acc_t[ci]);
               }
               acc_s[ci] = acc_t[ci] = 0.f;
             }
@@ -405,7 +463,65 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             ptx::tma_store_commit();
           }
           store_pending = true;
-          if (p.stats && !(p.dbg & 2)) {
+          if constexpr (kBnRed) {
+            // fused BN-backward reduction: dz = G * act'(y*scale+shift) from the STORED gradient tile and the
+            // TMA-loaded y tile; per column sum dz and sum dz*(y-mean) (rstd is applied at the flush)
+            const int yslot = ycount & (yslots - 1);
+            ptx::mbar_wait(&ybar[yslot], (ycount >> ylog) & 1, p.err, 5);
+            const uint8_t* yrd = ybuf + yslot * 2048 + y_off;
+            const int ncol = n_base + 8 * rq;
+            float sc[8], sh[8], mu[8];
+            if (ncol + 8 <= p.Cout) {
+#pragma unroll
+              for (int k = 0; k < 8; k += 4) {
+                const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.bn_scale + ncol + k));
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bn_shift + ncol + k));
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.bn_mean + ncol + k));
+                sc[k] = a4.x; sc[k + 1] = a4.y; sc[k + 2] = a4.z; sc[k + 3] = a4.w;
+                sh[k] = b4.x; sh[k + 1] = b4.y; sh[k + 2] = b4.z; sh[k + 3] = b4.w;
+                mu[k] = c4.x; mu[k + 1] = c4.y; mu[k + 2] = c4.z; mu[k + 3] = c4.w;
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) sc[k] = sh[k] = mu[k] = 0.f;
+            }
+            float s[8], t[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s[k] = t[k] = 0.f;
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+              const uint4 ug = *reinterpret_cast<const uint4*>(rd0 + i * (32 / NR) * RB);
+              const uint4 uy = *reinterpret_cast<const uint4*>(yrd + i * (32 / NR) * RB);
+              const __nv_bfloat162* hg = reinterpret_cast<const __nv_bfloat162*>(&ug);
+              const __nv_bfloat162* hy = reinterpret_cast<const __nv_bfloat162*>(&uy);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 g2 = __bfloat1622float2(hg[e]);
+                const float2 y2 = __bfloat1622float2(hy[e]);
+                const float dz0 = g2.x * (fmaf(y2.x, sc[2 * e], sh[2 * e]) > 0.f ? 1.f : p.bn_neg);
+                const float dz1 = g2.y * (fmaf(y2.y, sc[2 * e + 1], sh[2 * e + 1]) > 0.f ? 1.f : p.bn_neg);
+                s[2 * e] += dz0;
+                s[2 * e + 1] += dz1;
+                t[2 * e] = fmaf(dz0, y2.x - mu[2 * e], t[2 * e]);
+                t[2 * e + 1] = fmaf(dz1, y2.y - mu[2 * e + 1], t[2 * e + 1]);
+              }
+            }
+            keep_half_step<4, 16>(s, t, lane);
+            keep_half_step<2, 8>(s, t, lane);
+            keep_half_step<1, 4>(s, t, lane);
+            if (RB == 32) {
+              s[0] += __shfl_xor_sync(0xffffffffu, s[0], 2);
+              t[0] += __shfl_xor_sync(0xffffffffu, t[0], 2);
+            }
+            acc_s[ci] += s[0];
+            acc_t[ci] += t[0];
+            ++ycount;
+            __syncwarp();  // both tiles are free again: refill the y slot with the chunk `yslots` ahead
+            if (pf_tile < num_tiles) {
+              issue_y(pf_tile, pf_ci, yslot);
+              next_chunk(pf_tile, pf_ci);
+            }
+          } else if (p.stats && !(p.dbg & 2)) {
             // column sums of the STORED (bf16-rounded) tile: each lane adds NR rows of one 16-byte piece, a
             // keep-half butterfly over the row-group lanes leaves one column per lane
             float s[8], t[8];
@@ -445,13 +561,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           acc_phase ^= 1;
         }
       }
-      if (p.stats && stat_nt >= 0) {
+      if (stat_base && stat_nt >= 0) {
 #pragma unroll
         for (int ci = 0; ci < C::kChunksPerWarp; ++ci) {
           const int n = stat_nt * BN + (half + 2 * ci) * C::kChunk + my_col;
           if (col_owner && (half + 2 * ci) < C::kNumChunks && n < p.Cout) {
             atomicAdd(stats_row + n, acc_s[ci]);
-            atomicAdd(stats_row + p.Cout + n, acc_t[ci]);
+            atomicAdd(stats_row + p.Cout + n, kBnRed ? acc_t[ci] * __ldg(p.bn_rstd + n) : acc_t[ci]);
           }
         }
       }
@@ -670,16 +786,30 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 }
 
-template <int KC, int BN, bool kTma>
+template <int KC, int BN, int kMode>
 int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmI,
-               const CUtensorMap& tmR, const IgemmParams& p, cudaStream_t stream) {
-  using C = Cfg<KC, BN, kTma>;
-  static_assert(C::kStages >= 2, "pipeline too shallow");
+               const CUtensorMap& tmR, const CUtensorMap& tmY, const IgemmParams& p, cudaStream_t stream) {
+  using C = Cfg<KC, BN, kMode>;
+  static_assert(C::stages_for(C::kBnRed ? 1 : 0) >= 2, "pipeline too shallow");
+  IgemmParams q = p;
+  // y ring depth of the fused BN-backward reduction: tiles with few k-iterations (1x1 layers) finish a chunk in
+  // less than one memory latency, so they need several y tiles in flight and can spare pipeline stages
+  q.y_slots = 0;
+  q.y_slots_log2 = 0;
+  if (C::kBnRed) {
+    const int kit = p.num_taps * p.cblocks + p.res_iters;
+    q.y_slots = kit >= 16 ? 1 : 4;
+    while (q.y_slots > 1 && C::stages_for(q.y_slots) < 3) q.y_slots >>= 1;
+    q.y_slots_log2 = q.y_slots == 4 ? 2 : (q.y_slots == 2 ? 1 : 0);
+  }
+  q.stages = C::stages_for(q.y_slots);
+  const int smem_bytes = C::extra_bytes(q.y_slots) + q.stages * C::kStageBytes;
+  constexpr int kSmemAttr = C::kCtasPerSm == 2 ? kSmemMax2 : kSmemMax;
   static bool configured = false;  // benign race: attribute set is idempotent
-  auto kern = igemm_kernel<KC, BN, kTma>;
+  auto kern = igemm_kernel<KC, BN, kMode>;
   if (!configured) {
     cudaError_t e =
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttr);
     if (e != cudaSuccess) return set_error(static_cast<int>(e), "igemm smem attr: %s", cudaGetErrorString(e));
     configured = true;
   }
@@ -687,22 +817,26 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
   int grid = sm_count() * C::kCtasPerSm;
   if (grid > tiles) grid = tiles;
   if (grid < 1) return 0;
-  kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, tmO, tmI, tmR, p);
+  kern<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmO, tmI, tmR, tmY, q);
   return check_launch("igemm_kernel");
 }
 
 }  // namespace
 
 int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmO, const CUtensorMap* tmI,
-                 const CUtensorMap* tmR, const IgemmParams& p, int kc, int block_n, cudaStream_t stream) {
+                 const CUtensorMap* tmR, const CUtensorMap* tmY, const IgemmParams& p, int kc, int block_n,
+                 cudaStream_t stream) {
+  if (p.bn_sums && (!tmO || !tmY))
+    return set_error(B200CV_ERR_ARG, "igemm: the fused BN-backward reduction needs the staged (TMA-store) epilogue");
   if (p.res_iters && (!tmI || !tmR || block_n % 64 != 0))
     return set_error(B200CV_ERR_ARG, "igemm: tensor-core residual needs identity/residual maps and block_n %% 64 == 0");
   const CUtensorMap& mI = tmI ? *tmI : tmA;  // unused copies when the feature is off
   const CUtensorMap& mR = tmR ? *tmR : tmA;
 #define B200CV_IGEMM_CASE(KC_, BN_)                                                        \
   if (kc == KC_ && block_n == BN_)                                                         \
-    return tmO ? launch_one<KC_, BN_, true>(tmA, tmB, *tmO, mI, mR, p, stream)             \
-               : launch_one<KC_, BN_, false>(tmA, tmB, tmA, mI, mR, p, stream);
+    return !tmO ? launch_one<KC_, BN_, 0>(tmA, tmB, tmA, mI, mR, tmA, p, stream)           \
+                : (p.bn_sums ? launch_one<KC_, BN_, 2>(tmA, tmB, *tmO, mI, mR, *tmY, p, stream) \
+                             : launch_one<KC_, BN_, 1>(tmA, tmB, *tmO, mI, mR, tmA, p, stream));
   B200CV_IGEMM_CASE(64, 256)
   B200CV_IGEMM_CASE(64, 128)
   B200CV_IGEMM_CASE(64, 64)

@@ -61,6 +61,16 @@ struct IgemmParams {
   float* stats;  // [stats_parts][2*Cout]: sum, sum of squares (added), or null
   int stats_parts;
   int* err;
+  // fused BN-backward reduction (dgrad, staged epilogue only): sums of dz and dz*(y-mean)*rstd, see b200cv.h
+  float* bn_sums;
+  int bn_parts;
+  const float* bn_scale;
+  const float* bn_shift;
+  const float* bn_mean;
+  const float* bn_rstd;
+  float bn_neg;  // act'(z) for z <= 0
+  int stages;                 // pipeline stages of this launch (set by launch_igemm)
+  int y_slots, y_slots_log2;  // y tiles per epilogue warp of the fused BN-backward reduction (power of two)
   int res_iters;  // residual added by the tensor core: extra k-iterations D += I[:, k-slice] * R[k-slice rows, :] (0 = off)
   int dbg;  // B200CV_DBG bits (bring-up timing experiments only): 1 no stores, 2 no stats, 4 no TMEM read
   short tap_w[kMaxTaps];
@@ -73,8 +83,10 @@ struct IgemmParams {
 // tmO: 2-D map over a row-major bf16 output [M][Cout] with box {epilogue chunk, 32 rows} (staged TMA-store
 // epilogue), or null for the generic (direct-store) epilogue.
 // tmI / tmR (both or neither): 128x128 bf16 identity and the row-major residual [M][ld] for p.res_iters > 0.
+// tmY: map over the BN input y laid out like the output (same box as tmO) for p.bn_sums != null.
 int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmO, const CUtensorMap* tmI,
-                 const CUtensorMap* tmR, const IgemmParams& p, int kc, int block_n, cudaStream_t stream);
+                 const CUtensorMap* tmR, const CUtensorMap* tmY, const IgemmParams& p, int kc, int block_n,
+                 cudaStream_t stream);
 const void* device_identity128();    // bf16 [128][128] identity matrix (library-owned, per device)
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }

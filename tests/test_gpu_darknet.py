@@ -145,9 +145,9 @@ def test_every_backward_op_in_context(cfg_dir, cfg_name, S, B):
         errs.append(("wgrad", tuple(x.shape), rel(out, w.grad.permute(0, 2, 3, 1).reshape(cout, k * k, -1))))
         return out
 
-    def dgrad(dy, wpk_t, cin_fwd, k, stride, pad, dil, out_hw, out=None, residual=None):
+    def dgrad(dy, wpk_t, cin_fwd, k, stride, pad, dil, out_hw, out=None, residual=None, bn_reduce=None):
         res = residual.clone() if residual is not None else None
-        o = orig[1](dy, wpk_t, cin_fwd, k, stride, pad, dil, out_hw, out=out, residual=residual)
+        o = orig[1](dy, wpk_t, cin_fwd, k, stride, pad, dil, out_hw, out=out, residual=residual, bn_reduce=bn_reduce)
         w = wpk_t.float().view(cin_fwd, k, k, wpk_t.shape[-1]).permute(3, 0, 1, 2).contiguous()
         xz = torch.zeros(dy.shape[0], cin_fwd, out_hw[0], out_hw[1], device=dy.device, requires_grad=True)
         with torch.enable_grad():
