@@ -328,46 +328,110 @@ struct PackEntry {          // mirrors b200cv_pack_entry (include/b200cv.h)
   void* dst;                // packed bf16 (pack) / OIHW fp32 gradient (unpack)
   int O, I, RS, Ipad, Opad, transpose;
 };
-__global__ void pack_weights_multi_kernel(const PackEntry* __restrict__ table) {
+// Layout changes of the weights are transposes of small matrices: every block stages one contiguous piece of the
+// source in shared memory so that BOTH the global reads and the global writes are coalesced (the first version
+// gathered with a stride of RS floats and ran at ~1 TB/s).
+constexpr int kPackSmemFloats = 9600;  // 37.5 KB: one [I*RS] row (I*RS <= 9600) or a 32 x (32*RS+1) tile (RS <= 9)
+
+__global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackEntry* __restrict__ table) {
+  __shared__ float sm[kPackSmemFloats];
   const PackEntry e = table[blockIdx.y];
-  // transpose == 2: "flat" pack [O][Ipad] with k = tap*I + i (whole filter in one padded K run)
-  const long long total = e.transpose == 2 ? (long long)e.O * e.Ipad
-                          : (e.transpose ? (long long)e.I * e.RS * e.Opad : (long long)e.O * e.RS * e.Ipad);
   __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(e.dst);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    float v = 0.f;
-    if (e.transpose == 2) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (e.transpose == 2) {
+    // "flat" pack [O][Ipad] with k = tap*I + i (whole filter in one padded K run); tiny (image layers only)
+    const long long total = (long long)e.O * e.Ipad;
+    for (long long i = blockIdx.x * (long long)nt + tid; i < total; i += (long long)gridDim.x * nt) {
       const int k = (int)(i % e.Ipad);
       const int o = (int)(i / e.Ipad);
+      float v = 0.f;
       if (k < e.RS * e.I) v = e.src[((long long)o * e.I + (k % e.I)) * e.RS + (k / e.I)];
-    } else if (!e.transpose) {
-      const int ip = (int)(i % e.Ipad);
-      const long long r = i / e.Ipad;
-      const int t = (int)(r % e.RS);
-      const int o = (int)(r / e.RS);
-      if (ip < e.I) v = e.src[((long long)o * e.I + ip) * e.RS + t];
-    } else {
-      const int op = (int)(i % e.Opad);
-      const long long r = i / e.Opad;
-      const int t = (int)(r % e.RS);
-      const int ii = (int)(r / e.RS);
-      if (op < e.O) v = e.src[((long long)op * e.I + ii) * e.RS + t];
+      dst[i] = __float2bfloat16_rn(v);
     }
-    dst[i] = __float2bfloat16_rn(v);
+  } else if (!e.transpose) {
+    // dst[o][t][ip] <- src[o][i][t]: one output channel (I*RS contiguous floats) per block iteration
+    const int row = e.I * e.RS;
+    const bool staged = row <= kPackSmemFloats;
+    for (int o = blockIdx.x; o < e.O; o += gridDim.x) {
+      const float* sp = e.src + (long long)o * row;
+      __nv_bfloat16* dp = dst + (long long)o * e.RS * e.Ipad;
+      if (staged) {
+        for (int j = tid; j < row; j += nt) sm[j] = sp[j];
+        __syncthreads();
+      }
+      for (int j = tid; j < e.RS * e.Ipad; j += nt) {
+        const int t = j / e.Ipad, ip = j - t * e.Ipad;
+        float v = 0.f;
+        if (ip < e.I) v = staged ? sm[ip * e.RS + t] : sp[ip * e.RS + t];
+        dp[j] = __float2bfloat16_rn(v);
+      }
+      if (staged) __syncthreads();
+    }
+  } else {
+    // dst[i][t][op] <- src[op][i][t]: 32 (input) x 32 (output) channel tiles
+    const int ld = 32 * e.RS + 1;
+    const int tiles_i = (e.I + 31) / 32, tiles_o = (e.Opad + 31) / 32;
+    if (32 * ld > kPackSmemFloats) {  // huge filters: per-element gather
+      const long long total = (long long)e.I * e.RS * e.Opad;
+      for (long long i = blockIdx.x * (long long)nt + tid; i < total; i += (long long)gridDim.x * nt) {
+        const int op = (int)(i % e.Opad);
+        const long long r = i / e.Opad;
+        const int t = (int)(r % e.RS);
+        const int ii = (int)(r / e.RS);
+        dst[i] = __float2bfloat16_rn(op < e.O ? e.src[((long long)op * e.I + ii) * e.RS + t] : 0.f);
+      }
+      return;
+    }
+    for (int tile = blockIdx.x; tile < tiles_i * tiles_o; tile += gridDim.x) {
+      const int i0 = (tile / tiles_o) * 32, o0 = (tile % tiles_o) * 32;
+      const int ni = min(32, e.I - i0);
+      for (int j = tid; j < 32 * 32 * e.RS; j += nt) {
+        const int ol = j / (32 * e.RS), k = j - ol * 32 * e.RS;  // k = il*RS + t
+        float v = 0.f;
+        if (o0 + ol < e.O && k < ni * e.RS) v = e.src[((long long)(o0 + ol) * e.I + i0) * e.RS + k];
+        sm[ol * ld + k] = v;
+      }
+      __syncthreads();
+      for (int j = tid; j < ni * e.RS * 32; j += nt) {
+        const int ol = j & 31, k = j >> 5;  // k = il*RS + t
+        if (o0 + ol < e.Opad)
+          dst[((long long)i0 * e.RS + k) * e.Opad + o0 + ol] = __float2bfloat16_rn(sm[ol * ld + k]);
+      }
+      __syncthreads();
+    }
   }
 }
-__global__ void unpack_wgrad_multi_kernel(const PackEntry* __restrict__ table) {
+__global__ void __launch_bounds__(256) unpack_wgrad_multi_kernel(const PackEntry* __restrict__ table) {
+  __shared__ float sm[kPackSmemFloats];
   const PackEntry e = table[blockIdx.y];
-  const long long total = (long long)e.O * e.I * e.RS;
   float* dst = static_cast<float*>(e.dst);
-  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < total;
-       j += (long long)gridDim.x * blockDim.x) {
-    const int t = (int)(j % e.RS);
-    const long long r = j / e.RS;
-    const int i = (int)(r % e.I);
-    const long long o = r / e.I;
-    dst[j] = e.transpose == 2 ? e.src[o * e.Ipad + t * e.I + i] : e.src[(o * e.RS + t) * e.Ipad + i];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int ld = e.I + 1;
+  if (e.transpose == 2 || e.RS * ld > kPackSmemFloats) {
+    const long long total = (long long)e.O * e.I * e.RS;
+    for (long long j = blockIdx.x * (long long)nt + tid; j < total; j += (long long)gridDim.x * nt) {
+      const int t = (int)(j % e.RS);
+      const long long r = j / e.RS;
+      const int i = (int)(r % e.I);
+      const long long o = r / e.I;
+      dst[j] = e.transpose == 2 ? e.src[o * e.Ipad + t * e.I + i] : e.src[(o * e.RS + t) * e.Ipad + i];
+    }
+    return;
+  }
+  // dst[o][i][t] = src[o][t][i]: one output channel per block iteration through shared memory
+  for (int o = blockIdx.x; o < e.O; o += gridDim.x) {
+    const float* sp = e.src + (long long)o * e.RS * e.Ipad;
+    for (int j = tid; j < e.RS * e.I; j += nt) {
+      const int t = j / e.I, i = j - t * e.I;
+      sm[t * ld + i] = sp[(long long)t * e.Ipad + i];
+    }
+    __syncthreads();
+    float* dp = dst + (long long)o * e.I * e.RS;
+    for (int j = tid; j < e.I * e.RS; j += nt) {
+      const int i = j / e.RS, t = j - i * e.RS;
+      dp[j] = sm[t * ld + i];
+    }
+    __syncthreads();
   }
 }
 

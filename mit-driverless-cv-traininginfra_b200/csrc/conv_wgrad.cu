@@ -24,12 +24,13 @@
 namespace b200cv {
 namespace {
 
-constexpr int kWThreads = 192;
+constexpr int kWThreads = 256;   // warp 0, 6, 7: TMA producers; warp 1: MMA issuer; warps 2..5: epilogue
+constexpr int kWProducers = 3;
 constexpr int kKB = 64;         // pixels per k-block
 constexpr int kMaxWStages = 8;
 
 struct WgradParams {
-  int M_pix, OHW, OW;
+  int M_pix, OHW, OW, OH;
   int lower_w, lower_h, trav_w, trav_h;
   int Cout, Cin, RS, Ipad;  // Ipad: row pitch of dW in channels (== Cin)
   int num_o_tiles, num_i_tiles, num_tap_groups, ksplit;
@@ -86,8 +87,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmDY);
     ptx::prefetch_tmap(&tmX);
+    const int np = p.T < kWProducers ? p.T : kWProducers;  // active producers, each arrives once per stage
     for (int i = 0; i < p.stages; ++i) {
-      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&full_bar[i], np);
       ptx::mbar_init(&empty_bar[i], 1);
     }
     ptx::mbar_init(done_bar, 1);
@@ -100,33 +102,59 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
   const uint32_t tmem_base = *tmem_slot;
 
   if (nkb > 0) {
-    if (warp == 0) {
-      if (lane == 0) {
+    if (warp == 0 || warp >= 6) {
+      // ---- TMA producers.  A single thread issuing all (2 + 2T) loads of a k-block (plus two integer divisions
+      // for the pixel coordinates) took ~0.9 us per k-block and starved the tensor core (42 % active): the taps are
+      // now split over up to three single-thread producers and the coordinates advance incrementally.
+      const int pj = warp == 0 ? 0 : warp - 5;  // producer index 0..2: taps t with t % 3 == pj (+ dY for pj == 0)
+      if (lane == 0 && pj < p.T) {
+        int my_taps = 0;
+        uint16_t tw[3], th[3];
+        int tt[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int t = pj + kWProducers * k;
+          tt[k] = t;
+          if (t < p.T) {
+            tw[k] = static_cast<uint16_t>(p.tap_w[tg * p.T + t]);
+            th[k] = static_cast<uint16_t>(p.tap_h[tg * p.T + t]);
+            ++my_taps;
+          } else {
+            tw[k] = th[k] = 0;
+          }
+        }
+        const uint32_t my_bytes = (pj == 0 ? a_bytes : 0) + my_taps * kBTapBytes;
+        int m0 = kb0 * kKB;
+        int n_img = m0 / p.OHW;
+        int pr = (m0 - n_img * p.OHW) / p.OW;
+        int qc = m0 - n_img * p.OHW - pr * p.OW;
         int stage = 0;
         uint32_t phase = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
-          const int m0 = kb * kKB;
-          const int n_img = m0 / p.OHW;
-          const int rem = m0 - n_img * p.OHW;
-          const int pr = rem / p.OW;
-          const int qc = rem - pr * p.OW;
           const int cw = p.lower_w + qc * p.trav_w;
           const int ch = p.lower_h + pr * p.trav_h;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err, 11);
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + 2 * kASlabBytes;
-          ptx::mbar_expect_tx(&full_bar[stage], a_bytes + p.T * kBTapBytes);
-          for (int s = 0; s < p.a_slabs; ++s)
-            ptx::tma_load_2d(sa + s * kASlabBytes, &tmDY, &full_bar[stage], ot * 128 + s * 64, m0);
-          for (int t = 0; t < p.T; ++t) {
-            const int tap = tg * p.T + t;
-            for (int s = 0; s < kBSlabs; ++s)
-              ptx::tma_load_im2col_4d(sb + t * kBTapBytes + s * kBSlabBytes, &tmX, &full_bar[stage],
-                                      it * BNW + s * CB, cw, ch, n_img,
-                                      static_cast<uint16_t>(p.tap_w[tap]),
-                                      static_cast<uint16_t>(p.tap_h[tap]));
+          ptx::mbar_expect_tx(&full_bar[stage], my_bytes);
+          if (pj == 0)
+            for (int sl = 0; sl < p.a_slabs; ++sl)
+              ptx::tma_load_2d(sa + sl * kASlabBytes, &tmDY, &full_bar[stage], ot * 128 + sl * 64, m0);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            if (tt[k] < p.T) {
+#pragma unroll
+              for (int sl = 0; sl < kBSlabs; ++sl)
+                ptx::tma_load_im2col_4d(sb + tt[k] * kBTapBytes + sl * kBSlabBytes, &tmX, &full_bar[stage],
+                                        it * BNW + sl * CB, cw, ch, n_img, tw[k], th[k]);
+            }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          // next k-block: 64 output pixels further in (image, row, column) order
+          m0 += kKB;
+          qc += kKB;
+          while (qc >= p.OW) { qc -= p.OW; ++pr; }
+          while (pr >= p.OH) { pr -= p.OH; ++n_img; }
         }
       }
     } else if (warp == 1) {
@@ -261,6 +289,7 @@ extern "C" int b200cv_conv_wgrad(const void* x, const void* dy, float* dw_packed
   WgradParams p{};
   p.OHW = OH * OW;
   p.OW = OW;
+  p.OH = OH;
   p.M_pix = N * p.OHW;
   p.lower_w = -pad;
   p.lower_h = -pad;

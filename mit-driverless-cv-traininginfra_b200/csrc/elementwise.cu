@@ -6,6 +6,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "internal.h"
 
@@ -122,13 +123,37 @@ __device__ __forceinline__ void load4f(const float* p, float (&v)[4]) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p));
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
 }
+// width-generic forms (V = 4 or 8 channels per thread)
+template <int V> struct VecT;
+template <> struct VecT<4> { typedef uint2 type; };
+template <> struct VecT<8> { typedef uint4 type; };
+template <int V> __device__ __forceinline__ typename VecT<V>::type ldg_streamV(const __nv_bfloat16* p);
+template <> __device__ __forceinline__ uint2 ldg_streamV<4>(const __nv_bfloat16* p) { return ldg_stream8(p); }
+template <> __device__ __forceinline__ uint4 ldg_streamV<8>(const __nv_bfloat16* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void unpackV(const uint2& r, float (&f)[4]) { unpack4(r, f); }
+__device__ __forceinline__ void unpackV(const uint4& r, float (&f)[8]) { unpack8(r, f); }
+__device__ __forceinline__ void storeV(__nv_bfloat16* p, const float (&f)[4]) { stg8(p, pack4(f)); }
+__device__ __forceinline__ void storeV(__nv_bfloat16* p, const float (&f)[8]) { stg16(p, pack8(f)); }
+template <int V> __device__ __forceinline__ void loadVf(const float* p, float (&v)[V]) {
+#pragma unroll
+  for (int j = 0; j < V; j += 4) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p + j));
+    v[j] = a.x; v[j + 1] = a.y; v[j + 2] = a.z; v[j + 3] = a.w;
+  }
+}
 constexpr int kEwThreads = 256;
 constexpr int kEwUnroll = 4;      // rows in flight per thread
 constexpr int kEwBlocksPerSm = 6;
 
 // grid of a row-streaming kernel: blocks walk rows with stride gridDim * rows_per_pass
-int stream_grid(long long rows, int C) {
-  const int rpp = kEwThreads / (C / 4);
+int stream_grid(long long rows, int C, int V = 4) {
+  const int rpp = kEwThreads / (C / V);
   const long long passes = (rows + (long long)rpp * kEwUnroll - 1) / ((long long)rpp * kEwUnroll);
   return (int)std::max<long long>(1, std::min<long long>(passes, (long long)sm_count() * kEwBlocksPerSm));
 }
@@ -207,8 +232,8 @@ struct FusedFwdArgs {
   float* running_mean; float* running_var;
   float* scale; float* shift; float* save_mean; float* save_rstd;
 };
-template <bool kPost>
-__global__ void __launch_bounds__(kEwThreads, 4) bn_stats_apply_kernel(const FusedFwdArgs f, const ApplyArgs a) {
+template <bool kPost, int V>
+__global__ void __launch_bounds__(kEwThreads, V == 8 ? 2 : 4) bn_stats_apply_kernel(const FusedFwdArgs f, const ApplyArgs a) {
   extern __shared__ float s_ss[];  // [scale | shift]
   const int C = a.C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -239,48 +264,48 @@ __global__ void __launch_bounds__(kEwThreads, 4) bn_stats_apply_kernel(const Fus
     }
   }
   __syncthreads();
-  const int vpr = C >> 2;
+  const int vpr = C / V;
   const int rpp = kEwThreads / vpr;
   const int cv = threadIdx.x % vpr;
   const int r0 = threadIdx.x / vpr;
-  const int c0 = cv << 2;
+  const int c0 = cv * V;
   if (r0 >= rpp) return;
-  float sc[4], sh[4];
+  float sc[V], sh[V];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < V; ++j) {
     sc[j] = s_ss[c0 + j];
     sh[j] = s_ss[C + c0 + j];
   }
   const float neg = a.act == B200CV_ACT_LEAKY ? a.slope : (a.act == B200CV_ACT_RELU ? 0.f : 1.f);
   const long long stride = (long long)gridDim.x * rpp;
   for (long long r = (long long)blockIdx.x * rpp + r0; r < a.rows; r += stride * kEwUnroll) {
-    uint2 qy[kEwUnroll], qp[kEwUnroll];
+    typename VecT<V>::type qy[kEwUnroll], qp[kEwUnroll];
 #pragma unroll
     for (int u = 0; u < kEwUnroll; ++u) {
       const long long rr = r + u * stride;
       if (rr < a.rows) {
-        qy[u] = ldg_stream8(a.y + rr * a.y_ld + c0);
-        if (kPost) qp[u] = ldg_stream8(a.post + rr * a.post_ld + c0);
+        qy[u] = ldg_streamV<V>(a.y + rr * a.y_ld + c0);
+        if (kPost) qp[u] = ldg_streamV<V>(a.post + rr * a.post_ld + c0);
       }
     }
 #pragma unroll
     for (int u = 0; u < kEwUnroll; ++u) {
       const long long rr = r + u * stride;
       if (rr < a.rows) {
-        float v[4], z[4];
-        unpack4(qy[u], v);
+        float v[V], z[V];
+        unpackV(qy[u], v);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < V; ++j) {
           z[j] = v[j] * sc[j] + sh[j];
           z[j] = z[j] > 0.f ? z[j] : z[j] * neg;
         }
         if (kPost) {
-          float w[4];
-          unpack4(qp[u], w);
+          float w[V];
+          unpackV(qp[u], w);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) z[j] += w[j];
+          for (int j = 0; j < V; ++j) z[j] += w[j];
         }
-        stg8(a.out + rr * a.out_ld + c0, pack4(z));
+        storeV(a.out + rr * a.out_ld + c0, z);
       }
     }
   }
@@ -304,52 +329,54 @@ struct BwdArgs {
   long long rows; int C; int act; float slope;
 };
 
-template <bool kAout>
-__global__ void __launch_bounds__(kEwThreads, 4) bn_bwd_reduce_kernel(const BwdArgs a) {
+template <bool kAout, int V>
+__global__ void __launch_bounds__(kEwThreads, V == 8 ? 2 : 4) bn_bwd_reduce_kernel(const BwdArgs a) {
   extern __shared__ float s_acc[];  // [2C]
   const int C = a.C;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
-  const int vpr = C >> 2;
+  const int vpr = C / V;
   const int rpp = kEwThreads / vpr;
   const int cv = threadIdx.x % vpr;
   const int r0 = threadIdx.x / vpr;
-  const int c0 = cv << 2;
+  const int c0 = cv * V;
   if (r0 < rpp) {
-    float sc[4], sh[4], mean[4];
+    float sc[V], sh[V], mean[V];
     if (!kAout) {
-      load4f(a.scale + c0, sc);
-      load4f(a.shift + c0, sh);
+      loadVf<V>(a.scale + c0, sc);
+      loadVf<V>(a.shift + c0, sh);
     }
-    load4f(a.mean + c0, mean);
+    loadVf<V>(a.mean + c0, mean);
     const float neg = a.act == B200CV_ACT_LEAKY ? a.slope : (a.act == B200CV_ACT_RELU ? 0.f : 1.f);
-    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    float s1[V], s2[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) s1[j] = s2[j] = 0.f;
     const long long stride = (long long)gridDim.x * rpp;
     for (long long r = (long long)blockIdx.x * rpp + r0; r < a.rows; r += stride * kEwUnroll) {
-      uint2 qda[kEwUnroll], qy[kEwUnroll], qa[kEwUnroll];
+      typename VecT<V>::type qda[kEwUnroll], qy[kEwUnroll], qa[kEwUnroll];
 #pragma unroll
       for (int u = 0; u < kEwUnroll; ++u) {
         const long long rr = r + u * stride;
         if (rr < a.rows) {
-          qda[u] = ldg_stream8(a.da + rr * a.da_ld + c0);
-          qy[u] = ldg_stream8(a.y + rr * a.y_ld + c0);
-          if (kAout) qa[u] = ldg_stream8(a.aout + rr * a.aout_ld + c0);
+          qda[u] = ldg_streamV<V>(a.da + rr * a.da_ld + c0);
+          qy[u] = ldg_streamV<V>(a.y + rr * a.y_ld + c0);
+          if (kAout) qa[u] = ldg_streamV<V>(a.aout + rr * a.aout_ld + c0);
         }
       }
 #pragma unroll
       for (int u = 0; u < kEwUnroll; ++u) {
         if (r + u * stride < a.rows) {
-          float da[4], y[4], zs[4];
-          unpack4(qda[u], da);
-          unpack4(qy[u], y);
+          float da[V], y[V], zs[V];
+          unpackV(qda[u], da);
+          unpackV(qy[u], y);
           if (kAout) {
-            unpack4(qa[u], zs);
+            unpackV(qa[u], zs);
           } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) zs[j] = y[j] * sc[j] + sh[j];
+            for (int j = 0; j < V; ++j) zs[j] = y[j] * sc[j] + sh[j];
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < V; ++j) {
             const float dz = da[j] * (zs[j] > 0.f ? 1.f : neg);
             s1[j] += dz;
             s2[j] = fmaf(dz, y[j] - mean[j], s2[j]);
@@ -357,10 +384,10 @@ __global__ void __launch_bounds__(kEwThreads, 4) bn_bwd_reduce_kernel(const BwdA
         }
       }
     }
-    float rstd[4];
-    load4f(a.rstd + c0, rstd);
+    float rstd[V];
+    loadVf<V>(a.rstd + c0, rstd);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < V; ++j) {
       atomicAdd(&s_acc[c0 + j], s1[j]);
       atomicAdd(&s_acc[C + c0 + j], s2[j] * rstd[j]);
     }
@@ -476,7 +503,8 @@ struct FusedBwdArgs {
   const float* partials; int nparts; float count;
   const float* gamma; float* coef; float* dgamma; float* dbeta;
 };
-__global__ void __launch_bounds__(kEwThreads, 4) bn_bwd_stats_apply_kernel(const FusedBwdArgs f, const BwdArgs a) {
+template <int V>
+__global__ void __launch_bounds__(kEwThreads, V == 8 ? 2 : 4) bn_bwd_stats_apply_kernel(const FusedBwdArgs f, const BwdArgs a) {
   extern __shared__ float s_gab[];  // [g | A | B]
   const int C = a.C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -503,17 +531,17 @@ __global__ void __launch_bounds__(kEwThreads, 4) bn_bwd_stats_apply_kernel(const
     }
   }
   __syncthreads();
-  const int vpr = C >> 2;
+  const int vpr = C / V;
   const int rpp = kEwThreads / vpr;
   const int cv = threadIdx.x % vpr;
   const int r0 = threadIdx.x / vpr;
-  const int c0 = cv << 2;
+  const int c0 = cv * V;
   if (r0 >= rpp) return;
-  float sc[4], sh[4], g[4], A[4], B[4];
-  load4f(a.scale + c0, sc);
-  load4f(a.shift + c0, sh);
+  float sc[V], sh[V], g[V], A[V], B[V];
+  loadVf<V>(a.scale + c0, sc);
+  loadVf<V>(a.shift + c0, sh);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < V; ++j) {
     g[j] = s_gab[c0 + j];
     A[j] = s_gab[C + c0 + j];
     B[j] = s_gab[2 * C + c0 + j];
@@ -521,29 +549,29 @@ __global__ void __launch_bounds__(kEwThreads, 4) bn_bwd_stats_apply_kernel(const
   const float neg = a.act == B200CV_ACT_LEAKY ? a.slope : (a.act == B200CV_ACT_RELU ? 0.f : 1.f);
   const long long stride = (long long)gridDim.x * rpp;
   for (long long r = (long long)blockIdx.x * rpp + r0; r < a.rows; r += stride * kEwUnroll) {
-    uint2 qda[kEwUnroll], qy[kEwUnroll];
+    typename VecT<V>::type qda[kEwUnroll], qy[kEwUnroll];
 #pragma unroll
     for (int u = 0; u < kEwUnroll; ++u) {
       const long long rr = r + u * stride;
       if (rr < a.rows) {
-        qda[u] = ldg_stream8(a.da + rr * a.da_ld + c0);
-        qy[u] = ldg_stream8(a.y + rr * a.y_ld + c0);
+        qda[u] = ldg_streamV<V>(a.da + rr * a.da_ld + c0);
+        qy[u] = ldg_streamV<V>(a.y + rr * a.y_ld + c0);
       }
     }
 #pragma unroll
     for (int u = 0; u < kEwUnroll; ++u) {
       const long long rr = r + u * stride;
       if (rr < a.rows) {
-        float da[4], y[4], o[4];
-        unpack4(qda[u], da);
-        unpack4(qy[u], y);
+        float da[V], y[V], o[V];
+        unpackV(qda[u], da);
+        unpackV(qy[u], y);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < V; ++j) {
           const float z = y[j] * sc[j] + sh[j];
           const float dz = da[j] * (z > 0.f ? 1.f : neg);
           o[j] = fmaf(g[j], dz, fmaf(A[j], y[j], B[j]));
         }
-        stg8(a.dy + rr * a.dy_ld + c0, pack4(o));
+        storeV(a.dy + rr * a.dy_ld + c0, o);
       }
     }
   }
@@ -750,6 +778,13 @@ __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long
   }
 }
 
+// channels per thread of the streaming BN kernels (B200CV_EW_VEC=4|8 overrides; tuning aid)
+int ew_vec(int C) {
+  static const int forced = getenv("B200CV_EW_VEC") ? atoi(getenv("B200CV_EW_VEC")) : 0;
+  const int v = forced == 4 || forced == 8 ? forced : 4;  // measured: 8 is no faster (5.0-5.6 TB/s either way)
+  return (v == 8 && C % 8 == 0 && C / 8 <= kEwThreads) ? 8 : 4;
+}
+
 bool ok_vec(const void* p, long long ld, int C) {
   return p && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && ld % 8 == 0 && C % 8 == 0 && C > 0;
 }
@@ -818,10 +853,16 @@ extern "C" int b200cv_bn_bwd_reduce(const void* da, int64_t da_ld, const void* y
   B200CV_CHECK_ARG(partials != nullptr && nparts > 0, "bn_bwd_reduce: null partials");
   a.sums = partials;  // [nparts][2C], zeroed by the caller: block b ADDS its sums to row b % nparts
   a.nparts = nparts;
-  const int grid = stream_grid(rows, C);
+  const int V = ew_vec(C);
+  const int grid = stream_grid(rows, C, V);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (aout) bn_bwd_reduce_kernel<true><<<grid, kEwThreads, 2 * C * sizeof(float), st>>>(a);
-  else bn_bwd_reduce_kernel<false><<<grid, kEwThreads, 2 * C * sizeof(float), st>>>(a);
+  if (V == 8) {
+    if (aout) bn_bwd_reduce_kernel<true, 8><<<grid, kEwThreads, 2 * C * sizeof(float), st>>>(a);
+    else bn_bwd_reduce_kernel<false, 8><<<grid, kEwThreads, 2 * C * sizeof(float), st>>>(a);
+  } else {
+    if (aout) bn_bwd_reduce_kernel<true, 4><<<grid, kEwThreads, 2 * C * sizeof(float), st>>>(a);
+    else bn_bwd_reduce_kernel<false, 4><<<grid, kEwThreads, 2 * C * sizeof(float), st>>>(a);
+  }
   return check_launch("bn_bwd_reduce");
 }
 
@@ -867,11 +908,17 @@ extern "C" int b200cv_bn_stats_apply_act(const float* stats, int stats_parts, in
                  scale, shift, save_mean, save_rstd};
   ApplyArgs a{(const bf16*)y, y_ld, nullptr, nullptr, nullptr, 0, nullptr, nullptr,
               (const bf16*)post, post_ld, (bf16*)out, out_ld, rows, C, act, slope};
-  const int grid = stream_grid(rows, C);
+  const int V = ew_vec(C);
+  const int grid = stream_grid(rows, C, V);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = 2 * (size_t)C * sizeof(float);
-  if (post) bn_stats_apply_kernel<true><<<grid, kEwThreads, smem, st>>>(f, a);
-  else bn_stats_apply_kernel<false><<<grid, kEwThreads, smem, st>>>(f, a);
+  if (V == 8) {
+    if (post) bn_stats_apply_kernel<true, 8><<<grid, kEwThreads, smem, st>>>(f, a);
+    else bn_stats_apply_kernel<false, 8><<<grid, kEwThreads, smem, st>>>(f, a);
+  } else {
+    if (post) bn_stats_apply_kernel<true, 4><<<grid, kEwThreads, smem, st>>>(f, a);
+    else bn_stats_apply_kernel<false, 4><<<grid, kEwThreads, smem, st>>>(f, a);
+  }
   return check_launch("bn_stats_apply_act");
 }
 
@@ -886,8 +933,11 @@ extern "C" int b200cv_bn_bwd_stats_apply(const float* partials, int nparts, int6
                    "bn_bwd_stats_apply: bad args");
   a.dy = (bf16*)dy; a.dy_ld = dy_ld;
   FusedBwdArgs f{partials, nparts, (float)count, gamma, coef, dgamma, dbeta};
-  const int grid = stream_grid(rows, C);
-  bn_bwd_stats_apply_kernel<<<grid, kEwThreads, 3 * (size_t)C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(f, a);
+  const int V = ew_vec(C);
+  const int grid = stream_grid(rows, C, V);
+  const size_t smem = 3 * (size_t)C * sizeof(float);
+  if (V == 8) bn_bwd_stats_apply_kernel<8><<<grid, kEwThreads, smem, static_cast<cudaStream_t>(stream)>>>(f, a);
+  else bn_bwd_stats_apply_kernel<4><<<grid, kEwThreads, smem, static_cast<cudaStream_t>(stream)>>>(f, a);
   return check_launch("bn_bwd_stats_apply");
 }
 
