@@ -41,6 +41,18 @@ def peaks():
     return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "src": "fallback"}
 
 
+def ncu_traffic():
+    """DRAM bytes of the conv launches of one step, from the committed ncu launch list (profiles/roofline_rNN.json,
+    written by tools/make_profile_summary.py); None when no capture is committed."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    if os.path.isdir(pdir):
+        for name in sorted(os.listdir(pdir)):
+            if name.startswith("roofline_") and name.endswith(".json"):
+                best = json.load(open(os.path.join(pdir, name)))
+    return best
+
+
 def conv_flops_per_image(spec_layers, size):
     """Algorithmic conv FLOPs per image (2*Cin*Cout*k*k*Hout*Wout), forward; and fwd+dgrad+wgrad."""
     h = size
@@ -304,7 +316,11 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["bf16_sustained"], "traffic": None, "peak_source": pk["src"],
+                         "frac": achieved / pk["bf16_sustained"],
+                         "traffic": (ncu_traffic() or {}).get("conv_dram_bytes_per_step"),
+                         "traffic_note": "DRAM bytes (read+write) of all conv launches of one step, ncu launch list "
+                                         "of round " + str((ncu_traffic() or {}).get("round")),
+                         "peak_source": pk["src"],
                          "kernel": "igemm_kernel + wgrad_kernel (tcgen05 conv fwd/dgrad/wgrad)",
                          "algorithmic_gflop_per_image": tot_f / 1e9, "conv_ms_per_step": conv_ms,
                          "conv_share_of_step": conv_ms / step_ms,
