@@ -49,10 +49,11 @@ struct Cfg {
   static constexpr int kABytes = kBlockM * KC * 2;
   static constexpr int kBBytes = BN * KC * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  // Small stages (<= 16 KB: the 16/32-channel layers) are latency- not bandwidth-bound per k-iteration:
-  // run two CTAs per SM (each with a shallower ring) so their TMA / mbarrier round trips overlap.
+  // Small stages (<= 24 KB: the 16/32/64-channel layers) are bound by the per-k-iteration overhead of the single
+  // producer / MMA threads (~150 cycles per TMA instruction issued), not by bandwidth: run two CTAs per SM (each
+  // with a shallower ring) so that two producers and two MMA issuers work per SM.
   static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : (2 * BN);
-  static constexpr int kCtasPerSm = (kStageBytes <= 16 * 1024 && kTmemCols <= 256) ? 2 : 1;
+  static constexpr int kCtasPerSm = (kStageBytes <= 24 * 1024 && kTmemCols <= 256) ? 2 : 1;
   static constexpr int kRowBytes = KC * 2;               // 32 / 64 / 128
   static constexpr int kLayout = KC == 64 ? 2 : (KC == 32 ? 4 : 6);
   static constexpr int kSBO = 8 * kRowBytes;             // 8-row swizzle atom pitch

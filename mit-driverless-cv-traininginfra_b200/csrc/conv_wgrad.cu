@@ -159,7 +159,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
       }
     } else if (warp == 1) {
       if (lane == 0) {
-        constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BNW, 1, 1);
+        // The T tap tiles of a stage are consecutive BNW-channel slabs of ONE MN-major B operand (slab pitch =
+        // kBSlabBytes), and their accumulators are consecutive TMEM columns: a single MMA covers up to 256 columns
+        // = several taps.  Issuing one N = BNW MMA per tap made the 32/64-channel layers MMA-issue-bound
+        // (36 tiny MMAs per k-block from one thread).
+        const int ntot = p.T * BNW;
         int stage = 0;
         uint32_t phase = 0;
         for (int kb = 0; kb < nkb; ++kb) {
@@ -167,15 +171,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
           const uint32_t sb = sa + 2 * kASlabBytes;
-#pragma unroll 1
-          for (int t = 0; t < p.T; ++t) {
 #pragma unroll
-            for (int k = 0; k < kKB / 16; ++k) {
-              // MN-major: LBO = distance between 64-channel slabs, SBO = 8 pixel rows
-              const uint64_t adesc = ptx::make_smem_desc(sa + k * 16 * 128, kASlabBytes, 8 * 128, 2);
-              const uint64_t bdesc = ptx::make_smem_desc(sb + t * kBTapBytes + k * 16 * kBRow,
-                                                         kBSlabBytes, 8 * kBRow, kBLayout);
-              ptx::umma_bf16(tmem_base + t * BNW, adesc, bdesc, idesc, (kb | k) != 0);
+          for (int k = 0; k < kKB / 16; ++k) {
+            // MN-major: LBO = distance between channel slabs, SBO = 8 pixel rows
+            const uint64_t adesc = ptx::make_smem_desc(sa + k * 16 * 128, kASlabBytes, 8 * 128, 2);
+#pragma unroll 1
+            for (int n0 = 0; n0 < ntot; n0 += 256) {
+              const int n = ntot - n0 < 256 ? ntot - n0 : 256;
+              const uint64_t bdesc = ptx::make_smem_desc(sb + (n0 / CB) * kBSlabBytes + k * 16 * kBRow, kBSlabBytes,
+                                                         8 * kBRow, kBLayout);
+              ptx::umma_bf16(tmem_base + n0, adesc, bdesc, ptx::make_idesc_bf16(128, n, 1, 1), (kb | k) != 0);
             }
           }
           ptx::umma_commit(&empty_bar[stage]);
