@@ -34,6 +34,14 @@ def _fuse_bn_reduce() -> bool:
     return os.environ.get("B200CV_FUSE_BN_REDUCE", "1") != "0"
 
 
+def _wgrad_side_stream() -> bool:
+    import os
+
+    # opt-in: measured no gain on B200 (26.5 vs 26.6 ms/step) -- a wgrad CTA (~200 KB of shared memory) cannot share
+    # an SM with the persistent dgrad CTAs, and the BN passes it could overlap are short
+    return os.environ.get("B200CV_WGRAD_STREAM", "0") != "0"
+
+
 def _graphs_enabled() -> bool:
     import os
 
@@ -282,6 +290,29 @@ class DarknetEngine:
         grads: List[Optional[torch.Tensor]] = [None] * len(self.layers)
         reduced = set()  # BN layers whose backward sums were already produced by a dgrad epilogue
         fuse = _fuse_bn_reduce()
+        # Weight gradients run on a side stream: wgrad(i) only needs dy(i) and its result is not read before the
+        # un-pack at the end, so it overlaps dgrad(i) and -- more importantly -- the HBM-bound BatchNorm backward
+        # passes of layer i-1 (tensor-bound and bandwidth-bound kernels share the SMs).  The operands are kept alive
+        # until the join (no allocator reuse while the side stream may still read them).
+        main = torch.cuda.current_stream()
+        side = None
+        if _wgrad_side_stream():
+            if getattr(self, "_side", None) is None or self._side.device != dev:
+                self._side = torch.cuda.Stream(device=dev)
+            side = self._side
+            side.wait_stream(main)
+        keep = []
+
+        def wgrad(x_, dy_, cout_, k_, st_, pd_, out_):
+            if side is None:
+                ops.conv_wgrad(x_, dy_, cout_, k_, st_, pd_, out=out_)
+                return
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                ops.conv_wgrad(x_, dy_, cout_, k_, st_, pd_, out=out_)
+            keep.append((x_, dy_))
 
         def add_grad(j, t):
             if j < 0:
@@ -327,9 +358,9 @@ class DarknetEngine:
                     ops.col_sum(dy, tmp)
                     gview[id(L.conv.bias)].copy_(tmp[:L.cout])
                 if i == 0 and self._flat_convs():
-                    ops.conv_wgrad(xin, dy, L.cout, 1, 1, 0, out=packs.dwp[id(L.conv)])  # xin = im2col patches
+                    wgrad(xin, dy, L.cout, 1, 1, 0, packs.dwp[id(L.conv)])  # xin = im2col patches
                 else:
-                    ops.conv_wgrad(xin, dy, L.cout, L.k, L.stride, L.pad, out=packs.dwp[id(L.conv)])
+                    wgrad(xin, dy, L.cout, L.k, L.stride, L.pad, packs.dwp[id(L.conv)])
                 if i > 0:
                     prev = grads[i - 1]
                     # this dgrad completes grads[i-1]; when that is the activation gradient of a conv+BN layer the
@@ -374,6 +405,9 @@ class DarknetEngine:
                     add_grad(L.inputs[0], G)
                     add_grad(L.inputs[1], G)
             grads[i] = None
+        if side is not None:
+            main.wait_stream(side)
+        keep.clear()
         packs.unpack_all()
         if do_allreduce:
             allreduce_gradients(arena.flat)

@@ -126,6 +126,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   float* s_stats = reinterpret_cast<float*>(s_extra);
   float* s_scratch = s_stats + kEpiWarps * 2 * C::kAccPerWarp;
 
+  ptx::pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
@@ -162,6 +163,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_wait();  // everything above touched only shared / tensor memory
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -818,7 +820,8 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
   int grid = sm_count() * C::kCtasPerSm;
   if (grid > tiles) grid = tiles;
   if (grid < 1) return 0;
-  kern<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmO, tmI, tmR, tmY, q);
+  cudaError_t le = launch_pdl(kern, dim3(grid), dim3(kThreads), smem_bytes, stream, tmA, tmB, tmO, tmI, tmR, tmY, q);
+  if (le != cudaSuccess) return set_error(static_cast<int>(le), "igemm launch: %s", cudaGetErrorString(le));
   return check_launch("igemm_kernel");
 }
 

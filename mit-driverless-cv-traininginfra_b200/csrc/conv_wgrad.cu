@@ -70,6 +70,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
   uint8_t* s_stage = reinterpret_cast<uint8_t*>(tmem_slot + 4);
   s_stage += (1024u - (ptx::smem_u32(s_stage) & 1023u)) & 1023u;
 
+  ptx::pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
@@ -100,6 +101,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_wait();  // everything above touched only shared / tensor memory
 
   if (nkb > 0) {
     if (warp == 0 || warp >= 6) {
@@ -268,7 +270,8 @@ int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const CUtensor
     configured_smem = 227 * 1024;
   }
   const int grid = p.num_o_tiles * p.num_i_tiles * p.num_tap_groups * p.ksplit;
-  kern<<<grid, kWThreads, smem, stream>>>(tmDY, tmX, tmDW, p);
+  cudaError_t le = launch_pdl(kern, dim3(grid), dim3(kWThreads), (size_t)smem, stream, tmDY, tmX, tmDW, p);
+  if (le != cudaSuccess) return set_error(static_cast<int>(le), "wgrad launch: %s", cudaGetErrorString(le));
   return check_launch("wgrad_kernel");
 }
 

@@ -147,6 +147,8 @@ template <int V> __device__ __forceinline__ void loadVf(const float* p, float (&
     v[j] = a.x; v[j + 1] = a.y; v[j + 2] = a.z; v[j + 3] = a.w;
   }
 }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 constexpr int kEwThreads = 256;
 constexpr int kEwUnroll = 4;      // rows in flight per thread
 constexpr int kEwBlocksPerSm = 6;
@@ -234,6 +236,8 @@ struct FusedFwdArgs {
 };
 template <bool kPost, int V>
 __global__ void __launch_bounds__(kEwThreads, V == 8 ? 2 : 4) bn_stats_apply_kernel(const FusedFwdArgs f, const ApplyArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float s_ss[];  // [scale | shift]
   const int C = a.C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -331,6 +335,8 @@ struct BwdArgs {
 
 template <bool kAout, int V>
 __global__ void __launch_bounds__(kEwThreads, V == 8 ? 2 : 4) bn_bwd_reduce_kernel(const BwdArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float s_acc[];  // [2C]
   const int C = a.C;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
@@ -505,6 +511,8 @@ struct FusedBwdArgs {
 };
 template <int V>
 __global__ void __launch_bounds__(kEwThreads, V == 8 ? 2 : 4) bn_bwd_stats_apply_kernel(const FusedBwdArgs f, const BwdArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float s_gab[];  // [g | A | B]
   const int C = a.C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -857,11 +865,11 @@ extern "C" int b200cv_bn_bwd_reduce(const void* da, int64_t da_ld, const void* y
   const int grid = stream_grid(rows, C, V);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (V == 8) {
-    if (aout) bn_bwd_reduce_kernel<true, 8><<<grid, kEwThreads, 2 * C * sizeof(float), st>>>(a);
-    else bn_bwd_reduce_kernel<false, 8><<<grid, kEwThreads, 2 * C * sizeof(float), st>>>(a);
+    if (aout) launch_pdl(bn_bwd_reduce_kernel<true, 8>, dim3(grid), dim3(kEwThreads), 2 * C * sizeof(float), st, a);
+    else launch_pdl(bn_bwd_reduce_kernel<false, 8>, dim3(grid), dim3(kEwThreads), 2 * C * sizeof(float), st, a);
   } else {
-    if (aout) bn_bwd_reduce_kernel<true, 4><<<grid, kEwThreads, 2 * C * sizeof(float), st>>>(a);
-    else bn_bwd_reduce_kernel<false, 4><<<grid, kEwThreads, 2 * C * sizeof(float), st>>>(a);
+    if (aout) launch_pdl(bn_bwd_reduce_kernel<true, 4>, dim3(grid), dim3(kEwThreads), 2 * C * sizeof(float), st, a);
+    else launch_pdl(bn_bwd_reduce_kernel<false, 4>, dim3(grid), dim3(kEwThreads), 2 * C * sizeof(float), st, a);
   }
   return check_launch("bn_bwd_reduce");
 }
@@ -913,11 +921,11 @@ extern "C" int b200cv_bn_stats_apply_act(const float* stats, int stats_parts, in
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = 2 * (size_t)C * sizeof(float);
   if (V == 8) {
-    if (post) bn_stats_apply_kernel<true, 8><<<grid, kEwThreads, smem, st>>>(f, a);
-    else bn_stats_apply_kernel<false, 8><<<grid, kEwThreads, smem, st>>>(f, a);
+    if (post) launch_pdl(bn_stats_apply_kernel<true, 8>, dim3(grid), dim3(kEwThreads), smem, st, f, a);
+    else launch_pdl(bn_stats_apply_kernel<false, 8>, dim3(grid), dim3(kEwThreads), smem, st, f, a);
   } else {
-    if (post) bn_stats_apply_kernel<true, 4><<<grid, kEwThreads, smem, st>>>(f, a);
-    else bn_stats_apply_kernel<false, 4><<<grid, kEwThreads, smem, st>>>(f, a);
+    if (post) launch_pdl(bn_stats_apply_kernel<true, 4>, dim3(grid), dim3(kEwThreads), smem, st, f, a);
+    else launch_pdl(bn_stats_apply_kernel<false, 4>, dim3(grid), dim3(kEwThreads), smem, st, f, a);
   }
   return check_launch("bn_stats_apply_act");
 }
@@ -936,8 +944,8 @@ extern "C" int b200cv_bn_bwd_stats_apply(const float* partials, int nparts, int6
   const int V = ew_vec(C);
   const int grid = stream_grid(rows, C, V);
   const size_t smem = 3 * (size_t)C * sizeof(float);
-  if (V == 8) bn_bwd_stats_apply_kernel<8><<<grid, kEwThreads, smem, static_cast<cudaStream_t>(stream)>>>(f, a);
-  else bn_bwd_stats_apply_kernel<4><<<grid, kEwThreads, smem, static_cast<cudaStream_t>(stream)>>>(f, a);
+  if (V == 8) launch_pdl(bn_bwd_stats_apply_kernel<8>, dim3(grid), dim3(kEwThreads), smem, static_cast<cudaStream_t>(stream), f, a);
+  else launch_pdl(bn_bwd_stats_apply_kernel<4>, dim3(grid), dim3(kEwThreads), smem, static_cast<cudaStream_t>(stream), f, a);
   return check_launch("bn_bwd_stats_apply");
 }
 

@@ -89,6 +89,25 @@ int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
                  cudaStream_t stream);
 const void* device_identity128();    // bf16 [128][128] identity matrix (library-owned, per device)
 
+// Launch with (optionally) programmatic dependent launch: the kernel must call ptx::pdl_wait() before its first
+// global-memory access (see ptx.cuh).  Off unless B200CV_PDL=1 (measured: no gain inside a CUDA graph).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 // Channel padding rule for NHWC bf16 activations: 16, 32, or a multiple of 64.
 inline int pad_channels(int c) { return c <= 16 ? 16 : (c <= 32 ? 32 : round_up(c, 64)); }

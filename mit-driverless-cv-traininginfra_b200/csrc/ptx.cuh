@@ -23,6 +23,13 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with the programmatic-stream-serialization attribute may start (barrier init, TMEM allocation,
+// descriptor prefetch) while its predecessor drains; pdl_wait() blocks until the predecessor has completed and its
+// memory operations are visible, and must precede EVERY global-memory access.  No-ops for ordinary launches.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
