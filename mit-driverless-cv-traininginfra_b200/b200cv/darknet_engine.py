@@ -28,10 +28,11 @@ BN_MOMENTUM = 0.1
 GRAPH_WARMUP_CALLS = 2  # eager steps with a given input shape before the step is captured as CUDA graphs
 
 
-def _fuse_bn_reduce() -> bool:
+def _fuse_bn_reduce() -> int:
+    """0: separate bn_bwd_reduce passes; 1: fused into the 3x3 data-gradient epilogues; 2: into every stride-1 one."""
     import os
 
-    return os.environ.get("B200CV_FUSE_BN_REDUCE", "1") != "0"
+    return int(os.environ.get("B200CV_FUSE_BN_REDUCE", "2"))
 
 
 def _wgrad_side_stream() -> bool:
@@ -365,9 +366,9 @@ class DarknetEngine:
                     prev = grads[i - 1]
                     # this dgrad completes grads[i-1]; when that is the activation gradient of a conv+BN layer the
                     # first pass of its BN backward (sum dz, sum dz*xhat) is folded into the epilogue
-                    # (3x3 gradients only: the 1x1 ones are HBM-bound and the extra y stream costs them more than the
-                    # separate reduce pass -- measured 91 us fused vs 36 + 45 us for 256->128 @52x52)
-                    owner = self._bn_owner(i - 1) if (fuse and L.stride == 1 and L.k > 1) else None
+                    # (with 32-column epilogue blocks the HBM-bound 1x1 gradients lost more than the separate pass costs:
+                    # 91 us fused vs 36 + 45 us for 256->128 @52x52; with 64-column blocks the fused form is 75 us)
+                    owner = self._bn_owner(i - 1) if (fuse and L.stride == 1 and (L.k > 1 or fuse >= 2)) else None
                     bn_red = None
                     if owner is not None:
                         T = self.layers[owner]

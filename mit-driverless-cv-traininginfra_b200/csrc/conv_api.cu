@@ -91,10 +91,11 @@ int run_igemm(const Geometry& g, const void* act, const void* wpk, int64_t w_row
                        (!p.res || p.res_vec_ok);
   if (tma_out) {
     CUtensorMap tmO, tmY;
-    rc = make_tmap_2d_bf16(&tmO, p.out, p.M_total, p.Cout, ld, 32, bn >= 32 ? 32 : 16);
+    const int ebox = bn >= 128 ? 64 : (bn >= 32 ? 32 : 16);  // epilogue block width (conv_igemm.cu: kWide)
+    rc = make_tmap_2d_bf16(&tmO, p.out, p.M_total, p.Cout, ld, 32, ebox);
     if (rc) return rc;
     if (p.bn_sums) {
-      rc = make_tmap_2d_bf16(&tmY, bn_y, p.M_total, p.Cout, bn_y_ld, 32, bn >= 32 ? 32 : 16);
+      rc = make_tmap_2d_bf16(&tmY, bn_y, p.M_total, p.Cout, bn_y_ld, 32, ebox);
       if (rc) return rc;
     }
     return launch_igemm(tmA, tmB, &tmO, pI, pR, p.bn_sums ? &tmY : nullptr, p, kc, bn, stream);

@@ -21,6 +21,8 @@
 // bounding-box corners and the output strides differ (see conv_api.cu).
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "internal.h"
 #include "ptx.cuh"
 
@@ -46,6 +48,8 @@ template <int KC, int BN, int kMode>
 struct Cfg {
   static constexpr bool kTma = kMode >= 1;
   static constexpr bool kBnRed = kMode == 2;
+  static constexpr bool kWide = BN >= 128;            // staged epilogue works on 64-column (128-byte) blocks
+  static constexpr int kStgTile = kWide ? 4096 : 2048;  // bytes of one staging / y tile
   static constexpr int kABytes = kBlockM * KC * 2;
   static constexpr int kBBytes = BN * KC * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -65,12 +69,12 @@ struct Cfg {
   static constexpr int kBarBytes = (2 * kMaxStages + 4 + kMaxYSlots * kEpiWarps) * 8 + 16;
   // generic: per-warp [sum | sumsq] rows + fp32 transpose scratch; TMA: one 1 KB-aligned staging tile per warp
   static constexpr int kStatBytes = kTma ? 0 : kEpiWarps * 2 * kAccPerWarp * 4;
-  static constexpr int kScratchBytes = kTma ? kEpiWarps * 2048 : kEpiWarps * 32 * kScratchLd * 4;
+  static constexpr int kScratchBytes = kTma ? kEpiWarps * kStgTile : kEpiWarps * 32 * kScratchLd * 4;
   // shared memory of a launch with `y_slots` y tiles per epilogue warp (0 unless kBnRed); the pipeline gets
   // whatever is left (stages are a RUN-TIME parameter: short-K layers trade stages for a deeper y ring)
   static constexpr int extra_bytes(int y_slots) {
     return 1024 /*align slack*/ + 2048 /*barrier block + align*/ + kStatBytes + kScratchBytes +
-           kEpiWarps * y_slots * 2048;
+           kEpiWarps * y_slots * kStgTile;
   }
   static constexpr int stages_for(int y_slots) {
     const int n = ((kCtasPerSm == 2 ? kSmemMax2 : kSmemMax) - extra_bytes(y_slots)) / kStageBytes;
@@ -281,7 +285,279 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int ew = warp - kEpiWarp0;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may read
     const int half = ew >> 2;      // which chunks of the accumulator: half, half + 2, ...
-    if constexpr (kTma) {
+    if constexpr (kTma && C::kWide) {
+      // ---- staged epilogue, wide form (BN >= 128): a warp owns 64-column blocks (two TMEM chunks) so that every
+      // TMA store / y-tile load moves full 128-byte rows (32 rows x 128 B = 4 KB, SWIZZLE_128B).  With 32-column
+      // blocks the fused BN-backward reduction of the HBM-bound 1x1 gradients read y in 64-byte pieces and ran at
+      // half the DRAM efficiency.
+      constexpr int kBlocks = BN / 64;        // 2 or 4 blocks per tile
+      constexpr int kBPW = kBlocks / 2;       // blocks per warp: block = half + 2 * bi
+      uint8_t* stg = s_extra + ew * 4096;
+      const int sw_w = lane & 7;              // writer: row = lane, 16-byte piece j -> j ^ (row & 7)
+      const int rq = lane & 7, rg = lane >> 3;  // reader: piece rq, rows rg + 4 i (i = 0..7)
+      const int my_col = 8 * rq + 4 * ((lane >> 4) & 1) + 2 * ((lane >> 3) & 1);  // first of the 2 columns owned
+      float acc_s[kBPW][2], acc_t[kBPW][2];
+#pragma unroll
+      for (int i = 0; i < kBPW; ++i) acc_s[i][0] = acc_s[i][1] = acc_t[i][0] = acc_t[i][1] = 0.f;
+      float* const stat_base = kBnRed ? p.bn_sums : p.stats;
+      const int stat_parts = kBnRed ? p.bn_parts : p.stats_parts;
+      float* stats_row =
+          stat_base ? stat_base + static_cast<long long>(blockIdx.x % stat_parts) * 2 * p.Cout : nullptr;
+      auto flush = [&](int nt_) {
+#pragma unroll
+        for (int bi = 0; bi < kBPW; ++bi) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int n = nt_ * BN + (half + 2 * bi) * 64 + my_col + e;
+            if (n < p.Cout) {
+              atomicAdd(stats_row + n, acc_s[bi][e]);
+              atomicAdd(stats_row + p.Cout + n, kBnRed ? acc_t[bi][e] * __ldg(p.bn_rstd + n) : acc_t[bi][e]);
+            }
+            acc_s[bi][e] = acc_t[bi][e] = 0.f;
+          }
+        }
+      };
+      // ---- fused BN backward: ring of TMA-loaded y tiles (4 KB each), `yslots` blocks ahead
+      const int yslots = p.y_slots, ylog = p.y_slots_log2;
+      uint8_t* const ybuf = s_extra + kEpiWarps * 4096 + ew * yslots * 4096;
+      uint64_t* const ybar = y_bar + kMaxYSlots * ew;
+      auto block_valid = [&](int tile, int bi) { return bi < kBPW && (tile % p.num_n_tiles) * BN + (half + 2 * bi) * 64 < p.Cout; };
+      auto next_block = [&](int& tile, int& bi) {
+        do {
+          if (++bi >= kBPW) {
+            bi = 0;
+            tile += gridDim.x;
+          }
+        } while (tile < num_tiles && !block_valid(tile, bi));
+      };
+      auto issue_y = [&](int tile, int bi, int slot) {
+        if (lane == 0) {
+          const int mt = tile / p.num_n_tiles;
+          const int nt = tile - mt * p.num_n_tiles;
+          ptx::mbar_expect_tx(&ybar[slot], 4096);
+          ptx::tma_load_2d(ybuf + slot * 4096, &tmY, &ybar[slot], nt * BN + (half + 2 * bi) * 64,
+                           mt * kBlockM + quarter * 32);
+        }
+      };
+      uint32_t ycount = 0;
+      int pf_tile = blockIdx.x, pf_bi = 0;
+      if (kBnRed) {
+        if (pf_tile < num_tiles && !block_valid(pf_tile, pf_bi)) next_block(pf_tile, pf_bi);
+        for (int d = 0; d < yslots && pf_tile < num_tiles; ++d) {
+          issue_y(pf_tile, pf_bi, d);
+          next_block(pf_tile, pf_bi);
+        }
+      }
+      int stat_nt = -1;
+      bool store_pending = false;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile / p.num_n_tiles;
+        const int nt = tile - mt * p.num_n_tiles;
+        if (stat_base && nt != stat_nt) {
+          if (stat_nt >= 0) flush(stat_nt);
+          stat_nt = nt;
+        }
+        const int m_warp = mt * kBlockM + quarter * 32;
+        const int m = m_warp + lane;
+        const bool row_ok = m < p.M_total;
+        long long r_row = 0;
+        if (p.res) {
+          const int mm = row_ok ? m : 0;
+          const int n_img = mm / p.OHW;
+          const int rem = mm - n_img * p.OHW;
+          const int pr = rem / p.OW;
+          const int qc = rem - pr * p.OW;
+          r_row = n_img * p.r_sn + pr * p.r_sh + qc * p.r_sw;
+        }
+        ptx::mbar_wait(&tfull_bar[acc], acc_phase, p.err, 4);
+        ptx::tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+
+#pragma unroll
+        for (int bi = 0; bi < kBPW; ++bi) {
+          const int b0 = (half + 2 * bi) * 64;
+          const int nb_base = nt * BN + b0;
+          if (nb_base >= p.Cout || (p.dbg & 4)) break;  // warp-uniform
+          // the previous bulk store of this warp must have finished READING the staging tile
+          if (store_pending) {
+            if (lane == 0) ptx::tma_store_wait_read<0>();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const int n_base = nb_base + 32 * cc;
+            float v[32];
+            {
+              uint32_t r[32];
+              ptx::tmem_ld_32x32(t_row + b0 + 32 * cc, r);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            }
+            if (n_base < p.Cout) {
+              const bool full = n_base + 32 <= p.Cout;
+              if (p.scale) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  if (full || n_base + j + 4 <= p.Cout) {
+                    const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + n_base + j));
+                    v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
+                  }
+                }
+              }
+              if (p.shift) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  if (full || n_base + j + 4 <= p.Cout) {
+                    const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.shift + n_base + j));
+                    v[j] += s4.x; v[j + 1] += s4.y; v[j + 2] += s4.z; v[j + 3] += s4.w;
+                  }
+                }
+              }
+              const float neg = p.act == 1 ? p.slope : (p.act == 2 ? 0.f : 1.f);
+              if (p.res) {
+                if (p.res_after_act) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * neg;
+                }
+                const uint4* rp = reinterpret_cast<const uint4*>(p.res + r_row + n_base);
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  if (full || n_base + j + 8 <= p.Cout) {
+                    const uint4 q = __ldg(rp + (j >> 3));
+                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      const float2 f = __bfloat1622float2(h[e]);
+                      v[j + 2 * e] += f.x;
+                      v[j + 2 * e + 1] += f.y;
+                    }
+                  }
+                }
+                if (!p.res_after_act && p.act != 0) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * neg;
+                }
+              } else if (p.act != 0) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * neg;
+              }
+            }
+            if (!row_ok || n_base >= p.Cout) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 pk;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+              *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 * cc + j) ^ sw_w) * 16)) = pk;
+            }
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && !(p.dbg & 1)) {
+            ptx::tma_store_2d(&tmO, stg, nb_base, m_warp);
+            ptx::tma_store_commit();
+          }
+          store_pending = true;
+          if ((kBnRed || p.stats) && !(p.dbg & 2)) {
+            float s[8], t[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s[k] = t[k] = 0.f;
+            if constexpr (kBnRed) {
+              // dz = G * act'(y*scale+shift) from the STORED gradient tile and the TMA-loaded y tile
+              const int yslot = ycount & (yslots - 1);
+              ptx::mbar_wait(&ybar[yslot], (ycount >> ylog) & 1, p.err, 5);
+              const uint8_t* ytile = ybuf + yslot * 4096;
+              const int ncol = nb_base + 8 * rq;
+              float sc[8], sh[8], mu[8];
+              if (ncol + 8 <= p.Cout) {
+#pragma unroll
+                for (int k = 0; k < 8; k += 4) {
+                  const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.bn_scale + ncol + k));
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bn_shift + ncol + k));
+                  const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.bn_mean + ncol + k));
+                  sc[k] = a4.x; sc[k + 1] = a4.y; sc[k + 2] = a4.z; sc[k + 3] = a4.w;
+                  sh[k] = b4.x; sh[k + 1] = b4.y; sh[k + 2] = b4.z; sh[k + 3] = b4.w;
+                  mu[k] = c4.x; mu[k + 1] = c4.y; mu[k + 2] = c4.z; mu[k + 3] = c4.w;
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) sc[k] = sh[k] = mu[k] = 0.f;
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int row = rg + 4 * i;
+                const int off = row * 128 + ((rq ^ (row & 7)) * 16);
+                const uint4 ug = *reinterpret_cast<const uint4*>(stg + off);
+                const uint4 uy = *reinterpret_cast<const uint4*>(ytile + off);
+                const __nv_bfloat162* hg = reinterpret_cast<const __nv_bfloat162*>(&ug);
+                const __nv_bfloat162* hy = reinterpret_cast<const __nv_bfloat162*>(&uy);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 g2 = __bfloat1622float2(hg[e]);
+                  const float2 y2 = __bfloat1622float2(hy[e]);
+                  const float dz0 = g2.x * (fmaf(y2.x, sc[2 * e], sh[2 * e]) > 0.f ? 1.f : p.bn_neg);
+                  const float dz1 = g2.y * (fmaf(y2.y, sc[2 * e + 1], sh[2 * e + 1]) > 0.f ? 1.f : p.bn_neg);
+                  s[2 * e] += dz0;
+                  s[2 * e + 1] += dz1;
+                  t[2 * e] = fmaf(dz0, y2.x - mu[2 * e], t[2 * e]);
+                  t[2 * e + 1] = fmaf(dz1, y2.y - mu[2 * e + 1], t[2 * e + 1]);
+                }
+              }
+            } else {
+              // column sums / sums of squares of the STORED (bf16-rounded) tile
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int row = rg + 4 * i;
+                const uint4 u = *reinterpret_cast<const uint4*>(stg + row * 128 + ((rq ^ (row & 7)) * 16));
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __bfloat1622float2(h[e]);
+                  s[2 * e] += f.x;
+                  s[2 * e + 1] += f.y;
+                  t[2 * e] = fmaf(f.x, f.x, t[2 * e]);
+                  t[2 * e + 1] = fmaf(f.y, f.y, t[2 * e + 1]);
+                }
+              }
+            }
+            // keep-half butterfly over the 4 row-group lanes (lane bits 4, 3): two columns per lane remain
+            keep_half_step<4, 16>(s, t, lane);
+            keep_half_step<2, 8>(s, t, lane);
+            acc_s[bi][0] += s[0];
+            acc_s[bi][1] += s[1];
+            acc_t[bi][0] += t[0];
+            acc_t[bi][1] += t[1];
+            __syncwarp();  // all lanes are done reading: the tiles may be overwritten / refilled
+            if constexpr (kBnRed) {
+              const int yslot = ycount & (yslots - 1);
+              ++ycount;
+              if (pf_tile < num_tiles) {
+                issue_y(pf_tile, pf_bi, yslot);
+                next_block(pf_tile, pf_bi);
+              }
+            }
+          }
+        }
+        // accumulator drained: hand the TMEM stage back to the MMA warp
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+      if (stat_base && stat_nt >= 0) flush(stat_nt);
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
+      __syncwarp();
+    } else if constexpr (kTma) {
       // ---- staged epilogue: registers -> swizzled smem tile -> TMA bulk store; statistics from the staged tile
       constexpr int RB = C::kChunk * 2;  // bytes per staged row: 64 (SWIZZLE_64B) or 32 (SWIZZLE_32B)
       constexpr int NJ = RB / 16;        // 16-byte pieces per row
@@ -801,8 +1077,9 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
   q.y_slots_log2 = 0;
   if (C::kBnRed) {
     const int kit = p.num_taps * p.cblocks + p.res_iters;
-    q.y_slots = kit >= 16 ? 1 : 4;
-    while (q.y_slots > 1 && C::stages_for(q.y_slots) < 3) q.y_slots >>= 1;
+    static const int forced = getenv("B200CV_Y_SLOTS") ? atoi(getenv("B200CV_Y_SLOTS")) : 0;  // tuning aid
+    q.y_slots = forced ? forced : (kit >= 16 ? 1 : 4);
+    while (q.y_slots > 1 && C::stages_for(q.y_slots) < (forced ? 2 : 3)) q.y_slots >>= 1;
     q.y_slots_log2 = q.y_slots == 4 ? 2 : (q.y_slots == 2 ? 1 : 0);
   }
   q.stages = C::stages_for(q.y_slots);
