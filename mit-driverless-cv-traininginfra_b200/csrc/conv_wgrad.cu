@@ -195,7 +195,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
       const int quarter = warp & 3;
       constexpr int RB = kChunk * 4;  // bytes per staged row: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
       constexpr int NJ = RB / 16;
-      uint8_t* stg = s_stage + (warp - 2) * 4096;
+      // Staging: once done_bar has fired every TMA load has landed and every MMA has read its operands, so the whole
+      // pipeline ring is free -- each epilogue warp takes a quarter of it as a ring of 4 KB tiles and keeps all its
+      // reduce-adds in flight (with the single 4 KB tile of the first version every chunk waited ~0.4 us for the
+      // previous reduce to finish reading it: ~5 us of non-overlapped tail per CTA).
+      const int ring_slots = max(1, (p.stages * stage_bytes / 4) / 4096);
+      uint8_t* const ring = (p.stages * stage_bytes / 4 >= 4096) ? smem + (warp - 2) * ring_slots * 4096
+                                                                 : s_stage + (warp - 2) * 4096;
+      int slot = 0;
       const int sw = RB == 128 ? (lane & 7) : ((lane >> 1) & 3);
       const int o_row = ot * 128 + quarter * 32;
       ptx::mbar_wait(done_bar, 0, p.err, 13);
@@ -222,10 +229,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
           }
           const int i0 = it * BNW + c0;
           if (o_row < p.Cout && i0 < p.Cin) {  // warp-uniform
-            if (pending) {  // the previous reduce of this warp must have finished reading the staging tile
+            if (pending && slot == 0) {  // ring wrapped: the earlier reduces must have finished reading their tiles
               if (lane == 0) ptx::tma_store_wait_read<0>();
               __syncwarp();
             }
+            uint8_t* stg = ring + slot * 4096;
 #pragma unroll
             for (int j = 0; j < NJ; ++j)
               *reinterpret_cast<float4*>(stg + lane * RB + ((j ^ sw) * 16)) =
@@ -237,6 +245,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
               ptx::tma_store_commit();
             }
             pending = true;
+            if (++slot == ring_slots) slot = 0;
           }
         }
       }

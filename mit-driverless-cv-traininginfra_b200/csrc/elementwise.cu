@@ -287,14 +287,16 @@ __global__ void __launch_bounds__(kEwThreads, V == 8 ? 2 : 4) bn_stats_apply_ker
 #pragma unroll
     for (int u = 0; u < kEwUnroll; ++u) {
       const long long rr = r + u * stride;
+      const long long rw = a.rows - 1 - rr;  // walk the rows backwards: the producer wrote the tail last (L2-hot)
       if (rr < a.rows) {
-        qy[u] = ldg_streamV<V>(a.y + rr * a.y_ld + c0);
-        if (kPost) qp[u] = ldg_streamV<V>(a.post + rr * a.post_ld + c0);
+        qy[u] = ldg_streamV<V>(a.y + rw * a.y_ld + c0);
+        if (kPost) qp[u] = ldg_streamV<V>(a.post + rw * a.post_ld + c0);
       }
     }
 #pragma unroll
     for (int u = 0; u < kEwUnroll; ++u) {
       const long long rr = r + u * stride;
+      const long long rw = a.rows - 1 - rr;  // walk the rows backwards: the producer wrote the tail last (L2-hot)
       if (rr < a.rows) {
         float v[V], z[V];
         unpackV(qy[u], v);
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(kEwThreads, V == 8 ? 2 : 4) bn_stats_apply_ker
 #pragma unroll
           for (int j = 0; j < V; ++j) z[j] += w[j];
         }
-        storeV(a.out + rr * a.out_ld + c0, z);
+        storeV(a.out + rw * a.out_ld + c0, z);
       }
     }
   }
@@ -561,14 +563,16 @@ __global__ void __launch_bounds__(kEwThreads, V == 8 ? 2 : 4) bn_bwd_stats_apply
 #pragma unroll
     for (int u = 0; u < kEwUnroll; ++u) {
       const long long rr = r + u * stride;
+      const long long rw = a.rows - 1 - rr;  // walk the rows backwards: the producer wrote the tail last (L2-hot)
       if (rr < a.rows) {
-        qda[u] = ldg_streamV<V>(a.da + rr * a.da_ld + c0);
-        qy[u] = ldg_streamV<V>(a.y + rr * a.y_ld + c0);
+        qda[u] = ldg_streamV<V>(a.da + rw * a.da_ld + c0);
+        qy[u] = ldg_streamV<V>(a.y + rw * a.y_ld + c0);
       }
     }
 #pragma unroll
     for (int u = 0; u < kEwUnroll; ++u) {
       const long long rr = r + u * stride;
+      const long long rw = a.rows - 1 - rr;  // walk the rows backwards: the producer wrote the tail last (L2-hot)
       if (rr < a.rows) {
         float da[V], y[V], o[V];
         unpackV(qda[u], da);
@@ -579,7 +583,7 @@ __global__ void __launch_bounds__(kEwThreads, V == 8 ? 2 : 4) bn_bwd_stats_apply
           const float dz = da[j] * (z > 0.f ? 1.f : neg);
           o[j] = fmaf(g[j], dz, fmaf(A[j], y[j], B[j]));
         }
-        storeV(a.dy + rr * a.dy_ld + c0, o);
+        storeV(a.dy + rw * a.dy_ld + c0, o);
       }
     }
   }
