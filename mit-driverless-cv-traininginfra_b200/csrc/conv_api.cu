@@ -89,6 +89,16 @@ int run_igemm(const Geometry& g, const void* act, const void* wpk, int64_t w_row
   const bool tma_out = !no_tma_store && !p.out_fp32 && p.vec_ok && p.o_sc == 1 && ld >= p.Cout && ld % 8 == 0 &&
                        p.o_sh == (long long)p.OW * ld && p.o_sn == (long long)p.OHW * ld && p.Cout % 8 == 0 &&
                        (!p.res || p.res_vec_ok);
+  // 256-row tiles for 128-wide GEMMs (data gradients of the 128-channel 3x3 layers, forward 64->128): the weight
+  // tile is shared by two sub-tiles.  Only when there are enough tiles left to fill the machine twice.
+  static const bool no_m2 = getenv("B200CV_NO_M2") != nullptr;
+  p.tile_m = 128;
+  // (not for short K loops: the HBM-bound 1x1 layers lose -- 35 -> 52 us for 256->128 @52x52)
+  if (tma_out && !no_m2 && kc == 64 && bn == 128 && p.num_taps * p.cblocks >= 8 &&
+      (p.M_total + 255) / 256 * p.num_n_tiles >= 2 * sm_count()) {
+    p.tile_m = 256;
+    p.num_m_tiles = (p.M_total + 255) / 256;
+  }
   if (tma_out) {
     CUtensorMap tmO, tmY;
     const int ebox = bn >= 128 ? 64 : (bn >= 32 ? 32 : 16);  // epilogue block width (conv_igemm.cu: kWide)

@@ -44,19 +44,27 @@ constexpr int kMaxYSlots = 4;
 // swizzled shared memory and writes them with TMA bulk stores; BN statistics are read back from the staged
 // tile.  Otherwise ("generic": fp32 / strided / ragged outputs) rows are stored directly from registers.
 // kMode 2 = kTma plus the fused BN-backward reduction (a 2-deep ring of TMA-loaded y tiles per epilogue warp).
-template <int KC, int BN, int kMode>
+// kM2: the tile is 256 output pixels = two 128-row sub-tiles that share every B (weight) tile -- for GEMMs whose N is
+// only 128 wide this cuts the L2->SM bytes per FLOP by a quarter (A 32 KB + B 16 KB per 512 tensor cycles, the
+// ratio of a 128x256 tile).  Epilogue warps 2..5 take sub-tile 0, warps 6..9 sub-tile 1.
+template <int KC, int BN, int kMode, bool kM2 = false>
 struct Cfg {
+  static_assert(!kM2 || (BN == 128 && kMode >= 1), "the 256-row tile exists for BN == 128 with the staged epilogue");
+  static constexpr int kSub = kM2 ? 2 : 1;           // 128-row sub-tiles per tile
+  static constexpr int kTileM = 128 * kSub;
+  static constexpr int kAccCols = BN * kSub;         // TMEM columns of one accumulator stage
   static constexpr bool kTma = kMode >= 1;
   static constexpr bool kBnRed = kMode == 2;
   static constexpr bool kWide = BN >= 128;            // staged epilogue works on 64-column (128-byte) blocks
   static constexpr int kStgTile = kWide ? 4096 : 2048;  // bytes of one staging / y tile
-  static constexpr int kABytes = kBlockM * KC * 2;
+  static constexpr int kASubBytes = kBlockM * KC * 2;
+  static constexpr int kABytes = kSub * kASubBytes;
   static constexpr int kBBytes = BN * KC * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   // Small stages (<= 24 KB: the 16/32/64-channel layers) are bound by the per-k-iteration overhead of the single
   // producer / MMA threads (~150 cycles per TMA instruction issued), not by bandwidth: run two CTAs per SM (each
   // with a shallower ring) so that two producers and two MMA issuers work per SM.
-  static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : (2 * BN);
+  static constexpr int kTmemCols = (2 * kAccCols) < 32 ? 32 : (2 * kAccCols);
   static constexpr int kCtasPerSm = (kStageBytes <= 24 * 1024 && kTmemCols <= 256) ? 2 : 1;
   static constexpr int kRowBytes = KC * 2;               // 32 / 64 / 128
   static constexpr int kLayout = KC == 64 ? 2 : (KC == 32 ? 4 : 6);
@@ -104,13 +112,13 @@ __device__ __forceinline__ void keep_half_step(float (&s)[8], float (&t)[8], int
   }
 }
 
-template <int KC, int BN, int kMode>
-__global__ void __launch_bounds__(kThreads, Cfg<KC, BN, kMode>::kCtasPerSm)
+template <int KC, int BN, int kMode, bool kM2>
+__global__ void __launch_bounds__(kThreads, Cfg<KC, BN, kMode, kM2>::kCtasPerSm)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmI,
              const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmY,
              const __grid_constant__ IgemmParams p) {
-  using C = Cfg<KC, BN, kMode>;
+  using C = Cfg<KC, BN, kMode, kM2>;
   constexpr bool kTma = C::kTma;
   constexpr bool kBnRed = C::kBnRed;
   extern __shared__ uint8_t smem_raw[];
@@ -177,13 +185,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mt = tile / p.num_n_tiles;
         const int nt = tile - mt * p.num_n_tiles;
-        const int m0 = mt * kBlockM;
+        const int m0 = mt * C::kTileM;
         const int n_img = m0 / p.OHW;
         const int rem = m0 - n_img * p.OHW;
         const int pr = rem / p.OW;
         const int qc = rem - pr * p.OW;
         const int cw = p.lower_w + qc * p.trav_w;
         const int ch = p.lower_h + pr * p.trav_h;
+        // second 128-row sub-tile (kM2): its own base pixel; past the last image the loads are zero-filled
+        const int m1 = m0 + kBlockM;
+        const int n_img1 = m1 / p.OHW;
+        const int rem1 = m1 - n_img1 * p.OHW;
+        const int pr1 = rem1 / p.OW;
+        const int cw1 = p.lower_w + (rem1 - pr1 * p.OW) * p.trav_w;
+        const int ch1 = p.lower_h + pr1 * p.trav_h;
         for (int tap = 0; tap < p.num_taps; ++tap) {
           const uint16_t ow = static_cast<uint16_t>(p.tap_w[tap]);
           const uint16_t oh = static_cast<uint16_t>(p.tap_h[tap]);
@@ -194,6 +209,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             uint8_t* sb = sa + C::kABytes;
             ptx::mbar_expect_tx(&full_bar[stage], C::kStageBytes);
             ptx::tma_load_im2col_4d(sa, &tmA, &full_bar[stage], cb * KC, cw, ch, n_img, ow, oh);
+            if constexpr (kM2)
+              ptx::tma_load_im2col_4d(sa + C::kASubBytes, &tmA, &full_bar[stage], cb * KC, cw1, ch1, n_img1, ow, oh);
             ptx::tma_load_2d(sb, &tmB, &full_bar[stage], kb + cb * KC, nt * BN);
             if (++stage == nstages) {
               stage = 0;
@@ -213,6 +230,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int sl = 0; sl < BN / 64; ++sl)
               ptx::tma_load_2d(sb + sl * KC * 128, &tmR, &full_bar[stage], nt * BN + sl * 64, m0 + j * KC);
+            if constexpr (kM2) {  // residual rows of sub-tile 1 go where its A tile would be (same size: BN == 128)
+#pragma unroll
+              for (int sl = 0; sl < BN / 64; ++sl)
+                ptx::tma_load_2d(sa + C::kASubBytes + sl * KC * 128, &tmR, &full_bar[stage], nt * BN + sl * 64,
+                                 m1 + j * KC);
+            }
             if (++stage == nstages) {
               stage = 0;
               phase ^= 1;
@@ -232,7 +255,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (lane == 0) {
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err, 2);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * C::kAccCols;
         for (int it = 0; it < kiters; ++it) {
           ptx::mbar_wait(&full_bar[stage], phase, p.err, 3);
           ptx::tc_fence_after();
@@ -244,6 +267,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int k = 0; k < KC / 16; ++k) {
             // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the >>4 field
             ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+            if constexpr (kM2) {
+              const uint64_t adesc1 = ptx::make_smem_desc(sa + C::kASubBytes, 16, C::kSBO, C::kLayout);
+              ptx::umma_bf16(d_tmem + BN, adesc1 + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+            }
           }
           ptx::umma_commit(&empty_bar[stage]);
           if (++stage == nstages) {
@@ -264,6 +291,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               // MN-major B: LBO = distance between 64-channel slabs, SBO = 8 rows of 128 bytes
               const uint64_t bdesc = ptx::make_smem_desc(sb + k * 16 * 128, KC * 128, 8 * 128, 2);
               ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc, idesc_res, 1u);
+              if constexpr (kM2) {
+                const uint64_t bdesc1 =
+                    ptx::make_smem_desc(sa + C::kASubBytes + k * 16 * 128, KC * 128, 8 * 128, 2);
+                ptx::umma_bf16(d_tmem + BN, adesc + 2 * k, bdesc1, idesc_res, 1u);
+              }
             }
             ptx::umma_commit(&empty_bar[stage]);
             if (++stage == nstages) {
@@ -291,7 +323,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // blocks the fused BN-backward reduction of the HBM-bound 1x1 gradients read y in 64-byte pieces and ran at
       // half the DRAM efficiency.
       constexpr int kBlocks = BN / 64;        // 2 or 4 blocks per tile
-      constexpr int kBPW = kBlocks / 2;       // blocks per warp: block = half + 2 * bi
+      // blocks per warp: block = half + 2 * bi; with 256-row tiles `half` selects the sub-tile and a warp takes all
+      constexpr int kBPW = kM2 ? kBlocks : kBlocks / 2;
+      auto block_of = [&](int bi) { return kM2 ? bi : half + 2 * bi; };
+      const int sub_m = kM2 ? half * kBlockM : 0;   // row offset of this warp's sub-tile
+      const int sub_c = kM2 ? half * BN : 0;        // TMEM column offset of its accumulator
       uint8_t* stg = s_extra + ew * 4096;
       const int sw_w = lane & 7;              // writer: row = lane, 16-byte piece j -> j ^ (row & 7)
       const int rq = lane & 7, rg = lane >> 3;  // reader: piece rq, rows rg + 4 i (i = 0..7)
@@ -308,7 +344,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int bi = 0; bi < kBPW; ++bi) {
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const int n = nt_ * BN + (half + 2 * bi) * 64 + my_col + e;
+            const int n = nt_ * BN + block_of(bi) * 64 + my_col + e;
             if (n < p.Cout) {
               atomicAdd(stats_row + n, acc_s[bi][e]);
               atomicAdd(stats_row + p.Cout + n, kBnRed ? acc_t[bi][e] * __ldg(p.bn_rstd + n) : acc_t[bi][e]);
@@ -321,7 +357,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int yslots = p.y_slots, ylog = p.y_slots_log2;
       uint8_t* const ybuf = s_extra + kEpiWarps * 4096 + ew * yslots * 4096;
       uint64_t* const ybar = y_bar + kMaxYSlots * ew;
-      auto block_valid = [&](int tile, int bi) { return bi < kBPW && (tile % p.num_n_tiles) * BN + (half + 2 * bi) * 64 < p.Cout; };
+      auto block_valid = [&](int tile, int bi) { return bi < kBPW && (tile % p.num_n_tiles) * BN + block_of(bi) * 64 < p.Cout; };
       auto next_block = [&](int& tile, int& bi) {
         do {
           if (++bi >= kBPW) {
@@ -335,8 +371,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const int mt = tile / p.num_n_tiles;
           const int nt = tile - mt * p.num_n_tiles;
           ptx::mbar_expect_tx(&ybar[slot], 4096);
-          ptx::tma_load_2d(ybuf + slot * 4096, &tmY, &ybar[slot], nt * BN + (half + 2 * bi) * 64,
-                           mt * kBlockM + quarter * 32);
+          ptx::tma_load_2d(ybuf + slot * 4096, &tmY, &ybar[slot], nt * BN + block_of(bi) * 64,
+                           mt * C::kTileM + sub_m + quarter * 32);
         }
       };
       uint32_t ycount = 0;
@@ -359,7 +395,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (stat_nt >= 0) flush(stat_nt);
           stat_nt = nt;
         }
-        const int m_warp = mt * kBlockM + quarter * 32;
+        const int m_warp = mt * C::kTileM + sub_m + quarter * 32;
         const int m = m_warp + lane;
         const bool row_ok = m < p.M_total;
         long long r_row = 0;
@@ -373,11 +409,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         ptx::mbar_wait(&tfull_bar[acc], acc_phase, p.err, 4);
         ptx::tc_fence_after();
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+        const uint32_t t_row =
+            tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * C::kAccCols + sub_c;
 
 #pragma unroll
         for (int bi = 0; bi < kBPW; ++bi) {
-          const int b0 = (half + 2 * bi) * 64;
+          const int b0 = block_of(bi) * 64;
           const int nb_base = nt * BN + b0;
           if (nb_base >= p.Cout || (p.dbg & 4)) break;  // warp-uniform
           // the previous bulk store of this warp must have finished READING the staging tile
@@ -1065,10 +1102,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 }
 
-template <int KC, int BN, int kMode>
+template <int KC, int BN, int kMode, bool kM2 = false>
 int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmI,
                const CUtensorMap& tmR, const CUtensorMap& tmY, const IgemmParams& p, cudaStream_t stream) {
-  using C = Cfg<KC, BN, kMode>;
+  using C = Cfg<KC, BN, kMode, kM2>;
   static_assert(C::stages_for(C::kBnRed ? 1 : 0) >= 2, "pipeline too shallow");
   IgemmParams q = p;
   // y ring depth of the fused BN-backward reduction: tiles with few k-iterations (1x1 layers) finish a chunk in
@@ -1086,7 +1123,7 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
   const int smem_bytes = C::extra_bytes(q.y_slots) + q.stages * C::kStageBytes;
   constexpr int kSmemAttr = C::kCtasPerSm == 2 ? kSmemMax2 : kSmemMax;
   static bool configured = false;  // benign race: attribute set is idempotent
-  auto kern = igemm_kernel<KC, BN, kMode>;
+  auto kern = igemm_kernel<KC, BN, kMode, kM2>;
   if (!configured) {
     cudaError_t e =
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAttr);
@@ -1113,6 +1150,12 @@ int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
     return set_error(B200CV_ERR_ARG, "igemm: tensor-core residual needs identity/residual maps and block_n %% 64 == 0");
   const CUtensorMap& mI = tmI ? *tmI : tmA;  // unused copies when the feature is off
   const CUtensorMap& mR = tmR ? *tmR : tmA;
+  if (p.tile_m == 256) {  // two 128-row sub-tiles per tile: BN == 128, KC == 64, staged epilogue only
+    if (kc != 64 || block_n != 128 || !tmO)
+      return set_error(B200CV_ERR_ARG, "igemm: the 256-row tile needs kc 64, block_n 128 and the staged epilogue");
+    return p.bn_sums ? launch_one<64, 128, 2, true>(tmA, tmB, *tmO, mI, mR, *tmY, p, stream)
+                     : launch_one<64, 128, 1, true>(tmA, tmB, *tmO, mI, mR, tmA, p, stream);
+  }
 #define B200CV_IGEMM_CASE(KC_, BN_)                                                        \
   if (kc == KC_ && block_n == BN_)                                                         \
     return !tmO ? launch_one<KC_, BN_, 0>(tmA, tmB, tmA, mI, mR, tmA, p, stream)           \

@@ -17,6 +17,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "internal.h"
 #include "ptx.cuh"
@@ -340,6 +341,10 @@ extern "C" int b200cv_conv_wgrad(const void* x, const void* dy, float* dw_packed
   // split-K so that the grid fills (at most) two full waves of one CTA per SM: rounding the split UP left a
   // third, nearly empty wave (e.g. 312 CTAs on 148 SMs)
   int ksplit = std::max(1, (2 * sm_count()) / base_ctas);
+  // short K ranges (1x1 layers at 13^2 / 26^2): one wave of longer CTAs halves the per-CTA fixed cost
+  // (prologue, pipeline fill, epilogue) that dominates them
+  static const int one_wave_below = getenv("B200CV_WGRAD_1WAVE") ? atoi(getenv("B200CV_WGRAD_1WAVE")) : 24;
+  if (p.kb_total / ksplit < one_wave_below && base_ctas <= sm_count()) ksplit = std::max(1, sm_count() / base_ctas);
   ksplit = std::min(ksplit, std::max(1, p.kb_total / 4));
   p.ksplit = ksplit;
 

@@ -45,6 +45,7 @@ struct IgemmParams {
   int num_taps, cblocks;  // k-iterations = num_taps * cblocks
   int Cout;               // valid columns of D
   int num_m_tiles, num_n_tiles;
+  int tile_m;  // 128, or 256 = two sub-tiles sharing the weight tiles (see conv_igemm.cu, kM2)
   // epilogue: v = acc*scale[n] + shift[n] (+ residual) -> act -> store; stats on the stored value
   void* out;
   int out_fp32;  // 0: bf16, 1: fp32
