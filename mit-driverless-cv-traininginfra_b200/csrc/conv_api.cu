@@ -564,14 +564,14 @@ extern "C" int b200cv_unpack_wgrad(const float* src, float* dst, int O, int I, i
 extern "C" int b200cv_pack_weights_multi(const void* table_dev, int n, void* stream) {
   B200CV_CHECK_ARG(table_dev && n > 0 && n <= 65535, "pack_weights_multi: bad args");
   static_assert(sizeof(PackEntry) == sizeof(b200cv_pack_entry), "pack entry ABI mismatch");
-  pack_weights_multi_kernel<<<dim3(64, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  pack_weights_multi_kernel<<<dim3(256, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const PackEntry*>(table_dev));
   return check_launch("pack_weights_multi");
 }
 
 extern "C" int b200cv_unpack_wgrad_multi(const void* table_dev, int n, void* stream) {
   B200CV_CHECK_ARG(table_dev && n > 0 && n <= 65535, "unpack_wgrad_multi: bad args");
-  unpack_wgrad_multi_kernel<<<dim3(64, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  unpack_wgrad_multi_kernel<<<dim3(256, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const PackEntry*>(table_dev));
   return check_launch("unpack_wgrad_multi");
 }
