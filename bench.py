@@ -349,7 +349,10 @@ def bench_rektnet(dev, rank, world, steps, warmup, timed):
     torch.manual_seed(17)
     net = keypoint_net.KeypointNet().to(dev).train()
     x, thm, tpts = (t.to(dev) for t in RO.synth_batch(B, seed=rank))
-    loss_fn = cross_ratio_loss.CrossRatioLoss("l2_heatmap", True, 0.055, 0.038)
+    import contextlib
+
+    with contextlib.redirect_stdout(sys.stderr):  # the reference-compatible constructor prints its settings
+        loss_fn = cross_ratio_loss.CrossRatioLoss("l2_heatmap", True, 0.055, 0.038)
     params = list(net.parameters())
 
     def step():
