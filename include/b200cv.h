@@ -266,6 +266,44 @@ int b200cv_kpt_loss_bwd(const float* hm, const float* thm, const float* pts, con
                         const float* g_loc, const float* g_geo, int B, int K, int H, int W, int loss_type,
                         int include_geo, float gamma_h, float gamma_v, float* d_pts, float* d_hm, void* stream);
 
+/* ---- detection post-processing and the detect -> RektNet joint ----------------------- */
+/* Confidence filter + greedy top-k NMS, one image per CTA, no host round trip.
+ * Replaces CVC-YOLOv3/detect.py:84-90 (rows with conf > conf_thres, (cx,cy,w,h) -> corners) and
+ * CVC-YOLOv3/utils/nms.py:4-61 (visit in descending score, drop boxes with IoU > nms_thres, at most top_k
+ * candidates).  det = Darknet eval output [B][rows][row_len] fp32 (row = cx,cy,w,h,conf,cls... for box_format 0;
+ * x1,y1,x2,y2,score,... for box_format 1 = the arguments of nms() itself), images det_batch_stride elements apart;
+ * conf_thres = -inf keeps every row as a candidate.  Equal scores are visited later-row-first (= the reversed STABLE ascending sort;
+ * the reference's unstable sort leaves that order open).  Outputs, in visiting order and zero / -1 filled past
+ * counts[b]: boxes [B][top_k][4] (x1,y1,x2,y2), scores [B][top_k], det_rows int32 [B][top_k] (row of `det`),
+ * counts int32 [B].  top_k <= 512. */
+int b200cv_detect_nms(const float* det, int64_t det_batch_stride, int B, int rows, int row_len, int box_format,
+                      float conf_thres, float nms_thres, int top_k, float* boxes, float* scores, int32_t* det_rows,
+                      int32_t* counts, void* stream);
+/* counts int32 [B] -> offsets int32 [B+1] (exclusive scan, offsets[B] = number of crops) and src int32 [n][2] =
+ * (image, slot) of crop n; src must hold B*top_k rows.  B <= 1024. */
+int b200cv_detect_compact(const int32_t* counts, int B, int top_k, int32_t* offsets, int32_t* src, void* stream);
+/* Crop + `cv2.resize(crop, (out_w,out_h))` (8-bit INTER_LINEAR, bit-exact with OpenCV's fixed-point kernel) +
+ * HWC->CHW + /255.0 -> fp32: RektNet/utils.py:73-76 (prep_image), RektNet/detect.py:32-34.
+ * frames u8 [B][H][W][3]; crop n takes boxes[src[n][0]][src[n][1]] (network-input corners), maps it to the frame by
+ * x / ratio - pad (CVC-YOLOv3/detect.py:93-96) with geom = (ratio, pad_w, pad_h) per image (geom_stride floats
+ * apart, 0 = shared), floors / ceils it to a non-empty rectangle inside the frame.
+ * out fp32 [n_crops][3][out_h][out_w]; rects int32 [n_crops][4] = x0,y0,x1,y1 (exclusive). */
+int b200cv_crop_resize_u8(const uint8_t* frames, int B, int H, int W, const float* boxes, int top_k,
+                          const int32_t* src, int n_crops, const float* geom, int geom_stride, int out_w, int out_h,
+                          float* out, int32_t* rects, void* stream);
+
+/* ---- optimizer steps ------------------------------------------------------------------ */
+/* One launch per param group.  table: device int64 [n_chunks][5] = {param*, grad*, state1*, state2*, count} (fp32
+ * arrays; a chunk is processed by one CTA, keep count around 16K).
+ * Adam = torch.optim.Adam(lr, betas, eps, weight_decay) as called at CVC-YOLOv3/train.py:181, RektNet/train_eval.py:263:
+ * state1 = exp_avg, state2 = exp_avg_sq, step_size = lr / (1 - beta1^t), bias_correction2_sqrt = sqrt(1 - beta2^t). */
+int b200cv_adam_step_multi(const int64_t* table, int n_chunks, float step_size, float beta1, float beta2, float eps,
+                           float weight_decay, float bias_correction2_sqrt, void* stream);
+/* SGD = torch.optim.SGD(lr, momentum, weight_decay) of CVC-YOLOv3/train.py:185: state1 = momentum_buffer (NULL when
+ * momentum == 0), first_step != 0 initialises the buffer with the gradient. */
+int b200cv_sgd_step_multi(const int64_t* table, int n_chunks, float lr, float momentum, float weight_decay,
+                          int first_step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,377 @@
+// Detection post-processing and the detect -> RektNet joint (BASELINE config 5):
+//   * detect_nms_kernel: confidence filter + (cx,cy,w,h) -> corners (CVC-YOLOv3/detect.py:84-90) and the greedy
+//     top-k NMS of CVC-YOLOv3/utils/nms.py:4-61, one CTA per image, no host round trip;
+//   * detect_compact_kernel: per-image keep counts -> a flat crop list;
+//   * crop_resize_kernel: `cv2.resize(frame[y0:y1, x0:x1], (w,h))` (8-bit INTER_LINEAR, the fixed-point algorithm of
+//     OpenCV's resize.cpp) + HWC->CHW + /255.0 of RektNet/utils.py:73-76, RektNet/detect.py:32-34.
+// Compiled with -fmad=false: box corners, areas, IoUs and the interpolation tables must reproduce the reference's
+// fp32/fp64 arithmetic exactly (kept-index sets and crop bytes are compared bit-for-bit).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "internal.h"
+
+namespace b200cv {
+namespace {
+
+constexpr int kNmsThreads = 512;
+constexpr int kNmsMaxK = 512;  // top_k limit: the suppression bit matrix is kNmsMaxK x kNmsMaxK/32 words of smem
+
+// Order-preserving map float -> uint32 (any sign), so that (score, row) pairs compare as one 64-bit integer.
+__device__ __forceinline__ unsigned long long nms_key(float conf, int row) {
+  const unsigned u = __float_as_uint(conf);
+  const unsigned m = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ((unsigned long long)m << 32) | (unsigned)row;
+}
+__device__ __forceinline__ float nms_key_score(unsigned long long k) {
+  const unsigned m = (unsigned)(k >> 32);
+  return __uint_as_float((m & 0x80000000u) ? (m & 0x7fffffffu) : ~m);
+}
+
+// One CTA per image.  Order of visit = (score descending, row descending): the reversed stable ascending sort.
+__global__ void __launch_bounds__(kNmsThreads)
+detect_nms_kernel(const float* __restrict__ det, long long batch_stride, int rows, int row_len, float conf_thres,
+                  float nms_thres, int top_k, int corners, float* __restrict__ boxes_out, float* __restrict__ scores_out,
+                  int* __restrict__ rows_out, int* __restrict__ counts) {
+  __shared__ unsigned hist[256];  // radix-select histogram; reused as the keep list (shorts) after the selection
+  __shared__ unsigned long long keys[kNmsMaxK];
+  __shared__ float4 box[kNmsMaxK];
+  __shared__ float area[kNmsMaxK];
+  __shared__ unsigned supp[kNmsMaxK][kNmsMaxK / 32];
+  static_assert(sizeof(hist) >= kNmsMaxK * sizeof(short), "keep list must fit in the histogram");
+  short* keep = reinterpret_cast<short*>(hist);
+  __shared__ unsigned s_cnt, s_need, s_nkeep;
+  __shared__ unsigned long long s_prefix;
+
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x;
+  const float* d = det + (size_t)b * batch_stride;
+
+  // ---- candidates: conf > thres
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  unsigned mine = 0;
+  for (int r = tid; r < rows; r += kNmsThreads) mine += d[(size_t)r * row_len + 4] > conf_thres;
+  for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if ((tid & 31) == 0 && mine) atomicAdd(&s_cnt, mine);
+  __syncthreads();
+  const int n_cand = (int)s_cnt;
+  const int n_sel = n_cand < top_k ? n_cand : top_k;
+
+  // ---- the top_k-th largest key by MSB-first radix select (keys are unique: the row is part of the key)
+  unsigned long long thresh_key = 0;
+  if (n_cand > top_k) {
+    if (tid == 0) {
+      s_prefix = 0;
+      s_need = (unsigned)top_k;
+    }
+    unsigned long long known = 0;  // mask of the key bits already fixed
+    for (int pass = 7; pass >= 0; --pass) {
+      if (tid < 256) hist[tid] = 0;
+      __syncthreads();
+      const unsigned long long prefix = s_prefix;
+      const unsigned need = s_need;
+      const int shift = pass * 8;
+      for (int r = tid; r < rows; r += kNmsThreads) {
+        const float c = d[(size_t)r * row_len + 4];
+        if (c > conf_thres) {
+          const unsigned long long k = nms_key(c, r);
+          if ((k & known) == prefix) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
+        }
+      }
+      __syncthreads();
+      if (tid < 32) {
+        // lane l owns digits 255-8l .. 248-8l (descending); suffix counts by a shuffle scan over the lanes
+        unsigned h[8], s = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          h[j] = hist[255 - 8 * tid - j];
+          s += h[j];
+        }
+        unsigned incl = s;
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (tid >= o) incl += v;
+        }
+        unsigned above = incl - s;  // keys with a larger digit than this lane's
+        if (above < need && need <= incl) {  // exactly one lane: the digit of the need-th largest key is here
+          for (int j = 0; j < 8; ++j) {
+            if (need <= above + h[j]) {
+              s_prefix = prefix | ((unsigned long long)(255 - 8 * tid - j) << shift);
+              s_need = need - above;
+              break;
+            }
+            above += h[j];
+          }
+        }
+      }
+      known |= 0xffull << shift;
+      __syncthreads();
+    }
+    thresh_key = s_prefix;
+  }
+
+  // ---- gather the selected keys, sort them descending (bitonic, padded with zeros)
+  int P = 1;
+  while (P < n_sel) P <<= 1;
+  for (int i = tid; i < P; i += kNmsThreads) keys[i] = 0;
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  for (int r = tid; r < rows; r += kNmsThreads) {
+    const float c = d[(size_t)r * row_len + 4];
+    if (c > conf_thres) {
+      const unsigned long long k = nms_key(c, r);
+      if (k >= thresh_key) {
+        const unsigned slot = atomicAdd(&s_cnt, 1u);
+        if (slot < (unsigned)kNmsMaxK) keys[slot] = k;
+      }
+    }
+  }
+  __syncthreads();
+  for (int k2 = 2; k2 <= P; k2 <<= 1) {
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < P; i += kNmsThreads) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = keys[i], c = keys[l];
+          const bool desc = (i & k2) == 0;
+          if (desc ? (a < c) : (a > c)) {
+            keys[i] = c;
+            keys[l] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- corner boxes and areas (detect.py:86-89, nms.py:19-23)
+  for (int i = tid; i < n_sel; i += kNmsThreads) {
+    const int r = (int)(unsigned)(keys[i] & 0xffffffffull);
+    const float* q = d + (size_t)r * row_len;
+    float4 bx;
+    if (corners) {
+      bx = make_float4(q[0], q[1], q[2], q[3]);
+    } else {
+      const float hw = q[2] / 2.f, hh = q[3] / 2.f;
+      bx.x = q[0] - hw;
+      bx.y = q[1] - hh;
+      bx.z = q[0] + hw;
+      bx.w = q[1] + hh;
+    }
+    box[i] = bx;
+    area[i] = (bx.z - bx.x) * (bx.w - bx.y);
+  }
+  __syncthreads();
+
+  // ---- suppression bits: supp[i] bit j (j > i) = box i, once kept, removes box j  (nms.py:43-60)
+  const int words = (n_sel + 31) >> 5;
+  for (int item = tid; item < n_sel * words; item += kNmsThreads) {
+    const int i = item / words, w = item - i * words;
+    const float4 bi = box[i];
+    const float ai = area[i];
+    unsigned bits = 0;
+    const int j0 = w << 5;
+    for (int t = 0; t < 32; ++t) {
+      const int j = j0 + t;
+      if (j > i && j < n_sel) {
+        const float4 bj = box[j];
+        const float xx1 = fmaxf(bj.x, bi.x), yy1 = fmaxf(bj.y, bi.y);
+        const float xx2 = fminf(bj.z, bi.z), yy2 = fminf(bj.w, bi.w);
+        const float iw = fmaxf(xx2 - xx1, 0.f), ih = fmaxf(yy2 - yy1, 0.f);
+        const float inter = iw * ih;
+        const float uni = (area[j] - inter) + ai;
+        const float iou = inter / uni;
+        if (!(iou <= nms_thres)) bits |= 1u << t;  // NaN is suppressed, like IoU.le(overlap)
+      }
+    }
+    supp[i][w] = bits;
+  }
+  __syncthreads();
+
+  // ---- greedy scan in score order by one warp (lane l holds removed-word l; kNmsMaxK/32 = 16 words)
+  if (tid < 32) {
+    unsigned removed = 0;
+    unsigned nk = 0;
+    for (int i = 0; i < n_sel; ++i) {
+      const unsigned rw = __shfl_sync(0xffffffffu, removed, i >> 5);
+      if (!((rw >> (i & 31)) & 1u)) {
+        if (tid == 0) keep[nk] = (short)i;
+        ++nk;
+        if (tid < words) removed |= supp[i][tid];
+      }
+    }
+    if (tid == 0) s_nkeep = nk;
+  }
+  __syncthreads();
+
+  const int nk = (int)s_nkeep;
+  for (int s = tid; s < top_k; s += kNmsThreads) {
+    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+    float sc = 0.f;
+    int r = -1;
+    if (s < nk) {
+      const int i = keep[s];
+      bx = box[i];
+      sc = nms_key_score(keys[i]);
+      r = (int)(unsigned)(keys[i] & 0xffffffffull);
+    }
+    reinterpret_cast<float4*>(boxes_out)[(size_t)b * top_k + s] = bx;
+    scores_out[(size_t)b * top_k + s] = sc;
+    rows_out[(size_t)b * top_k + s] = r;
+  }
+  if (tid == 0) counts[b] = nk;
+}
+
+// counts[B] -> offsets[B+1] (exclusive scan; offsets[B] = total) and src[n] = (image, slot) of crop n.
+__global__ void detect_compact_kernel(const int* __restrict__ counts, int B, int top_k, int* __restrict__ offsets,
+                                      int2* __restrict__ src) {
+  __shared__ int s_off[1025];
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    int acc = 0;
+    for (int b = 0; b < B; ++b) {
+      s_off[b] = acc;
+      acc += counts[b];
+    }
+    s_off[B] = acc;
+  }
+  __syncthreads();
+  for (int b = tid; b <= B; b += blockDim.x) offsets[b] = s_off[b];
+  for (int b = 0; b < B; ++b) {
+    const int n = s_off[b + 1] - s_off[b];
+    for (int s = tid; s < n; s += blockDim.x) src[s_off[b] + s] = make_int2(b, s);
+  }
+}
+
+// resize.cpp's table entry for destination index d: source index and the two 11-bit weights.
+__device__ __forceinline__ void linear_tab(int d, int src, int dst, bool clamp, int* s_idx, short* a0, short* a1) {
+  const double scale = (double)src / (double)dst;
+  float f = (float)(((double)d + 0.5) * scale - 0.5);
+  int i = (int)floorf(f);
+  f = f - (float)i;
+  if (clamp && i < 0) {
+    i = 0;
+    f = 0.f;
+  }
+  if (clamp && i >= src - 1) {
+    i = src - 1;
+    f = 0.f;
+  }
+  *s_idx = i;
+  // saturate_cast<short>(float) = round half to even
+  *a0 = (short)__float2int_rn((1.f - f) * 2048.f);
+  *a1 = (short)__float2int_rn(f * 2048.f);
+}
+
+constexpr int kCropMaxDim = 256;
+
+// One CTA per crop.  frames u8 [B][H][W][3]; out fp32 [n][3][dh][dw]; rects int32 [n][4] = x0,y0,x1,y1.
+__global__ void __launch_bounds__(256)
+crop_resize_kernel(const unsigned char* __restrict__ frames, int H, int W, const float* __restrict__ boxes, int top_k,
+                   const int2* __restrict__ src, const float* __restrict__ geom, int geom_stride, int dw, int dh,
+                   float* __restrict__ out, int* __restrict__ rects) {
+  __shared__ int sx[kCropMaxDim], sy[kCropMaxDim];
+  __shared__ short ax0[kCropMaxDim], ax1[kCropMaxDim], ay0[kCropMaxDim], ay1[kCropMaxDim];
+  __shared__ float lut[256];
+  __shared__ int rect[4];
+  const int n = blockIdx.x, tid = threadIdx.x;
+  const int2 bs = src[n];
+  if (tid == 0) {
+    const float* bx = boxes + ((size_t)bs.x * top_k + bs.y) * 4;
+    const float* g = geom + (size_t)bs.x * geom_stride;  // ratio, pad_w, pad_h (per image, or shared when stride 0)
+    const float x0 = bx[0] / g[0] - g[1], y0 = bx[1] / g[0] - g[2];
+    const float x1 = bx[2] / g[0] - g[1], y1 = bx[3] / g[0] - g[2];
+    // float -> int with clamping done in float first (boxes can be far outside the frame or NaN)
+    const float fx0 = fminf(fmaxf(floorf(x0), 0.f), (float)(W - 1));
+    const float fy0 = fminf(fmaxf(floorf(y0), 0.f), (float)(H - 1));
+    const int ix0 = (fx0 == fx0) ? (int)fx0 : 0, iy0 = (fy0 == fy0) ? (int)fy0 : 0;
+    const float fx1 = fminf(fmaxf(ceilf(x1), (float)(ix0 + 1)), (float)W);
+    const float fy1 = fminf(fmaxf(ceilf(y1), (float)(iy0 + 1)), (float)H);
+    rect[0] = ix0;
+    rect[1] = iy0;
+    rect[2] = (fx1 == fx1) ? (int)fx1 : ix0 + 1;
+    rect[3] = (fy1 == fy1) ? (int)fy1 : iy0 + 1;
+  }
+  lut[tid] = (float)((double)tid / 255.0);  // (u8 / 255.0).astype(float32)
+  __syncthreads();
+  const int x0 = rect[0], y0 = rect[1];
+  const int cw = rect[2] - x0, ch = rect[3] - y0;
+  if (tid < 4) rects[(size_t)n * 4 + tid] = rect[tid];
+  for (int d = tid; d < dw; d += 256) linear_tab(d, cw, dw, true, &sx[d], &ax0[d], &ax1[d]);
+  for (int d = tid; d < dh; d += 256) linear_tab(d, ch, dh, false, &sy[d], &ay0[d], &ay1[d]);
+  __syncthreads();
+  const unsigned char* f = frames + ((size_t)bs.x * H + y0) * W * 3 + (size_t)x0 * 3;
+  const size_t rowb = (size_t)W * 3;
+  float* o = out + (size_t)n * 3 * dh * dw;
+  const int plane = dh * dw;
+  const bool same = (cw == dw && ch == dh);
+  const bool half = (cw == 2 * dw && ch == 2 * dh);  // resize.cpp: exact 2x decimation runs the INTER_AREA kernel
+  for (int e = tid; e < 3 * plane; e += 256) {
+    const int c = e / plane, p = e - c * plane;
+    const int dy = p / dw, dx = p - dy * dw;
+    int v;
+    if (same) {
+      v = f[dy * rowb + dx * 3 + c];
+    } else if (half) {
+      const unsigned char* q = f + (size_t)(2 * dy) * rowb + (2 * dx) * 3 + c;
+      v = (q[0] + q[3] + q[rowb] + q[rowb + 3] + 2) >> 2;
+    } else {
+      const int xa = sx[dx], xb = min(xa + 1, cw - 1);
+      const int ya = min(max(sy[dy], 0), ch - 1), yb = min(max(sy[dy] + 1, 0), ch - 1);
+      const int a0 = ax0[dx], a1 = ax1[dx];
+      const unsigned char* r0 = f + (size_t)ya * rowb + c;
+      const unsigned char* r1 = f + (size_t)yb * rowb + c;
+      const int S0 = r0[xa * 3] * a0 + r0[xb * 3] * a1;
+      const int S1 = r1[xa * 3] * a0 + r1[xb * 3] * a1;
+      v = ((((int)ay0[dy] * (S0 >> 4)) >> 16) + (((int)ay1[dy] * (S1 >> 4)) >> 16) + 2) >> 2;
+      v = min(max(v, 0), 255);
+    }
+    o[e] = lut[v];
+  }
+}
+
+}  // namespace
+}  // namespace b200cv
+
+using namespace b200cv;
+
+extern "C" int b200cv_detect_nms(const float* det, int64_t det_batch_stride, int B, int rows, int row_len,
+                                 int box_format, float conf_thres, float nms_thres, int top_k, float* boxes,
+                                 float* scores, int32_t* det_rows, int32_t* counts, void* stream) {
+  if (B == 0) return B200CV_OK;
+  B200CV_CHECK_ARG(det && boxes && scores && det_rows && counts, "detect_nms: null pointer");
+  B200CV_CHECK_ARG(B >= 0 && rows >= 0 && row_len >= 5, "detect_nms: bad shape B=%d rows=%d row_len=%d", B, rows,
+                   row_len);
+  B200CV_CHECK_ARG(top_k >= 1 && top_k <= kNmsMaxK, "detect_nms: top_k=%d outside [1,%d]", top_k, kNmsMaxK);
+  B200CV_CHECK_ARG(box_format == 0 || box_format == 1, "detect_nms: box_format must be 0 (centre) or 1 (corners)");
+  B200CV_CHECK_ARG((reinterpret_cast<uintptr_t>(boxes) & 15) == 0, "detect_nms: boxes must be 16-byte aligned");
+  detect_nms_kernel<<<B, kNmsThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      det, det_batch_stride, rows, row_len, conf_thres, nms_thres, top_k, box_format, boxes, scores, det_rows,
+      counts);
+  return check_launch("detect_nms");
+}
+
+extern "C" int b200cv_detect_compact(const int32_t* counts, int B, int top_k, int32_t* offsets, int32_t* src,
+                                     void* stream) {
+  B200CV_CHECK_ARG(counts && offsets && src, "detect_compact: null pointer");
+  B200CV_CHECK_ARG(B >= 0 && B <= 1024, "detect_compact: B=%d outside [0,1024]", B);
+  detect_compact_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(counts, B, top_k, offsets,
+                                                                         reinterpret_cast<int2*>(src));
+  return check_launch("detect_compact");
+}
+
+extern "C" int b200cv_crop_resize_u8(const uint8_t* frames, int B, int H, int W, const float* boxes, int top_k,
+                                     const int32_t* src, int n_crops, const float* geom, int geom_stride, int out_w,
+                                     int out_h, float* out, int32_t* rects, void* stream) {
+  if (n_crops <= 0) return B200CV_OK;
+  B200CV_CHECK_ARG(frames && boxes && src && geom && out && rects, "crop_resize_u8: null pointer");
+  B200CV_CHECK_ARG(B >= 1 && H >= 1 && W >= 1, "crop_resize_u8: bad frame shape");
+  B200CV_CHECK_ARG(out_w >= 1 && out_w <= kCropMaxDim && out_h >= 1 && out_h <= kCropMaxDim,
+                   "crop_resize_u8: output size %dx%d outside [1,%d]", out_w, out_h, kCropMaxDim);
+  B200CV_CHECK_ARG(geom_stride == 0 || geom_stride >= 3, "crop_resize_u8: geom_stride must be 0 or >= 3");
+  if (n_crops <= 0) return B200CV_OK;
+  crop_resize_kernel<<<n_crops, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      frames, H, W, boxes, top_k, reinterpret_cast<const int2*>(src), geom, geom_stride, out_w, out_h, out, rects);
+  return check_launch("crop_resize_u8");
+}

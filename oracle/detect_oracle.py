@@ -1,0 +1,198 @@
+"""ORACLE (test infrastructure, not product code) for the detect -> NMS -> crop -> RektNet joint
+(BASELINE config 5): a CPU restatement of
+
+  * the confidence filter + xywh->xyxy of CVC-YOLOv3/detect.py:84-90,
+  * the greedy top-k NMS of CVC-YOLOv3/utils/nms.py:4-61,
+  * the RektNet pre-processing of RektNet/utils.py:73-76 (`cv2.resize` to the network size) and
+    RektNet/detect.py:32-34 (HWC BGR u8 -> CHW, / 255.0, float32).
+
+`cv2.resize` is a third-party dependency of the reference (opencv-python, unpinned in
+RektNet/requirements.txt); its 8-bit INTER_LINEAR path is restated here from the published algorithm
+(modules/imgproc/src/resize.cpp: 11-bit fixed-point coefficients, HResizeLinear / VResizeLinear<uchar>,
+and the exact-2x-downscale shortcut to INTER_AREA) and pinned against the cv2 4.13 of this image by
+tests/test_detect_oracle.py and the committed tests/golden/detect_golden.pt.
+
+The reference has NO code that joins the two networks (the crop step lives in a separate inference
+repository); `crop_rect` below is therefore OUR definition of the joint, built from the box mapping of
+detect.py:93-96 (x / ratio - pad).
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this file.
+"""
+import numpy as np
+import torch
+
+
+# ------------------------------------------------------------------------------------------ NMS
+def filter_and_corners(det, conf_thres):
+    """detect.py:84-90: rows with conf > thres, boxes (cx,cy,w,h) -> (x1,y1,x2,y2) in fp32.
+    Returns (rows kept [n] int64, box_corner [n,4], scores [n])."""
+    det = det.float()
+    rows = torch.nonzero(det[:, 4] > conf_thres).flatten()
+    d = det[rows]
+    box = torch.zeros((d.shape[0], 4), dtype=torch.float32)
+    xy = d[:, 0:2]
+    wh = d[:, 2:4] / 2
+    box[:, 0:2] = xy - wh
+    box[:, 2:4] = xy + wh
+    return rows, box, d[:, 4].clone()
+
+
+def nms(boxes, scores, overlap=0.5, top_k=200):
+    """utils/nms.py:4-61 with the sort made STABLE (the reference's `scores.sort(0)` leaves the order of equal
+    scores unspecified; the stable ascending order = "among equal scores the later row is visited first" is the
+    rule the CUDA kernel implements).  Returns kept indices (into `boxes`) in visiting order."""
+    n = boxes.shape[0]
+    if n == 0:
+        return torch.zeros(0, dtype=torch.long)
+    b = boxes.float().numpy()
+    x1, y1, x2, y2 = b[:, 0], b[:, 1], b[:, 2], b[:, 3]
+    area = (x2 - x1) * (y2 - y1)  # :23 fp32
+    order = torch.sort(scores.float(), stable=True, dim=0)[1].numpy()[-top_k:]  # :24-26
+    keep = []
+    idx = order
+    with np.errstate(invalid="ignore", divide="ignore"):
+        while idx.size > 0:
+            i = idx[-1]
+            keep.append(int(i))
+            if idx.size == 1:
+                break
+            idx = idx[:-1]
+            xx1 = np.maximum(x1[idx], x1[i])  # clamp(min=x1[i]) :43-46
+            yy1 = np.maximum(y1[idx], y1[i])
+            xx2 = np.minimum(x2[idx], x2[i])
+            yy2 = np.minimum(y2[idx], y2[i])
+            w = np.maximum(xx2 - xx1, np.float32(0))
+            h = np.maximum(yy2 - yy1, np.float32(0))
+            inter = w * h
+            union = (area[idx] - inter) + area[i]  # :57
+            iou = inter / union
+            idx = idx[iou <= np.float32(overlap)]  # NaN (0/0) is dropped, like IoU.le() :60
+    return torch.tensor(keep, dtype=torch.long)
+
+
+def detect_nms(det, conf_thres, nms_thres, top_k=200):
+    """One image: det [rows, 5+C] -> (rows of the kept detections in visiting order, their corner boxes, scores)."""
+    rows, box, sc = filter_and_corners(det, conf_thres)
+    keep = nms(box, sc, nms_thres, top_k)
+    return rows[keep], box[keep], sc[keep]
+
+
+# ------------------------------------------------------------------------------------------ cv2.resize (8U, INTER_LINEAR)
+_COEF_BITS = 11
+_ONE = 1 << _COEF_BITS
+
+
+def _cv_round_short(v):
+    # saturate_cast<short>(float): cvRound = round half to even
+    return np.clip(np.rint(v), -32768, 32767).astype(np.int32)
+
+
+def _linear_tab(src, dst, clamp=True):
+    """Per destination index: source index s and the two 11-bit weights, as resize.cpp computes them
+    (float32 arithmetic for the fraction, double for the scale).  Horizontally (clamp=True) indices outside the row
+    are clamped AND their fraction zeroed; vertically (clamp=False) resize.cpp keeps index and fraction and clips
+    the two ROW indices when it loads them -- the same row then enters twice with weights (1-f, f), which is not
+    the same number in the two-step fixed-point arithmetic of the vertical pass."""
+    scale = float(src) / float(dst)
+    s = np.zeros(dst, np.int32)
+    a = np.zeros((dst, 2), np.int32)
+    for d in range(dst):
+        f = np.float32((d + 0.5) * scale - 0.5)
+        i = int(np.floor(f))
+        f = np.float32(f - np.float32(i))
+        if clamp and i < 0:
+            i, f = 0, np.float32(0)
+        if clamp and i >= src - 1:
+            i, f = src - 1, np.float32(0)
+        s[d] = i
+        a[d, 0] = _cv_round_short(np.float32((np.float32(1) - f) * np.float32(_ONE)))
+        a[d, 1] = _cv_round_short(np.float32(f * np.float32(_ONE)))
+    return s, a
+
+
+def resize_linear_u8(img, dsize):
+    """cv2.resize(img, dsize) for uint8 HxWxC, default INTER_LINEAR.  dsize = (width, height)."""
+    img = np.ascontiguousarray(img)
+    assert img.dtype == np.uint8 and img.ndim == 3
+    H, W, C = img.shape
+    dw, dh = int(dsize[0]), int(dsize[1])
+    if (W, H) == (dw, dh):
+        return img.copy()
+    if W == 2 * dw and H == 2 * dh:
+        # resize.cpp: INTER_LINEAR with an exact 2x2 decimation runs the fast INTER_AREA kernel
+        v = img.astype(np.int32)
+        return ((v[0::2, 0::2] + v[0::2, 1::2] + v[1::2, 0::2] + v[1::2, 1::2] + 2) >> 2).astype(np.uint8)
+    sx, ax = _linear_tab(W, dw)
+    sy, ay = _linear_tab(H, dh, clamp=False)
+    v = img.astype(np.int32)
+    sx1 = np.minimum(sx + 1, W - 1)
+    # HResizeLinear: rows of int32 = S[sx]*a0 + S[sx+1]*a1 (a1 == 0 wherever sx+1 would run off the row)
+    hrow = v[:, sx, :] * ax[None, :, 0, None] + v[:, sx1, :] * ax[None, :, 1, None]
+    S0 = hrow[np.clip(sy, 0, H - 1)]
+    S1 = hrow[np.clip(sy + 1, 0, H - 1)]
+    b0 = ay[:, 0][:, None, None]
+    b1 = ay[:, 1][:, None, None]
+    # VResizeLinear<uchar,int,short,FixedPtCast<int,uchar,22>>: the two-step shift of the SIMD kernel
+    out = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+# ------------------------------------------------------------------------------------------ the joint (ours)
+def crop_rect(box, ratio, pad_w, pad_h, W, H):
+    """Network-input corner box -> integer crop rectangle [x0,x1) x [y0,y1) of the original W x H frame.
+    Mapping of detect.py:93-96 (x / ratio - pad) in fp32, then floor / ceil, clipped so the rectangle is never
+    empty."""
+    f = np.float32
+    x0 = f(f(box[0]) / f(ratio)) - f(pad_w)
+    y0 = f(f(box[1]) / f(ratio)) - f(pad_h)
+    x1 = f(f(box[2]) / f(ratio)) - f(pad_w)
+    y1 = f(f(box[3]) / f(ratio)) - f(pad_h)
+    ix0 = int(min(max(np.floor(x0), 0), W - 1))
+    iy0 = int(min(max(np.floor(y0), 0), H - 1))
+    ix1 = int(min(max(np.ceil(x1), ix0 + 1), W))
+    iy1 = int(min(max(np.ceil(y1), iy0 + 1), H))
+    return ix0, iy0, ix1, iy1
+
+
+def prep_crop(frame, rect, size=(80, 80)):
+    """RektNet/utils.py:73-76 + detect.py:33-34 on a crop: resize -> CHW -> /255.0 -> float32."""
+    x0, y0, x1, y1 = rect
+    img = resize_linear_u8(frame[y0:y1, x0:x1], size)
+    return (img.transpose((2, 0, 1)) / 255.0).astype(np.float32)
+
+
+def synth_frames(B, H, W, seed=0):
+    """Synthetic BGR u8 frames: smooth gradients + noise (so that interpolation errors are visible)."""
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:H, 0:W]
+    out = np.empty((B, H, W, 3), np.uint8)
+    for b in range(B):
+        base = np.stack([(xx * (b + 1) + yy) % 256, (xx + 2 * yy * (b + 1)) % 256, (xx * yy // 7) % 256], -1)
+        out[b] = ((base + rng.randint(0, 64, size=(H, W, 3))) % 256).astype(np.uint8)
+    return out
+
+
+def synth_detections(B, rows, C, seed=0, hot=24, img=416.0, ties=True):
+    """Detections like Darknet.forward's eval output [B, rows, 5+C]: mostly low confidence, `hot` clustered
+    high-confidence rows per image (overlapping groups so that NMS has work), a few exactly tied scores."""
+    g = torch.Generator().manual_seed(seed)
+    det = torch.zeros(B, rows, 5 + C)
+    det[..., 0:2] = torch.rand(B, rows, 2, generator=g) * img
+    det[..., 2:4] = 8 + torch.rand(B, rows, 2, generator=g) * 60
+    det[..., 4] = torch.rand(B, rows, generator=g) * 0.7
+    det[..., 5:] = torch.rand(B, rows, C, generator=g)
+    for b in range(B):
+        n = int(torch.randint(0, hot + 1, (1,), generator=g)) if b else hot
+        if n == 0:
+            continue
+        sel = torch.randperm(rows, generator=g)[:n]
+        centres = torch.rand(max(1, n // 3), 2, generator=g) * (img - 80) + 40
+        for j, r in enumerate(sel.tolist()):
+            c = centres[j % centres.shape[0]]
+            det[b, r, 0:2] = c + torch.randn(2, generator=g) * 4
+            det[b, r, 2:4] = torch.tensor([24.0, 40.0]) + torch.randn(2, generator=g) * 3
+            det[b, r, 4] = 0.8 + 0.2 * torch.rand(1, generator=g).item()
+        if ties and n >= 4:  # exact ties
+            det[b, sel[1], 4] = det[b, sel[0], 4]
+            det[b, sel[3], 4] = det[b, sel[2], 4]
+    return det

@@ -1,0 +1,71 @@
+"""Pins oracle/detect_oracle.py (CPU): its NMS must reproduce what the REFERENCE's utils/nms.py produced
+(tests/golden/detect_golden.pt, written by oracle/gen_golden_detect.py), its resize what cv2 produced."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import detect_oracle as DO
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def golden_detect():
+    return torch.load(os.path.join(ROOT, "tests", "golden", "detect_golden.pt"), weights_only=False)
+
+
+def test_nms_matches_reference_outputs(golden_detect):
+    assert len(golden_detect["nms"]) >= 4
+    for name, c in golden_detect["nms"].items():
+        det = DO.synth_detections(c["B"], c["rows"], c["C"], seed=c["seed"], hot=c["hot"], ties=False)
+        for b, ref in enumerate(c["out"]):
+            rows, boxes, scores = DO.detect_nms(det[b], c["conf"], c["nms"])
+            assert torch.equal(rows, ref["rows"]), (name, b)  # kept set AND order: bit-exact
+            assert torch.equal(boxes, ref["boxes"]), (name, b)
+            assert torch.equal(scores, ref["scores"]), (name, b)
+
+
+def test_nms_tie_rule_and_nan():
+    # equal scores: the later row is visited first (stable ascending sort read from the end)
+    boxes = torch.tensor([[0, 0, 10, 10], [0, 0, 10, 10], [20, 20, 30, 30.0]])
+    scores = torch.tensor([0.9, 0.9, 0.5])
+    assert DO.nms(boxes, scores, 0.5).tolist() == [1, 2]
+    # zero-area duplicates: IoU = 0/0 = NaN is dropped by `IoU.le(overlap)`
+    boxes = torch.tensor([[5, 5, 5, 5], [5, 5, 5, 5.0]])
+    assert DO.nms(boxes, torch.tensor([0.9, 0.8]), 0.5).tolist() == [0]
+    assert DO.nms(torch.zeros(0, 4), torch.zeros(0), 0.5).numel() == 0
+
+
+def test_resize_matches_cv2_golden(golden_detect):
+    assert len(golden_detect["resize"]) >= 12
+    for name, c in golden_detect["resize"].items():
+        got = DO.resize_linear_u8(c["img"].numpy(), c.get("size", (80, 80)))
+        assert np.array_equal(got, c["out"].numpy()), name
+
+
+def test_resize_matches_live_cv2():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.RandomState(3)
+    for _ in range(60):
+        h, w = int(rng.randint(1, 200)), int(rng.randint(1, 200))
+        img = rng.randint(0, 256, size=(h, w, 3)).astype(np.uint8)
+        assert np.array_equal(DO.resize_linear_u8(img, (80, 80)), cv2.resize(img, (80, 80))), (h, w)
+
+
+def test_crop_rect_is_inside_and_non_empty():
+    rng = np.random.RandomState(0)
+    for _ in range(200):
+        box = rng.uniform(-100, 600, size=4).astype(np.float32)
+        x0, y0, x1, y1 = DO.crop_rect(box, 0.325, 0.0, 140.0, 1280, 720)
+        assert 0 <= x0 < x1 <= 1280 and 0 <= y0 < y1 <= 720
+    assert DO.crop_rect(np.array([50.0, 140.0, 100.0, 210.0], np.float32), 0.5, 0.0, 140.0, 1280, 720) == \
+        (100, 140, 200, 280)
+
+
+def test_prep_crop_layout():
+    frames = DO.synth_frames(1, 120, 160, seed=1)
+    out = DO.prep_crop(frames[0], (10, 20, 90, 100))
+    assert out.shape == (3, 80, 80) and out.dtype == np.float32
+    assert np.array_equal(out, (frames[0][20:100, 10:90].transpose(2, 0, 1) / 255.0).astype(np.float32))  # identity size

@@ -111,6 +111,30 @@ def test_darknet_loss_matches_oracle_on_device_weights(cfg_dir):
         assert abs(float(a) - float(b)) <= LOSS_RTOL * max(abs(float(b)), 1e-3)
 
 
+def test_darknet53_608_odd_grids_match_oracle(cfg_dir):
+    """BASELINE config 4's shape (Darknet-53 at 608x608: grids 19/38/76, pixel counts that are not multiples of the
+    128-row GEMM tile) at a batch the CPU oracle finishes in seconds: 7-tuple vs the oracle on the same weights, and a
+    backward pass whose gradients are finite and non-trivial for every parameter."""
+    model, path = helpers.make_darknet(cfg_dir, "yolo_baseline.cfg", 608, 80, seed=5)
+    params = {k: v.detach().clone() for k, v in model.named_parameters()}
+    buffers = {k: v.clone() for k, v in model.named_buffers()}
+    x, tg = YO.synth_images(2, 608, 608, seed=6), YO.synth_targets(2, 16, seed=7)
+    with torch.no_grad():
+        want = YO.darknet_forward(YO.NetSpec(path), params, buffers, x, tg)
+    model = model.to(DEV).train()
+    got = model(x.to(DEV), tg.to(DEV))
+    for a, b in zip(got, want):
+        assert abs(float(a) - float(b)) <= LOSS_RTOL * max(abs(float(b)), 1e-3)
+    got[0].sum().backward()
+    for k, p in model.named_parameters():
+        assert p.grad is not None and bool(torch.isfinite(p.grad).all()), k
+    assert sum(float(p.grad.abs().sum()) > 0 for p in model.parameters()) >= 0.95 * len(list(model.parameters()))
+    model.eval()
+    with torch.no_grad():
+        det = model(x.to(DEV))
+    assert det.shape == (2, 22743, 85)  # SURVEY 8a-5: eval rows at 608
+
+
 def test_no_grad_pass_and_step_with_optimizer(cfg_dir):
     model, _ = helpers.make_darknet(cfg_dir, "yolo_baseline_tiny.cfg", 128, 1)
     model = model.to(DEV).train()
