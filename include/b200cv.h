@@ -296,8 +296,9 @@ int b200cv_crop_resize_u8(const uint8_t* frames, int B, int H, int W, const floa
 /* One launch per param group.  table: device int64 [n_chunks][5] = {param*, grad*, state1*, state2*, count} (fp32
  * arrays; a chunk is processed by one CTA, keep count around 16K).
  * Adam = torch.optim.Adam(lr, betas, eps, weight_decay) as called at CVC-YOLOv3/train.py:181, RektNet/train_eval.py:263:
- * state1 = exp_avg, state2 = exp_avg_sq, step_size = lr / (1 - beta1^t), bias_correction2_sqrt = sqrt(1 - beta2^t). */
-int b200cv_adam_step_multi(const int64_t* table, int n_chunks, float step_size, float beta1, float beta2, float eps,
+ * state1 = exp_avg, state2 = exp_avg_sq, step_size = lr / (1 - beta1^t), bias_correction2_sqrt = sqrt(1 - beta2^t);
+ * the betas are doubles because torch forms 1 - beta in double before rounding it to fp32. */
+int b200cv_adam_step_multi(const int64_t* table, int n_chunks, float step_size, double beta1, double beta2, float eps,
                            float weight_decay, float bias_correction2_sqrt, void* stream);
 /* SGD = torch.optim.SGD(lr, momentum, weight_decay) of CVC-YOLOv3/train.py:185: state1 = momentum_buffer (NULL when
  * momentum == 0), first_step != 0 initialises the buffer with the gradient. */

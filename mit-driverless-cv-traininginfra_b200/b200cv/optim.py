@@ -22,23 +22,24 @@ CHUNK = 16384  # elements per CTA (a multiple of 4: chunk starts keep the 16-byt
 
 
 class _FusedBase(torch.optim.Optimizer):
-    _n_state = 0
+    """Host side of a fused step.  The per-step fast path is: list the parameters that have a gradient, form the key
+    (param pointer, grad pointer) per tensor, look the chunk table up, bump ONE shared step counter, launch."""
 
-    def _group_tensors(self, group):
-        ps = [p for p in group["params"] if p.grad is not None]
+    def _validate(self, ps):
         for p in ps:
             require_cuda(p, type(self).__name__)
             if p.dtype != torch.float32 or p.grad.dtype != torch.float32:
                 raise TypeError(f"{type(self).__name__}: fp32 parameters and gradients only")
             if p.grad.is_sparse:
                 raise RuntimeError(f"{type(self).__name__} does not support sparse gradients")
-            if not p.is_contiguous():
-                raise RuntimeError(f"{type(self).__name__}: parameters must be contiguous")
-        return ps
+            if not p.is_contiguous() or not p.grad.is_contiguous():
+                raise RuntimeError(f"{type(self).__name__}: parameters and gradients must be contiguous")
 
-    def _ensure_state(self, group, ps, names):
-        """State tensors are views of one flat arena per (group, name); created on a parameter's first step."""
-        new = [p for p in ps if not all(n in self.state[p] for n in names)]
+    def _ensure_state(self, ps, names):
+        """State tensors are views of one flat arena per name; created on a parameter's first step.  All parameters
+        that start together share ONE step-counter tensor (torch keeps one per parameter; sharing makes the per-step
+        host cost independent of the number of tensors and reads the same through state_dict())."""
+        new = [p for p in ps if "step" not in self.state[p]]
         if not new:
             return
         total = sum((p.numel() + 3) // 4 * 4 for p in new)
@@ -48,23 +49,32 @@ class _FusedBase(torch.optim.Optimizer):
             for p in new:
                 self.state[p][n] = arena[off:off + p.numel()].view_as(p)
                 off += (p.numel() + 3) // 4 * 4
+        step = torch.tensor(0.0)
         for p in new:
-            self.state[p].setdefault("step", torch.tensor(0.0))
+            self.state[p]["step"] = step
+
+    def _bump_steps(self, ps):
+        """Increment every distinct step tensor once; returns {step value: [params]}."""
+        seen, by_step = {}, {}
+        for p in ps:
+            t = self.state[p]["step"]
+            if id(t) not in seen:
+                t += 1
+                seen[id(t)] = int(t)
+            by_step.setdefault(seen[id(t)], []).append(p)
+        return by_step
 
     def _table(self, ps, names):
-        """Device chunk table, cached until a pointer changes (e.g. a new gradient arena)."""
-        key = []
-        for p in ps:
-            if not p.grad.is_contiguous():
-                p.grad = p.grad.contiguous()
-            key.append((p.data_ptr(), p.grad.data_ptr(), p.numel()) + tuple(self.state[p][n].data_ptr() for n in names))
-        key = tuple(key)
+        """Device chunk table for these parameters, cached until a parameter or gradient pointer changes."""
+        key = tuple([(p.data_ptr(), p.grad.data_ptr()) for p in ps])
         cache = self.__dict__.setdefault("_b200cv_tables", {})
         table = cache.get(key)
         if table is None:
+            self._validate(ps)
             rows = []
-            for pp, gp, n, *sp in key:
-                sp = list(sp) + [0] * (2 - len(sp))
+            for p in ps:
+                n, pp, gp = p.numel(), p.data_ptr(), p.grad.data_ptr()
+                sp = [self.state[p][nm].data_ptr() for nm in names] + [0, 0]
                 for o in range(0, n, CHUNK):
                     rows.append((pp + 4 * o, gp + 4 * o, sp[0] + 4 * o if sp[0] else 0, sp[1] + 4 * o if sp[1] else 0,
                                  min(CHUNK, n - o)))
@@ -73,6 +83,10 @@ class _FusedBase(torch.optim.Optimizer):
                 cache.clear()
             cache[key] = table
         return table
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self.__dict__.pop("_b200cv_tables", None)  # the loaded state lives in new tensors
 
 
 class FusedAdam(_FusedBase):
@@ -91,17 +105,13 @@ class FusedAdam(_FusedBase):
                 loss = closure()
         names = ("exp_avg", "exp_avg_sq")
         for group in self.param_groups:
-            ps = self._group_tensors(group)
+            ps = [p for p in group["params"] if p.grad is not None]
             if not ps:
                 continue
-            self._ensure_state(group, ps, names)
+            self._ensure_state(ps, names)
             b1, b2 = group["betas"]
-            # parameters that joined later have their own step count: one launch per distinct count
-            by_step = {}
-            for p in ps:
-                self.state[p]["step"] += 1
-                by_step.setdefault(int(self.state[p]["step"]), []).append(p)
-            for t, plist in by_step.items():
+            # parameters that joined later carry their own step count: one launch per distinct count
+            for t, plist in self._bump_steps(ps).items():
                 table = self._table(plist, names)
                 bc1 = 1.0 - b1 ** t
                 bc2 = 1.0 - b2 ** t
@@ -126,13 +136,12 @@ class FusedSGD(_FusedBase):
             with torch.enable_grad():
                 loss = closure()
         for group in self.param_groups:
-            ps = self._group_tensors(group)
+            ps = [p for p in group["params"] if p.grad is not None]
             if not ps:
                 continue
             names = ("momentum_buffer",) if group["momentum"] != 0 else ()
-            self._ensure_state(group, ps, names)  # zero-filled buffers: mu*0 + g = g is torch's first step exactly
-            for p in ps:
-                self.state[p]["step"] = self.state[p].get("step", torch.tensor(0.0)) + 1
+            self._ensure_state(ps, names)  # zero-filled buffers: mu*0 + g = g is torch's first step exactly
+            self._bump_steps(ps)
             table = self._table(ps, names)
             lib().call("b200cv_sgd_step_multi", ptr(table), table.shape[0], float(group["lr"]),
                        float(group["momentum"]), float(group["weight_decay"]), 0, stream_ptr())

@@ -37,10 +37,9 @@ __device__ __forceinline__ void for_each4(const OptChunk& c, F f) {
 // torch.optim.Adam (amsgrad=False, maximize=False), single-tensor formulation of torch 2.x:
 //   g += wd*p; m = lerp(m, g, 1-b1); v = v*b2 + (1-b2)*g*g; p -= step_size * m / (sqrt(v)/sqrt(bc2) + eps)
 __global__ void __launch_bounds__(256)
-adam_multi_kernel(const OptChunk* __restrict__ table, float step_size, float beta1, float beta2, float eps,
-                  float weight_decay, float bc2_sqrt) {
+adam_multi_kernel(const OptChunk* __restrict__ table, float step_size, float beta1, float omb1, float beta2,
+                  float omb2, float eps, float weight_decay, float bc2_sqrt) {
   const OptChunk c = table[blockIdx.x];
-  const float omb1 = 1.f - beta1, omb2 = 1.f - beta2;
   auto upd = [&](float& p, float g, float& m, float& v) {
     if (weight_decay != 0.f) g = g + weight_decay * p;
     m = m + (g - m) * omb1;
@@ -109,13 +108,14 @@ sgd_multi_kernel(const OptChunk* __restrict__ table, float lr, float momentum, f
 
 using namespace b200cv;
 
-extern "C" int b200cv_adam_step_multi(const int64_t* table, int n_chunks, float step_size, float beta1, float beta2,
+extern "C" int b200cv_adam_step_multi(const int64_t* table, int n_chunks, float step_size, double beta1, double beta2,
                                       float eps, float weight_decay, float bias_correction2_sqrt, void* stream) {
   B200CV_CHECK_ARG(table || n_chunks == 0, "adam_step_multi: null table");
   B200CV_CHECK_ARG(bias_correction2_sqrt > 0.f, "adam_step_multi: bias_correction2_sqrt must be > 0");
   if (n_chunks <= 0) return B200CV_OK;
   adam_multi_kernel<<<n_chunks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const OptChunk*>(table), step_size, beta1, beta2, eps, weight_decay, bias_correction2_sqrt);
+      reinterpret_cast<const OptChunk*>(table), step_size, (float)beta1, (float)(1.0 - beta1), (float)beta2,
+      (float)(1.0 - beta2), eps, weight_decay, bias_correction2_sqrt);  // 1 - beta in double, like torch's scalars
   return check_launch("adam_step_multi");
 }
 
