@@ -70,28 +70,36 @@ def test_fused_sgd_matches_torch(momentum, wd):
                                   atol=1e-7)
 
 
-def test_fused_adam_trains_keypointnet_like_torch_adam():
-    """RektNet/train_eval.py:59-72 with the fused step: same losses as torch.optim.Adam over a few iterations."""
+def test_fused_adam_drives_the_rektnet_step():
+    """RektNet/train_eval.py:59-72 with the fused step on the engine's own gradients (views of its flat arena): the
+    first update equals torch.optim.Adam's on the same gradients, and a few iterations descend.  (Whole trajectories
+    of two runs are not comparable: the step is reproducible only to ~1e-3, see tools/determinism_probe.py, and
+    Adam's normalised update amplifies that.)"""
     import cross_ratio_loss
     import keypoint_net
     from oracle import rektnet_oracle as RO
 
-    losses = {}
-    for kind in ("torch", "fused"):
-        torch.manual_seed(5)
-        net = keypoint_net.KeypointNet().cuda().train()
-        opt = (torch.optim.Adam if kind == "torch" else boptim.FusedAdam)(net.parameters(), lr=1e-3)
-        loss_fn = cross_ratio_loss.CrossRatioLoss("l2_softargmax", True, 0.055, 0.038)
-        x, thm, tpts = (t.cuda() for t in RO.synth_batch(8, seed=0))
-        out = []
-        for _ in range(4):
-            opt.zero_grad()
-            hm, pts = net(x)
-            _, _, loss = loss_fn(hm, pts, thm, tpts)
-            loss.backward()
-            opt.step()
-            out.append(float(loss))
-        losses[kind] = out
-    # two runs of the same step differ at the 1e-3 level (bf16 activations + atomically accumulated BN statistics)
-    assert losses["fused"] == pytest.approx(losses["torch"], rel=3e-2)
-    assert losses["fused"][-1] < losses["fused"][0]
+    torch.manual_seed(5)
+    net = keypoint_net.KeypointNet().cuda().train()
+    params = list(net.parameters())
+    opt = boptim.FusedAdam(params, lr=1e-3, weight_decay=1e-4)
+    loss_fn = cross_ratio_loss.CrossRatioLoss("l2_heatmap", True, 0.055, 0.038)
+    x, thm, tpts = (t.cuda() for t in RO.synth_batch(8, seed=0))
+    losses = []
+    for it in range(5):
+        opt.zero_grad()
+        hm, pts = net(x)
+        _, _, loss = loss_fn(hm, pts, thm, tpts)
+        loss.backward()
+        if it == 0:  # shadow copy updated by torch's Adam from the same gradients
+            shadow = [torch.nn.Parameter(p.detach().clone()) for p in params]
+            for s, p in zip(shadow, params):
+                s.grad = p.grad.detach().clone()
+            ref = torch.optim.Adam(shadow, lr=1e-3, weight_decay=1e-4)
+            ref.step()
+        opt.step()
+        if it == 0:
+            for s, p in zip(shadow, params):
+                assert torch.allclose(s, p, rtol=1e-5, atol=1e-7)
+        losses.append(float(loss))
+    assert losses[-1] < losses[0], losses
