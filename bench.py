@@ -331,6 +331,16 @@ def main():
         sec = bench_rektnet(dev, rank, world, steps, warmup, timed)
         if rank == 0:
             out["secondary"] = sec
+    # tertiary workload (BASELINE config 5): detect -> NMS -> crop -> RektNet inference latency, one GPU only
+    if rank == 0 and world == 1 and not args.no_secondary:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_pipeline
+
+            torch.cuda.empty_cache()
+            out["pipeline"] = bench_pipeline.run(iters=20)
+        except Exception as e:  # never lose the headline line to the extra workload
+            out["pipeline"] = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0 and not args.no_cpu_baseline and world >= 1:
         out["cpu_baseline"] = cpu_baseline()
     if rank == 0:

@@ -52,7 +52,7 @@ def _graphs_enabled() -> bool:
 class _Layer:
     __slots__ = ("index", "type", "conv", "bn", "act", "slope", "k", "stride", "pad", "cin", "cout", "inputs",
                  "post_from", "fused_alias", "yolo", "stats", "bstats", "scale", "shift", "mean", "rstd", "sums",
-                 "coef", "wpk", "wpk_t", "pool_stride")
+                 "coef", "wpk", "wpk_t", "pool_stride", "eval_key", "eval_affine")
 
     def __init__(self, index, type_):
         self.index, self.type = index, type_
@@ -61,6 +61,7 @@ class _Layer:
         self.fused_alias = False   # shortcut: output is the previous conv's post-add output
         self.inputs: List[int] = []
         self.stats = None
+        self.eval_key = self.eval_affine = None
 
 
 class DarknetEngine:
@@ -115,6 +116,7 @@ class DarknetEngine:
         self._arena = None
         self._packs = None
         self._anchor_cache = {}
+        self._pack_key = None   # versions/pointers of the conv weights at the last inference-pass pack
         self._graphs = {}       # (shapes) -> _GraphedStep | int (eager warm-up calls seen so far)
 
     # ------------------------------------------------------------------ helpers
@@ -163,8 +165,32 @@ class DarknetEngine:
         L0 = self.layers[0]
         return [L0.conv] if (L0.type == "convolutional" and ops.use_flat_path(L0.cin, L0.k)) else []
 
-    def _pack(self, need_t: bool):
+    def _pack(self, need_t: bool, frozen: bool = False):
+        """Re-pack the fp32 weights into the bf16 operand layouts.  `frozen` (inference passes): skip the launch when
+        no weight tensor was modified or re-homed since the last pack (tensor version counters + data pointers)."""
+        if frozen:
+            key = tuple((L.conv.weight._version, L.conv.weight.data_ptr()) for L in self.layers
+                        if L.type == "convolutional")
+            if key == self._pack_key:
+                return
+            self._packs.pack_all(need_t)
+            self._pack_key = key
+            return
+        self._pack_key = None  # a training pass: the optimizer is about to change the weights
         self._packs.pack_all(need_t)
+
+    def _eval_affine(self, L):
+        """Inference BatchNorm folded into the conv epilogue: y*scale + shift with scale = gamma/sqrt(var+eps),
+        shift = beta - mean*scale (models.py:64 in eval mode).  Cached per layer until gamma / beta / the running
+        statistics change (version counters), so a steady-state inference pass launches no per-layer fold kernels."""
+        bn = L.bn
+        key = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
+               bn.weight.data_ptr(), bn.running_mean.data_ptr())
+        if L.eval_key != key:
+            scale = bn.weight.detach() * torch.rsqrt(bn.running_var + BN_EPS)
+            L.eval_affine = (scale, bn.bias.detach() - bn.running_mean * scale)
+            L.eval_key = key
+        return L.eval_affine
 
     def _anchors(self, L, gh, dev):
         key = (L.index, gh, str(dev))
@@ -183,7 +209,7 @@ class DarknetEngine:
         model = self.model
         dev = x.device
         self._setup(dev)
-        self._pack(need_t=want_grad)
+        self._pack(need_t=want_grad, frozen=not bn_train and not want_grad)
         flat0 = bool(self._flat_convs())
         cur = ops.im2col_nchw(x, self.layers[0].k, self.layers[0].stride, self.layers[0].pad) if flat0 \
             else ops.nchw_to_nhwc(x)
@@ -192,6 +218,8 @@ class DarknetEngine:
         training = targets is not None
         out7 = torch.zeros(7, dtype=torch.float32, device=dev) if training else None
         if bn_train:
+            for L in self.layers:  # our kernels update the running statistics behind torch's version counters
+                L.eval_key = None
             self._fstat_arena.zero_()
             if self._nbt:
                 torch._foreach_add_(self._nbt, 1)
@@ -212,8 +240,7 @@ class DarknetEngine:
                                                      L.rstd, y, L.act, L.slope, post=post)
                         saved[i] = (xin, y)
                     else:
-                        scale = L.bn.weight.detach() * torch.rsqrt(L.bn.running_var + BN_EPS)
-                        shift = L.bn.bias.detach() - L.bn.running_mean * scale
+                        scale, shift = self._eval_affine(L)
                         cur = ops.conv_fwd(xin, L.wpk, L.cout, k_, st_, pd_, scale=scale, shift=shift,
                                            residual=post, act=L.act, slope=L.slope, res_after_act=True)
                         if want_grad:
@@ -513,6 +540,8 @@ class _DarknetGraphFn(torch.autograd.Function):
         step.static_t.copy_(targets, non_blocking=True)
         step.fwd_graph.replay()
         _count_launches(step.fwd_launches)
+        for L in step.engine.layers:  # the replay moved the running statistics: drop the folded inference affines
+            L.eval_key = None
         ctx.step = step
         return step.out7.clone()
 

@@ -46,6 +46,7 @@ class _ConvBN:
 
     def fwd_train(self, x):
         self.vecs(x.device)
+        self._eval_key = None  # bn_finalize updates the running statistics behind torch's version counters
         self.stats.zero_()
         y = ops.conv_fwd(x, self.wpk, self.cout, self.k, 1, self.pad, self.dil, stats=self.stats)
         count = y.numel() // y.shape[-1]
@@ -57,9 +58,15 @@ class _ConvBN:
         return y
 
     def eval_affine(self):
-        scale = self.bn.weight.detach() * torch.rsqrt(self.bn.running_var + BN_EPS)
-        shift = self.bn.bias.detach() + (self.conv.bias.detach() - self.bn.running_mean) * scale
-        return scale, shift
+        """Inference BN (+ conv bias) folded into the conv epilogue; cached until a source tensor changes."""
+        bn, cb = self.bn, self.conv.bias
+        key = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version, cb._version,
+               bn.weight.data_ptr(), bn.running_mean.data_ptr())
+        if getattr(self, "_eval_key", None) != key:
+            scale = bn.weight.detach() * torch.rsqrt(bn.running_var + BN_EPS)
+            self._eval_affine = (scale, bn.bias.detach() + (cb.detach() - bn.running_mean) * scale)
+            self._eval_key = key
+        return self._eval_affine
 
     def bwd(self, x_in, y, da, aout, act, gview, packs, dx_out=None, want_dx=True):
         """BN+act backward then wgrad (+ dgrad).  Returns dx (or None)."""

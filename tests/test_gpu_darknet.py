@@ -266,3 +266,41 @@ def test_cuda_graph_step_matches_eager(cfg_dir):
         w = res["1"][2][k]
         cos = float((v.double() * w.double()).sum() / (v.double().norm() * w.double().norm() + 1e-30))
         assert cos > 0.95, (k, cos)  # first-layer gradients flip LeakyReLU signs on atomics-order noise
+
+
+def test_eval_caches_follow_weight_and_statistic_updates(cfg_dir):
+    """Inference passes reuse the packed weights and the folded BN affines; both must be refreshed after a training
+    step (running statistics move behind torch's version counters) and after an in-place weight update."""
+    model, _ = helpers.make_darknet(cfg_dir, "yolo_baseline_tiny.cfg", 128, 1)
+    model = model.to(DEV)
+    x, tg = YO.synth_images(2, 128, 128).to(DEV), YO.synth_targets(2, 16).to(DEV)
+
+    def detect():
+        model.eval()
+        with torch.no_grad():
+            return model(x).clone()
+
+    d0 = detect()
+    assert torch.equal(d0, detect())  # cached pass == first pass
+    model.train()
+    for _ in range(4):  # eager and graph-replayed training passes both move the running statistics
+        model(x, tg)[0].sum().backward()
+    d1 = detect()
+    assert not torch.equal(d0, d1)
+    fresh = DarknetEngineFresh(model)
+    assert torch.allclose(d1, fresh, rtol=1e-5, atol=1e-5)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.mul_(1.01)
+    d2 = detect()
+    assert not torch.equal(d1, d2)
+    assert torch.allclose(d2, DarknetEngineFresh(model), rtol=1e-5, atol=1e-5)
+
+
+def DarknetEngineFresh(model):
+    """Detections from a brand-new engine over the same module (no caches)."""
+    from b200cv.darknet_engine import DarknetEngine
+
+    x = YO.synth_images(2, 128, 128).to(DEV)
+    model.eval()
+    return DarknetEngine(model).detect(x)

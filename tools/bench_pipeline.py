@@ -31,17 +31,8 @@ def percentile(xs, q):
     return xs[i]
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=128)
-    ap.add_argument("--iters", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--boxes", type=float, default=8.0, help="candidate boxes per image the threshold lets through")
-    ap.add_argument("--classes", type=int, default=80)
-    ap.add_argument("--frame", type=int, nargs=2, default=(720, 1280))
-    ap.add_argument("--out", default=None)
-    args = ap.parse_args()
-
+def run(batch=128, iters=30, warmup=3, boxes=8.0, classes=80, frame=(720, 1280)):
+    args = argparse.Namespace(batch=batch, iters=iters, warmup=warmup, boxes=boxes, classes=classes, frame=frame)
     import keypoint_net
     import models
     from b200cv import cfg_gen, pipeline
@@ -118,7 +109,20 @@ def main():
                                                  d2h_bytes=out.n_crops * (14 * 4 + 16) + 4 * B),
         "stage_device_ms": {k_: round(v, 3) for k_, v in stages.items()},
     }
-    s = json.dumps(line)
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--iters", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--boxes", type=float, default=8.0, help="candidate boxes per image the threshold lets through")
+    ap.add_argument("--classes", type=int, default=80)
+    ap.add_argument("--frame", type=int, nargs=2, default=(720, 1280))
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+    s = json.dumps(run(args.batch, args.iters, args.warmup, args.boxes, args.classes, tuple(args.frame)))
     print(s)
     if args.out:
         with open(os.path.join(ROOT, args.out), "w") as f:
