@@ -341,7 +341,7 @@ def main():
             out["pipeline"] = bench_pipeline.run(iters=20)
         except Exception as e:  # never lose the headline line to the extra workload
             out["pipeline"] = {"error": f"{type(e).__name__}: {e}"}
-    if rank == 0 and not args.no_cpu_baseline and world >= 1:
+    if rank == 0 and not args.no_cpu_baseline and world == 1:  # reported at N=1 only
         out["cpu_baseline"] = cpu_baseline()
     if rank == 0:
         print(json.dumps(out))

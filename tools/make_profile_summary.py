@@ -77,7 +77,8 @@ for rep in sorted(os.listdir(SRC)):
         with open(os.path.join(DST, "ncu_" + rep.replace(".ncu-rep", ".txt")), "a") as f:
             f.write("# SASS mnemonics (static count over the captured kernels): " + ", ".join(f"{k} x{v}" for k, v in sorted(ops.items())) + "\n")
 
-for name in (f"bench_{R}.json", f"layer_times_{R}.txt", f"yolo_loss_timing_{R}.log", "tma_bench.txt", "harness_bench_h.txt", "dbg_sweep.txt"):
+for name in (f"bench_{R}.json", f"layer_times_{R}.txt", f"yolo_loss_timing_{R}.log", f"pipeline_{R}.json", f"optim_{R}.json",
+             f"determinism_{R}.txt", "tma_bench.txt", "harness_bench_h.txt", "dbg_sweep.txt"):
     p = os.path.join(SRC, name)
     if os.path.exists(p):
         shutil.copy(p, os.path.join(DST, name if R in name else name.replace(".txt", f"_{R}.txt")))
