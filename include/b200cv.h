@@ -292,6 +292,17 @@ int b200cv_crop_resize_u8(const uint8_t* frames, int B, int H, int W, const floa
                           const int32_t* src, int n_crops, const float* geom, int geom_stride, int out_w, int out_h,
                           float* out, int32_t* rects, void* stream);
 
+/* Per-image detection metric on the NMS output: CVC-YOLOv3/validate.py:98-128 (target boxes from the
+ * normalised labels, bbox_iou with the +1 convention, greedy matching in score order at iou_thres) and
+ * utils/utils.py:58-119 (average_precision, compute_ap).  boxes [B][top_k][4] / counts [B] from b200cv_detect_nms;
+ * targets [B][T][5] = (cls,cx,cy,w,h) normalised, rows with a non-positive box number are padding; width/height =
+ * network input size.  Outputs per image: ap, recall, precision (0 when skipped), valid int32 (0 = the reference
+ * skips the image: no detection or no label), correct u8 [B][top_k] (true-positive flag per kept detection).
+ * Single class, like the reference.  T <= 4096. */
+int b200cv_detect_match_ap(const float* boxes, const int32_t* counts, int B, int top_k, const float* targets, int T,
+                           float width, float height, float iou_thres, float* ap, float* recall, float* precision,
+                           int32_t* valid, uint8_t* correct, void* stream);
+
 /* ---- optimizer steps ------------------------------------------------------------------ */
 /* One launch per param group.  table: device int64 [n_chunks][5] = {param*, grad*, state1*, state2*, count} (fp32
  * arrays; a chunk is processed by one CTA, keep count around 16K).

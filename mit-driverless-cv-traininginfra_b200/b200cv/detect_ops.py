@@ -76,3 +76,37 @@ def crop_resize(frames: torch.Tensor, d: Detections, src: torch.Tensor, n_crops:
     lib().call("b200cv_crop_resize_u8", ptr(frames), b, h, w, ptr(d.boxes), d.top_k, ptr(src), int(n_crops),
                ptr(geom), gstride, ow, oh, ptr(out), ptr(rects), stream_ptr())
     return out, rects
+
+
+@dataclass
+class ImageMetrics:
+    ap: torch.Tensor         # fp32 [B]  average precision per image (0 where skipped)
+    recall: torch.Tensor     # fp32 [B]
+    precision: torch.Tensor  # fp32 [B]
+    valid: torch.Tensor      # int32 [B] 0 = the reference skips the image (no detection / no label)
+    correct: torch.Tensor    # uint8 [B, top_k] true-positive flag of each kept detection
+
+    def means(self):
+        """(mean AP, mean recall, mean precision) over the images the reference counts (validate.py:170-174)."""
+        m = self.valid.bool()
+        if not bool(m.any()):
+            return float("nan"), float("nan"), float("nan")
+        return float(self.ap[m].mean()), float(self.recall[m].mean()), float(self.precision[m].mean())
+
+
+def match_ap(d: Detections, targets: torch.Tensor, width: float, height: float, iou_thres: float) -> ImageMetrics:
+    """Per-image AP / recall / precision of the NMS output against normalised labels [B,T,5] (validate.py:98-130,
+    utils/utils.py:58-119), single class like the reference."""
+    require_cuda(targets, "match_ap")
+    targets = targets.float().contiguous()
+    b = d.counts.shape[0]
+    if targets.dim() != 3 or targets.shape[0] != b or targets.shape[2] != 5:
+        raise ValueError(f"match_ap: expected targets [B={b}, T, 5], got {tuple(targets.shape)}")
+    dev = targets.device
+    f = lambda: torch.empty(b, dtype=torch.float32, device=dev)
+    out = ImageMetrics(f(), f(), f(), torch.empty(b, dtype=torch.int32, device=dev),
+                       torch.empty(b, d.top_k, dtype=torch.uint8, device=dev))
+    lib().call("b200cv_detect_match_ap", ptr(d.boxes), ptr(d.counts), b, d.top_k, ptr(targets), targets.shape[1],
+               float(width), float(height), float(iou_thres), ptr(out.ap), ptr(out.recall), ptr(out.precision),
+               ptr(out.valid), ptr(out.correct), stream_ptr())
+    return out

@@ -331,6 +331,119 @@ crop_resize_kernel(const unsigned char* __restrict__ frames, int H, int W, const
   }
 }
 
+
+// Per-image detection metric of CVC-YOLOv3/validate.py:80-128 + utils/utils.py:58-119 (average_precision, compute_ap)
+// on the NMS output (already in descending-score order; the reference's two re-sorts by -conf are stable no-ops).
+// One CTA per image: threads find each detection's best target (bbox_iou with the "+1 pixel" convention, first maximum
+// wins), thread 0 runs the greedy matching and the precision/recall sweep.  Single class, like the reference.
+constexpr int kApMaxT = 4096;
+
+__global__ void __launch_bounds__(128)
+detect_match_ap_kernel(const float* __restrict__ boxes, const int* __restrict__ counts, int top_k,
+                       const float* __restrict__ targets, int T, float width, float height, float iou_thres,
+                       float* __restrict__ ap_out, float* __restrict__ r_out, float* __restrict__ p_out,
+                       int* __restrict__ valid, unsigned char* __restrict__ correct_out) {
+  __shared__ float best_iou[kNmsMaxK];
+  __shared__ int best_t[kNmsMaxK];
+  __shared__ unsigned char detected[kApMaxT];
+  __shared__ unsigned char correct[kNmsMaxK];
+  __shared__ float prec[kNmsMaxK + 2];
+  __shared__ int s_ngt;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int n = counts[b];
+  const float* tg = targets + (size_t)b * T * 5;
+  if (tid == 0) s_ngt = 0;
+  for (int t = tid; t < T; t += blockDim.x) detected[t] = 0;
+  __syncthreads();
+  // labels[(labels[:, 1:5] <= 0).sum(dim=1) == 0]: rows whose four box numbers are all positive
+  int mine = 0;
+  for (int t = tid; t < T; t += blockDim.x) {
+    const float* q = tg + (size_t)t * 5;
+    mine += (q[1] > 0.f && q[2] > 0.f && q[3] > 0.f && q[4] > 0.f);
+  }
+  if (mine) atomicAdd(&s_ngt, mine);
+  __syncthreads();
+  const int n_gt = s_ngt;
+  for (int i = tid; i < top_k; i += blockDim.x) correct_out[(size_t)b * top_k + i] = 0;
+  if (n == 0 || n_gt == 0) {  // validate.py:95-96 (no detection) and :117-118 (no label): the image is skipped
+    if (tid == 0) {
+      ap_out[b] = 0.f;
+      r_out[b] = 0.f;
+      p_out[b] = 0.f;
+      valid[b] = 0;
+    }
+    return;
+  }
+  for (int i = tid; i < n; i += blockDim.x) {
+    const float4 d = reinterpret_cast<const float4*>(boxes)[(size_t)b * top_k + i];
+    const float d_area = ((d.z - d.x) + 1.f) * ((d.w - d.y) + 1.f);
+    float bi = -1.f;
+    int bt = 0;
+    bool first = true;
+    for (int t = 0; t < T; ++t) {
+      const float* q = tg + (size_t)t * 5;
+      if (!(q[1] > 0.f && q[2] > 0.f && q[3] > 0.f && q[4] > 0.f)) continue;
+      // xywh2xyxy (utils.py:121-126), then *= width / height (validate.py:105-106)
+      const float tx1 = (q[1] - q[3] / 2.f) * width, ty1 = (q[2] - q[4] / 2.f) * height;
+      const float tx2 = (q[1] + q[3] / 2.f) * width, ty2 = (q[2] + q[4] / 2.f) * height;
+      const float iw = fmaxf((fminf(d.z, tx2) - fmaxf(d.x, tx1)) + 1.f, 0.f);
+      const float ih = fmaxf((fminf(d.w, ty2) - fmaxf(d.y, ty1)) + 1.f, 0.f);
+      const float inter = iw * ih;
+      const float t_area = ((tx2 - tx1) + 1.f) * ((ty2 - ty1) + 1.f);
+      const float iou = inter / (((d_area + t_area) - inter) + 1e-12f);
+      if (first || iou > bi) {  // torch.argmax: first maximum
+        bi = iou;
+        bt = t;
+        first = false;
+      }
+    }
+    best_iou[i] = bi;
+    best_t[i] = bt;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    // greedy matching in score order (validate.py:123-127)
+    for (int i = 0; i < n; ++i) {
+      const int t = best_t[i];
+      const bool ok = best_iou[i] > iou_thres && !detected[t];
+      correct[i] = ok;
+      if (ok) detected[t] = 1;
+    }
+    // average_precision (utils.py:58-89): cumulative TP / FP, recall = tpc / n_gt, precision = tpc / (tpc + fpc)
+    const float ngt = (float)n_gt;  // n_gt + 1e-16 == n_gt
+    float tpc = 0.f, fpc = 0.f;
+    prec[0] = 0.f;
+    for (int i = 0; i < n; ++i) {
+      tpc += correct[i] ? 1.f : 0.f;
+      fpc += correct[i] ? 0.f : 1.f;
+      prec[i + 1] = tpc / (tpc + fpc);
+    }
+    prec[n + 1] = 0.f;
+    const float r = tpc / ngt, p = tpc / (tpc + fpc);
+    // compute_ap (utils.py:91-119): precision envelope from the right, area under the steps of the recall curve
+    for (int i = n + 1; i > 0; --i) prec[i - 1] = fmaxf(prec[i - 1], prec[i]);
+    double ap = 0.0;
+    float prev_rec = 0.f, tp2 = 0.f;
+    for (int k = 0; k <= n; ++k) {  // mrec[k+1] vs mrec[k]; mrec = [0, recall..., 1]
+      float rec_next;
+      if (k < n) {
+        tp2 += correct[k] ? 1.f : 0.f;
+        rec_next = tp2 / ngt;
+      } else {
+        rec_next = 1.f;
+      }
+      if (rec_next != prev_rec) ap += (double)((rec_next - prev_rec) * prec[k + 1]);
+      prev_rec = rec_next;
+    }
+    ap_out[b] = (float)ap;
+    r_out[b] = r;
+    p_out[b] = p;
+    valid[b] = 1;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += blockDim.x) correct_out[(size_t)b * top_k + i] = correct[i];
+}
+
 }  // namespace
 }  // namespace b200cv
 
@@ -374,4 +487,19 @@ extern "C" int b200cv_crop_resize_u8(const uint8_t* frames, int B, int H, int W,
   crop_resize_kernel<<<n_crops, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       frames, H, W, boxes, top_k, reinterpret_cast<const int2*>(src), geom, geom_stride, out_w, out_h, out, rects);
   return check_launch("crop_resize_u8");
+}
+
+extern "C" int b200cv_detect_match_ap(const float* boxes, const int32_t* counts, int B, int top_k,
+                                      const float* targets, int T, float width, float height, float iou_thres,
+                                      float* ap, float* recall, float* precision, int32_t* valid, uint8_t* correct,
+                                      void* stream) {
+  if (B == 0) return B200CV_OK;
+  B200CV_CHECK_ARG(boxes && counts && targets && ap && recall && precision && valid && correct,
+                   "detect_match_ap: null pointer");
+  B200CV_CHECK_ARG(top_k >= 1 && top_k <= kNmsMaxK, "detect_match_ap: top_k=%d outside [1,%d]", top_k, kNmsMaxK);
+  B200CV_CHECK_ARG(T >= 0 && T <= kApMaxT, "detect_match_ap: T=%d outside [0,%d]", T, kApMaxT);
+  B200CV_CHECK_ARG((reinterpret_cast<uintptr_t>(boxes) & 15) == 0, "detect_match_ap: boxes must be 16-byte aligned");
+  detect_match_ap_kernel<<<B, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      boxes, counts, top_k, targets, T, width, height, iou_thres, ap, recall, precision, valid, correct);
+  return check_launch("detect_match_ap");
 }

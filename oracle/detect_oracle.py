@@ -196,3 +196,93 @@ def synth_detections(B, rows, C, seed=0, hot=24, img=416.0, ties=True):
             det[b, sel[1], 4] = det[b, sel[0], 4]
             det[b, sel[3], 4] = det[b, sel[2], 4]
     return det
+
+
+# ------------------------------------------------------------------------------------------ validation metric
+def _bbox_iou_plus1(b1, b2):
+    """utils/utils.py:163-193, corner branch (+1 pixel convention), broadcasting [n,1,4] x [1,t,4]."""
+    ix1, iy1 = torch.max(b1[..., 0], b2[..., 0]), torch.max(b1[..., 1], b2[..., 1])
+    ix2, iy2 = torch.min(b1[..., 2], b2[..., 2]), torch.min(b1[..., 3], b2[..., 3])
+    inter = torch.clamp(ix2 - ix1 + 1, min=0) * torch.clamp(iy2 - iy1 + 1, min=0)
+    a1 = (b1[..., 2] - b1[..., 0] + 1) * (b1[..., 3] - b1[..., 1] + 1)
+    a2 = (b2[..., 2] - b2[..., 0] + 1) * (b2[..., 3] - b2[..., 1] + 1)
+    return inter / (a1 + a2 - inter + 1e-12)
+
+
+def compute_ap(recall, precision):
+    """utils/utils.py:91-119."""
+    mrec = torch.cat((torch.zeros(1), recall, torch.ones(1)))
+    mpre = torch.cat((torch.zeros(1), precision, torch.zeros(1)))
+    for i in range(len(mpre) - 1, 0, -1):
+        mpre[i - 1] = torch.max(mpre[i - 1], mpre[i])
+    i = torch.nonzero(mrec[1:] != mrec[:-1])
+    return torch.sum((mrec[i + 1] - mrec[i]) * mpre[i + 1])
+
+
+def average_precision(tp, conf, n_gt):
+    """utils/utils.py:58-89 (the sort made stable: equal confidences keep their order)."""
+    i = torch.sort(-conf, stable=True)[1]
+    tp, conf = tp[i].float(), conf[i].float()
+    fpc = torch.cumsum(1 - tp, dim=0)
+    tpc = torch.cumsum(tp, dim=0)
+    recall_curve = tpc / (n_gt + 1e-16)
+    r = tpc[-1] / (n_gt + 1e-16)
+    precision_curve = tpc / (tpc + fpc)
+    p = tpc[-1] / (tpc[-1] + fpc[-1])
+    return compute_ap(recall_curve, precision_curve), r, p
+
+
+def image_ap(box_corner, probabilities, labels, width, height, iou_thres):
+    """validate.py:95-130 for one image, after NMS: box_corner [n,4] / probabilities [n] in NMS order, labels [T,5]
+    normalised with zero padding.  Returns (ap, r, p, correct u8 [n]) or None where the reference skips the image."""
+    if box_corner.shape[0] == 0:
+        return None
+    inds = torch.sort(-probabilities, stable=True)[1]
+    box_corner, probabilities = box_corner[inds], probabilities[inds]
+    labels = labels[(labels[:, 1:5] <= 0).sum(dim=1) == 0]
+    if labels.shape[0] == 0:  # `if [] in ious.data.tolist(): continue`
+        return None
+    x = labels[:, 1:5]
+    tb = torch.zeros(x.shape)
+    tb[:, 0] = x[:, 0] - x[:, 2] / 2
+    tb[:, 1] = x[:, 1] - x[:, 3] / 2
+    tb[:, 2] = x[:, 0] + x[:, 2] / 2
+    tb[:, 3] = x[:, 1] + x[:, 3] / 2
+    tb[:, (0, 2)] *= width
+    tb[:, (1, 3)] *= height
+    detected = torch.zeros(tb.shape[0], dtype=torch.uint8)
+    correct = torch.zeros(box_corner.shape[0], dtype=torch.uint8)
+    ious = _bbox_iou_plus1(box_corner.unsqueeze(1), tb.unsqueeze(0))
+    best_is = torch.argmax(ious, dim=1)
+    for i in range(ious.shape[0]):
+        best_i = best_is[i]
+        if ious[i, best_i] > iou_thres and detected[best_i] == 0:
+            correct[i] = 1
+            detected[best_i] = 1
+    ap, r, p = average_precision(correct, probabilities, labels.shape[0])
+    return float(ap), float(r), float(p), correct
+
+
+def synth_labels_for(det, B, T, conf_thres, seed=0, img=416.0):
+    """Ground-truth labels that partly coincide with the confident detections of `det` (so that TP, FP and misses all
+    occur): per image, jittered copies of some confident boxes + random boxes, zero padded to T rows."""
+    g = torch.Generator().manual_seed(seed)
+    out = torch.zeros(B, T, 5)
+    for b in range(B):
+        hot = torch.nonzero(det[b, :, 4] > conf_thres).flatten()
+        if b % 5 == 4:
+            continue  # an image without labels
+        n_copy = min(int(hot.numel()), T // 2)
+        pick = hot[torch.randperm(hot.numel(), generator=g)[:n_copy]]
+        rows = []
+        for r in pick.tolist():
+            box = det[b, r, 0:4].clone()
+            box[0:2] += torch.randn(2, generator=g) * 2.0
+            box[2:4] *= 1.0 + 0.1 * torch.randn(2, generator=g)
+            rows.append(box / img)
+        for _ in range(int(torch.randint(0, 4, (1,), generator=g))):
+            rows.append(torch.cat([0.1 + 0.8 * torch.rand(2, generator=g), 0.03 + 0.1 * torch.rand(2, generator=g)]))
+        rows = rows[:T]
+        for j, bx in enumerate(rows):
+            out[b, j, 1:5] = bx.clamp(1e-3, 0.999)
+    return out

@@ -69,3 +69,29 @@ def test_prep_crop_layout():
     out = DO.prep_crop(frames[0], (10, 20, 90, 100))
     assert out.shape == (3, 80, 80) and out.dtype == np.float32
     assert np.array_equal(out, (frames[0][20:100, 10:90].transpose(2, 0, 1) / 255.0).astype(np.float32))  # identity size
+
+
+def test_image_ap_matches_reference_functions(golden_detect):
+    """AP / recall / precision / TP flags vs the reference's own bbox_iou + average_precision + compute_ap."""
+    assert len(golden_detect["ap"]) >= 2
+    n_valid = 0
+    for name, c in golden_detect["ap"].items():
+        det = DO.synth_detections(c["B"], c["rows"], c["C"], seed=c["seed"], hot=c["hot"], ties=False)
+        labels = DO.synth_labels_for(det, c["B"], c["T"], c["conf"], seed=c["seed"])
+        for b, ref in enumerate(c["out"]):
+            _, boxes, scores = DO.detect_nms(det[b], c["conf"], c["nms"])
+            got = DO.image_ap(boxes, scores, labels[b], 416, 416, c["iou"])
+            assert (got is None) == (ref is None), (name, b)
+            if ref is None:
+                continue
+            n_valid += 1
+            assert torch.equal(got[3], ref[3]), (name, b)  # true-positive flags: exact
+            assert got[:3] == ref[:3], (name, b)            # same torch ops, same floats
+    assert n_valid >= 10
+
+
+def test_compute_ap_hand_case():
+    # TP, FP, TP with 4 labels: recall .25 .25 .5, precision 1 .5 .667 -> envelope 1, .667, .667 -> AP = .25 + .25*.667
+    ap, r, p = DO.average_precision(torch.tensor([1, 0, 1], dtype=torch.uint8), torch.tensor([0.9, 0.8, 0.7]), 4)
+    assert float(ap) == pytest.approx(0.25 + 0.25 * 2 / 3, rel=1e-6)
+    assert float(r) == pytest.approx(0.5) and float(p) == pytest.approx(2 / 3)

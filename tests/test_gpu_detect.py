@@ -159,3 +159,54 @@ def test_pipeline_end_to_end_vs_oracle_composition(cfg_dir):
     assert torch.allclose(out.heatmaps.sum((2, 3)), torch.ones(n, 7, device="cuda"), atol=1e-4)
     pf = out.points_in_frame()
     assert bool((pf[..., 0] >= out.rects[:, None, 0]).all()) and bool((pf[..., 0] <= out.rects[:, None, 2]).all())
+
+
+def _check_metrics(m, d, det, labels, conf, nmst, iou, topk, tag):
+    B = det.shape[0]
+    aps = []
+    for b in range(B):
+        _, boxes, scores = DO.detect_nms(det[b], conf, nmst, topk)
+        ref = DO.image_ap(boxes, scores, labels[b], 416, 416, iou)
+        if ref is None:
+            assert int(m.valid[b]) == 0 and float(m.ap[b]) == 0.0, (tag, b)
+            assert not bool(m.correct[b].any()), (tag, b)
+            continue
+        n = int(d.counts[b])
+        assert int(m.valid[b]) == 1, (tag, b)
+        assert torch.equal(m.correct[b, :n].cpu(), ref[3]), (tag, b)   # matching: bit-exact
+        assert float(m.ap[b]) == pytest.approx(ref[0], rel=1e-6, abs=1e-7), (tag, b)
+        assert float(m.recall[b]) == pytest.approx(ref[1], rel=1e-6), (tag, b)
+        assert float(m.precision[b]) == pytest.approx(ref[2], rel=1e-6), (tag, b)
+        aps.append(ref[0])
+    if aps:
+        assert m.means()[0] == pytest.approx(sum(aps) / len(aps), rel=1e-5)
+
+
+def test_match_ap_against_reference_goldens(golden_detect):
+    for name, c in golden_detect["ap"].items():
+        det = DO.synth_detections(c["B"], c["rows"], c["C"], seed=c["seed"], hot=c["hot"], ties=False)
+        labels = DO.synth_labels_for(det, c["B"], c["T"], c["conf"], seed=c["seed"])
+        d = detect_ops.detect_nms(det.cuda(), c["conf"], c["nms"], 200)
+        m = detect_ops.match_ap(d, labels.cuda(), 416, 416, c["iou"])
+        for b, ref in enumerate(c["out"]):
+            if ref is None:
+                assert int(m.valid[b]) == 0, (name, b)
+                continue
+            n = int(d.counts[b])
+            assert int(m.valid[b]) == 1 and torch.equal(m.correct[b, :n].cpu(), ref[3]), (name, b)
+            assert float(m.ap[b]) == pytest.approx(ref[0], rel=1e-6, abs=1e-7), (name, b)
+            assert float(m.recall[b]) == pytest.approx(ref[1], rel=1e-6), (name, b)
+            assert float(m.precision[b]) == pytest.approx(ref[2], rel=1e-6), (name, b)
+
+
+@pytest.mark.parametrize("B,rows,hot,conf,nmst,iou,T,topk", [
+    (12, 10647, 40, 0.8, 0.25, 0.5, 16, 200),
+    (6, 2535, 300, 0.2, 0.6, 0.1, 128, 512),   # many detections per label: duplicates become false positives
+    (5, 500, 0, 0.95, 0.25, 0.5, 8, 200),      # no detections at all
+])
+def test_match_ap_random_vs_oracle(B, rows, hot, conf, nmst, iou, T, topk):
+    det = DO.synth_detections(B, rows, 1, seed=rows + B, hot=hot, ties=True)
+    labels = DO.synth_labels_for(det, B, T, conf, seed=B)
+    d = detect_ops.detect_nms(det.cuda(), conf, nmst, topk)
+    m = detect_ops.match_ap(d, labels.cuda(), 416, 416, iou)
+    _check_metrics(m, d, det, labels, conf, nmst, iou, topk, (B, rows))
