@@ -141,10 +141,14 @@ def test_darknet53_608_odd_grids_match_oracle(cfg_dir):
     assert det.shape == (2, 22743, 85)  # eval rows at 608
 
 
-def test_no_grad_pass_and_step_with_optimizer(cfg_dir):
+@pytest.mark.parametrize("fused", [False, True])
+def test_no_grad_pass_and_step_with_optimizer(cfg_dir, fused):
+    """train.py:62-84 with torch.optim.SGD and with the fused step (b200cv.optim.FusedSGD) on the engine's gradients."""
+    from b200cv import optim as boptim
+
     model, _ = helpers.make_darknet(cfg_dir, "yolo_baseline_tiny.cfg", 128, 1)
     model = model.to(DEV).train()
-    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9)
+    opt = (boptim.FusedSGD if fused else torch.optim.SGD)(model.parameters(), lr=1e-3, momentum=0.9)
     x, tg = YO.synth_images(2, 128, 128).to(DEV), YO.synth_targets(2, 16).to(DEV)
     first = None
     for _ in range(5):

@@ -72,9 +72,9 @@ def test_fused_sgd_matches_torch(momentum, wd):
 
 def test_fused_adam_drives_the_rektnet_step():
     """RektNet/train_eval.py:59-72 with the fused step on the engine's own gradients (views of its flat arena): the
-    first update equals torch.optim.Adam's on the same gradients, and a few iterations descend.  (Whole trajectories
-    of two runs are not comparable: the step is reproducible only to ~1e-3, see tools/determinism_probe.py, and
-    Adam's normalised update amplifies that.)"""
+    update of every iteration equals torch.optim.Adam's applied to the same gradients and state.  (Whole trajectories
+    of two separate runs are not comparable: the step is reproducible only to ~1e-3, see tools/determinism_probe.py,
+    and Adam's normalised update amplifies that; descent is asserted on the Darknet step in test_gpu_darknet.py.)"""
     import cross_ratio_loss
     import keypoint_net
     from oracle import rektnet_oracle as RO
@@ -85,21 +85,17 @@ def test_fused_adam_drives_the_rektnet_step():
     opt = boptim.FusedAdam(params, lr=1e-3, weight_decay=1e-4)
     loss_fn = cross_ratio_loss.CrossRatioLoss("l2_heatmap", True, 0.055, 0.038)
     x, thm, tpts = (t.cuda() for t in RO.synth_batch(8, seed=0))
-    losses = []
-    for it in range(5):
+    shadow = [torch.nn.Parameter(p.detach().clone()) for p in params]  # updated by torch's Adam, same gradients
+    ref = torch.optim.Adam(shadow, lr=1e-3, weight_decay=1e-4)
+    for it in range(4):
         opt.zero_grad()
         hm, pts = net(x)
         _, _, loss = loss_fn(hm, pts, thm, tpts)
         loss.backward()
-        if it == 0:  # shadow copy updated by torch's Adam from the same gradients
-            shadow = [torch.nn.Parameter(p.detach().clone()) for p in params]
-            for s, p in zip(shadow, params):
-                s.grad = p.grad.detach().clone()
-            ref = torch.optim.Adam(shadow, lr=1e-3, weight_decay=1e-4)
-            ref.step()
+        for s, p in zip(shadow, params):
+            s.grad = p.grad.detach().clone()
+        ref.step()
         opt.step()
-        if it == 0:
-            for s, p in zip(shadow, params):
-                assert torch.allclose(s, p, rtol=1e-5, atol=1e-7)
-        losses.append(float(loss))
-    assert losses[-1] < losses[0], losses
+        for s, p in zip(shadow, params):
+            assert torch.allclose(s, p, rtol=2e-5, atol=1e-6), it
+        assert torch.isfinite(loss.detach())
