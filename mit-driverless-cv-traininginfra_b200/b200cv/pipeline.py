@@ -77,3 +77,22 @@ class ConePipeline:
         heat = (torch.cat(hms, 0) if hms else torch.empty(0, k, self.kpt_size[1], self.kpt_size[0],
                                                           device=imgs.device)) if keep_heatmaps else None
         return PipelineOutput(d, offsets, rects, points, heat, n)
+
+
+@torch.no_grad()
+def detection_metrics(darknet, imgs: torch.Tensor, targets: torch.Tensor, conf_thres: Optional[float] = None,
+                      nms_thres: Optional[float] = None, iou_thres: Optional[float] = None,
+                      top_k: int = 200) -> detect_ops.ImageMetrics:
+    """The per-batch body of CVC-YOLOv3/validate.py:73-130 on the device: eval forward, confidence filter + NMS, greedy
+    matching against the labels, AP / recall / precision per image -- three launches after the network, no per-image
+    Python loop and no host synchronisation.  Thresholds default to the cfg's (validate.py:66).  `.means()` of the
+    result is what validate() averages over the images of a batch."""
+    require_cuda(imgs, "detection_metrics")
+    if darknet.training:
+        raise RuntimeError("detection_metrics: put the network in eval() mode (validate.py:68)")
+    cfg_conf, cfg_nms, cfg_iou = darknet.get_threshs()
+    width, height = darknet.img_size()
+    det = darknet(imgs)
+    d = detect_ops.detect_nms(det, cfg_conf if conf_thres is None else conf_thres,
+                              cfg_nms if nms_thres is None else nms_thres, top_k)
+    return detect_ops.match_ap(d, targets.to(imgs.device), width, height, cfg_iou if iou_thres is None else iou_thres)

@@ -210,3 +210,19 @@ def test_match_ap_random_vs_oracle(B, rows, hot, conf, nmst, iou, T, topk):
     d = detect_ops.detect_nms(det.cuda(), conf, nmst, topk)
     m = detect_ops.match_ap(d, labels.cuda(), 416, 416, iou)
     _check_metrics(m, d, det, labels, conf, nmst, iou, topk, (B, rows))
+
+
+def test_detection_metrics_composition(cfg_dir):
+    """validate.py's batch body on the device vs the oracle applied to the device's own detections."""
+    model, _ = helpers.make_darknet(cfg_dir, "yolo_baseline_tiny.cfg", 416, 1)
+    model = model.cuda().eval()
+    B = 6
+    imgs = torch.rand(B, 3, 416, 416, generator=torch.Generator().manual_seed(1)).cuda()
+    with torch.no_grad():
+        det = model(imgs).float().cpu()
+    conf = float(det[..., 4].flatten().kthvalue(det[..., 4].numel() - 60).values)
+    labels = DO.synth_labels_for(det, B, 16, conf, seed=3)
+    m = pipeline.detection_metrics(model, imgs, labels.cuda(), conf_thres=conf, nms_thres=0.25, iou_thres=0.5)
+    d = detect_ops.detect_nms(det.cuda(), conf, 0.25, 200)
+    _check_metrics(m, d, det, labels, conf, 0.25, 0.5, 200, "composition")
+    assert int(m.valid.sum()) >= 3
