@@ -308,3 +308,23 @@ def DarknetEngineFresh(model):
     x = YO.synth_images(2, 128, 128).to(DEV)
     model.eval()
     return DarknetEngine(model).detect(x)
+
+
+def test_full_size_eval_is_permutation_equivariant_and_reproducible(cfg_dir):
+    """Size-independent properties at BASELINE's full size (Darknet-53, 416x416, batch 64, C=80), where the CPU
+    oracle would take minutes: (1) the inference pass is bit-reproducible, (2) permuting the batch permutes the
+    detections bit-exactly (GEMM tiles straddle image boundaries, so this exercises the im2col / tile addressing of
+    every layer at full size), (3) each image's detections equal those of the same image in a batch of 2."""
+    model, _ = helpers.make_darknet(cfg_dir, "yolo_baseline.cfg", 416, 80)
+    model = model.to(DEV).eval()
+    x = YO.synth_images(64, 416, 416, seed=2).to(DEV)
+    perm = torch.randperm(64, generator=torch.Generator().manual_seed(0)).to(DEV)
+    with torch.no_grad():
+        d0 = model(x).clone()
+        d1 = model(x).clone()
+        dp = model(x[perm].contiguous()).clone()
+        d2 = model(x[5:7].contiguous()).clone()
+    assert d0.shape == (64, 10647, 85) and bool(torch.isfinite(d0).all())
+    assert torch.equal(d0, d1)
+    assert torch.equal(dp, d0[perm])
+    assert torch.equal(d2, d0[5:7])
