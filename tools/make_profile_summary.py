@@ -5,7 +5,8 @@ import collections, csv, json, os, re, shutil, subprocess, sys
 
 R = sys.argv[1] if len(sys.argv) > 1 else "r01"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SRC, DST = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+SRC = os.path.join(ROOT, "gpurun_out")
+DST = os.path.join(ROOT, sys.argv[2]) if len(sys.argv) > 2 else os.path.join(ROOT, "profiles")
 os.makedirs(DST, exist_ok=True)
 
 def short(name):
@@ -13,38 +14,41 @@ def short(name):
     return name.replace("void b200cv::<unnamed>::", "").replace("b200cv::<unnamed>::", "").replace("void ", "")
 
 # ---- launch list ---------------------------------------------------------------------------------------------
-rows = list(csv.reader(open(os.path.join(SRC, f"launches_{R}.csv"))))
-hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
-h = rows[hi]
-kn, mn, mv, gs, ident = h.index("Kernel Name"), h.index("Metric Name"), h.index("Metric Value"), h.index("Grid Size"), h.index("ID")
-launch = collections.OrderedDict()
-for r in rows[hi + 1:]:
-    if len(r) <= mv:
-        continue
-    d = launch.setdefault(r[ident], {"name": short(r[kn]), "grid": r[gs]})
-    d[r[mn]] = float(r[mv].replace(",", ""))
-agg = collections.OrderedDict()
-for d in launch.values():
-    a = agg.setdefault(d["name"], [0, 0.0, 0.0, 0.0])
-    a[0] += 1
-    a[1] += d.get("gpu__time_duration.sum", 0.0) / 1e3       # ns -> us
-    a[2] += d.get("dram__bytes_read.sum", 0.0)
-    a[3] += d.get("dram__bytes_write.sum", 0.0)
-tot = sum(a[1] for a in agg.values())
-with open(os.path.join(DST, f"launches_{R}_summary.txt"), "w") as f:
-    f.write(f"# ncu launch list of ONE eager Darknet-53 416^2 bs64 training step (bench.py --ncu-window), {len(launch)} launches,\n"
-            f"# sum of gpu__time_duration = {tot/1e3:.2f} ms (cold-cache, serialised: the SHARE is what compares with the bench).\n"
-            f"# units: us, MB per step over all launches of the kernel\n")
-    f.write(f"{'kernel':58s} {'n':>5s} {'us':>10s} {'share':>7s} {'us/launch':>10s} {'dram_rd_MB':>11s} {'dram_wr_MB':>11s}\n")
-    for k, (n, us, rd, wr) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        f.write(f"{k[:58]:58s} {n:5d} {us:10.1f} {100*us/tot:6.1f}% {us/n:10.2f} {rd/1e6:11.1f} {wr/1e6:11.1f}\n")
-conv = [a for k, a in agg.items() if k.startswith(("igemm_kernel", "wgrad_kernel"))]
-roof = {"round": R, "conv_launches_per_step": sum(a[0] for a in conv), "conv_us_ncu": sum(a[1] for a in conv),
-        "conv_share_of_step_ncu": sum(a[1] for a in conv) / tot,
-        "conv_dram_bytes_per_step": sum(a[2] + a[3] for a in conv),
-        "note": "DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) summed over the igemm/wgrad launches of one "
-                "eager step, from the ncu launch-list pass"}
-json.dump(roof, open(os.path.join(DST, f"roofline_{R}.json"), "w"), indent=1)
+roof = None
+if os.path.exists(os.path.join(SRC, f"launches_{R}.csv")):
+    rows = list(csv.reader(open(os.path.join(SRC, f"launches_{R}.csv"))))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    h = rows[hi]
+    kn, mn, mv, gs, ident = h.index("Kernel Name"), h.index("Metric Name"), h.index("Metric Value"), h.index("Grid Size"), h.index("ID")
+    launch = collections.OrderedDict()
+    for r in rows[hi + 1:]:
+        if len(r) <= mv:
+            continue
+        d = launch.setdefault(r[ident], {"name": short(r[kn]), "grid": r[gs]})
+        d[r[mn]] = float(r[mv].replace(",", ""))
+    agg = collections.OrderedDict()
+    for d in launch.values():
+        a = agg.setdefault(d["name"], [0, 0.0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += d.get("gpu__time_duration.sum", 0.0) / 1e3       # ns -> us
+        a[2] += d.get("dram__bytes_read.sum", 0.0)
+        a[3] += d.get("dram__bytes_write.sum", 0.0)
+    tot = sum(a[1] for a in agg.values())
+    with open(os.path.join(DST, f"launches_{R}_summary.txt"), "w") as f:
+        f.write(f"# ncu launch list of ONE eager Darknet-53 416^2 bs64 training step (bench.py --ncu-window), {len(launch)} launches,\n"
+                f"# sum of gpu__time_duration = {tot/1e3:.2f} ms (cold-cache, serialised: the SHARE is what compares with the bench).\n"
+                f"# units: us, MB per step over all launches of the kernel\n")
+        f.write(f"{'kernel':58s} {'n':>5s} {'us':>10s} {'share':>7s} {'us/launch':>10s} {'dram_rd_MB':>11s} {'dram_wr_MB':>11s}\n")
+        for k, (n, us, rd, wr) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"{k[:58]:58s} {n:5d} {us:10.1f} {100*us/tot:6.1f}% {us/n:10.2f} {rd/1e6:11.1f} {wr/1e6:11.1f}\n")
+    conv = [a for k, a in agg.items() if k.startswith(("igemm_kernel", "wgrad_kernel"))]
+    roof = {"round": R, "conv_launches_per_step": sum(a[0] for a in conv), "conv_us_ncu": sum(a[1] for a in conv),
+            "conv_share_of_step_ncu": sum(a[1] for a in conv) / tot,
+            "conv_dram_bytes_per_step": sum(a[2] + a[3] for a in conv),
+            "note": "DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) summed over the igemm/wgrad launches of one "
+                    "eager step, from the ncu launch-list pass"}
+    json.dump(roof, open(os.path.join(DST, f"roofline_{R}.json"), "w"), indent=1)
+
 
 # ---- --set full captures ---------------------------------------------------------------------------------------
 KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
@@ -71,7 +75,7 @@ for rep in sorted(os.listdir(SRC)):
                     i = hdr.index(k)
                     f.write(f"   {k:72s} {r[i]:>18s} {units[i]}\n")
     # SASS evidence of tcgen05 / TMA for the conv kernels
-    if rep.startswith(("igemm", "wgrad", "dgrad")):
+    if rep.startswith(("igemm", "wgrad", "dgrad", "optim", "detect")):
         src = subprocess.run(["ncu", "-i", os.path.join(SRC, rep), "--page", "source", "--csv"], capture_output=True, text=True).stdout
         ops = collections.Counter(m for m in re.findall(r"\b(UTCHMMA|UTMALDG[.\w]*|UTMASTG[.\w]*|UTMAREDG[.\w]*|UTCBAR|LDTM[.\w]*|UTCATOMSWS[.\w]*|SYNCS[.\w]*)", src))
         with open(os.path.join(DST, "ncu_" + rep.replace(".ncu-rep", ".txt")), "a") as f:
@@ -82,5 +86,6 @@ for name in (f"bench_{R}.json", f"layer_times_{R}.txt", f"yolo_loss_timing_{R}.l
     p = os.path.join(SRC, name)
     if os.path.exists(p):
         shutil.copy(p, os.path.join(DST, name if R in name else name.replace(".txt", f"_{R}.txt")))
-print(open(os.path.join(DST, f"launches_{R}_summary.txt")).read())
-print(json.dumps(roof))
+if roof is not None:
+    print(open(os.path.join(DST, f"launches_{R}_summary.txt")).read())
+    print(json.dumps(roof))

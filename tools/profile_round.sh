@@ -24,12 +24,4 @@ timeout 600 ncu --profile-from-start off --set full --clock-control none -k rege
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:yolo_ -s 6 -c 6 \
     -o gpurun_out/yolo_loss_full_$R -f python tools/bench_yolo_loss.py > gpurun_out/yolo_loss_$R.log 2>&1
 python tools/bench_yolo_loss.py > gpurun_out/yolo_loss_timing_$R.log 2>&1
-# inference joint (BASELINE config 5), optimizer step, reproducibility probe
-python tools/bench_pipeline.py --out gpurun_out/pipeline_$R.json > /dev/null 2> gpurun_out/pipeline_$R.err
-python tools/bench_optim.py > gpurun_out/optim_$R.json 2> gpurun_out/optim_$R.err
-python tools/determinism_probe.py 2>/dev/null | grep "rel spread" > gpurun_out/determinism_$R.txt
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:"adam_multi|sgd_multi" -s 3 -c 2 \
-    -o gpurun_out/optim_full_$R -f python tools/bench_optim.py --iters 2 > gpurun_out/optim_full_$R.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:"detect_nms|crop_resize|detect_compact" -s 3 -c 3 \
-    -o gpurun_out/detect_full_$R -f python tools/bench_pipeline.py --iters 2 --warmup 1 > gpurun_out/detect_full_$R.log 2>&1
-ls -la gpurun_out
+bash tools/profile_extras.sh $R
