@@ -404,6 +404,14 @@ static void run_bench() {
   bench_case("rekt 3x3 128->128 @80", 256, 80, 80, 128, 128, 3, 1, 1, 1);
   bench_case("rekt 3x3 16->16 @80", 256, 80, 80, 16, 16, 3, 1, 1, 1);
   bench_case("rekt 7x7 3->16 @80", 256, 80, 80, 3, 16, 7, 1, 3, 1);
+  bench_case("rekt 3x3d2 16->32 @80", 256, 80, 80, 16, 32, 3, 1, 2, 2);
+  bench_case("rekt 3x3 32->32 @80", 256, 80, 80, 32, 32, 3, 1, 1, 1);
+  bench_case("rekt 3x3d2 32->64 @80", 256, 80, 80, 32, 64, 3, 1, 2, 2);
+  bench_case("rekt 3x3 64->64 @80", 256, 80, 80, 64, 64, 3, 1, 1, 1);
+  bench_case("rekt 1x1 16->32 @80", 256, 80, 80, 16, 32, 1, 1, 0, 1);
+  bench_case("dk53 1x1 64->32 @208", 64, 208, 208, 64, 32, 1, 1, 0, 1);
+  bench_case("dk53 1x1 128->64 @104", 64, 104, 104, 128, 64, 1, 1, 0, 1);
+  bench_case("dk53 3x3s2 64->128 @208", 64, 208, 208, 64, 128, 3, 2, 1, 1);
 }
 
 static Case mk(const char* name, int N, int H, int W, int Cin, int Cout, int R, int stride, int pad, int dil) {
@@ -446,6 +454,11 @@ int main(int argc, char** argv) {
   { Case c = mk("3x3_c64_o64_affine_leaky_res", 2, 13, 13, 64, 64, 3, 1, 1, 1); c.affine = true; c.act = 1; c.residual = true; fwd.push_back(c); }
   { Case c = mk("3x3_c128_o256_big_stats", 8, 52, 52, 128, 256, 3, 1, 1, 1); c.stats = true; fwd.push_back(c); }
   fwd.push_back(mk("1x1_c1024_o512", 4, 13, 13, 1024, 512, 1, 1, 0, 1));
+  // several tiles per CTA on the small-stage configurations (multi-lane TMA producers, ring wraps, ragged last tile)
+  fwd.push_back(mk("3x3_c16_o16_many_tiles", 33, 80, 79, 16, 16, 3, 1, 1, 1));
+  fwd.push_back(mk("3x3_dil2_c32_o64_many_tiles", 17, 80, 80, 32, 64, 3, 1, 2, 2));
+  fwd.push_back(mk("1x1_c64_o32_many_tiles", 9, 104, 104, 64, 32, 1, 1, 0, 1));
+  { Case c = mk("3x3_c64_o64_many_tiles_stats_res", 9, 80, 80, 64, 64, 3, 1, 1, 1); c.stats = true; c.affine = true; c.act = 1; c.residual = true; fwd.push_back(c); }
   for (auto& c : fwd) run_fwd(c);
 
   std::vector<Case> dg;
@@ -457,6 +470,9 @@ int main(int argc, char** argv) {
   dg.push_back(mk("3x3_dil2_c16_o16", 2, 20, 20, 16, 16, 3, 1, 2, 2));
   dg.push_back(mk("1x1_c256_o18", 2, 13, 13, 256, 18, 1, 1, 0, 1));
   { Case c = mk("3x3_c64_o64_residual", 2, 13, 13, 64, 64, 3, 1, 1, 1); c.residual = true; dg.push_back(c); }
+  dg.push_back(mk("3x3_c16_o32_many_tiles", 17, 80, 80, 16, 32, 3, 1, 1, 1));
+  dg.push_back(mk("3x3_s2_c32_o64_many_tiles", 9, 104, 104, 32, 64, 3, 2, 1, 1));
+  { Case c = mk("3x3_c64_o64_residual_many_tiles", 9, 80, 80, 64, 64, 3, 1, 1, 1); c.residual = true; dg.push_back(c); }
   for (auto& c : dg) run_dgrad(c);
 
   std::vector<Case> wg;
