@@ -448,45 +448,70 @@ __global__ void __launch_bounds__(256) unpack_wgrad_multi_kernel(const PackEntry
 
 // explicit im2col for the 3-channel input layers: NCHW fp32 image -> bf16 patch matrix [N*OH*OW][Kp],
 // k = (r*S+s)*C + c.  One thread per output pixel (plane reads coalesce across threads); R,S,C are
-// compile-time so the patch lives in registers and goes out as 16-byte stores.
+// compile-time so the patch lives in registers.  The 32 rows of a warp are contiguous in the patch matrix: each lane
+// parks its row in shared memory (row pitch + 16 bytes: conflict-free 16-byte stores) and the warp then streams the
+// 32*Kp*2 bytes out as fully coalesced 16-byte stores (per-lane row stores touched 32 different rows per
+// instruction: 0.435 -> 0.33 ms for the 384-byte rows of the RektNet 7x7 stem at 80x80 bs256; rows of <= 64 bytes are
+// stored directly, staging them was 15 % slower).
 template <int R, int S, int C>
 __global__ void __launch_bounds__(256)
 im2col_nchw_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H, int W, int stride,
                    int pad, int dil, int OH, int OW, int Kp) {
   constexpr int K = R * S * C;
   constexpr int K8 = (K + 7) / 8 * 8;
+  extern __shared__ uint4 im2col_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int chunks = Kp >> 3;        // 16-byte chunks per row
+  const int pitch = chunks + 1;      // in 16-byte units
+  const bool staged = chunks > 4;
+  uint4* wbuf = im2col_smem + (size_t)warp * 32 * pitch;
   const long long total = (long long)N * OH * OW;
-  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < total;
-       m += (long long)gridDim.x * blockDim.x) {
-    const int ow = (int)(m % OW);
-    const long long t = m / OW;
-    const int oh = (int)(t % OH);
-    const long long n = t / OH;
-    const float* xn = x + n * C * H * W;
-    __nv_bfloat16* o = out + m * Kp;
-    float v[K8];
+  const long long step = (long long)gridDim.x * blockDim.x;
+  // whole warps iterate together (the tail warp keeps its inactive lanes for the cooperative copy)
+  for (long long m0 = blockIdx.x * (long long)blockDim.x + warp * 32; m0 < total; m0 += step) {
+    const long long m = m0 + lane;
+    if (m < total) {
+      const int ow = (int)(m % OW);
+      const long long t = m / OW;
+      const int oh = (int)(t % OH);
+      const long long n = t / OH;
+      const float* xn = x + n * C * H * W;
+      float v[K8];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int ih = oh * stride - pad + r * dil;
+      for (int r = 0; r < R; ++r) {
+        const int ih = oh * stride - pad + r * dil;
 #pragma unroll
-      for (int s = 0; s < S; ++s) {
-        const int iw = ow * stride - pad + s * dil;
-        const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
+        for (int s = 0; s < S; ++s) {
+          const int iw = ow * stride - pad + s * dil;
+          const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
 #pragma unroll
-        for (int c = 0; c < C; ++c) v[(r * S + s) * C + c] = ok ? __ldg(xn + ((long long)c * H + ih) * W + iw) : 0.f;
+          for (int c = 0; c < C; ++c) v[(r * S + s) * C + c] = ok ? __ldg(xn + ((long long)c * H + ih) * W + iw) : 0.f;
+        }
       }
+#pragma unroll
+      for (int k = K; k < K8; ++k) v[k] = 0.f;
+      // short rows (<= 64 bytes: the 3x3 stem) go straight out -- measured faster than staging them
+      uint4* row = staged ? wbuf + lane * pitch : reinterpret_cast<uint4*>(out + m * Kp);
+#pragma unroll
+      for (int k0 = 0; k0 < K8; k0 += 8) {
+        uint4 pk;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[k0 + 2 * j], v[k0 + 2 * j + 1]);
+        row[k0 >> 3] = pk;
+      }
+      for (int j = K8 >> 3; j < chunks; ++j) row[j] = make_uint4(0, 0, 0, 0);
     }
-#pragma unroll
-    for (int k = K; k < K8; ++k) v[k] = 0.f;
-#pragma unroll
-    for (int k0 = 0; k0 < K8; k0 += 8) {
-      uint4 pk;
-      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[k0 + 2 * j], v[k0 + 2 * j + 1]);
-      *reinterpret_cast<uint4*>(o + k0) = pk;
+    if (!staged) continue;
+    __syncwarp();
+    const long long rows = total - m0 < 32 ? total - m0 : 32;
+    uint4* dst = reinterpret_cast<uint4*>(out + m0 * Kp);
+    const int n16 = (int)rows * chunks;
+    for (int q = lane; q < n16; q += 32) {
+      const int r = q / chunks, j = q - r * chunks;
+      dst[q] = wbuf[r * pitch + j];
     }
-    for (int k0 = K8; k0 < Kp; k0 += 8) *reinterpret_cast<uint4*>(o + k0) = make_uint4(0, 0, 0, 0);
+    __syncwarp();
   }
 }
 // generic fallback (any R,S,C)
@@ -588,12 +613,21 @@ extern "C" int b200cv_im2col_nchw_f32(const float* x, void* patches, int N, int 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(patches);
   const int grid = grid_for(total, 256);
-  if (R == 3 && S == 3 && C == 3)
-    im2col_nchw_kernel<3, 3, 3><<<grid, 256, 0, st>>>(x, o, N, H, W, stride, pad, dil, OH, OW, Kp);
-  else if (R == 7 && S == 7 && C == 3)
-    im2col_nchw_kernel<7, 7, 3><<<grid, 256, 0, st>>>(x, o, N, H, W, stride, pad, dil, OH, OW, Kp);
-  else if (R == 3 && S == 3 && C == 1)
-    im2col_nchw_kernel<3, 3, 1><<<grid, 256, 0, st>>>(x, o, N, H, W, stride, pad, dil, OH, OW, Kp);
+  // staging: 8 warps x 32 rows x (Kp*2 + 16) bytes
+  const size_t stage_bytes = Kp / 8 > 4 ? (size_t)8 * 32 * (Kp / 8 + 1) * 16 : 0;
+  auto launch = [&](auto kern) -> int {
+    static size_t configured = 48 * 1024;  // per instantiation; benign race: the attribute set is idempotent
+    if (stage_bytes > configured) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes);
+      if (e != cudaSuccess) return set_error(static_cast<int>(e), "im2col smem attr: %s", cudaGetErrorString(e));
+      configured = stage_bytes;
+    }
+    kern<<<grid, 256, stage_bytes, st>>>(x, o, N, H, W, stride, pad, dil, OH, OW, Kp);
+    return check_launch("im2col_nchw");
+  };
+  if (stage_bytes <= 200 * 1024 && R == 3 && S == 3 && C == 3) return launch(im2col_nchw_kernel<3, 3, 3>);
+  if (stage_bytes <= 200 * 1024 && R == 7 && S == 7 && C == 3) return launch(im2col_nchw_kernel<7, 7, 3>);
+  if (stage_bytes <= 200 * 1024 && R == 3 && S == 3 && C == 1) return launch(im2col_nchw_kernel<3, 3, 1>);
   else
     im2col_nchw_generic_kernel<<<grid, 256, 0, st>>>(x, o, N, C, H, W, R, S, stride, pad, dil, OH, OW, Kp);
   return check_launch("im2col_nchw");
