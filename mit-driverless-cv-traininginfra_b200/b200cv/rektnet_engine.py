@@ -13,6 +13,8 @@ tensors take the un-fused kernels (b200cv_kpt_loss_bwd).
 """
 from __future__ import annotations
 
+import os
+
 from typing import List, Optional
 
 import torch
@@ -68,10 +70,18 @@ class _ConvBN:
             self._eval_key = key
         return self._eval_affine
 
-    def bwd(self, x_in, y, da, aout, act, gview, packs, dx_out=None, want_dx=True):
-        """BN+act backward then wgrad (+ dgrad).  Returns dx (or None)."""
+    def reduce_spec(self, y, act):
+        """(bn_reduce tuple for ops.conv_dgrad, zeroed partial sums): lets the data gradient that PRODUCES this
+        layer's dL/da also accumulate its BN-backward sums (no separate pass over da and y)."""
+        parts = ops.stats_buffer(self.cout, y.device)
+        return (y, self.scale, self.shift, self.mean, self.rstd, act, 0.0, parts), parts
+
+    def bwd(self, x_in, y, da, aout, act, gview, packs, dx_out=None, want_dx=True, parts=None, bn_reduce=None):
+        """BN+act backward then wgrad (+ dgrad).  Returns dx (or None).  `parts`: BN-backward sums already produced by
+        the dgrad that wrote `da`; `bn_reduce`: fused reduction for the layer whose dL/da this dgrad writes."""
         count = y.numel() // y.shape[-1]
-        parts = ops.bn_bwd_reduce(da, y, aout, self.scale, self.shift, self.mean, self.rstd, act, 0.0)
+        if parts is None:
+            parts = ops.bn_bwd_reduce(da, y, aout, self.scale, self.shift, self.mean, self.rstd, act, 0.0)
         ops.bn_bwd_finalize(parts, self.bn.weight, self.rstd, count, self.coef, gview[id(self.bn.weight)],
                             gview[id(self.bn.bias)])
         dy = ops.bn_bwd_apply(da, y, aout, self.scale, self.shift, self.mean, self.rstd, self.coef, act, 0.0)
@@ -80,7 +90,7 @@ class _ConvBN:
         if not want_dx:
             return None
         return ops.conv_dgrad(dy, self.wpk_t, self.cin, self.k, 1, self.pad, self.dil, (x_in.shape[1], x_in.shape[2]),
-                              out=dx_out, residual=dx_out)
+                              out=dx_out, residual=dx_out, bn_reduce=bn_reduce)
 
 
 class _HeadHandle:
@@ -215,12 +225,21 @@ class RektNetEngine:
         gview[id(m.out.bias)].copy_(tmp[:k])
         ops.conv_wgrad(a_last, dl, k, 1, 1, 0, out=packs.dwp[id(m.out)])
         g = ops.conv_dgrad(dl, saved["out_wpk_t"], m.out.in_channels, 1, 1, 0, 1, (h, w))
-        for (c1, c2, cs), (a_in, y1, a1, y2, ys, out) in zip(reversed(self.blocks), reversed(saved["blocks"])):
+        fuse = os.environ.get("B200CV_FUSE_BN_REDUCE", "2") != "0"
+        stem_parts = None
+        for bi, ((c1, c2, cs), (a_in, y1, a1, y2, ys, out)) in enumerate(
+                zip(reversed(self.blocks), reversed(saved["blocks"]))):
             # out = relu(bn_s(ys) + bn_2(y2)): both branches see dz = g * relu'(out)
             g_in = cs.bwd(a_in, ys, g, out, ops.ACT_RELU, gview, packs)
-            g_a1 = c2.bwd(a1, y2, g, out, ops.ACT_RELU, gview, packs)
-            g = c1.bwd(a_in, y1, g_a1, None, ops.ACT_RELU, gview, packs, dx_out=g_in)
-        self.stem.bwd(saved["x"], saved["y0"], g, None, ops.ACT_RELU, gview, packs, want_dx=False)
+            # a1 = relu(bn_1(y1)) has ONE consumer: conv2's data gradient is dL/da1, so its epilogue also forms the
+            # BN-backward sums of bn_1; likewise the last data gradient into the first block's input for the stem
+            red1, parts1 = c1.reduce_spec(y1, ops.ACT_RELU) if fuse else (None, None)
+            g_a1 = c2.bwd(a1, y2, g, out, ops.ACT_RELU, gview, packs, bn_reduce=red1)
+            red0 = None
+            if fuse and bi == len(self.blocks) - 1:
+                red0, stem_parts = self.stem.reduce_spec(saved["y0"], ops.ACT_RELU)
+            g = c1.bwd(a_in, y1, g_a1, None, ops.ACT_RELU, gview, packs, dx_out=g_in, parts=parts1, bn_reduce=red0)
+        self.stem.bwd(saved["x"], saved["y0"], g, None, ops.ACT_RELU, gview, packs, want_dx=False, parts=stem_parts)
         packs.unpack_all()
         allreduce_gradients(arena.flat)
         return views
