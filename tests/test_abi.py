@@ -58,3 +58,46 @@ def test_product_has_no_cpu_path():
 
     with pytest.raises(L.B200CVError):
         ops.nchw_to_nhwc(torch.zeros(1, 3, 4, 4))
+
+
+def test_new_rows_have_no_cpu_path_either():
+    """The 8f rows (NMS / crop / AP kernels, fused optimizers, the pipeline) refuse CPU tensors instead of silently
+    computing on the host."""
+    import pytest
+    import torch
+
+    from b200cv import detect_ops
+    from b200cv import optim as boptim
+
+    with pytest.raises(L.B200CVError):
+        detect_ops.detect_nms(torch.zeros(1, 10, 6), 0.5, 0.3)
+    from utils.nms import nms
+
+    with pytest.raises(L.B200CVError):
+        nms(torch.zeros(3, 4), torch.ones(3))
+    p = torch.nn.Parameter(torch.zeros(4))
+    p.grad = torch.ones(4)
+    for opt in (boptim.FusedAdam([p], lr=0.1), boptim.FusedSGD([p], lr=0.1, momentum=0.9)):
+        with pytest.raises(L.B200CVError):
+            opt.step()
+    assert torch.equal(p.detach(), torch.zeros(4))  # nothing was updated on the host
+
+
+def test_fused_optimizer_host_logic():
+    """Constructor validation and torch.optim plumbing that need no GPU: param_groups, schedulers, state_dict keys."""
+    import pytest
+    import torch
+
+    from b200cv import optim as boptim
+
+    with pytest.raises(ValueError):
+        boptim.FusedAdam([torch.nn.Parameter(torch.zeros(1))], lr=-1.0)
+    with pytest.raises(ValueError):
+        boptim.FusedSGD([torch.nn.Parameter(torch.zeros(1))], momentum=-0.1)
+    ps = [torch.nn.Parameter(torch.zeros(3)), torch.nn.Parameter(torch.zeros(2, 2))]
+    opt = boptim.FusedAdam(ps, lr=0.1, weight_decay=5e-4)
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=1, gamma=0.95)   # CVC-YOLOv3/train.py:199
+    opt.step()          # no gradients yet: a no-op, like torch.optim
+    sched.step()
+    assert opt.param_groups[0]["lr"] == pytest.approx(0.095)
+    assert opt.state_dict()["param_groups"][0]["weight_decay"] == 5e-4
