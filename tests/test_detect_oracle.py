@@ -95,3 +95,51 @@ def test_compute_ap_hand_case():
     ap, r, p = DO.average_precision(torch.tensor([1, 0, 1], dtype=torch.uint8), torch.tensor([0.9, 0.8, 0.7]), 4)
     assert float(ap) == pytest.approx(0.25 + 0.25 * 2 / 3, rel=1e-6)
     assert float(r) == pytest.approx(0.5) and float(p) == pytest.approx(2 / 3)
+
+
+REF = os.environ.get("B200CV_REFERENCE", "/root/reference")
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "CVC-YOLOv3")), reason="reference tree not present (GPU box)")
+def test_oracle_vs_live_reference_nms_and_ap():
+    """Where the reference tree is mounted (the build container), compare the oracle with the reference's own nms() and
+    average_precision() on fresh random cases (untied scores), beyond the committed goldens."""
+    import importlib.util
+    import sys
+    import types
+
+    def load(name, rel):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(REF, "CVC-YOLOv3", rel))
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        return m
+
+    ref_nms = load("_ref_nms_live", "utils/nms.py").nms
+    stubbed = []
+    for name in ("imgaug", "imgaug.augmenters", "tqdm", "matplotlib", "matplotlib.pyplot"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                sys.modules[name] = types.ModuleType(name)
+                stubbed.append(name)
+    try:
+        U = load("_ref_utils_live", "utils/utils.py")
+    finally:
+        for name in stubbed:
+            sys.modules.pop(name, None)
+    g = torch.Generator().manual_seed(123)
+    for case in range(25):
+        n = int(torch.randint(1, 400, (1,), generator=g))
+        ctr = torch.rand(n, 2, generator=g) * 100
+        wh = 2 + torch.rand(n, 2, generator=g) * 40
+        boxes = torch.cat([ctr - wh / 2, ctr + wh / 2], 1)
+        scores = torch.rand(n, generator=g)
+        if scores.unique().numel() != n:
+            continue
+        thr = float(torch.rand(1, generator=g)) * 0.8
+        assert torch.equal(DO.nms(boxes, scores, thr, 200), ref_nms(boxes, scores, thr, 200)), case
+        tp = (torch.rand(n, generator=g) > 0.5).to(torch.uint8)
+        n_gt = int(torch.randint(1, 50, (1,), generator=g))
+        got, want = DO.average_precision(tp, scores, n_gt), U.average_precision(tp, scores, n_gt)
+        assert [float(v) for v in got] == [float(v) for v in want], case
