@@ -292,6 +292,17 @@ int b200cv_crop_resize_u8(const uint8_t* frames, int B, int H, int W, const floa
                           const int32_t* src, int n_crops, const float* geom, int geom_stride, int out_w, int out_h,
                           float* out, int32_t* rects, void* stream);
 
+/* Letterbox front end of CVC-YOLOv3/detect.py:62-72 (and validate.py / datasets.py's scale step): pad the frame to the
+ * network's aspect ratio with `fill` (torchvision pad, fill=127), resize with PIL BILINEAR (Pillow's 8-bit two-pass
+ * resampler, bit-exact), to_tensor (/255).  frames u8 [B][H][W][3]; the padded image (H+2*pad_h) x (W+2*pad_w) is
+ * resampled to out_h x out_w with host-made tables (Resample.c precompute_coeffs + normalize_coeffs_8bpc, see
+ * b200cv/preprocess.py): per output column hx_min/hx_cnt int32 [out_w] and hx_k int32 [out_w][ksize_h] (22-bit fixed
+ * point), per output row vy_*; NULL tables = that pass is the identity.  out fp32 [B][3][out_h][out_w];
+ * reverse_channels != 0 writes input channel c to plane 2-c (BGR frames -> RGB planes). */
+int b200cv_letterbox_u8(const uint8_t* frames, int B, int H, int W, int pad_w, int pad_h, int fill,
+                        int reverse_channels, const int32_t* hx_min, const int32_t* hx_cnt, const int32_t* hx_k,
+                        int ksize_h, const int32_t* vy_min, const int32_t* vy_cnt, const int32_t* vy_k, int ksize_v,
+                        int out_w, int out_h, float* out, void* stream);
 /* Per-image detection metric on the NMS output: CVC-YOLOv3/validate.py:98-128 (target boxes from the
  * normalised labels, bbox_iou with the +1 convention, greedy matching in score order at iou_thres) and
  * utils/utils.py:58-119 (average_precision, compute_ap).  boxes [B][top_k][4] / counts [B] from b200cv_detect_nms;

@@ -51,6 +51,21 @@ class ConePipeline:
         self.top_k = int(top_k)
         self.kpt_size = tuple(kpt_size)
         self.max_crops_per_pass = int(max_crops_per_pass)
+        self._letterbox = {}
+
+    @torch.no_grad()
+    def from_frames(self, frames: torch.Tensor, keep_heatmaps: bool = False) -> PipelineOutput:
+        """The joint from raw camera frames: u8 [B,H,W,3] BGR (cv2 order) on the device.  The network input is made by
+        the letterbox kernel (detect.py:62-72: pad 127, PIL-bilinear resize, /255; BGR -> RGB planes), the crops are
+        cut from the same frames."""
+        require_cuda(frames, "ConePipeline.from_frames")
+        key = (tuple(frames.shape[1:3]), str(frames.device))
+        if key not in self._letterbox:
+            from .preprocess import Letterbox
+
+            self._letterbox[key] = Letterbox(frames.shape[1:3], self.darknet.img_size(), frames.device)
+        lb = self._letterbox[key]
+        return self(lb(frames, reverse_channels=True), frames, lb.geom, keep_heatmaps)
 
     @torch.no_grad()
     def __call__(self, imgs: torch.Tensor, frames: torch.Tensor, geom: torch.Tensor,

@@ -444,6 +444,81 @@ detect_match_ap_kernel(const float* __restrict__ boxes, const int* __restrict__ 
   for (int i = tid; i < n; i += blockDim.x) correct_out[(size_t)b * top_k + i] = correct[i];
 }
 
+
+// Letterbox front end of CVC-YOLOv3/detect.py:62-72: pad to the network's aspect ratio with 127 (torchvision pad),
+// PIL BILINEAR resize (Pillow's 8-bit two-pass convolution resampler, src/libImaging/Resample.c: 22-bit fixed-point
+// coefficients, horizontal pass rounded to u8, then the vertical pass), to_tensor (/255).  The coefficient tables depend
+// only on the geometry and come from the host (b200cv/preprocess.py), so the kernel is pure integer arithmetic and
+// bit-exact with Pillow.  One thread per output pixel, three channels; the padded image is never materialised.
+constexpr int kPilBits = 22;
+
+__global__ void __launch_bounds__(256)
+letterbox_kernel(const unsigned char* __restrict__ frames, int H, int W, int pad_w, int pad_h, int fill, int reverse,
+                 const int* __restrict__ hx_min, const int* __restrict__ hx_cnt, const int* __restrict__ hx_k, int ksh,
+                 const int* __restrict__ vy_min, const int* __restrict__ vy_cnt, const int* __restrict__ vy_k, int ksv,
+                 int out_w, int out_h, float* __restrict__ out) {
+  __shared__ float lut[256];
+  lut[threadIdx.x] = (float)threadIdx.x / 255.f;  // to_tensor: uint8 -> float32, .div(255)
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= out_w * out_h) return;
+  const int yy = e / out_w, xx = e - yy * out_w;
+  const unsigned char* f = frames + (size_t)b * H * W * 3;
+  const int x0 = hx_k ? hx_min[xx] : xx, xn = hx_k ? hx_cnt[xx] : 1;
+  const int y0 = vy_k ? vy_min[yy] : yy, yn = vy_k ? vy_cnt[yy] : 1;
+  const int* kh = hx_k ? hx_k + (size_t)xx * ksh : nullptr;
+  const int* kv = vy_k ? vy_k + (size_t)yy * ksv : nullptr;
+  int accv[3] = {1 << (kPilBits - 1), 1 << (kPilBits - 1), 1 << (kPilBits - 1)};
+  int last[3] = {0, 0, 0};
+  for (int r = 0; r < yn; ++r) {
+    const int fy = y0 + r - pad_h;
+    const bool row_in = fy >= 0 && fy < H;
+    int hv[3];
+    if (kh) {
+      int acc[3] = {1 << (kPilBits - 1), 1 << (kPilBits - 1), 1 << (kPilBits - 1)};
+      for (int x = 0; x < xn; ++x) {
+        const int fx = x0 + x - pad_w;
+        const int k = kh[x];
+        if (row_in && fx >= 0 && fx < W) {
+          const unsigned char* q = f + ((size_t)fy * W + fx) * 3;
+          acc[0] += q[0] * k;
+          acc[1] += q[1] * k;
+          acc[2] += q[2] * k;
+        } else {
+          acc[0] += fill * k;
+          acc[1] += fill * k;
+          acc[2] += fill * k;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) hv[c] = min(max(acc[c] >> kPilBits, 0), 255);
+    } else {
+      const int fx = x0 - pad_w;
+      if (row_in && fx >= 0 && fx < W) {
+        const unsigned char* q = f + ((size_t)fy * W + fx) * 3;
+        hv[0] = q[0];
+        hv[1] = q[1];
+        hv[2] = q[2];
+      } else {
+        hv[0] = hv[1] = hv[2] = fill;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      last[c] = hv[c];
+      if (kv) accv[c] += hv[c] * kv[r];
+    }
+  }
+  const size_t plane = (size_t)out_h * out_w;
+  float* o = out + (size_t)b * 3 * plane + e;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int v = kv ? min(max(accv[c] >> kPilBits, 0), 255) : last[c];
+    o[(size_t)(reverse ? 2 - c : c) * plane] = lut[v];
+  }
+}
+
 }  // namespace
 }  // namespace b200cv
 
@@ -502,4 +577,24 @@ extern "C" int b200cv_detect_match_ap(const float* boxes, const int32_t* counts,
   detect_match_ap_kernel<<<B, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       boxes, counts, top_k, targets, T, width, height, iou_thres, ap, recall, precision, valid, correct);
   return check_launch("detect_match_ap");
+}
+
+extern "C" int b200cv_letterbox_u8(const uint8_t* frames, int B, int H, int W, int pad_w, int pad_h, int fill,
+                                   int reverse_channels, const int32_t* hx_min, const int32_t* hx_cnt,
+                                   const int32_t* hx_k, int ksize_h, const int32_t* vy_min, const int32_t* vy_cnt,
+                                   const int32_t* vy_k, int ksize_v, int out_w, int out_h, float* out, void* stream) {
+  if (B == 0) return B200CV_OK;
+  B200CV_CHECK_ARG(frames && out, "letterbox_u8: null pointer");
+  B200CV_CHECK_ARG(B > 0 && B <= 65535 && H > 0 && W > 0 && out_w > 0 && out_h > 0 && pad_w >= 0 && pad_h >= 0,
+                   "letterbox_u8: bad shape");
+  B200CV_CHECK_ARG(fill >= 0 && fill <= 255, "letterbox_u8: fill must be a byte");
+  B200CV_CHECK_ARG(hx_k ? (hx_min && hx_cnt && ksize_h > 0) : (W + 2 * pad_w == out_w),
+                   "letterbox_u8: no horizontal tables although the padded width differs from the output width");
+  B200CV_CHECK_ARG(vy_k ? (vy_min && vy_cnt && ksize_v > 0) : (H + 2 * pad_h == out_h),
+                   "letterbox_u8: no vertical tables although the padded height differs from the output height");
+  const dim3 grid((out_w * out_h + 255) / 256, B);
+  letterbox_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      frames, H, W, pad_w, pad_h, fill, reverse_channels, hx_min, hx_cnt, hx_k, ksize_h, vy_min, vy_cnt, vy_k, ksize_v,
+      out_w, out_h, out);
+  return check_launch("letterbox_u8");
 }

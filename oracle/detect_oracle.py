@@ -286,3 +286,103 @@ def synth_labels_for(det, B, T, conf_thres, seed=0, img=416.0):
         for j, bx in enumerate(rows):
             out[b, j, 1:5] = bx.clamp(1e-3, 0.999)
     return out
+
+
+# ------------------------------------------------------------------------------------------ letterbox front end
+# CVC-YOLOv3/detect.py:62-72: calculate_padding (utils/utils.py:36-48) -> torchvision pad(fill=127) -> torchvision
+# resize (PIL BILINEAR, i.e. Pillow's two-pass convolution resampler, which widens its support when it shrinks an
+# image) -> to_tensor (/255).  Pillow (unpinned in requirements.txt, 12.2 in this image) is third-party: its 8-bit
+# resampler is restated here from the published algorithm (src/libImaging/Resample.c: precompute_coeffs,
+# normalize_coeffs_8bpc, ImagingResampleHorizontal_8bpc / Vertical_8bpc) and pinned against the installed Pillow /
+# torchvision by tests/test_detect_oracle.py and the committed goldens.
+PIL_PRECISION_BITS = 32 - 8 - 2
+
+
+def calculate_padding(orig_height, orig_width, new_height, new_width):
+    """utils/utils.py:36-48."""
+    if max(orig_height, orig_width) == orig_height:
+        new_img_width = orig_height * new_width / new_height
+        scale_factor = new_height / orig_height
+        pad_h = 0
+        pad_w = int((new_img_width - orig_width) / 2)
+    else:
+        scale_factor = new_width / orig_width
+        new_img_height = orig_width * new_height / new_width
+        pad_w = 0
+        pad_h = int((new_img_height - orig_height) / 2)
+    return pad_h, pad_w, scale_factor
+
+
+def pil_bilinear_coeffs(in_size, out_size):
+    """Resample.c precompute_coeffs + normalize_coeffs_8bpc for the BILINEAR filter over the whole axis.
+    Returns (xmin int32 [out], xcount int32 [out], coeff int32 [out, ksize])."""
+    scale = filterscale = float(in_size) / out_size
+    if filterscale < 1.0:
+        filterscale = 1.0
+    support = 1.0 * filterscale
+    ksize = int(np.ceil(support)) * 2 + 1
+    xmin_a = np.zeros(out_size, np.int32)
+    cnt_a = np.zeros(out_size, np.int32)
+    kk = np.zeros((out_size, ksize), np.int32)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = 0.0 + (xx + 0.5) * scale
+        xmin = int(center - support + 0.5)
+        if xmin < 0:
+            xmin = 0
+        xmax = int(center + support + 0.5)
+        if xmax > in_size:
+            xmax = in_size
+        xmax -= xmin
+        k = np.zeros(ksize, np.float64)
+        ww = 0.0
+        for x in range(xmax):
+            a = (x + xmin - center + 0.5) * ss
+            if a < 0.0:
+                a = -a
+            w = 1.0 - a if a < 1.0 else 0.0
+            k[x] = w
+            ww += w
+        for x in range(xmax):
+            if ww != 0.0:
+                k[x] /= ww
+        for x in range(ksize):
+            v = k[x] * (1 << PIL_PRECISION_BITS)
+            kk[xx, x] = int(-0.5 + v) if k[x] < 0 else int(0.5 + v)
+        xmin_a[xx] = xmin
+        cnt_a[xx] = xmax
+    return xmin_a, cnt_a, kk
+
+
+def _pil_pass(img, xmin, cnt, kk, axis):
+    """One 8-bit resampling pass along `axis` (0 = vertical, 1 = horizontal) of an HxWxC uint8 array."""
+    src = np.moveaxis(img.astype(np.int64), axis, 0)
+    out = np.empty((len(xmin),) + src.shape[1:], np.int64)
+    for o in range(len(xmin)):
+        acc = np.full(src.shape[1:], 1 << (PIL_PRECISION_BITS - 1), np.int64)
+        for x in range(int(cnt[o])):
+            acc += src[xmin[o] + x] * int(kk[o, x])
+        out[o] = np.clip(acc >> PIL_PRECISION_BITS, 0, 255)
+    return np.moveaxis(out, 0, axis).astype(np.uint8)
+
+
+def pil_resize_bilinear_u8(img, out_w, out_h):
+    """PIL.Image.resize((out_w, out_h), BILINEAR) for an HxWxC uint8 array: horizontal pass, then vertical pass on the
+    8-bit intermediate (each pass skipped when the size along it does not change)."""
+    H, W, _ = img.shape
+    if W != out_w:
+        img = _pil_pass(img, *pil_bilinear_coeffs(W, out_w), axis=1)
+    if H != out_h:
+        img = _pil_pass(img, *pil_bilinear_coeffs(H, out_h), axis=0)
+    return img
+
+
+def letterbox(frame_rgb, new_w, new_h):
+    """detect.py:62-72 on one HxWx3 uint8 RGB frame -> (fp32 [3,new_h,new_w] in [0,1], (ratio, pad_w, pad_h))."""
+    h, w, _ = frame_rgb.shape
+    pad_h, pad_w, ratio = calculate_padding(h, w, new_h, new_w)
+    padded = np.full((h + 2 * pad_h, w + 2 * pad_w, 3), 127, np.uint8)
+    padded[pad_h:pad_h + h, pad_w:pad_w + w] = frame_rgb
+    out = pil_resize_bilinear_u8(padded, new_w, new_h)
+    chw = torch.from_numpy(out.transpose(2, 0, 1).copy()).to(torch.float32).div(255)  # to_tensor
+    return chw.numpy(), (ratio, pad_w, pad_h)

@@ -133,6 +133,22 @@ def main():
     img = rng.randint(0, 256, size=(60, 90, 3)).astype(np.uint8)
     out["resize"]["nonsquare_64x48"] = {"img": torch.from_numpy(img), "out": torch.from_numpy(cv2.resize(img, (64, 48))),
                                         "size": (64, 48)}
+    # ---- letterbox: torchvision pad(127) + resize (PIL BILINEAR) + to_tensor, exactly detect.py:62-72
+    from PIL import Image
+    import PIL
+    import torchvision
+    import torchvision.transforms.functional as TF
+
+    out["letterbox"] = {"pil_version": PIL.__version__, "torchvision_version": torchvision.__version__, "cases": {}}
+    for name, (h, w, S) in {"wide_down": (90, 160, 64), "tall_down": (150, 70, 64), "wide_up": (30, 48, 64),
+                            "square_same": (64, 64, 64), "wide_to_96": (120, 200, 96), "odd": (77, 131, 64)}.items():
+        img = rng.randint(0, 256, size=(h, w, 3)).astype(np.uint8)
+        pad_h, pad_w, ratio = DO.calculate_padding(h, w, S, S)
+        pil = TF.pad(Image.fromarray(img), padding=(pad_w, pad_h, pad_w, pad_h), fill=(127, 127, 127),
+                     padding_mode="constant")
+        ref = TF.to_tensor(TF.resize(pil, (S, S)))
+        out["letterbox"]["cases"][name] = {"img": torch.from_numpy(img), "S": S, "out": ref.clone(),
+                                           "geom": (ratio, pad_w, pad_h)}
     path = os.path.join(ROOT, "tests", "golden", "detect_golden.pt")
     torch.save(out, path)
     print("wrote", path, os.path.getsize(path), "bytes")

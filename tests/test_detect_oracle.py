@@ -143,3 +143,38 @@ def test_oracle_vs_live_reference_nms_and_ap():
         n_gt = int(torch.randint(1, 50, (1,), generator=g))
         got, want = DO.average_precision(tp, scores, n_gt), U.average_precision(tp, scores, n_gt)
         assert [float(v) for v in got] == [float(v) for v in want], case
+
+
+def test_letterbox_matches_pil_torchvision_golden(golden_detect):
+    cases = golden_detect["letterbox"]["cases"]
+    assert len(cases) >= 6
+    for name, c in cases.items():
+        got, geom = DO.letterbox(c["img"].numpy(), c["S"], c["S"])
+        assert np.array_equal(got, c["out"].numpy()), name
+        assert geom == c["geom"], name
+
+
+def test_letterbox_matches_live_pil():
+    PIL = pytest.importorskip("PIL")
+    TF = pytest.importorskip("torchvision.transforms.functional")
+    from PIL import Image
+
+    rng = np.random.RandomState(5)
+    for h, w, S in [(72, 128, 52), (200, 90, 64), (33, 57, 96)]:
+        img = rng.randint(0, 256, size=(h, w, 3)).astype(np.uint8)
+        pad_h, pad_w, _ = DO.calculate_padding(h, w, S, S)
+        pil = TF.pad(Image.fromarray(img), padding=(pad_w, pad_h, pad_w, pad_h), fill=(127, 127, 127))
+        ref = TF.to_tensor(TF.resize(pil, (S, S))).numpy()
+        assert np.array_equal(DO.letterbox(img, S, S)[0], ref), (h, w, S)
+
+
+def test_product_resampling_tables_equal_the_oracle():
+    """b200cv/preprocess.py computes the Pillow coefficient tables on the host (product code, vectorised); they must
+    be identical to the oracle's loop restatement for up- and down-scaling, tiny and large axes."""
+    from b200cv import preprocess as PP
+
+    for a, b in [(1280, 416), (720, 416), (1280, 608), (300, 416), (37, 64), (162, 64), (100, 128), (999, 7), (5, 300)]:
+        for x, y in zip(DO.pil_bilinear_coeffs(a, b), PP.bilinear_tables(a, b)):
+            assert x.shape == y.shape and np.array_equal(x, y), (a, b)
+    for hw in [(720, 1280), (1280, 720), (300, 500), (37, 100), (416, 416)]:
+        assert PP.calculate_padding(*hw, 416, 416) == DO.calculate_padding(*hw, 416, 416)

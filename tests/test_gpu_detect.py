@@ -226,3 +226,48 @@ def test_detection_metrics_composition(cfg_dir):
     d = detect_ops.detect_nms(det.cuda(), conf, 0.25, 200)
     _check_metrics(m, d, det, labels, conf, 0.25, 0.5, 200, "composition")
     assert int(m.valid.sum()) >= 3
+
+
+def test_letterbox_bit_exact_against_pil_goldens(golden_detect):
+    from b200cv import preprocess
+
+    for name, c in golden_detect["letterbox"]["cases"].items():
+        img = c["img"]
+        lb = preprocess.Letterbox(img.shape[:2], (c["S"], c["S"]), "cuda")
+        frames = torch.stack([img, img.flip(0)]).contiguous().cuda()   # second frame: upside-down copy
+        got = lb(frames)
+        assert torch.equal(got[0].cpu(), c["out"]), name
+        want1, _ = DO.letterbox(img.flip(0).numpy().copy(), c["S"], c["S"])
+        assert np.array_equal(got[1].cpu().numpy(), want1), name
+        assert lb.geom.tolist() == pytest.approx(list(c["geom"])), name
+        # BGR frames -> RGB planes
+        rev = lb(frames.flip(-1).contiguous(), reverse_channels=True)
+        assert torch.equal(rev, got), name
+
+
+def test_letterbox_full_frame_vs_oracle_and_pipeline_from_frames(cfg_dir):
+    """720x1280 camera frames -> 416x416 network input (3.08x anti-aliased reduction, 280-row 127 borders) vs the
+    oracle; then the whole joint from raw frames."""
+    import keypoint_net
+    from b200cv import preprocess
+
+    B, H, W = 3, 720, 1280
+    frames_np = DO.synth_frames(B, H, W, seed=6)  # treated as BGR
+    frames = torch.from_numpy(frames_np).cuda()
+    lb = preprocess.Letterbox((H, W), (416, 416), "cuda")
+    imgs = lb(frames, reverse_channels=True)
+    for b in range(B):
+        want, geom = DO.letterbox(np.ascontiguousarray(frames_np[b][..., ::-1]), 416, 416)
+        assert np.array_equal(imgs[b].cpu().numpy(), want), b
+    assert geom == (416 / 1280, 0, 280)
+    model, _ = helpers.make_darknet(cfg_dir, "yolo_baseline_tiny.cfg", 416, 1)
+    model = model.cuda().eval()
+    kp = keypoint_net.KeypointNet().cuda().eval()
+    with torch.no_grad():
+        det = model(imgs)
+    conf = float(det[..., 4].flatten().float().kthvalue(det[..., 4].numel() - 30).values)
+    pipe = pipeline.ConePipeline(model, kp, conf_thres=conf, nms_thres=0.25)
+    out = pipe.from_frames(frames)
+    ref = pipe(imgs, frames, lb.geom)
+    assert out.n_crops == ref.n_crops > 0
+    assert torch.equal(out.rects, ref.rects) and torch.equal(out.points, ref.points)
