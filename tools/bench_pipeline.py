@@ -50,12 +50,15 @@ def run(batch=128, iters=30, warmup=3, boxes=8.0, classes=80, frame=(720, 1280))
     net = net.to(dev).eval()
     kp = keypoint_net.KeypointNet().to(dev).eval()
 
-    imgs_h = torch.rand(B, 3, 416, 416, generator=torch.Generator().manual_seed(0)).pin_memory()
-    base = torch.from_numpy(DO.synth_frames(4, H, W, seed=0))
-    frames_h = base.repeat((B + 3) // 4, 1, 1, 1)[:B].contiguous().pin_memory()
-    ratio = 416.0 / max(H, W)
-    geom = torch.tensor([ratio, (max(H, W) - W) / 2.0, (max(H, W) - H) / 2.0], device=dev)
-    imgs, frames = imgs_h.to(dev), frames_h.to(dev)
+    from b200cv.preprocess import Letterbox
+
+    base = torch.from_numpy(DO.synth_frames(8, H, W, seed=0))
+    frames_h = base.repeat((B + 7) // 8, 1, 1, 1)[:B].contiguous().pin_memory()
+    frames = frames_h.to(dev)
+    lb = Letterbox((H, W), (416, 416), dev)
+    imgs = lb(frames, reverse_channels=True)  # every path sees the same network input: the letterboxed frames
+    imgs_h = imgs.cpu().pin_memory()
+    geom = lb.geom
 
     with torch.no_grad():
         det = net(imgs)
@@ -110,7 +113,9 @@ def run(batch=128, iters=30, warmup=3, boxes=8.0, classes=80, frame=(720, 1280))
         "metric": "latency ms per batch, detect -> NMS -> crop -> RektNet (BASELINE config 5)", "n_gpus": 1,
         "config": {"workload": f"Darknet-53 416x416 C={args.classes} eval bs{B} -> NMS top-200 -> crop+resize 80x80 "
                                f"from {W}x{H} BGR frames -> KeypointNet eval",
+                   "network_input": "letterboxed synthetic frames (pad 127, PIL-bilinear resize)",
                    "conf_thres": thres, "nms_thres": pipe.nms_thres, "crops_per_batch": out.n_crops,
+                   "crops_per_batch_from_frames": run_frames_resident().n_crops,
                    "candidate_boxes_per_image": args.boxes},
         "iters": args.iters, "warmup": args.warmup, "dtype": "bf16", "data": "synthetic",
         "resident": res["resident"], "e2e": dict(res["e2e"], h2d_bytes=imgs_h.numel() * 4 + frames_h.numel(),
