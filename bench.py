@@ -209,10 +209,10 @@ def main():
     model = model.to(dev).train()
     params = list(model.parameters())
 
-    from oracle import yolo_oracle as YO  # synthetic input recipe only (shared with the tests)
+    from b200cv import synth  # synthetic inputs of the named shapes (host-side torch; the oracle is not involved)
 
-    imgs_h = YO.synth_images(BATCH, IMG, IMG, seed=rank).pin_memory()
-    tg_h = YO.synth_targets(BATCH, TMAX, seed=1 + rank).pin_memory()
+    imgs_h = synth.synth_images(BATCH, IMG, IMG, seed=rank).pin_memory()
+    tg_h = synth.synth_targets(BATCH, TMAX, seed=1 + rank).pin_memory()
     imgs_d, tg_d = imgs_h.to(dev), tg_h.to(dev)
 
     def step(x, t):
@@ -298,8 +298,7 @@ def main():
     prof = lib().profile_step(lambda: step(imgs_d, tg_d))
     os.environ["B200CV_CUDA_GRAPH"] = "1"
     if rank == 0:
-        spec = YO.NetSpec(cfg)
-        fwd_f, tot_f = conv_flops_per_image(spec.layers, IMG)
+        fwd_f, tot_f = conv_flops_per_image(synth.conv_layer_table(model), IMG)
         pk = peaks()
         conv_ms = sum(v for k, v in prof.items() if k in ("b200cv_conv_fwd", "b200cv_conv_dgrad", "b200cv_conv_wgrad"))
         step_ms = sum(prof.values())
@@ -353,12 +352,12 @@ def main():
 def bench_rektnet(dev, rank, world, steps, warmup, timed):
     import cross_ratio_loss
     import keypoint_net
-    from oracle import rektnet_oracle as RO
+    from b200cv import synth
 
     B = 256
     torch.manual_seed(17)
     net = keypoint_net.KeypointNet().to(dev).train()
-    x, thm, tpts = (t.to(dev) for t in RO.synth_batch(B, seed=rank))
+    x, thm, tpts = (t.to(dev) for t in synth.synth_keypoint_batch(B, seed=rank))
     import contextlib
 
     with contextlib.redirect_stdout(sys.stderr):  # the reference-compatible constructor prints its settings

@@ -66,3 +66,35 @@ def test_getters(cfg_dir):
     assert model.get_threshs() == (0.8, 0.25, 0.5)
     assert model.get_num_classes() == 1 and model.get_bw() is False
     assert model.get_onnx_name() == os.path.basename(path).split(".")[0] + "_416320.onnx"
+
+
+def test_product_synthetic_recipes_equal_the_oracle_recipes():
+    """bench.py and the tools draw their synthetic inputs from b200cv.synth (product side, no oracle); the parity tests
+    draw theirs from the oracle modules.  Both must be the same data."""
+    import numpy as np
+
+    from b200cv import synth
+    from oracle import detect_oracle as DO
+    from oracle import rektnet_oracle as RO
+    from oracle import yolo_oracle as YO
+
+    assert torch.equal(synth.synth_images(2, 32, 48, seed=3), YO.synth_images(2, 32, 48, seed=3))
+    assert torch.equal(synth.synth_targets(5, 16, seed=4), YO.synth_targets(5, 16, seed=4))
+    for a, b in zip(synth.synth_keypoint_batch(3, seed=2), RO.synth_batch(3, seed=2)):
+        assert torch.equal(a, b)
+    assert np.array_equal(synth.synth_frames(2, 20, 30, seed=1), DO.synth_frames(2, 20, 30, seed=1))
+
+
+def test_conv_flop_table_from_the_executor_matches_the_survey(cfg_dir):
+    """bench.py counts the algorithmic conv FLOPs from the product's own layer list: SURVEY 8a-3 gives 65.86 GFLOP
+    forward per image for Darknet-53 at 416x416 with C=80, 5.44 for the tiny network (C=1)."""
+    import bench
+
+    from b200cv import synth
+
+    model, _ = helpers.make_darknet(cfg_dir, "yolo_baseline.cfg", 416, 80)
+    fwd, tot = bench.conv_flops_per_image(synth.conv_layer_table(model), 416)
+    assert abs(fwd / 1e9 - 65.86) < 0.01 and abs(tot / 1e9 - 197.293) < 0.01
+    tiny, _ = helpers.make_darknet(cfg_dir, "yolo_baseline_tiny.cfg", 416, 1)
+    fwd_t, _ = bench.conv_flops_per_image(synth.conv_layer_table(tiny), 416)
+    assert abs(fwd_t / 1e9 - 5.44) < 0.01

@@ -37,7 +37,7 @@ def run(batch=128, iters=30, warmup=3, boxes=8.0, classes=80, frame=(720, 1280))
     import models
     from b200cv import cfg_gen, pipeline
     from b200cv.lib import lib
-    from oracle import detect_oracle as DO  # synthetic-frame recipe only
+    from b200cv import synth
     from utils.utils import weights_init_normal
 
     dev = torch.device("cuda:0")
@@ -52,7 +52,7 @@ def run(batch=128, iters=30, warmup=3, boxes=8.0, classes=80, frame=(720, 1280))
 
     from b200cv.preprocess import Letterbox
 
-    base = torch.from_numpy(DO.synth_frames(8, H, W, seed=0))
+    base = torch.from_numpy(synth.synth_frames(8, H, W, seed=0))
     frames_h = base.repeat((B + 7) // 8, 1, 1, 1)[:B].contiguous().pin_memory()
     frames = frames_h.to(dev)
     lb = Letterbox((H, W), (416, 416), dev)
