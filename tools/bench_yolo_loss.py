@@ -6,17 +6,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import conftest  # noqa
 import torch
+import models
 from b200cv import yolo_ops
-from oracle import yolo_oracle as YO
+from b200cv import synth
 
 dev = "cuda"
 B, C, T = 64, 80, 16
-tg = YO.synth_targets(B, T, seed=1).to(dev)
+tg = synth.synth_targets(B, T, seed=1).to(dev)
 consts = (2.0, 1.6, 0.1, 25.0)
 work = []
 for G, mask in ((13, (6, 7, 8)), (26, (3, 4, 5)), (52, (0, 1, 2))):
     z = torch.randn(B, G, G, 256, device=dev)
-    sa = yolo_ops.scaled_anchors([YO.VANILLA_ANCHORS[i] for i in mask], 416 / G, dev)
+    sa = yolo_ops.scaled_anchors([models.vanilla_anchor_list[i] for i in mask], 416 / G, dev)
     yt = yolo_ops.yolo_targets(tg, sa, G, G, 0.5)
     work.append((z, yt, torch.empty(B, G, G, 256, device=dev, dtype=torch.bfloat16), torch.zeros(6, dtype=torch.float64, device=dev),
                  torch.empty(B * G * G, 16, device=dev)))

@@ -5,12 +5,12 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import conftest  # noqa
 import torch
 import helpers
-from oracle import yolo_oracle as YO
+from b200cv import synth
 d = tempfile.mkdtemp()
 model, _ = helpers.make_darknet(d, "yolo_baseline.cfg", 416, 80)
 model = model.cuda().train()
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-x, tg = YO.synth_images(B, 416, 416).cuda(), YO.synth_targets(B, 16).cuda()
+x, tg = synth.synth_images(B, 416, 416).cuda(), synth.synth_targets(B, 16).cuda()
 params = list(model.parameters())
 def step():
     for p in params: p.grad = None

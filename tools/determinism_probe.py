@@ -27,8 +27,7 @@ def main():
     import keypoint_net
     import models
     from b200cv import cfg_gen
-    from oracle import rektnet_oracle as RO
-    from oracle import yolo_oracle as YO
+    from b200cv import synth
     from utils.utils import weights_init_normal
 
     dev = torch.device("cuda:0")
@@ -39,7 +38,7 @@ def main():
         net = models.Darknet(cfg_gen.write_cfg(d, kind, S, S, 1), 2.0, 1.6, 25.0, 0.1, True)
         net.apply(weights_init_normal)
         net = net.to(dev).train()
-        x, tg = YO.synth_images(B, S, S).to(dev), YO.synth_targets(B, 16).to(dev)
+        x, tg = synth.synth_images(B, S, S).to(dev), synth.synth_targets(B, 16).to(dev)
         rows = []
         with torch.no_grad():
             for _ in range(n):
@@ -50,7 +49,7 @@ def main():
     kp = keypoint_net.KeypointNet().to(dev).train()
     with contextlib.redirect_stdout(sys.stderr):
         loss_fn = cross_ratio_loss.CrossRatioLoss("l2_softargmax", True, 0.055, 0.038)
-    x, thm, tpts = (t.to(dev) for t in RO.synth_batch(8, seed=0))
+    x, thm, tpts = (t.to(dev) for t in synth.synth_keypoint_batch(8, seed=0))
     rows = []
     with torch.no_grad():
         for _ in range(n):

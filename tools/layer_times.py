@@ -9,7 +9,7 @@ import torch
 import models
 from b200cv import cfg_gen
 from b200cv.lib import lib
-from oracle import yolo_oracle as YO  # synthetic input recipe
+from b200cv import synth  # synthetic input recipe
 from utils.utils import weights_init_normal
 
 size = int(sys.argv[1]) if len(sys.argv) > 1 else 416
@@ -21,7 +21,7 @@ torch.manual_seed(0)
 model = models.Darknet(cfg, 2.0, 1.6, 25.0, 0.1, True)
 model.apply(weights_init_normal)
 model = model.to(dev).train()
-x, t = YO.synth_images(B, size, size).to(dev), YO.synth_targets(B, 16).to(dev)
+x, t = synth.synth_images(B, size, size).to(dev), synth.synth_targets(B, 16).to(dev)
 
 def step():
     for p in model.parameters():

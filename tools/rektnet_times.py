@@ -7,13 +7,13 @@ import time
 import torch
 import cross_ratio_loss, keypoint_net
 from b200cv.lib import lib
-from oracle import rektnet_oracle as RO  # synthetic input recipe
+from b200cv import synth  # synthetic input recipe
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 dev = torch.device("cuda")
 torch.manual_seed(17)
 net = keypoint_net.KeypointNet().to(dev).train()
-x, thm, tpts = (t.to(dev) for t in RO.synth_batch(B, seed=0))
+x, thm, tpts = (t.to(dev) for t in synth.synth_keypoint_batch(B, seed=0))
 loss_fn = cross_ratio_loss.CrossRatioLoss("l2_heatmap", True, 0.055, 0.038)
 
 def step():
