@@ -50,8 +50,11 @@ def detect_nms(det: torch.Tensor, conf_thres: float, nms_thres: float, top_k: in
 def compact(d: Detections):
     """counts -> (offsets int32 [B+1], src int32 [B*top_k, 2] = (image, slot) per crop)."""
     b = d.counts.shape[0]
+    if b == 0:
+        return (torch.zeros(1, dtype=torch.int32, device=d.counts.device),
+                torch.zeros(0, 2, dtype=torch.int32, device=d.counts.device))
     offsets = torch.empty(b + 1, dtype=torch.int32, device=d.counts.device)
-    src = torch.empty(max(1, b * d.top_k), 2, dtype=torch.int32, device=d.counts.device)
+    src = torch.empty(b * d.top_k, 2, dtype=torch.int32, device=d.counts.device)
     lib().call("b200cv_detect_compact", ptr(d.counts), b, d.top_k, ptr(offsets), ptr(src), stream_ptr())
     return offsets, src
 

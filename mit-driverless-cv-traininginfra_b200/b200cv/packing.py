@@ -3,7 +3,6 @@ multi-tensor launch per step, weight gradients are accumulated in one flat packe
 un-packed into the OIHW gradient arena with one more launch."""
 from __future__ import annotations
 
-import ctypes
 
 import numpy as np
 import torch

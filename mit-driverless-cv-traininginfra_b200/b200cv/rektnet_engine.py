@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import os
 
-from typing import List, Optional
+from typing import Optional
 
 import torch
 
