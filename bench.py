@@ -129,7 +129,7 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------- reference arm
 def run_reference(args):
     """The reference's own CPU implementation of the path = the oracle port (PyTorch fp32 on the host cores),
-    same metric/config, each step a bounded sample (batch 4 of the bs64 workload)."""
+    same metric/config, each step a bounded sample (batch 8 of the bs64 workload)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -138,7 +138,7 @@ def run_reference(args):
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample_b = 4
+    sample_b = 8
     d = tempfile.mkdtemp()
     spec = YO.NetSpec(cfg_gen.write_cfg(d, "darknet53", IMG, IMG, CLASSES))
     params, buffers = YO.init_params(spec, seed=0)
@@ -384,7 +384,7 @@ def cpu_baseline():
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample_b = 4
+    sample_b = 8  # ~10-20 s of host work in all: 1 warm-up + 6 timed steps
     d = tempfile.mkdtemp()
     spec = YO.NetSpec(cfg_gen.write_cfg(d, "darknet53", IMG, IMG, CLASSES))
     params, buffers = YO.init_params(spec, seed=0)
@@ -398,7 +398,7 @@ def cpu_baseline():
         YO.darknet_forward(spec, params, buffers, x, tg, LOSS_CONSTS)[0].backward()
 
     step()
-    k = 3
+    k = 6
     t0 = time.perf_counter()
     for _ in range(k):
         step()
