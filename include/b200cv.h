@@ -171,6 +171,17 @@ int b200cv_bn_bwd_apply(const void* da, int64_t da_ld, const void* y, int64_t y_
                         int64_t aout_ld, const float* scale, const float* shift, const float* mean,
                         const float* rstd, const float* coef, void* dy, int64_t dy_ld, int64_t rows, int C,
                         int act, float slope, void* stream);
+/* Two BatchNorms under one activation, out = act(bn_A(yA) + bn_B(yB)) (RektNet/resnet.py:21-27: shortcut BN + second
+ * conv's BN, one ReLU): both layers see dz = da * act'(aout).  One pass for both layers instead of one per layer;
+ * partials / coef / dy as in b200cv_bn_bwd_reduce / b200cv_bn_bwd_apply, one set per layer. */
+int b200cv_bn_bwd_reduce2(const void* da, int64_t da_ld, const void* aout, int64_t aout_ld, const void* yA,
+                          int64_t yA_ld, const void* yB, int64_t yB_ld, const float* meanA, const float* rstdA,
+                          const float* meanB, const float* rstdB, float* partialsA, float* partialsB, int nparts,
+                          int64_t rows, int C, int act, float slope, void* stream);
+int b200cv_bn_bwd_apply2(const void* da, int64_t da_ld, const void* aout, int64_t aout_ld, const void* yA, int64_t yA_ld,
+                         const void* yB, int64_t yB_ld, const float* meanA, const float* rstdA, const float* meanB,
+                         const float* rstdB, const float* coefA, const float* coefB, void* dyA, int64_t dyA_ld,
+                         void* dyB, int64_t dyB_ld, int64_t rows, int C, int act, float slope, void* stream);
 /* Fused forms used by the Darknet engine (one launch instead of finalize + apply): every block first folds the
  * [parts][2C] partial statistics into the per-channel constants in shared memory, block 0 also publishes them
  * (scale/shift/save_mean/save_rstd, running statistics; dgamma/dbeta/coef) exactly like b200cv_bn_finalize /

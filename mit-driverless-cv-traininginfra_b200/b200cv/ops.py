@@ -262,6 +262,27 @@ def bn_bwd_apply(da, y, aout, scale, shift, mean, rstd, coef, act, slope, out=No
     return out
 
 
+def bn_bwd_reduce2(da, aout, y_a, y_b, mean_a, rstd_a, mean_b, rstd_b, act, slope):
+    """BN-backward sums of two BatchNorms that meet in one activation (out = act(bn_a(y_a) + bn_b(y_b))): one pass
+    over da / aout for both.  Returns the two zero-initialised-and-filled partial matrices."""
+    rows, c = _rows(y_a), y_a.shape[-1]
+    pa, pb = stats_buffer(c, y_a.device), stats_buffer(c, y_a.device)
+    lib().call("b200cv_bn_bwd_reduce2", ptr(da), da.stride(-2), ptr(aout), aout.stride(-2), ptr(y_a), y_a.stride(-2),
+               ptr(y_b), y_b.stride(-2), ptr(mean_a), ptr(rstd_a), ptr(mean_b), ptr(rstd_b), ptr(pa), ptr(pb),
+               pa.shape[0], rows, c, act, float(slope), stream_ptr(), tag=(rows, c))
+    return pa, pb
+
+
+def bn_bwd_apply2(da, aout, y_a, y_b, mean_a, rstd_a, mean_b, rstd_b, coef_a, coef_b, act, slope):
+    """dy of both layers of bn_bwd_reduce2 in one pass.  Returns (dy_a, dy_b)."""
+    dy_a, dy_b = torch.empty_like(y_a), torch.empty_like(y_b)
+    lib().call("b200cv_bn_bwd_apply2", ptr(da), da.stride(-2), ptr(aout), aout.stride(-2), ptr(y_a), y_a.stride(-2),
+               ptr(y_b), y_b.stride(-2), ptr(mean_a), ptr(rstd_a), ptr(mean_b), ptr(rstd_b), ptr(coef_a), ptr(coef_b),
+               ptr(dy_a), dy_a.stride(-2), ptr(dy_b), dy_b.stride(-2), _rows(y_a), y_a.shape[-1], act, float(slope),
+               stream_ptr(), tag=(_rows(y_a), y_a.shape[-1]))
+    return dy_a, dy_b
+
+
 def act_bwd(da, aout, act, slope):
     out = torch.empty_like(aout)
     lib().call("b200cv_act_bwd", ptr(da), da.stride(-2), ptr(aout), aout.stride(-2), ptr(out), out.stride(-2),

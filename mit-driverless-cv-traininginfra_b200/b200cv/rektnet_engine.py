@@ -85,6 +85,15 @@ class _ConvBN:
         ops.bn_bwd_finalize(parts, self.bn.weight, self.rstd, count, self.coef, gview[id(self.bn.weight)],
                             gview[id(self.bn.bias)])
         dy = ops.bn_bwd_apply(da, y, aout, self.scale, self.shift, self.mean, self.rstd, self.coef, act, 0.0)
+        return self.finish(x_in, dy, gview, packs, dx_out, want_dx, bn_reduce)
+
+    def finalize_bwd(self, parts, count, gview):
+        """BN-backward sums -> d(gamma), d(beta) and the per-channel constants of the apply pass."""
+        ops.bn_bwd_finalize(parts, self.bn.weight, self.rstd, count, self.coef, gview[id(self.bn.weight)],
+                            gview[id(self.bn.bias)])
+
+    def finish(self, x_in, dy, gview, packs, dx_out=None, want_dx=True, bn_reduce=None):
+        """wgrad (+ dgrad) from the conv-output gradient dy."""
         ops.conv_wgrad(x_in, dy, self.cout, self.k, 1, self.pad, self.dil, out=packs.dwp[id(self.conv)])
         gview[id(self.conv.bias)].zero_()  # analytically zero under train-mode BN
         if not want_dx:
@@ -230,11 +239,26 @@ class RektNetEngine:
         for bi, ((c1, c2, cs), (a_in, y1, a1, y2, ys, out)) in enumerate(
                 zip(reversed(self.blocks), reversed(saved["blocks"]))):
             # out = relu(bn_s(ys) + bn_2(y2)): both branches see dz = g * relu'(out)
-            g_in = cs.bwd(a_in, ys, g, out, ops.ACT_RELU, gview, packs)
+            dual = os.environ.get("B200CV_DUAL_BN", "1") != "0"
+            if dual:
+                # bn_s and bn_2 share da = g and the ReLU mask of `out`: one reduction pass and one apply pass for both
+                count = ys.numel() // ys.shape[-1]
+                parts_s, parts_2 = ops.bn_bwd_reduce2(g, out, ys, y2, cs.mean, cs.rstd, c2.mean, c2.rstd,
+                                                      ops.ACT_RELU, 0.0)
+                cs.finalize_bwd(parts_s, count, gview)
+                c2.finalize_bwd(parts_2, count, gview)
+                dys, dy2 = ops.bn_bwd_apply2(g, out, ys, y2, cs.mean, cs.rstd, c2.mean, c2.rstd, cs.coef, c2.coef,
+                                             ops.ACT_RELU, 0.0)
+                g_in = cs.finish(a_in, dys, gview, packs)
+            else:
+                g_in = cs.bwd(a_in, ys, g, out, ops.ACT_RELU, gview, packs)
             # a1 = relu(bn_1(y1)) has ONE consumer: conv2's data gradient is dL/da1, so its epilogue also forms the
             # BN-backward sums of bn_1; likewise the last data gradient into the first block's input for the stem
             red1, parts1 = c1.reduce_spec(y1, ops.ACT_RELU) if fuse else (None, None)
-            g_a1 = c2.bwd(a1, y2, g, out, ops.ACT_RELU, gview, packs, bn_reduce=red1)
+            if dual:
+                g_a1 = c2.finish(a1, dy2, gview, packs, bn_reduce=red1)
+            else:
+                g_a1 = c2.bwd(a1, y2, g, out, ops.ACT_RELU, gview, packs, bn_reduce=red1)
             red0 = None
             if fuse and bi == len(self.blocks) - 1:
                 red0, stem_parts = self.stem.reduce_spec(saved["y0"], ops.ACT_RELU)

@@ -506,6 +506,163 @@ __global__ void __launch_bounds__(kEwThreads, 4) bn_bwd_apply_kernel(const BwdAr
   }
 }
 
+// ---- two BatchNorms under one activation: out = act(bn_A(yA) + bn_B(yB))  (RektNet/resnet.py:21-27: the shortcut
+// BN and the second conv's BN meet in one ReLU).  Both see dz = da * act'(out): one pass reads da and the saved output
+// once for the two layers instead of once per layer (4 tensor reads instead of 6 in the reduction, 4 reads + 2 writes
+// instead of 6 + 2 in the apply pass).
+struct Bwd2Args {
+  const __nv_bfloat16* da; long long da_ld;
+  const __nv_bfloat16* aout; long long aout_ld;
+  const __nv_bfloat16* yA; long long yA_ld;
+  const __nv_bfloat16* yB; long long yB_ld;
+  const float* meanA; const float* rstdA;
+  const float* meanB; const float* rstdB;
+  float* sumsA; float* sumsB; int nparts;          // reduce: [nparts][2C] each, ADDED to
+  const float* coefA; const float* coefB;          // apply: [3C] each (g, k1, k2)
+  __nv_bfloat16* dyA; long long dyA_ld;
+  __nv_bfloat16* dyB; long long dyB_ld;
+  long long rows; int C; int act; float slope;
+};
+
+__global__ void __launch_bounds__(kEwThreads, 2) bn_bwd_reduce2_kernel(const Bwd2Args a) {
+  extern __shared__ float s_acc2[];  // [3C]: sum dz | sum dz*(yA-meanA)*rstdA | sum dz*(yB-meanB)*rstdB
+  const int C = a.C;
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_acc2[i] = 0.f;
+  __syncthreads();
+  const int vpr = C >> 2;
+  const int rpp = kEwThreads / vpr;
+  const int cv = threadIdx.x % vpr;
+  const int r0 = threadIdx.x / vpr;
+  const int c0 = cv << 2;
+  if (r0 < rpp) {
+    float meanA[4], meanB[4];
+    load4f(a.meanA + c0, meanA);
+    load4f(a.meanB + c0, meanB);
+    const float neg = a.act == B200CV_ACT_LEAKY ? a.slope : (a.act == B200CV_ACT_RELU ? 0.f : 1.f);
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, sA[4] = {0.f, 0.f, 0.f, 0.f}, sB[4] = {0.f, 0.f, 0.f, 0.f};
+    const long long stride = (long long)gridDim.x * rpp;
+    for (long long r = (long long)blockIdx.x * rpp + r0; r < a.rows; r += stride * kEwUnroll) {
+      uint2 qda[kEwUnroll], qa[kEwUnroll], qyA[kEwUnroll], qyB[kEwUnroll];
+#pragma unroll
+      for (int u = 0; u < kEwUnroll; ++u) {
+        const long long rr = r + u * stride;
+        if (rr < a.rows) {
+          qda[u] = ldg_stream8(a.da + rr * a.da_ld + c0);
+          qa[u] = ldg_stream8(a.aout + rr * a.aout_ld + c0);
+          qyA[u] = ldg_stream8(a.yA + rr * a.yA_ld + c0);
+          qyB[u] = ldg_stream8(a.yB + rr * a.yB_ld + c0);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kEwUnroll; ++u) {
+        if (r + u * stride < a.rows) {
+          float da[4], zs[4], yA[4], yB[4];
+          unpack4(qda[u], da);
+          unpack4(qa[u], zs);
+          unpack4(qyA[u], yA);
+          unpack4(qyB[u], yB);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float dz = da[j] * (zs[j] > 0.f ? 1.f : neg);
+            s1[j] += dz;
+            sA[j] = fmaf(dz, yA[j] - meanA[j], sA[j]);
+            sB[j] = fmaf(dz, yB[j] - meanB[j], sB[j]);
+          }
+        }
+      }
+    }
+    float rstdA[4], rstdB[4];
+    load4f(a.rstdA + c0, rstdA);
+    load4f(a.rstdB + c0, rstdB);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      atomicAdd(&s_acc2[c0 + j], s1[j]);
+      atomicAdd(&s_acc2[C + c0 + j], sA[j] * rstdA[j]);
+      atomicAdd(&s_acc2[2 * C + c0 + j], sB[j] * rstdB[j]);
+    }
+  }
+  __syncthreads();
+  const long long part = (long long)(blockIdx.x % a.nparts) * 2 * C;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    const float v1 = s_acc2[i], vA = s_acc2[C + i], vB = s_acc2[2 * C + i];
+    if (v1 != 0.f) {
+      atomicAdd(a.sumsA + part + i, v1);
+      atomicAdd(a.sumsB + part + i, v1);
+    }
+    if (vA != 0.f) atomicAdd(a.sumsA + part + C + i, vA);
+    if (vB != 0.f) atomicAdd(a.sumsB + part + C + i, vB);
+  }
+}
+
+__global__ void __launch_bounds__(kEwThreads, 2) bn_bwd_apply2_kernel(const Bwd2Args a) {
+  const int C = a.C;
+  const int vpr = C >> 2;
+  const int rpp = kEwThreads / vpr;
+  const int cv = threadIdx.x % vpr;
+  const int r0 = threadIdx.x / vpr;
+  const int c0 = cv << 2;
+  if (r0 >= rpp) return;
+  // dy = g*dz + A*y + B per layer, A = -g*k2*rstd, B = -g*k1 - A*mean (see bn_bwd_apply_kernel)
+  float gA[4], AA[4], BA[4], gB[4], AB[4], BB[4];
+  {
+    float k1[4], k2[4], mean[4], rstd[4];
+    load4f(a.coefA + c0, gA);
+    load4f(a.coefA + C + c0, k1);
+    load4f(a.coefA + 2 * C + c0, k2);
+    load4f(a.meanA + c0, mean);
+    load4f(a.rstdA + c0, rstd);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      AA[j] = -gA[j] * k2[j] * rstd[j];
+      BA[j] = -gA[j] * k1[j] - AA[j] * mean[j];
+    }
+    load4f(a.coefB + c0, gB);
+    load4f(a.coefB + C + c0, k1);
+    load4f(a.coefB + 2 * C + c0, k2);
+    load4f(a.meanB + c0, mean);
+    load4f(a.rstdB + c0, rstd);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      AB[j] = -gB[j] * k2[j] * rstd[j];
+      BB[j] = -gB[j] * k1[j] - AB[j] * mean[j];
+    }
+  }
+  const float neg = a.act == B200CV_ACT_LEAKY ? a.slope : (a.act == B200CV_ACT_RELU ? 0.f : 1.f);
+  const long long stride = (long long)gridDim.x * rpp;
+  for (long long r = (long long)blockIdx.x * rpp + r0; r < a.rows; r += stride * kEwUnroll) {
+    uint2 qda[kEwUnroll], qa[kEwUnroll], qyA[kEwUnroll], qyB[kEwUnroll];
+#pragma unroll
+    for (int u = 0; u < kEwUnroll; ++u) {
+      const long long rr = r + u * stride;
+      if (rr < a.rows) {
+        qda[u] = ldg_stream8(a.da + rr * a.da_ld + c0);
+        qa[u] = ldg_stream8(a.aout + rr * a.aout_ld + c0);
+        qyA[u] = ldg_stream8(a.yA + rr * a.yA_ld + c0);
+        qyB[u] = ldg_stream8(a.yB + rr * a.yB_ld + c0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kEwUnroll; ++u) {
+      const long long rr = r + u * stride;
+      if (rr < a.rows) {
+        float da[4], zs[4], yA[4], yB[4], oA[4], oB[4];
+        unpack4(qda[u], da);
+        unpack4(qa[u], zs);
+        unpack4(qyA[u], yA);
+        unpack4(qyB[u], yB);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float dz = da[j] * (zs[j] > 0.f ? 1.f : neg);
+          oA[j] = fmaf(gA[j], dz, fmaf(AA[j], yA[j], BA[j]));
+          oB[j] = fmaf(gB[j], dz, fmaf(AB[j], yB[j], BB[j]));
+        }
+        stg8(a.dyA + rr * a.dyA_ld + c0, pack4(oA));
+        stg8(a.dyB + rr * a.dyB_ld + c0, pack4(oB));
+      }
+    }
+  }
+}
+
 // ---- fused: fold the backward partial sums (bn_bwd_finalize) in the prologue of every block, then apply
 struct FusedBwdArgs {
   const float* partials; int nparts; float count;
@@ -902,6 +1059,52 @@ extern "C" int b200cv_bn_bwd_apply(const void* da, int64_t da_ld, const void* y,
     else bn_bwd_apply_kernel<false><<<grid, kEwThreads, 0, st>>>(a);
   }
   return check_launch("bn_bwd_apply");
+}
+
+static int fill_bwd2(Bwd2Args& a, const void* da, int64_t da_ld, const void* aout, int64_t aout_ld, const void* yA,
+                     int64_t yA_ld, const void* yB, int64_t yB_ld, const float* meanA, const float* rstdA,
+                     const float* meanB, const float* rstdB, int64_t rows, int C, int act, float slope) {
+  B200CV_CHECK_ARG(ok_vec(da, da_ld, C) && ok_vec(aout, aout_ld, C) && ok_vec(yA, yA_ld, C) && ok_vec(yB, yB_ld, C) &&
+                       meanA && rstdA && meanB && rstdB && rows > 0,
+                   "bn_bwd2: bad args");
+  B200CV_CHECK_ARG(C / 4 <= kEwThreads && kEwThreads % (C / 4) == 0, "bn_bwd2: unsupported C=%d", C);
+  a = Bwd2Args{};
+  a.da = (const bf16*)da; a.da_ld = da_ld; a.aout = (const bf16*)aout; a.aout_ld = aout_ld;
+  a.yA = (const bf16*)yA; a.yA_ld = yA_ld; a.yB = (const bf16*)yB; a.yB_ld = yB_ld;
+  a.meanA = meanA; a.rstdA = rstdA; a.meanB = meanB; a.rstdB = rstdB;
+  a.rows = rows; a.C = C; a.act = act; a.slope = slope;
+  return 0;
+}
+
+extern "C" int b200cv_bn_bwd_reduce2(const void* da, int64_t da_ld, const void* aout, int64_t aout_ld, const void* yA,
+                                     int64_t yA_ld, const void* yB, int64_t yB_ld, const float* meanA,
+                                     const float* rstdA, const float* meanB, const float* rstdB, float* partialsA,
+                                     float* partialsB, int nparts, int64_t rows, int C, int act, float slope,
+                                     void* stream) {
+  Bwd2Args a;
+  if (int rc = fill_bwd2(a, da, da_ld, aout, aout_ld, yA, yA_ld, yB, yB_ld, meanA, rstdA, meanB, rstdB, rows, C, act,
+                         slope))
+    return rc;
+  B200CV_CHECK_ARG(partialsA && partialsB && nparts > 0, "bn_bwd_reduce2: null partials");
+  a.sumsA = partialsA; a.sumsB = partialsB; a.nparts = nparts;
+  bn_bwd_reduce2_kernel<<<stream_grid(rows, C), kEwThreads, 3 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(a);
+  return check_launch("bn_bwd_reduce2");
+}
+
+extern "C" int b200cv_bn_bwd_apply2(const void* da, int64_t da_ld, const void* aout, int64_t aout_ld, const void* yA,
+                                    int64_t yA_ld, const void* yB, int64_t yB_ld, const float* meanA,
+                                    const float* rstdA, const float* meanB, const float* rstdB, const float* coefA,
+                                    const float* coefB, void* dyA, int64_t dyA_ld, void* dyB, int64_t dyB_ld,
+                                    int64_t rows, int C, int act, float slope, void* stream) {
+  Bwd2Args a;
+  if (int rc = fill_bwd2(a, da, da_ld, aout, aout_ld, yA, yA_ld, yB, yB_ld, meanA, rstdA, meanB, rstdB, rows, C, act,
+                         slope))
+    return rc;
+  B200CV_CHECK_ARG(coefA && coefB && ok_vec(dyA, dyA_ld, C) && ok_vec(dyB, dyB_ld, C), "bn_bwd_apply2: bad args");
+  a.coefA = coefA; a.coefB = coefB;
+  a.dyA = (bf16*)dyA; a.dyA_ld = dyA_ld; a.dyB = (bf16*)dyB; a.dyB_ld = dyB_ld;
+  bn_bwd_apply2_kernel<<<stream_grid(rows, C), kEwThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  return check_launch("bn_bwd_apply2");
 }
 
 extern "C" int b200cv_bn_stats_apply_act(const float* stats, int stats_parts, int64_t count, const float* gamma,
