@@ -14,6 +14,16 @@
  *   - `stream` is a cudaStream_t passed as void*.
  *   - activations are NHWC bf16 with the channel count padded by b200cv_pad_channels();
  *     "packed" weights are bf16 [rows][taps][channels] made by b200cv_pack_weights().
+ *   - fp32-parity mode ("split"): an fp32 value v is stored as THREE bf16 numbers p0 = bf16(v),
+ *     p1 = bf16(v - p0), p2 = bf16(v - p0 - p1) -- 3 x 8 = 24 mantissa bits, fp32's own precision.  A split
+ *     activation row is [p0(C) | p1(C) | p2(C)]: piece j lies j * `lo` elements after p0 (lo == C for a whole
+ *     tensor, the total width of the buffer for a channel slice of a concat buffer).  Entry points that take a
+ *     `*_lo` piece stride treat EVERY activation operand of the call as split when it is non-zero; 0 selects the
+ *     default bf16 mode.  Convolutions run six tensor-core passes (all piece products x_i * w_j with i + j <= 2,
+ *     fp32 accumulation in tensor memory; the dropped products are below 2^-24 of the result), element-wise
+ *     kernels compute on the summed pieces in fp32 and re-split what they store.  This is the mode whose results
+ *     match the reference's fp32 arithmetic (CVC-YOLOv3/models.py:59-69 is fp32 end to end): losses to 1e-3 and
+ *     better, gradients as closely as the reference's own fp32 rounding allows (tests/test_gpu_fp32_mode.py).
  */
 #ifndef B200CV_H_
 #define B200CV_H_
@@ -36,6 +46,11 @@ extern "C" {
 #define B200CV_DT_BF16 0
 #define B200CV_DT_F32 1
 
+/* One entry of a per-channel statistics matrix (see b200cv_conv_args.stats): 16 bytes, zero = empty. */
+typedef struct b200cv_stat {
+  int64_t w1, w2;
+} b200cv_stat;
+
 /* ---- library ------------------------------------------------------------------------- */
 const char* b200cv_version(void);
 const char* b200cv_last_error(void);
@@ -44,12 +59,17 @@ const char* b200cv_last_error(void);
 int b200cv_check_device_error(void* stream);
 /* 16 for c<=16, 32 for c<=32, otherwise the next multiple of 64. */
 int b200cv_pad_channels(int c);
+/* Number of bf16 pieces of a split (fp32-parity mode) value: 3. */
+int b200cv_split_pieces(void);
 
 /* ---- layout ---------------------------------------------------------------------------- */
 /* NCHW fp32 [N,C,H,W] -> NHWC bf16 [N,H,W,Cpad] (extra channels zero).
  * Replaces the implicit layout of `imgs.to(device)` CVC-YOLOv3/train.py:60, RektNet/train_eval.py:60. */
 int b200cv_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int N, int C, int H, int W, int Cpad,
                                  void* stream);
+/* the same into / out of a split tensor [N,H,W,3*Cpad] (fp32-parity mode). */
+int b200cv_nchw_f32_to_nhwc_split(const float* src, void* dst, int N, int C, int H, int W, int Cpad, void* stream);
+int b200cv_nhwc_split_to_nchw_f32(const void* src, float* dst, int N, int C, int H, int W, int Cpad, void* stream);
 /* NHWC bf16 [N,H,W,Cpad] (first C channels) -> NCHW fp32 [N,C,H,W]. */
 int b200cv_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C, int H, int W, int Cpad,
                                  void* stream);
@@ -58,6 +78,9 @@ int b200cv_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C, int 
  * The convolution then runs as a 1x1 conv over the patch matrix (Cin = Kp). */
 int b200cv_im2col_nchw_f32(const float* x, void* patches, int N, int C, int H, int W, int R, int S, int stride,
                            int pad, int dil, int Kp, void* stream);
+/* fp32-parity mode: split patch matrix [N*OH*OW][p0(Kp) | p1(Kp) | p2(Kp)]. */
+int b200cv_im2col_nchw_f32_split(const float* x, void* patches, int N, int C, int H, int W, int R, int S, int stride,
+                                 int pad, int dil, int Kp, void* stream);
 /* OIHW fp32 conv weight -> packed bf16.
  *   transpose == 0: [O][R*S][Ipad]      (forward operand;  K index = tap*Ipad + i)
  *   transpose == 1: [I][R*S][Opad]      (data-gradient operand; K index = tap*Opad + o)
@@ -77,7 +100,9 @@ typedef struct b200cv_pack_entry {
   int32_t O, I, RS, Ipad, Opad, transpose;
 } b200cv_pack_entry;
 /* entry.transpose == 2 selects the FLAT layout used with b200cv_im2col_nchw_f32: packed row = [Ipad] with
- * k = tap*I + i (Ipad >= R*S*I); the matching gradient row is un-packed the same way. */
+ * k = tap*I + i (Ipad >= R*S*I); the matching gradient row is un-packed the same way.
+ * transpose | 8 (also for b200cv_pack_weights) = fp32-parity (split) pack: every innermost run of W channels becomes
+ * [w0(W) | w1(W) | w2(W)], the three bf16 pieces of the fp32 weight. */
 int b200cv_pack_weights_multi(const void* table_dev, int n, void* stream);
 int b200cv_unpack_wgrad_multi(const void* table_dev, int n, void* stream);
 
@@ -102,9 +127,11 @@ typedef struct b200cv_conv_args {
   float slope;
   int32_t res_after_act; /* 1: y = act(acc*scale+shift) + residual (darknet shortcut after the activation) */
   /* per-channel [sum(y) | sum(y*y)] over N*OH*OW, ADDED into stats[stats_parts][2*Cout] (zero it first;
-   * CTA b adds into row b % stats_parts -- with stats_parts >= #SMs no two CTAs share a row, i.e. no
-   * contended global atomics); NULL = off.  Cout <= 1024 when stats are requested. */
-  float* stats;
+   * CTA b adds into row b % stats_parts); NULL = off.  Cout <= 1024 when stats are requested.
+   * Every entry of a statistics matrix is a b200cv_stat: two int64 words of a fixed-point sum
+   * (value = w1 * 2^-20 + w2 * 2^-70) added with INTEGER atomics, so the totals -- and the whole forward pass --
+   * are bit-reproducible whatever the CTA scheduling (csrc/stat_acc.cuh). */
+  void* stats;
   int32_t stats_parts;
   /* b200cv_conv_dgrad only -- fused first pass of the BatchNorm backward of the layer that PRODUCED the
    * activation whose gradient this call writes (b200cv_bn_bwd_reduce folded into the epilogue): with
@@ -112,7 +139,7 @@ typedef struct b200cv_conv_args {
    * [sum dz | sum dz*(bn_y-bn_mean)*bn_rstd] per channel into bn_sums[bn_parts][2*Cout] (zero it first).
    * bn_y: NHWC bf16 rows with pitch bn_y_ld laid out like the output.  Needs the row-major bf16 output form
    * (stride-1 gradients); otherwise the call fails with B200CV_ERR_ARG.  bn_sums == NULL = off. */
-  float* bn_sums;
+  void* bn_sums; /* b200cv_stat [bn_parts][2*Cout] */
   int32_t bn_parts;
   const void* bn_y;
   int64_t bn_y_ld;
@@ -122,6 +149,12 @@ typedef struct b200cv_conv_args {
   const float* bn_rstd;
   int32_t bn_act;
   float bn_slope;
+  /* fp32-parity ("split") mode -- see the top of this header.  x_lo != 0: x is a split tensor (row =
+   * [p0(Cin) | p1(Cin) | p2(Cin)], x_lo == Cin, pixel pitch 3*Cin) and w a split pack (K run of a tap =
+   * [w0(Cin) | w1(Cin) | w2(Cin)]); the GEMM accumulates the six products x_i*w_j, i + j <= 2, in fp32.  y_lo != 0:
+   * the bf16 output is written split with piece stride y_lo (direct-store epilogue).  r_lo: the residual is split.
+   * All three are 0 in the default bf16 mode. */
+  int64_t x_lo, y_lo, r_lo;
 } b200cv_conv_args;
 
 /* y = conv2d(x, w).  nn.Conv2d forward: CVC-YOLOv3/models.py:59-65,320-321;
@@ -136,16 +169,19 @@ int b200cv_conv_dgrad(const b200cv_conv_args* a, int out_h, int out_w, void* str
 
 /* Weight gradient: dw_packed[o][tap][i] += sum_pixels dY[pix][o] * X[pix+tap][i]  (fp32, atomically
  * accumulated; zero it first).  x: NHWC bf16 [N,H,W,Cin]; dy: NHWC bf16 [N,OH,OW,dy_ld].
+ * fp32-parity mode: x_lo == Cin (x rows are [p0|p1|p2], pitch 3*Cin) and dy_lo = piece stride of dy (dy_ld covers
+ * all pieces); 0, 0 in the bf16 mode.  The gradient is fp32 either way.
  * autograd of nn.Conv2d: CVC-YOLOv3/train.py:70, RektNet/train_eval.py:71. */
 int b200cv_conv_wgrad(const void* x, const void* dy, float* dw_packed, int N, int H, int W, int Cin,
-                      int Cout, int dy_ld, int R, int S, int stride, int pad, int dil, void* stream);
+                      int Cout, int dy_ld, int R, int S, int stride, int pad, int dil, int64_t x_lo, int64_t dy_lo,
+                      void* stream);
 
 /* ---- BatchNorm (training mode) + activation, NHWC bf16 rows with explicit pitch -------------- */
 /* From the conv epilogue's [sum | sumsq] produce scale/shift for the apply pass, the saved
  * mean/rstd for backward, and update running stats (momentum, unbiased var) -- nn.BatchNorm2d in
  * train(): CVC-YOLOv3/models.py:67, RektNet/keypoint_net.py:19, resnet.py:13,16,20.
  * conv_bias (optional) is the bias of a conv whose bias was folded out (it cancels in train-mode BN). */
-int b200cv_bn_finalize(const float* stats, int stats_parts, int64_t count, const float* gamma, const float* beta,
+int b200cv_bn_finalize(const void* stats, int stats_parts, int64_t count, const float* gamma, const float* beta,
                        const float* conv_bias, float eps, float momentum, float* running_mean,
                        float* running_var, float* scale, float* shift, float* save_mean, float* save_rstd,
                        int C, void* stream);
@@ -160,10 +196,10 @@ int b200cv_bn_apply_act(const void* y, int64_t y_ld, const float* scale, const f
  * y*scale+shift, or its sign taken from `aout` (saved activation output) when given. */
 int b200cv_bn_bwd_reduce(const void* da, int64_t da_ld, const void* y, int64_t y_ld, const void* aout,
                          int64_t aout_ld, const float* scale, const float* shift, const float* mean,
-                         const float* rstd, float* partials, int nparts, int64_t rows, int C, int act, float slope,
+                         const float* rstd, void* partials, int nparts, int64_t rows, int C, int act, float slope,
                          void* stream);
 /* coef = [gamma*rstd | sum_dz/M | sum_dz_xhat/M] from the nparts partial rows; dgamma/dbeta written if non-NULL. */
-int b200cv_bn_bwd_finalize(const float* partials, int nparts, const float* gamma, const float* rstd, int64_t count,
+int b200cv_bn_bwd_finalize(const void* partials, int nparts, const float* gamma, const float* rstd, int64_t count,
                            float* coef,
                            float* dgamma, float* dbeta, int C, void* stream);
 /* backward pass 2: dy = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)). */
@@ -176,7 +212,7 @@ int b200cv_bn_bwd_apply(const void* da, int64_t da_ld, const void* y, int64_t y_
  * partials / coef / dy as in b200cv_bn_bwd_reduce / b200cv_bn_bwd_apply, one set per layer. */
 int b200cv_bn_bwd_reduce2(const void* da, int64_t da_ld, const void* aout, int64_t aout_ld, const void* yA,
                           int64_t yA_ld, const void* yB, int64_t yB_ld, const float* meanA, const float* rstdA,
-                          const float* meanB, const float* rstdB, float* partialsA, float* partialsB, int nparts,
+                          const float* meanB, const float* rstdB, void* partialsA, void* partialsB, int nparts,
                           int64_t rows, int C, int act, float slope, void* stream);
 int b200cv_bn_bwd_apply2(const void* da, int64_t da_ld, const void* aout, int64_t aout_ld, const void* yA, int64_t yA_ld,
                          const void* yB, int64_t yB_ld, const float* meanA, const float* rstdA, const float* meanB,
@@ -186,13 +222,13 @@ int b200cv_bn_bwd_apply2(const void* da, int64_t da_ld, const void* aout, int64_
  * [parts][2C] partial statistics into the per-channel constants in shared memory, block 0 also publishes them
  * (scale/shift/save_mean/save_rstd, running statistics; dgamma/dbeta/coef) exactly like b200cv_bn_finalize /
  * b200cv_bn_bwd_finalize, then the block streams its rows like b200cv_bn_apply_act / b200cv_bn_bwd_apply. */
-int b200cv_bn_stats_apply_act(const float* stats, int stats_parts, int64_t count, const float* gamma,
+int b200cv_bn_stats_apply_act(const void* stats, int stats_parts, int64_t count, const float* gamma,
                               const float* beta, const float* conv_bias, float eps, float momentum,
                               float* running_mean, float* running_var, float* scale, float* shift,
                               float* save_mean, float* save_rstd, const void* y, int64_t y_ld, const void* post,
                               int64_t post_ld, void* out, int64_t out_ld, int64_t rows, int C, int act,
                               float slope, void* stream);
-int b200cv_bn_bwd_stats_apply(const float* partials, int nparts, int64_t count, const float* gamma, float* coef,
+int b200cv_bn_bwd_stats_apply(const void* partials, int nparts, int64_t count, const float* gamma, float* coef,
                               float* dgamma, float* dbeta, const void* da, int64_t da_ld, const void* y,
                               int64_t y_ld, const float* scale, const float* shift, const float* mean,
                               const float* rstd, void* dy, int64_t dy_ld, int64_t rows, int C, int act,
@@ -213,6 +249,37 @@ int b200cv_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int N, int H,
 int b200cv_upsample2x_fwd(const void* x, void* y, int64_t y_ld, int N, int H, int W, int C, void* stream);
 int b200cv_upsample2x_bwd(const void* dy, int64_t dy_ld, void* dx, int N, int H, int W, int C, int accumulate,
                           void* stream);
+
+/* ---- fp32-parity ("split") forms of the element-wise kernels (csrc/split_ops.cu) ----------------------------
+ * Same arithmetic as the bf16 entry points above on split rows: piece j of every activation operand of a call lies
+ * j * `lo` elements after piece 0 (row pitch >= 2*lo + C).  b200cv_bn_finalize / b200cv_bn_bwd_finalize are shared. */
+int b200cv_split_bn_apply_act(const void* y, int64_t y_ld, const float* scale, const float* shift, const void* y2,
+                              int64_t y2_ld, const float* scale2, const float* shift2, const void* post,
+                              int64_t post_ld, void* out, int64_t out_ld, int64_t rows, int C, int64_t lo, int act,
+                              float slope, void* stream);
+int b200cv_split_bn_bwd_reduce(const void* da, int64_t da_ld, const void* y, int64_t y_ld, const void* aout,
+                               int64_t aout_ld, const float* scale, const float* shift, const float* mean,
+                               const float* rstd, void* partials, int nparts, int64_t rows, int C, int64_t lo, int act,
+                               float slope, void* stream);
+int b200cv_split_bn_bwd_apply(const void* da, int64_t da_ld, const void* y, int64_t y_ld, const void* aout,
+                              int64_t aout_ld, const float* scale, const float* shift, const float* mean,
+                              const float* rstd, const float* coef, void* dy, int64_t dy_ld, int64_t rows, int C,
+                              int64_t lo, int act, float slope, void* stream);
+int b200cv_split_act_bwd(const void* da, int64_t da_ld, const void* aout, int64_t aout_ld, void* dz, int64_t dz_ld,
+                         int64_t rows, int C, int64_t lo, int act, float slope, void* stream);
+/* channel-slice copy / accumulate between split buffers with their own lo offsets (route concat, gradient fan-in). */
+int b200cv_split_copy_slice(const void* src, int64_t src_ld, int64_t src_lo, void* dst, int64_t dst_ld,
+                            int64_t dst_lo, int64_t rows, int C, int accumulate, void* stream);
+/* fp32 rows [rows][src_ld] -> split rows, and back (head gradients, module boundaries). */
+int b200cv_split_from_f32(const float* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t dst_lo, int64_t rows,
+                          int C, void* stream);
+int b200cv_split_to_f32(const void* src, int64_t src_ld, int64_t src_lo, float* dst, int64_t dst_ld, int64_t rows,
+                        int C, void* stream);
+/* whole split tensors [N,H,W,3C] (lo == C). */
+int b200cv_split_maxpool2x2_fwd(const void* x, void* y, int N, int H, int W, int C, int stride, void* stream);
+int b200cv_split_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C, int stride,
+                                void* stream);
+int b200cv_split_upsample2x_bwd(const void* dy, void* dx, int N, int H, int W, int C, int accumulate, void* stream);
 
 /* ---- YOLO head ------------------------------------------------------------------------------ */
 /* Target assignment (CVC-YOLOv3/utils/utils.py:195-275 build_targets, :163-193 bbox_iou).
@@ -266,7 +333,8 @@ int b200cv_kpt_loss(const float* hm, const float* pts, const float* thm, const f
                     int loss_type, int include_geo, float gamma_h, float gamma_v, double* ws, float* loss3,
                     float* ubar, void* stream);
 /* Fused backward: loss gradients (g_loc, g_geo device scalars) + optional upstream d_hm/d_pts ->
- * soft-argmax -> softmax Jacobian -> dlogits as NHWC bf16 [B*H*W][16]. */
+ * soft-argmax -> softmax Jacobian -> dlogits as NHWC bf16 [B*H*W][16] (ld == 16), or split rows
+ * [p0(16) | p1(16) | p2(16)] for ld == 48 (fp32-parity mode). */
 int b200cv_kpt_head_bwd(const float* hm, const float* thm, const float* pts, const float* tpts, const float* ubar,
                         const float* vx, const float* vy, const float* g_loc, const float* g_geo,
                         const float* d_hm_up, const float* d_pts_up, int B, int K, int H, int W, int loss_type,

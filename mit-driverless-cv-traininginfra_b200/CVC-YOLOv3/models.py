@@ -25,8 +25,20 @@ if _pkg_root not in sys.path:
 from utils.parse_config import parse_model_config  # noqa: E402
 from utils.utils import build_targets  # noqa: E402,F401
 
+from b200cv import parallel as _parallel  # noqa: E402
+
+_parallel.bind_process_to_local_gpu()  # B200CV_AUTO_DP=1 under torchrun: one GPU per process, before CUDA starts
+
 from b200cv import yolo_ops  # noqa: E402
 from b200cv.darknet_engine import DarknetEngine  # noqa: E402
+
+_DP_MESSAGE = (
+    "b200cv: nn.DataParallel (one process driving several GPUs) is not supported by the B200 engine.  The reference "
+    "wraps the model whenever torch.cuda.device_count() > 1 (train.py:193-195); run one process per GPU instead: "
+    "`B200CV_AUTO_DP=1 torchrun --nproc-per-node <N> train.py ...` keeps the script unchanged (every process binds to "
+    "its own GPU, so device_count() == 1 and nothing is wrapped; Darknet.forward takes that rank's DataParallel shard "
+    "of each batch and the gradients are SUMmed over NCCL like DataParallel's reduce-add), or expose a single GPU with "
+    "CUDA_VISIBLE_DEVICES.  See INTEGRATION.md.")
 
 vanilla_anchor_list = [[10, 13], [16, 30], [33, 23], [30, 61], [62, 45], [59, 119], [116, 90], [156, 198], [373, 326]]
 
@@ -210,12 +222,27 @@ class Darknet(nn.Module):
             object.__setattr__(self, "_engine", DarknetEngine(self))
         return self._engine
 
+    def _replicate_for_data_parallel(self):
+        raise RuntimeError(_DP_MESSAGE)
+
     def forward(self, x, targets=None):
         """Training (targets given): 7-tuple of 0-dim tensors (total, x, y, w, h, obj, noobj), the
         first differentiable (models.py:338).  Inference: [B, sum A*G*G, 5+C] detections."""
         eng = self.engine()
+        if x.is_cuda and next(self.parameters()).device != x.device:
+            raise RuntimeError(f"Darknet.forward: input on {x.device} but the parameters are on "
+                               f"{next(self.parameters()).device}. " + _DP_MESSAGE)
         if targets is not None:
-            out7 = eng.train_forward(x, targets)
+            if _parallel.auto_dp_enabled():
+                # DataParallel-equivalent step under torchrun: this rank's scatter chunk of the batch, per-replica
+                # mean loss, the returned values summed over the replicas (train.py:70 `losses[0].sum()`)
+                _parallel.ensure_group()
+                lo, hi = _parallel.dp_chunk(x.shape[0])
+                if hi <= lo:
+                    raise RuntimeError("B200CV_AUTO_DP: batch smaller than the number of processes")
+                out7 = _parallel.sum_over_replicas(eng.train_forward(x[lo:hi].contiguous(), targets[lo:hi].contiguous()))
+            else:
+                out7 = eng.train_forward(x, targets)
             parts = out7.detach()
             return (out7[0], parts[1], parts[2], parts[3], parts[4], parts[5], parts[6])
         return eng.detect(x)

@@ -14,6 +14,7 @@ autograd), which is what the data-parallel all-reduce sends over NCCL.
 """
 from __future__ import annotations
 
+import weakref
 from typing import List, Optional
 
 import torch
@@ -113,6 +114,9 @@ class DarknetEngine:
                     prev.post_from = L.inputs[1]
                     L.fused_alias = True
         self.params = list(model.parameters())
+        # "fp32" = the fp32-parity mode (split bf16x3 operands, see ops.py); chosen when the engine is created
+        # (B200CV_PRECISION / ops.set_default_precision) or later through set_precision()
+        self.split = ops.default_split()
         self._arena = None
         self._packs = None
         self._anchor_cache = {}
@@ -120,6 +124,20 @@ class DarknetEngine:
         self._graphs = {}       # (shapes) -> _GraphedStep | int (eager warm-up calls seen so far)
 
     # ------------------------------------------------------------------ helpers
+    @property
+    def precision(self) -> str:
+        return "fp32" if self.split else "bf16"
+
+    def set_precision(self, name: str):
+        """"bf16" (default) or "fp32" (bf16x3 split operands: parity with the reference's fp32 arithmetic)."""
+        if name not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        if (name == "fp32") != self.split:
+            self.split = name == "fp32"
+            self._arena = self._packs = self._pack_key = None  # operand layouts change: rebuild packs and graphs
+            self._graphs = {}
+        return self
+
     def _setup(self, dev):
         if self._arena is None or self._arena.flat.device != dev:
             # per-channel vectors of every BN layer; the partial-statistics matrices (forward: sum / sum of squares
@@ -130,21 +148,21 @@ class DarknetEngine:
                 if ops.pad_channels(L.cout) != L.cout:
                     raise ValueError(f"BatchNorm over {L.cout} channels: the B200 layout needs 16, 32 or a multiple "
                                      "of 64 channels in every normalised layer")
-            per = [ops.STAT_PARTS * 2 * L.cout for L in bn_layers]
-            self._fstat_arena = torch.zeros(sum(per), dtype=torch.float32, device=dev)
-            self._bstat_arena = torch.zeros(sum(per), dtype=torch.float32, device=dev)
+            per = [ops.STAT_PARTS * 2 * L.cout * ops.STAT_WORDS for L in bn_layers]
+            self._fstat_arena = torch.zeros(sum(per), dtype=torch.int64, device=dev)
+            self._bstat_arena = torch.zeros(sum(per), dtype=torch.int64, device=dev)
             off = 0
             f = lambda n: torch.empty(n, dtype=torch.float32, device=dev)
             for L, n in zip(bn_layers, per):
                 c = L.cout
-                L.stats = self._fstat_arena[off:off + n].view(ops.STAT_PARTS, 2 * c)
-                L.bstats = self._bstat_arena[off:off + n].view(ops.STAT_PARTS, 2 * c)
+                L.stats = self._fstat_arena[off:off + n].view(ops.STAT_PARTS, 2 * c, ops.STAT_WORDS)
+                L.bstats = self._bstat_arena[off:off + n].view(ops.STAT_PARTS, 2 * c, ops.STAT_WORDS)
                 L.scale, L.shift, L.mean, L.rstd, L.coef = f(c), f(c), f(c), f(c), f(3 * c)
                 off += n
             self._nbt = [L.bn.num_batches_tracked for L in bn_layers if L.bn.num_batches_tracked is not None]
             self._arena = GradArena(self.params, dev)
             convs = [(L.conv, L.index > 0) for L in self.layers if L.type == "convolutional"]
-            self._packs = ConvPackSet(convs, dev, self._arena, flat=self._flat_convs())
+            self._packs = ConvPackSet(convs, dev, self._arena, flat=self._flat_convs(), split=self.split)
             for L in self.layers:
                 if L.type == "convolutional":
                     L.wpk, L.wpk_t = self._packs.wpk[id(L.conv)], self._packs.wpk_t[id(L.conv)]
@@ -204,8 +222,18 @@ class DarknetEngine:
             raise ValueError(f"expected input [B,{self.layers[0].cin},H,W], got {tuple(x.shape)}")
 
     # ------------------------------------------------------------------ forward
-    def _run_forward(self, x, targets, bn_train: bool, want_grad: bool):
-        """Returns (out7 or detections, saved-state)."""
+    def _run_forward(self, x, targets, bn_train: bool, want_grad: bool, private: bool = False):
+        with ops.precision(self.split):
+            return self._run_forward_impl(x, targets, bn_train, want_grad, private)
+
+    def _run_backward(self, state, g7, force_persistent_arena=False, do_allreduce=True):
+        with ops.precision(self.split):
+            return self._run_backward_impl(state, g7, force_persistent_arena, do_allreduce)
+
+    def _run_forward_impl(self, x, targets, bn_train: bool, want_grad: bool, private: bool = False):
+        """Returns (out7 or detections, saved-state).  `private`: the per-layer BatchNorm vectors this pass saves for
+        its backward are fresh tensors instead of the engine's static ones (a second forward issued while an earlier
+        one still awaits its backward must not overwrite what that one saved)."""
         model = self.model
         dev = x.device
         self._setup(dev)
@@ -235,17 +263,17 @@ class DarknetEngine:
                     if bn_train:
                         y = ops.conv_fwd(xin, L.wpk, L.cout, k_, st_, pd_, stats=L.stats)
                         count = y.numel() // y.shape[-1]
+                        vec = (L.scale, L.shift, L.mean, L.rstd)
+                        if private:
+                            vec = tuple(torch.empty_like(v) for v in vec)
                         cur = ops.bn_stats_apply_act(L.stats, count, L.bn.weight, L.bn.bias, None, BN_EPS, BN_MOMENTUM,
-                                                     L.bn.running_mean, L.bn.running_var, L.scale, L.shift, L.mean,
-                                                     L.rstd, y, L.act, L.slope, post=post)
-                        saved[i] = (xin, y)
+                                                     L.bn.running_mean, L.bn.running_var, vec[0], vec[1], vec[2],
+                                                     vec[3], y, L.act, L.slope, post=post)
+                        saved[i] = (xin, y, vec)
                     else:
                         scale, shift = self._eval_affine(L)
                         cur = ops.conv_fwd(xin, L.wpk, L.cout, k_, st_, pd_, scale=scale, shift=shift,
                                            residual=post, act=L.act, slope=L.slope, res_after_act=True)
-                        if want_grad:
-                            raise RuntimeError("Darknet: backward through eval-mode BatchNorm is not supported; "
-                                               "call model.train() (or wrap the pass in torch.no_grad())")
                 else:  # pre-YOLO conv: bias, linear, fp32 logits
                     cur = ops.conv_fwd(xin, L.wpk, L.cout, k_, st_, pd_, out_dtype=torch.float32,
                                        shift=L.conv.bias.detach())
@@ -259,13 +287,7 @@ class DarknetEngine:
                 if len(L.inputs) == 1:
                     cur = outs[L.inputs[0]]
                 else:
-                    parts = [outs[j] for j in L.inputs]
-                    b, hh, ww = parts[0].shape[:3]
-                    cur = torch.empty(b, hh, ww, sum(p.shape[-1] for p in parts), dtype=parts[0].dtype, device=dev)
-                    c0 = 0
-                    for p in parts:
-                        ops.copy_slice(p, cur[..., c0:c0 + p.shape[-1]])
-                        c0 += p.shape[-1]
+                    cur = ops.concat_channels([outs[j] for j in L.inputs])
             elif L.type == "shortcut":
                 if L.fused_alias:
                     cur = outs[i - 1]
@@ -293,22 +315,22 @@ class DarknetEngine:
                     cur = d
             outs[i] = cur
         if training:
-            return out7, (outs, saved)
+            return out7, (outs, saved, private)
         return torch.cat(dets, 1), None
 
     # ------------------------------------------------------------------ backward
-    def _run_backward(self, state, g7, force_persistent_arena=False, do_allreduce=True):
-        outs, saved = state
+    def _run_backward_impl(self, state, g7, force_persistent_arena=False, do_allreduce=True):
+        outs, saved, private = state
         model = self.model
         dev = g7.device
         g = g7[0:1].contiguous().float()
         arena = self._arena
-        if not force_persistent_arena and arena.aliased_by_param_grads():
+        if not force_persistent_arena and (private or arena.aliased_by_param_grads()):
             # param.grad still aliases the arena (zero_grad(set_to_none=False)): use a private arena for this
             # backward so autograd's in-place accumulation stays correct
             arena = GradArena(self.params, dev)
             packs = ConvPackSet([(L.conv, L.index > 0) for L in self.layers if L.type == "convolutional"], dev, arena,
-                                flat=self._flat_convs())
+                                flat=self._flat_convs(), split=self.split)
         else:
             packs = self._packs
         packs.zero_grads()
@@ -369,22 +391,19 @@ class DarknetEngine:
                 continue
             if L.type == "convolutional":
                 if L.bn is not None:
-                    xin, y = saved[i]
+                    xin, y, (scale, shift, mean, rstd) = saved[i]
                     count = y.numel() // y.shape[-1]
                     parts = L.bstats
                     if i not in reduced:
-                        ops.bn_bwd_reduce(G, y, None, L.scale, L.shift, L.mean, L.rstd, L.act, L.slope, partials=parts)
+                        ops.bn_bwd_reduce(G, y, None, scale, shift, mean, rstd, L.act, L.slope, partials=parts)
                     dy = ops.bn_bwd_stats_apply(parts, count, L.bn.weight, L.coef, gview[id(L.bn.weight)],
-                                                gview[id(L.bn.bias)], G, y, L.scale, L.shift, L.mean, L.rstd, L.act,
-                                                L.slope)
+                                                gview[id(L.bn.bias)], G, y, scale, shift, mean, rstd, L.act, L.slope)
                     if L.post_from is not None:
                         add_grad(L.post_from, G)
                 else:
                     (xin,) = saved[i]
                     dy = G
-                    tmp = torch.zeros(dy.shape[-1], dtype=torch.float32, device=dev)
-                    ops.col_sum(dy, tmp)
-                    gview[id(L.conv.bias)].copy_(tmp[:L.cout])
+                    gview[id(L.conv.bias)].copy_(ops.bias_grad(dy, L.cout))
                 if i == 0 and self._flat_convs():
                     wgrad(xin, dy, L.cout, 1, 1, 0, packs.dwp[id(L.conv)])  # xin = im2col patches
                 else:
@@ -395,11 +414,12 @@ class DarknetEngine:
                     # first pass of its BN backward (sum dz, sum dz*xhat) is folded into the epilogue
                     # (with 32-column epilogue blocks the HBM-bound 1x1 gradients lost more than the separate pass costs:
                     # 91 us fused vs 36 + 45 us for 256->128 @52x52; with 64-column blocks the fused form is 75 us)
-                    owner = self._bn_owner(i - 1) if (fuse and L.stride == 1 and (L.k > 1 or fuse >= 2)) else None
+                    owner = self._bn_owner(i - 1) if (fuse and not self.split and L.stride == 1 and
+                                                      (L.k > 1 or fuse >= 2)) else None
                     bn_red = None
                     if owner is not None:
                         T = self.layers[owner]
-                        bn_red = (saved[owner][1], T.scale, T.shift, T.mean, T.rstd, T.act, T.slope, T.bstats)
+                        bn_red = (saved[owner][1], *saved[owner][2], T.act, T.slope, T.bstats)
                         reduced.add(owner)
                     dx = ops.conv_dgrad(dy, L.wpk_t, L.cin, L.k, L.stride, L.pad, 1, (xin.shape[1], xin.shape[2]),
                                         out=prev, residual=prev, bn_reduce=bn_red)
@@ -418,13 +438,11 @@ class DarknetEngine:
                 else:
                     c0 = 0
                     for j in L.inputs:
-                        c = outs[j].shape[-1]
-                        sl = G[..., c0:c0 + c]
+                        c = ops.channels(outs[j])
                         if grads[j] is None:
-                            dst = torch.empty(outs[j].shape, dtype=G.dtype, device=dev)
-                            grads[j] = ops.copy_slice(sl, dst)
+                            grads[j] = ops.slice_grad(G, c0, c)
                         else:
-                            ops.copy_slice(sl, grads[j], accumulate=True)
+                            ops.slice_grad(G, c0, c, into=grads[j])
                         c0 += c
             elif L.type == "shortcut":
                 if L.fused_alias:
@@ -445,18 +463,26 @@ class DarknetEngine:
     def train_forward(self, x, targets):
         self._check_input(x)
         require_cuda(targets, "Darknet.forward(targets)")
+        with torch.cuda.device(x.device):  # every launch below targets the tensors' device, whatever is current
+            return self._train_forward(x, targets)
+
+    def _train_forward(self, x, targets):
         targets = targets.float()
         grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.params)
         if grad and self.model.training and _graphs_enabled() and not torch.cuda.is_current_stream_capturing():
             key = (tuple(x.shape), tuple(targets.shape), str(x.device))
             entry = self._graphs.get(key, 0)
             if isinstance(entry, _GraphedStep):
-                if entry.usable():
-                    return _DarknetGraphFn.apply(entry, x, targets, *self.params)
+                # a replay re-uses the static activations of the previous one: while an earlier replayed forward can
+                # still be back-propagated (micro-batches whose losses are summed, probe forwards) this call takes the
+                # eager launches, which keep per-call state
+                if entry.usable() and not self._backward_pending():
+                    return self._track(_DarknetGraphFn.apply(entry, x, targets, *self.params))
             elif entry >= GRAPH_WARMUP_CALLS:
                 try:
-                    self._graphs[key] = _GraphedStep(self, x, targets)
-                    return _DarknetGraphFn.apply(self._graphs[key], x, targets, *self.params)
+                    if not self._backward_pending():
+                        self._graphs[key] = _GraphedStep(self, x, targets)
+                        return self._track(_DarknetGraphFn.apply(self._graphs[key], x, targets, *self.params))
                 except Exception as e:  # capture is an optimisation: fall back to the eager launches, loudly
                     import warnings
 
@@ -465,29 +491,52 @@ class DarknetEngine:
                     torch.cuda.synchronize()
             else:
                 self._graphs[key] = entry + 1
-        return _DarknetTrainFn.apply(self, x, targets, self.model.training, torch.is_grad_enabled(), *self.params)
+        private = grad and self._backward_pending()
+        out = _DarknetTrainFn.apply(self, x, targets, self.model.training, torch.is_grad_enabled(), private,
+                                    *self.params)
+        return out if (private or not grad) else self._track(out)
+
+    # A training forward whose backward has not run yet owns the engine's static state (per-layer BatchNorm vectors,
+    # the CUDA-graph activations, the gradient arena).  Further grad-enabled forwards issued meanwhile (micro-batches
+    # whose losses are summed, probe forwards) run eagerly with private state.
+    def _track(self, out):
+        self._pending = weakref.ref(out)
+        return out
+
+    def _backward_pending(self) -> bool:
+        ref = getattr(self, "_pending", None)
+        return ref is not None and ref() is not None and ref().grad_fn is not None
 
     @torch.no_grad()
     def detect(self, x):
         self._check_input(x)
-        det, _ = self._run_forward(x.float(), None, bn_train=self.model.training, want_grad=False)
+        with torch.cuda.device(x.device):
+            det, _ = self._run_forward(x.float(), None, bn_train=self.model.training, want_grad=False)
         return det
 
 
 class _DarknetTrainFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, engine, x, targets, bn_train, grad_enabled, *params):
-        want_grad = grad_enabled and any(ctx.needs_input_grad[5:])
-        out7, state = engine._run_forward(x.float(), targets, bn_train=bn_train, want_grad=want_grad)
+    def forward(ctx, engine, x, targets, bn_train, grad_enabled, private, *params):
+        # eval-mode BatchNorm (running statistics folded into the conv epilogues) has no backward here: such a pass
+        # is computed like the reference computes it and returned as a constant (autograd refuses to differentiate it)
+        want_grad = grad_enabled and bn_train and any(ctx.needs_input_grad[6:])
+        out7, state = engine._run_forward(x.float(), targets, bn_train=bn_train, want_grad=want_grad, private=private)
         ctx.engine = engine
-        ctx.state = state
+        ctx.state = state if want_grad else None
+        ctx.dev = x.device
+        if not want_grad:
+            ctx.mark_non_differentiable(out7)
         return out7
 
     @staticmethod
     def backward(ctx, g7):
-        views = ctx.engine._run_backward(ctx.state, g7)
+        with torch.cuda.device(ctx.dev):
+            views = ctx.engine._run_backward(ctx.state, g7)
+        if not ctx.state[2]:
+            ctx.engine._pending = None
         ctx.state = None
-        return (None, None, None, None, None, *views)
+        return (None, None, None, None, None, None, *views)
 
 
 def _count_launches(n: int):
@@ -525,6 +574,7 @@ class _GraphedStep:
                                                   do_allreduce=False)
         # kernel-launching ABI calls recorded in each graph: a replay launches that many of our kernels
         self.fwd_launches, self.bwd_launches = n1 - n0, lib().launches - n1
+        self.generation = 0        # bumped by every replayed forward (a stale backward is refused)
         torch.cuda.synchronize()
 
     def usable(self) -> bool:
@@ -543,13 +593,21 @@ class _DarknetGraphFn(torch.autograd.Function):
         for L in step.engine.layers:  # the replay moved the running statistics: drop the folded inference affines
             L.eval_key = None
         ctx.step = step
+        step.generation += 1
+        ctx.generation = step.generation
         return step.out7.clone()
 
     @staticmethod
     def backward(ctx, g7):
         step = ctx.step
-        step.static_g.copy_(g7)
-        step.bwd_graph.replay()
-        _count_launches(step.bwd_launches)
-        allreduce_gradients(step.engine._arena.flat)
+        if ctx.generation != step.generation:
+            raise RuntimeError("b200cv: this training forward was replayed from a CUDA graph and a LATER forward of the "
+                               "same shapes has overwritten its saved activations; back-propagate each forward before "
+                               "the next one, or set B200CV_CUDA_GRAPH=0")
+        step.engine._pending = None
+        with torch.cuda.device(step.static_g.device):
+            step.static_g.copy_(g7)
+            step.bwd_graph.replay()
+            _count_launches(step.bwd_launches)
+            allreduce_gradients(step.engine._arena.flat)
         return (None, None, None, *step.views)

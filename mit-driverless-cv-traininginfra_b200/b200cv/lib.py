@@ -40,6 +40,7 @@ class ConvArgs(ctypes.Structure):
         ("bn_y_ld", ctypes.c_int64), ("bn_scale", ctypes.c_void_p), ("bn_shift", ctypes.c_void_p),
         ("bn_mean", ctypes.c_void_p), ("bn_rstd", ctypes.c_void_p), ("bn_act", ctypes.c_int32),
         ("bn_slope", ctypes.c_float),
+        ("x_lo", ctypes.c_int64), ("y_lo", ctypes.c_int64), ("r_lo", ctypes.c_int64),
     ]
 
 

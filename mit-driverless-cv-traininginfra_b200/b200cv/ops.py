@@ -6,7 +6,10 @@ tensors of shape [N,H,W,C] (C padded by pad_channels), per-channel vectors are f
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
+import os
+import threading
 
 import torch
 
@@ -16,9 +19,60 @@ __all__ = [
     "ACT_NONE", "ACT_LEAKY", "ACT_RELU", "pad_channels", "conv_out_size", "nchw_to_nhwc", "nhwc_to_nchw",
     "pack_weights", "unpack_wgrad", "conv_fwd", "conv_dgrad", "conv_wgrad", "bn_finalize", "bn_apply_act",
     "bn_bwd_reduce", "bn_bwd_finalize", "bn_bwd_apply", "bn_stats_apply_act", "bn_bwd_stats_apply", "act_bwd", "copy_slice", "col_sum", "maxpool_fwd",
-    "maxpool_bwd", "upsample_fwd", "upsample_bwd", "act_code", "sm_count", "stats_buffer", "im2col_nchw",
-    "use_flat_path", "flat_k",
+    "maxpool_bwd", "upsample_fwd", "upsample_bwd", "act_code", "sm_count", "stats_buffer", "stats_value", "im2col_nchw",
+    "use_flat_path", "flat_k", "split_mode", "precision", "set_default_precision", "default_split", "channels",
+    "bias_grad", "concat_channels", "slice_grad", "split_from_f32", "split_to_f32",
 ]
+
+# ------------------------------------------------------------------------------ precision mode
+# "bf16" (default): NHWC bf16 activations / bf16 tensor-core operands, fp32 accumulation.
+# "fp32" (the fp32-parity mode, B200CV_PRECISION=fp32): every activation and weight is stored SPLIT as three bf16
+# pieces (p0 = bf16(v), p1 = bf16(v - p0), p2 = bf16(v - p0 - p1): 24 mantissa bits; a tensor is [N,H,W,3C] =
+# [p0(C) | p1(C) | p2(C)]), convolutions run six tensor-core passes over the piece products, element-wise kernels
+# compute on the summed pieces in fp32 (include/b200cv.h).
+# The mode is a thread-local switch set by the engines around their launches (autograd runs backward on its own thread).
+_tls = threading.local()
+_default_split = os.environ.get("B200CV_PRECISION", "bf16").lower() in ("fp32", "f32", "split", "bf16x3")
+
+
+def set_default_precision(name: str) -> None:
+    """Precision of engines created from now on: "bf16" or "fp32" (the bf16x3 split mode)."""
+    global _default_split
+    if name not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    _default_split = name == "fp32"
+
+
+def default_split() -> bool:
+    return _default_split
+
+
+def split_mode() -> bool:
+    return getattr(_tls, "split", False)
+
+
+@contextlib.contextmanager
+def precision(split: bool):
+    old = split_mode()
+    _tls.split = bool(split)
+    try:
+        yield
+    finally:
+        _tls.split = old
+
+
+def split_pieces() -> int:
+    """bf16 pieces per value of the split layout (3)."""
+    return int(lib().cdll.b200cv_split_pieces())
+
+
+def channels(t: torch.Tensor) -> int:
+    """Logical channel count of an activation tensor ([N,H,W,C], or [N,H,W,3C] in the split mode)."""
+    return t.shape[-1] // split_pieces() if split_mode() else t.shape[-1]
+
+
+def _mul() -> int:
+    return split_pieces() if split_mode() else 1
 
 
 def pad_channels(c: int) -> int:
@@ -44,15 +98,35 @@ def nchw_to_nhwc(x: torch.Tensor, cpad: int | None = None) -> torch.Tensor:
     x = x.contiguous().float()
     n, c, h, w = x.shape
     cpad = cpad or pad_channels(c)
-    out = torch.empty(n, h, w, cpad, dtype=torch.bfloat16, device=x.device)
-    lib().call("b200cv_nchw_f32_to_nhwc_bf16", ptr(x), ptr(out), n, c, h, w, cpad, stream_ptr())
+    out = torch.empty(n, h, w, _mul() * cpad, dtype=torch.bfloat16, device=x.device)
+    name = "b200cv_nchw_f32_to_nhwc_split" if split_mode() else "b200cv_nchw_f32_to_nhwc_bf16"
+    lib().call(name, ptr(x), ptr(out), n, c, h, w, cpad, stream_ptr())
     return out
 
 
 def nhwc_to_nchw(x: torch.Tensor, c: int) -> torch.Tensor:
-    n, h, w, cpad = x.shape
+    n, h, w, _ = x.shape
+    cpad = channels(x)
     out = torch.empty(n, c, h, w, dtype=torch.float32, device=x.device)
-    lib().call("b200cv_nhwc_bf16_to_nchw_f32", ptr(x), ptr(out), n, c, h, w, cpad, stream_ptr())
+    name = "b200cv_nhwc_split_to_nchw_f32" if split_mode() else "b200cv_nhwc_bf16_to_nchw_f32"
+    lib().call(name, ptr(x), ptr(out), n, c, h, w, cpad, stream_ptr())
+    return out
+
+
+def split_from_f32(src: torch.Tensor) -> torch.Tensor:
+    """fp32 [..., C] (C % 8 == 0) -> split bf16 [..., 3C]."""
+    c = src.shape[-1]
+    out = torch.empty(*src.shape[:-1], split_pieces() * c, dtype=torch.bfloat16, device=src.device)
+    lib().call("b200cv_split_from_f32", ptr(src), src.stride(-2), ptr(out), out.shape[-1], c, _rows(src), c,
+               stream_ptr())
+    return out
+
+
+def split_to_f32(src: torch.Tensor) -> torch.Tensor:
+    """split bf16 [..., 3C] -> fp32 [..., C] (tests / diagnostics)."""
+    c = src.shape[-1] // split_pieces()
+    out = torch.empty(*src.shape[:-1], c, dtype=torch.float32, device=src.device)
+    lib().call("b200cv_split_to_f32", ptr(src), src.stride(-2), c, ptr(out), c, _rows(src), c, stream_ptr())
     return out
 
 
@@ -74,8 +148,9 @@ def im2col_nchw(x: torch.Tensor, k: int, stride: int, pad: int, dil: int = 1) ->
     n, c, h, w = x.shape
     oh, ow = conv_out_size(h, k, stride, pad, dil), conv_out_size(w, k, stride, pad, dil)
     kp = flat_k(c, k)
-    out = torch.empty(n, oh, ow, kp, dtype=torch.bfloat16, device=x.device)
-    lib().call("b200cv_im2col_nchw_f32", ptr(x), ptr(out), n, c, h, w, k, k, stride, pad, dil, kp, stream_ptr())
+    out = torch.empty(n, oh, ow, _mul() * kp, dtype=torch.bfloat16, device=x.device)
+    name = "b200cv_im2col_nchw_f32_split" if split_mode() else "b200cv_im2col_nchw_f32"
+    lib().call(name, ptr(x), ptr(out), n, c, h, w, k, k, stride, pad, dil, kp, stream_ptr())
     return out
 
 
@@ -84,10 +159,11 @@ def pack_weights(w: torch.Tensor, transpose: bool) -> torch.Tensor:
     require_cuda(w, "pack_weights")
     o, i, r, s = w.shape
     ipad, opad = pad_channels(i), pad_channels(o)
-    shape = (i, r * s, opad) if transpose else (o, r * s, ipad)
+    m = _mul()
+    shape = (i, r * s, m * opad) if transpose else (o, r * s, m * ipad)
     out = torch.empty(shape, dtype=torch.bfloat16, device=w.device)
-    lib().call("b200cv_pack_weights", ptr(w.detach().contiguous()), ptr(out), o, i, r, s, ipad, opad, int(transpose),
-               stream_ptr())
+    lib().call("b200cv_pack_weights", ptr(w.detach().contiguous()), ptr(out), o, i, r, s, ipad, opad,
+               int(transpose) | (8 if split_mode() else 0), stream_ptr())
     return out
 
 
@@ -100,7 +176,12 @@ def unpack_wgrad(dw_packed: torch.Tensor, out_oihw: torch.Tensor):
 def _conv_args(x, wpk, y, cout, k, stride, pad, dil, y_strides, y_dtype, scale, shift, residual, r_strides, act,
                slope, res_after_act, stats) -> ConvArgs:
     a = ConvArgs()
-    a.N, a.H, a.W, a.Cin = x.shape
+    a.N, a.H, a.W, _ = x.shape
+    a.Cin = channels(x)
+    if split_mode():
+        a.x_lo = a.Cin
+        a.y_lo = y.shape[-1] // split_pieces() if y.dtype == torch.bfloat16 else 0
+        a.r_lo = residual.shape[-1] // split_pieces() if residual is not None else 0
     a.Cout = cout
     a.R = a.S = k
     a.stride, a.pad, a.dil = stride, pad, dil
@@ -112,7 +193,7 @@ def _conv_args(x, wpk, y, cout, k, stride, pad, dil, y_strides, y_dtype, scale, 
         a.r_sn, a.r_sh, a.r_sw, a.r_sc = r_strides
     a.act, a.slope, a.res_after_act = act, slope, int(res_after_act)
     a.stats = ptr(stats)
-    a.stats_parts = stats.shape[0] if stats is not None and stats.dim() == 2 else 1
+    a.stats_parts = stats.shape[0] if stats is not None and stats.dim() == 3 else 1
     return a
 
 
@@ -126,7 +207,8 @@ def conv_fwd(x, wpk, cout, k, stride, pad, dil=1, out=None, out_dtype=torch.bflo
         if nchw_out:
             out = torch.empty(n, cout, oh, ow, dtype=out_dtype, device=x.device)
         else:
-            out = torch.empty(n, oh, ow, out_channels or pad_channels(cout), dtype=out_dtype, device=x.device)
+            m = _mul() if out_dtype == torch.bfloat16 else 1
+            out = torch.empty(n, oh, ow, m * (out_channels or pad_channels(cout)), dtype=out_dtype, device=x.device)
     if nchw_out:
         ys = (out.stride(0), out.stride(2), out.stride(3), out.stride(1))
     else:
@@ -136,7 +218,7 @@ def conv_fwd(x, wpk, cout, k, stride, pad, dil=1, out=None, out_dtype=torch.bflo
         rs = (residual.stride(0), residual.stride(1), residual.stride(2), residual.stride(3))
     a = _conv_args(x, wpk, out, cout, k, stride, pad, dil, ys, DT_F32 if out.dtype == torch.float32 else DT_BF16,
                    scale, shift, residual, rs, act, slope, res_after_act, stats)
-    lib().call("b200cv_conv_fwd", ctypes.byref(a), stream_ptr(), tag=(x.shape[-1], cout, k, stride, n, oh, ow))
+    lib().call("b200cv_conv_fwd", ctypes.byref(a), stream_ptr(), tag=(channels(x), cout, k, stride, n, oh, ow))
     return out
 
 
@@ -148,7 +230,7 @@ def conv_dgrad(dy, wpk_t, cin_fwd, k, stride, pad, dil, out_hw, out=None, residu
     h, w = out_hw
     if out is None:
         cpad = pad_channels(cin_fwd)
-        out = torch.empty(n, h, w, cpad, dtype=torch.bfloat16, device=dy.device)
+        out = torch.empty(n, h, w, _mul() * cpad, dtype=torch.bfloat16, device=dy.device)
         if cpad != cin_fwd:
             out.zero_()
     ys = (out.stride(0), out.stride(1), out.stride(2), out.stride(3))
@@ -164,16 +246,19 @@ def conv_dgrad(dy, wpk_t, cin_fwd, k, stride, pad, dil, out_hw, out=None, residu
         a.bn_scale, a.bn_shift, a.bn_mean, a.bn_rstd = ptr(bsc), ptr(bsh), ptr(bmean), ptr(brstd)
         a.bn_act, a.bn_slope = bact, float(bslope)
     lib().call("b200cv_conv_dgrad", ctypes.byref(a), h, w, stream_ptr(),
-               tag=(cin_fwd, dy.shape[-1], k, stride, n, dy.shape[1], dy.shape[2]))
+               tag=(cin_fwd, channels(dy), k, stride, n, dy.shape[1], dy.shape[2]))
     return out
 
 
 def conv_wgrad(x, dy, cout, k, stride, pad, dil=1, out=None) -> torch.Tensor:
     """Accumulates into (and returns) the packed fp32 gradient [Cout][k*k][Cin_pad]; `out` must be zeroed."""
-    n, h, w, cin = x.shape
+    n, h, w, _ = x.shape
+    cin = channels(x)
     dwp = out if out is not None else torch.zeros(cout, k * k, cin, dtype=torch.float32, device=x.device)
+    sp = split_mode()
     lib().call("b200cv_conv_wgrad", ptr(x), ptr(dy), ptr(dwp), n, h, w, cin, cout, dy.shape[-1], k, k, stride, pad, dil,
-               stream_ptr(), tag=(cin, cout, k, stride, n, dy.shape[1], dy.shape[2]))
+               cin if sp else 0, dy.shape[-1] // split_pieces() if sp else 0, stream_ptr(),
+               tag=(cin, cout, k, stride, n, dy.shape[1], dy.shape[2]))
     return dwp
 
 
@@ -182,27 +267,50 @@ def sm_count(device=None) -> int:
     return torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device()).multi_processor_count
 
 
-STAT_PARTS = 8  # rows of a partial-statistics matrix: CTA / block b adds into row b % STAT_PARTS
+# rows of a partial-statistics matrix: CTA / block b adds into row b % STAT_PARTS (spreads the atomics)
+STAT_PARTS = int(__import__("os").environ.get("B200CV_STAT_PARTS", "2"))
+STAT_WORDS = 2  # int64 words of one entry (b200cv_stat: value = w1 * 2^-20 + w2 * 2^-70)
 
 
 def stats_buffer(cout: int, device) -> torch.Tensor:
-    """Zeroed [STAT_PARTS][2*Cout] partial-statistics matrix for conv_fwd(stats=...) / bn_bwd_reduce(partials=...):
-    the kernels ADD into it (a few CTAs per row, once per CTA lifetime), the finalize kernels sum the rows."""
-    return torch.zeros(STAT_PARTS, 2 * cout, dtype=torch.float32, device=device)
+    """Zeroed [STAT_PARTS][2*Cout] matrix of b200cv_stat entries (int64 pairs) for conv_fwd(stats=...) /
+    bn_bwd_reduce(partials=...): the kernels ADD into it with integer atomics (order-independent, hence
+    bit-reproducible), the finalize kernels sum the rows."""
+    return torch.zeros(STAT_PARTS, 2 * cout, STAT_WORDS, dtype=torch.int64, device=device)
+
+
+def stats_encode(values: torch.Tensor) -> torch.Tensor:
+    """[1][n] statistics matrix holding the given totals (tests: feed bn_finalize without a conv)."""
+    v = values.detach().double().flatten()
+    w1 = torch.trunc(v * 2.0 ** 20)
+    w2 = torch.round((v - w1 * 2.0 ** -20) * 2.0 ** 70)
+    return torch.stack([w1, w2], -1).to(torch.int64).unsqueeze(0).contiguous()
+
+
+def stats_value(stats: torch.Tensor) -> torch.Tensor:
+    """[2*Cout] fp64 totals of a statistics matrix (tests / diagnostics)."""
+    s = stats.reshape(-1, stats.shape[-2], STAT_WORDS).sum(0).double()
+    return s[:, 0] * 2.0 ** -20 + s[:, 1] * 2.0 ** -70
 
 
 def bn_finalize(stats, count, gamma, beta, conv_bias, eps, momentum, running_mean, running_var, scale, shift, mean,
                 rstd):
-    parts = stats.shape[0] if stats.dim() == 2 else 1
+    parts = stats.shape[0] if stats.dim() == 3 else 1
     lib().call("b200cv_bn_finalize", ptr(stats), parts, int(count), ptr(gamma), ptr(beta), ptr(conv_bias), float(eps),
                float(momentum), ptr(running_mean), ptr(running_var), ptr(scale), ptr(shift), ptr(mean), ptr(rstd),
                gamma.numel(), stream_ptr())
 
 
 def bn_apply_act(y, scale, shift, act, slope, out=None, y2=None, scale2=None, shift2=None, post=None):
-    c = y.shape[-1]
+    c = channels(y)
     if out is None:
         out = torch.empty_like(y)
+    if split_mode():
+        lib().call("b200cv_split_bn_apply_act", ptr(y), y.stride(-2), ptr(scale), ptr(shift), ptr(y2),
+                   0 if y2 is None else y2.stride(-2), ptr(scale2), ptr(shift2), ptr(post),
+                   0 if post is None else post.stride(-2), ptr(out), out.stride(-2), _rows(y), c, c, act, float(slope),
+                   stream_ptr(), tag=(_rows(y), c))
+        return out
     lib().call("b200cv_bn_apply_act", ptr(y), y.stride(-2), ptr(scale), ptr(shift), ptr(y2),
                0 if y2 is None else y2.stride(-2), ptr(scale2), ptr(shift2), ptr(post),
                0 if post is None else post.stride(-2), ptr(out), out.stride(-2), _rows(y), c, act, float(slope),
@@ -213,10 +321,14 @@ def bn_apply_act(y, scale, shift, act, slope, out=None, y2=None, scale2=None, sh
 def bn_stats_apply_act(stats, count, gamma, beta, conv_bias, eps, momentum, running_mean, running_var, scale, shift,
                        mean, rstd, y, act, slope, out=None, post=None):
     """bn_finalize + bn_apply_act in ONE launch (every block folds the partial statistics itself)."""
+    if split_mode():  # fp32-parity mode: the two un-fused launches
+        bn_finalize(stats, count, gamma, beta, conv_bias, eps, momentum, running_mean, running_var, scale, shift, mean,
+                    rstd)
+        return bn_apply_act(y, scale, shift, act, slope, out=out, post=post)
     c = y.shape[-1]
     if out is None:
         out = torch.empty_like(y)
-    parts = stats.shape[0] if stats.dim() == 2 else 1
+    parts = stats.shape[0] if stats.dim() == 3 else 1
     lib().call("b200cv_bn_stats_apply_act", ptr(stats), parts, int(count), ptr(gamma), ptr(beta), ptr(conv_bias),
                float(eps), float(momentum), ptr(running_mean), ptr(running_var), ptr(scale), ptr(shift), ptr(mean),
                ptr(rstd), ptr(y), y.stride(-2), ptr(post), 0 if post is None else post.stride(-2), ptr(out),
@@ -227,6 +339,9 @@ def bn_stats_apply_act(stats, count, gamma, beta, conv_bias, eps, momentum, runn
 def bn_bwd_stats_apply(partials, count, gamma, coef, dgamma, dbeta, da, y, scale, shift, mean, rstd, act, slope,
                        out=None):
     """bn_bwd_finalize + bn_bwd_apply in ONE launch."""
+    if split_mode():  # fp32-parity mode: the two un-fused launches
+        bn_bwd_finalize(partials, gamma, rstd, count, coef, dgamma, dbeta)
+        return bn_bwd_apply(da, y, None, scale, shift, mean, rstd, coef, act, slope, out=out)
     if out is None:
         out = torch.empty_like(y)
     lib().call("b200cv_bn_bwd_stats_apply", ptr(partials), partials.shape[0], int(count), ptr(gamma), ptr(coef),
@@ -238,9 +353,14 @@ def bn_bwd_stats_apply(partials, count, gamma, coef, dgamma, dbeta, da, y, scale
 
 def bn_bwd_reduce(da, y, aout, scale, shift, mean, rstd, act, slope, partials=None):
     """Adds the per-block sums into `partials` ([nparts][2C], zeroed by the caller; allocated if None)."""
-    rows, c = _rows(y), y.shape[-1]
+    rows, c = _rows(y), channels(y)
     if partials is None:
         partials = stats_buffer(c, y.device)
+    if split_mode():
+        lib().call("b200cv_split_bn_bwd_reduce", ptr(da), da.stride(-2), ptr(y), y.stride(-2), ptr(aout),
+                   0 if aout is None else aout.stride(-2), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), ptr(partials),
+                   partials.shape[0], rows, c, c, act, float(slope), stream_ptr(), tag=(rows, c))
+        return partials
     lib().call("b200cv_bn_bwd_reduce", ptr(da), da.stride(-2), ptr(y), y.stride(-2), ptr(aout),
                0 if aout is None else aout.stride(-2), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), ptr(partials),
                partials.shape[0], rows, c, act, float(slope), stream_ptr(), tag=(rows, c))
@@ -255,6 +375,12 @@ def bn_bwd_finalize(partials, gamma, rstd, count, coef, dgamma, dbeta):
 def bn_bwd_apply(da, y, aout, scale, shift, mean, rstd, coef, act, slope, out=None):
     if out is None:
         out = torch.empty_like(y)
+    if split_mode():
+        c = channels(y)
+        lib().call("b200cv_split_bn_bwd_apply", ptr(da), da.stride(-2), ptr(y), y.stride(-2), ptr(aout),
+                   0 if aout is None else aout.stride(-2), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), ptr(coef),
+                   ptr(out), out.stride(-2), _rows(y), c, c, act, float(slope), stream_ptr(), tag=(_rows(y), c))
+        return out
     lib().call("b200cv_bn_bwd_apply", ptr(da), da.stride(-2), ptr(y), y.stride(-2), ptr(aout),
                0 if aout is None else aout.stride(-2), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), ptr(coef),
                ptr(out), out.stride(-2), _rows(y), y.shape[-1], act, float(slope), stream_ptr(),
@@ -265,8 +391,12 @@ def bn_bwd_apply(da, y, aout, scale, shift, mean, rstd, coef, act, slope, out=No
 def bn_bwd_reduce2(da, aout, y_a, y_b, mean_a, rstd_a, mean_b, rstd_b, act, slope):
     """BN-backward sums of two BatchNorms that meet in one activation (out = act(bn_a(y_a) + bn_b(y_b))): one pass
     over da / aout for both.  Returns the two zero-initialised-and-filled partial matrices."""
-    rows, c = _rows(y_a), y_a.shape[-1]
+    rows, c = _rows(y_a), channels(y_a)
     pa, pb = stats_buffer(c, y_a.device), stats_buffer(c, y_a.device)
+    if split_mode():  # one pass per layer, the ReLU mask taken from the saved output
+        bn_bwd_reduce(da, y_a, aout, None, None, mean_a, rstd_a, act, slope, partials=pa)
+        bn_bwd_reduce(da, y_b, aout, None, None, mean_b, rstd_b, act, slope, partials=pb)
+        return pa, pb
     lib().call("b200cv_bn_bwd_reduce2", ptr(da), da.stride(-2), ptr(aout), aout.stride(-2), ptr(y_a), y_a.stride(-2),
                ptr(y_b), y_b.stride(-2), ptr(mean_a), ptr(rstd_a), ptr(mean_b), ptr(rstd_b), ptr(pa), ptr(pb),
                pa.shape[0], rows, c, act, float(slope), stream_ptr(), tag=(rows, c))
@@ -275,6 +405,9 @@ def bn_bwd_reduce2(da, aout, y_a, y_b, mean_a, rstd_a, mean_b, rstd_b, act, slop
 
 def bn_bwd_apply2(da, aout, y_a, y_b, mean_a, rstd_a, mean_b, rstd_b, coef_a, coef_b, act, slope):
     """dy of both layers of bn_bwd_reduce2 in one pass.  Returns (dy_a, dy_b)."""
+    if split_mode():
+        return (bn_bwd_apply(da, y_a, aout, None, None, mean_a, rstd_a, coef_a, act, slope),
+                bn_bwd_apply(da, y_b, aout, None, None, mean_b, rstd_b, coef_b, act, slope))
     dy_a, dy_b = torch.empty_like(y_a), torch.empty_like(y_b)
     lib().call("b200cv_bn_bwd_apply2", ptr(da), da.stride(-2), ptr(aout), aout.stride(-2), ptr(y_a), y_a.stride(-2),
                ptr(y_b), y_b.stride(-2), ptr(mean_a), ptr(rstd_a), ptr(mean_b), ptr(rstd_b), ptr(coef_a), ptr(coef_b),
@@ -285,16 +418,52 @@ def bn_bwd_apply2(da, aout, y_a, y_b, mean_a, rstd_a, mean_b, rstd_b, coef_a, co
 
 def act_bwd(da, aout, act, slope):
     out = torch.empty_like(aout)
+    if split_mode():
+        c = channels(aout)
+        lib().call("b200cv_split_act_bwd", ptr(da), da.stride(-2), ptr(aout), aout.stride(-2), ptr(out), out.stride(-2),
+                   _rows(aout), c, c, act, float(slope), stream_ptr())
+        return out
     lib().call("b200cv_act_bwd", ptr(da), da.stride(-2), ptr(aout), aout.stride(-2), ptr(out), out.stride(-2),
                _rows(aout), aout.shape[-1], act, float(slope), stream_ptr())
     return out
 
 
-def copy_slice(src, dst, accumulate=False):
-    """dst[..., :C] (=|+=) src[..., :C] for NHWC views with unit channel stride."""
+def copy_slice(src, dst, accumulate=False, c=None, src_lo=None, dst_lo=None):
+    """dst[..., :C] (=|+=) src[..., :C] for NHWC views with unit channel stride.  Split mode: whole tensors by
+    default (lo = half the width); channel slices of wider buffers pass their hi views plus c / src_lo / dst_lo."""
+    if split_mode():
+        c = c if c is not None else src.shape[-1] // split_pieces()
+        src_lo = src_lo if src_lo is not None else src.shape[-1] // split_pieces()
+        dst_lo = dst_lo if dst_lo is not None else dst.shape[-1] // split_pieces()
+        lib().call("b200cv_split_copy_slice", ptr(src), src.stride(-2), src_lo, ptr(dst), dst.stride(-2), dst_lo,
+                   _rows(src), c, int(accumulate), stream_ptr(), tag=(_rows(src), c))
+        return dst
     lib().call("b200cv_copy_slice", ptr(src), src.stride(-2), ptr(dst), dst.stride(-2), _rows(src), src.shape[-1],
                int(accumulate), stream_ptr(), tag=(_rows(src), src.shape[-1]))
     return dst
+
+
+def concat_channels(parts):
+    """torch.cat(parts, dim=channel) of NHWC activations (route layers, CVC-YOLOv3/models.py:322-324)."""
+    b, hh, ww = parts[0].shape[:3]
+    widths = [channels(p) for p in parts]
+    total = sum(widths)
+    out = torch.empty(b, hh, ww, _mul() * total, dtype=parts[0].dtype, device=parts[0].device)
+    c0 = 0
+    for p, c in zip(parts, widths):
+        copy_slice(p, out[..., c0:c0 + c], c=c, dst_lo=total)
+        c0 += c
+    return out
+
+
+def slice_grad(g, c0, c, into=None):
+    """Channels [c0, c0+c) of the gradient of a concat buffer, as a tensor of its own (or accumulated into `into`)."""
+    total = channels(g)
+    sl = g[..., c0:c0 + c]
+    if into is None:
+        dst = torch.empty(*g.shape[:3], _mul() * c, dtype=g.dtype, device=g.device)
+        return copy_slice(sl, dst, c=c, src_lo=total)
+    return copy_slice(sl, into, accumulate=True, c=c, src_lo=total)
 
 
 def col_sum(x, out):
@@ -302,10 +471,23 @@ def col_sum(x, out):
     return out
 
 
+def bias_grad(dy, cout):
+    """fp32 [cout] column sums of a gradient tensor (conv bias gradient)."""
+    tmp = torch.zeros(dy.shape[-1], dtype=torch.float32, device=dy.device)
+    col_sum(dy, tmp)  # split mode: the pieces are summed as separate columns ...
+    if split_mode():
+        w = dy.shape[-1] // split_pieces()
+        return tmp.view(split_pieces(), w)[:, :cout].sum(0)  # ... and added here
+    return tmp[:cout]
+
+
 def maxpool_fwd(x, stride):
     n, h, w, c = x.shape
     oh, ow = (h // 2, w // 2) if stride == 2 else (h, w)
     y = torch.empty(n, oh, ow, c, dtype=x.dtype, device=x.device)
+    if split_mode():
+        lib().call("b200cv_split_maxpool2x2_fwd", ptr(x), ptr(y), n, h, w, c // split_pieces(), stride, stream_ptr())
+        return y
     lib().call("b200cv_maxpool2x2_fwd", ptr(x), ptr(y), n, h, w, c, stride, stream_ptr())
     return y
 
@@ -313,6 +495,10 @@ def maxpool_fwd(x, stride):
 def maxpool_bwd(x, dy, stride):
     n, h, w, c = x.shape
     dx = torch.empty_like(x)
+    if split_mode():
+        lib().call("b200cv_split_maxpool2x2_bwd", ptr(x), ptr(dy), ptr(dx), n, h, w, c // split_pieces(), stride,
+                   stream_ptr())
+        return dx
     lib().call("b200cv_maxpool2x2_bwd", ptr(x), ptr(dy), ptr(dx), n, h, w, c, stride, stream_ptr())
     return dx
 
@@ -329,6 +515,10 @@ def upsample_bwd(dy, dx=None, accumulate=False):
     n, oh, ow, c = dy.shape
     if dx is None:
         dx = torch.empty(n, oh // 2, ow // 2, c, dtype=dy.dtype, device=dy.device)
+    if split_mode():
+        lib().call("b200cv_split_upsample2x_bwd", ptr(dy), ptr(dx), n, oh // 2, ow // 2, c // split_pieces(), int(accumulate),
+                   stream_ptr())
+        return dx
     lib().call("b200cv_upsample2x_bwd", ptr(dy), dy.stride(-2), ptr(dx), n, oh // 2, ow // 2, c, int(accumulate),
                stream_ptr())
     return dx

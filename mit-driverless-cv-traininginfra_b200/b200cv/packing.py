@@ -37,18 +37,21 @@ class GradArena:
 
 
 class ConvPackSet:
-    def __init__(self, convs, device, grad_arena: GradArena, flat=()):
+    def __init__(self, convs, device, grad_arena: GradArena, flat=(), split=False):
         """convs: list of (nn.Conv2d, need_transposed_pack); `flat`: convs that use the explicit-im2col
-        layout [O][1][Kp] (k = tap*I + i) instead of [O][taps][Ipad]."""
+        layout [O][1][Kp] (k = tap*I + i) instead of [O][taps][Ipad]; `split`: fp32-parity packs, every innermost
+        channel run stored as [hi | lo] (the fp32 gradient layout is the same in both modes)."""
         self.convs = [c for c, _ in convs]
         self.device = device
         self._flat = {id(c) for c in flat}
+        self.split = bool(split)
+        m = int(lib().cdll.b200cv_split_pieces()) if split else 1
         fwd_sizes, t_sizes, g_sizes = [], [], []
         for conv, need_t in convs:
             o, i, r, s = conv.weight.shape
             n_fwd = o * flat_k(i, r) if id(conv) in self._flat else o * r * s * pad_channels(i)
-            fwd_sizes.append(n_fwd)
-            t_sizes.append(i * r * s * pad_channels(o) if need_t else 0)
+            fwd_sizes.append(m * n_fwd)
+            t_sizes.append(m * i * r * s * pad_channels(o) if need_t else 0)
             g_sizes.append(n_fwd)
         al = lambda n: (n + 127) // 128 * 128  # keep every view 256-byte aligned
         self._wpk = torch.empty(sum(al(n) for n in fwd_sizes), dtype=torch.bfloat16, device=device)
@@ -59,10 +62,10 @@ class ConvPackSet:
         for (conv, need_t), nf, nt, ng in zip(convs, fwd_sizes, t_sizes, g_sizes):
             o, i, r, s = conv.weight.shape
             shape = (o, 1, flat_k(i, r)) if id(conv) in self._flat else (o, r * s, pad_channels(i))
-            self.wpk[id(conv)] = self._wpk[of:of + nf].view(shape)
+            self.wpk[id(conv)] = self._wpk[of:of + nf].view(shape[0], shape[1], m * shape[2])
             of += al(nf)
             if need_t:
-                self.wpk_t[id(conv)] = self._wpk_t[ot:ot + nt].view(i, r * s, pad_channels(o))
+                self.wpk_t[id(conv)] = self._wpk_t[ot:ot + nt].view(i, r * s, m * pad_channels(o))
                 ot += al(nt)
             else:
                 self.wpk_t[id(conv)] = None
@@ -95,13 +98,14 @@ class ConvPackSet:
         for conv, need_t in zip(self.convs, self._need_t):
             o, i, r, s = conv.weight.shape
             fl = id(conv) in self._flat
+            sp = 8 if self.split else 0  # b200cv_pack_entry.transpose | 8 = split pack
             e = (conv.weight.data_ptr(), self.wpk[id(conv)].data_ptr(), o, i, r * s,
-                 flat_k(i, r) if fl else pad_channels(i), pad_channels(o), 2 if fl else 0)
+                 flat_k(i, r) if fl else pad_channels(i), pad_channels(o), (2 if fl else 0) | sp)
             fwd.append(e)
             both.append(e)
             if need_t:
                 both.append((conv.weight.data_ptr(), self.wpk_t[id(conv)].data_ptr(), o, i, r * s, pad_channels(i),
-                             pad_channels(o), 1))
+                             pad_channels(o), 1 | sp))
         self._pack_table_fwd, self._n_fwd = self._to_device(fwd), len(fwd)
         self._pack_table, self._n_pack = self._to_device(both), len(both)
 

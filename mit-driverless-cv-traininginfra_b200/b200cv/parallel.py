@@ -39,6 +39,58 @@ def init_from_env(backend: str | None = None) -> int:
     return local
 
 
+# ---- unchanged single-GPU scripts under torchrun ("DataParallel-equivalent" mode) ------------------------------
+# CVC-YOLOv3/train.py:193-196 wraps the model in nn.DataParallel whenever torch.cuda.device_count() > 1 and always
+# uses device "cuda:0".  With B200CV_AUTO_DP=1 under torchrun every process is bound to ITS GPU before CUDA starts
+# (CUDA_VISIBLE_DEVICES = the LOCAL_RANK-th visible device), so the script sees one GPU, does not wrap, and
+# models.Darknet.forward takes this rank's DataParallel shard of the batch; gradients are summed over NCCL.
+def auto_dp_enabled() -> bool:
+    return os.environ.get("B200CV_AUTO_DP", "0") != "0" and int(os.environ.get("WORLD_SIZE", "1")) > 1
+
+
+def bind_process_to_local_gpu() -> None:
+    """Called when models / keypoint_net are imported.  No-op unless auto_dp_enabled()."""
+    if not auto_dp_enabled() or os.environ.get("B200CV_AUTO_DP_BOUND"):
+        return
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if torch.cuda.is_initialized():  # too late to mask devices: select ours instead
+        torch.cuda.set_device(local)
+        return
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    ids = [v for v in vis.split(",") if v] if vis else None
+    if ids is not None and local >= len(ids):
+        raise RuntimeError(f"B200CV_AUTO_DP: LOCAL_RANK={local} but CUDA_VISIBLE_DEVICES={vis!r}")
+    os.environ["CUDA_VISIBLE_DEVICES"] = ids[local] if ids is not None else str(local)
+    os.environ["B200CV_AUTO_DP_BOUND"] = "1"  # DataLoader workers inherit the environment: bind once
+
+
+def ensure_group() -> None:
+    if auto_dp_enabled() and not dist.is_initialized():
+        os.environ.setdefault("NCCL_P2P_LEVEL", "NVL")
+        os.environ.setdefault("NCCL_IB_DISABLE", "1")
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="nccl" if torch.cuda.is_available() else "gloo")
+
+
+def dp_chunk(n: int, r: int | None = None, w: int | None = None):
+    """[start, stop) of the chunk nn.DataParallel's scatter (torch.chunk along the batch: ceil(n / w) per replica,
+    trailing replicas may get less or nothing) hands replica r of w."""
+    r = rank() if r is None else r
+    w = world_size() if w is None else w
+    size = -(-n // w)
+    return min(n, r * size), min(n, (r + 1) * size)
+
+
+def sum_over_replicas(local: torch.Tensor) -> torch.Tensor:
+    """Value = sum over ranks (what nn.DataParallel's gather + `losses[0].sum()` give, train.py:70), gradient = this
+    rank's own (its shard is the only part of the sum this process computed)."""
+    if world_size() <= 1:
+        return local
+    tot = local.detach().clone()
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    return local + (tot - local.detach())
+
+
 def allreduce_gradients(arena: torch.Tensor) -> None:
     """SUM the flat gradient arena over all ranks (no-op for a single process)."""
     if world_size() > 1:

@@ -118,9 +118,22 @@ class RektNetEngine:
         for r in (model.res1, model.res2, model.res3, model.res4):
             self.blocks.append((_ConvBN(r.conv1, r.bn1), _ConvBN(r.conv2, r.bn2), _ConvBN(r.shortcut_conv, r.shortcut_bn)))
         self.params = list(model.parameters())
+        self.split = ops.default_split()  # "fp32" parity mode (split bf16x3 operands), see ops.py
         self._lin = None
         self._arena = None
         self._packs = None
+
+    @property
+    def precision(self) -> str:
+        return "fp32" if self.split else "bf16"
+
+    def set_precision(self, name: str):
+        if name not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        if (name == "fp32") != self.split:
+            self.split = name == "fp32"
+            self._arena = self._packs = None
+        return self
 
     def _conv_list(self):
         convs = [(self.stem.conv, False)]
@@ -132,7 +145,7 @@ class RektNetEngine:
     def _setup(self, dev):
         if self._arena is None or self._arena.flat.device != dev:
             self._arena = GradArena(self.params, dev)
-            self._packs = ConvPackSet(self._conv_list(), dev, self._arena, flat=[self.stem.conv])
+            self._packs = ConvPackSet(self._conv_list(), dev, self._arena, flat=[self.stem.conv], split=self.split)
             for c in self._all():
                 c.wpk, c.wpk_t = self._packs.wpk[id(c.conv)], self._packs.wpk_t[id(c.conv)]
 
@@ -150,6 +163,14 @@ class RektNetEngine:
 
     # ------------------------------------------------------------------ forward
     def _forward(self, x, train: bool, want_grad: bool):
+        with ops.precision(self.split):
+            return self._forward_impl(x, train, want_grad)
+
+    def _backward(self, saved, hm, pts, d_hm, d_pts, handle: Optional["_HeadHandle"], logits_grad=None):
+        with ops.precision(self.split):
+            return self._backward_impl(saved, hm, pts, d_hm, d_pts, handle, logits_grad)
+
+    def _forward_impl(self, x, train: bool, want_grad: bool):
         m = self.model
         dev = x.device
         self._setup(dev)
@@ -171,9 +192,6 @@ class RektNetEngine:
                 saved["blocks"].append((a, y1, a1, y2, ys, out))
                 a = out
         else:
-            if want_grad:
-                raise RuntimeError("KeypointNet: backward through eval-mode BatchNorm is not supported; call "
-                                   "model.train() or wrap the pass in torch.no_grad()")
             sc, sh = self.stem.eval_affine()
             a = ops.conv_fwd(xin, self.stem.wpk, self.stem.cout, 1, 1, 0, scale=sc, shift=sh, act=ops.ACT_RELU)
             for c1, c2, cs in self.blocks:
@@ -198,13 +216,13 @@ class RektNetEngine:
         return hm, pts
 
     # ------------------------------------------------------------------ backward
-    def _backward(self, saved, hm, pts, d_hm, d_pts, handle: Optional[_HeadHandle], logits_grad=None):
+    def _backward_impl(self, saved, hm, pts, d_hm, d_pts, handle: Optional[_HeadHandle], logits_grad=None):
         m = self.model
         dev = hm.device if hm is not None else logits_grad.device
         arena = self._arena
         if arena.aliased_by_param_grads():
             arena = GradArena(self.params, dev)
-            packs = ConvPackSet(self._conv_list(), dev, arena, flat=[self.stem.conv])
+            packs = ConvPackSet(self._conv_list(), dev, arena, flat=[self.stem.conv], split=self.split)
         else:
             packs = self._packs
         packs.zero_grads()
@@ -216,25 +234,24 @@ class RektNetEngine:
             dl = ops.nchw_to_nhwc(logits_grad, 16)
         else:
             vx, vy = self._coords(dev, h, w)
-            dl = torch.empty(b, h, w, 16, dtype=torch.bfloat16, device=dev)
+            dl_ld = 16 * ops.split_pieces() if self.split else 16
+            dl = torch.empty(b, h, w, dl_ld, dtype=torch.bfloat16, device=dev)
             p = handle.pending if handle is not None else None
             if p is not None:
                 handle.pending = None
                 lib().call("b200cv_kpt_head_bwd", ptr(hm), ptr(p["thm"]), ptr(pts), ptr(p["tpts"]), ptr(p["ubar"]),
                            ptr(vx), ptr(vy), ptr(p["g_loc"]), ptr(p["g_geo"]), ptr(d_hm), ptr(d_pts), b, k, h, w,
                            p["loss_type"], int(p["include_geo"]), float(p["gamma_h"]), float(p["gamma_v"]), ptr(dl),
-                           16, stream_ptr())
+                           dl_ld, stream_ptr())
             else:
                 zeros = torch.zeros(b, k, 2, dtype=torch.float32, device=dev)
                 lib().call("b200cv_kpt_head_bwd", ptr(hm), None, ptr(pts), ptr(zeros), None, ptr(vx), ptr(vy), None,
-                           None, ptr(d_hm), ptr(d_pts), b, k, h, w, 0, 0, 0.0, 0.0, ptr(dl), 16, stream_ptr())
+                           None, ptr(d_hm), ptr(d_pts), b, k, h, w, 0, 0, 0.0, 0.0, ptr(dl), dl_ld, stream_ptr())
         # head conv (bias, linear)
-        tmp = torch.zeros(16, dtype=torch.float32, device=dev)
-        ops.col_sum(dl, tmp)
-        gview[id(m.out.bias)].copy_(tmp[:k])
+        gview[id(m.out.bias)].copy_(ops.bias_grad(dl, k))
         ops.conv_wgrad(a_last, dl, k, 1, 1, 0, out=packs.dwp[id(m.out)])
         g = ops.conv_dgrad(dl, saved["out_wpk_t"], m.out.in_channels, 1, 1, 0, 1, (h, w))
-        fuse = os.environ.get("B200CV_FUSE_BN_REDUCE", "2") != "0"
+        fuse = os.environ.get("B200CV_FUSE_BN_REDUCE", "2") != "0" and not self.split
         stem_parts = None
         for bi, ((c1, c2, cs), (a_in, y1, a1, y2, ys, out)) in enumerate(
                 zip(reversed(self.blocks), reversed(saved["blocks"]))):
@@ -272,10 +289,11 @@ class RektNetEngine:
     def run(self, x):
         require_cuda(x, "KeypointNet.forward")
         m = self.model
-        if m.onnx_mode:
-            return _KeypointLogitsFn.apply(self, x.float(), m.training, torch.is_grad_enabled(), *self.params)
-        handle = _HeadHandle()
-        hm, pts = _KeypointNetFn.apply(self, x.float(), m.training, handle, torch.is_grad_enabled(), *self.params)
+        with torch.cuda.device(x.device):  # launches go to the tensors' device, whatever the current one is
+            if m.onnx_mode:
+                return _KeypointLogitsFn.apply(self, x.float(), m.training, torch.is_grad_enabled(), *self.params)
+            handle = _HeadHandle()
+            hm, pts = _KeypointNetFn.apply(self, x.float(), m.training, handle, torch.is_grad_enabled(), *self.params)
         hm._b200cv_head = handle
         pts._b200cv_head = handle
         return hm, pts
@@ -284,9 +302,14 @@ class RektNetEngine:
 class _KeypointNetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine, x, train, handle, grad_enabled, *params):
-        want_grad = grad_enabled and any(ctx.needs_input_grad[5:])
+        # eval-mode BatchNorm (folded running statistics) has no backward here: such a pass is computed like the
+        # reference computes it (RektNet/detect.py:38-39 calls it without no_grad) and returned as a constant
+        want_grad = grad_enabled and train and any(ctx.needs_input_grad[5:])
         logits, saved = engine._forward(x, train, want_grad)
         hm, pts = engine._softmax(logits)
+        if not want_grad:
+            ctx.mark_non_differentiable(hm, pts)
+            return hm, pts
         ctx.engine, ctx.saved, ctx.handle = engine, saved, handle
         ctx.save_for_backward(hm, pts)
         return hm, pts
@@ -296,7 +319,8 @@ class _KeypointNetFn(torch.autograd.Function):
         hm, pts = ctx.saved_tensors
         d_hm = d_hm.contiguous().float() if d_hm is not None else None
         d_pts = d_pts.contiguous().float() if d_pts is not None else None
-        views = ctx.engine._backward(ctx.saved, hm, pts, d_hm, d_pts, ctx.handle)
+        with torch.cuda.device(hm.device):
+            views = ctx.engine._backward(ctx.saved, hm, pts, d_hm, d_pts, ctx.handle)
         ctx.saved = None
         return (None, None, None, None, None, *views)
 
@@ -306,16 +330,119 @@ class _KeypointLogitsFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, engine, x, train, grad_enabled, *params):
-        want_grad = grad_enabled and any(ctx.needs_input_grad[4:])
+        want_grad = grad_enabled and train and any(ctx.needs_input_grad[4:])
         logits, saved = engine._forward(x, train, want_grad)
+        if not want_grad:
+            ctx.mark_non_differentiable(logits)
+            return logits
         ctx.engine, ctx.saved = engine, saved
         return logits
 
     @staticmethod
     def backward(ctx, d_logits):
-        views = ctx.engine._backward(ctx.saved, None, None, None, None, None, logits_grad=d_logits.contiguous().float())
+        with torch.cuda.device(d_logits.device):
+            views = ctx.engine._backward(ctx.saved, None, None, None, None, None,
+                                         logits_grad=d_logits.contiguous().float())
         ctx.saved = None
         return (None, None, None, None, *views)
+
+
+class ResBlockEngine:
+    """A single ``resnet.ResNet`` block called on its own (RektNet/resnet.py:22-27): NCHW fp32 in, NCHW fp32 out,
+    gradients for the block's parameters AND its input.  Same kernels and the same per-layer objects as inside
+    RektNetEngine; the block boundary costs one layout conversion each way."""
+
+    def __init__(self, block):
+        self.block = block
+        self.c1 = _ConvBN(block.conv1, block.bn1)
+        self.c2 = _ConvBN(block.conv2, block.bn2)
+        self.cs = _ConvBN(block.shortcut_conv, block.shortcut_bn)
+        if ops.pad_channels(self.c1.cout) != self.c1.cout:
+            raise ValueError(f"ResNet block with {self.c1.cout} output channels: the B200 layout needs 16, 32 or a "
+                             "multiple of 64 channels in every normalised layer")
+        self.params = list(block.parameters())
+        self.split = ops.default_split()
+        self._arena = None
+        self._packs = None
+
+    def _setup(self, dev):
+        if self._arena is None or self._arena.flat.device != dev:
+            self._arena = GradArena(self.params, dev)
+            convs = [(c.conv, True) for c in (self.c1, self.c2, self.cs)]
+            self._packs = ConvPackSet(convs, dev, self._arena, split=self.split)
+            for c in (self.c1, self.c2, self.cs):
+                c.wpk, c.wpk_t = self._packs.wpk[id(c.conv)], self._packs.wpk_t[id(c.conv)]
+
+    def forward(self, x, train: bool, want_grad: bool):
+        self._setup(x.device)
+        self._packs.pack_all(want_grad)
+        c1, c2, cs = self.c1, self.c2, self.cs
+        a = ops.nchw_to_nhwc(x)
+        if train:
+            y1 = c1.fwd_train(a)
+            a1 = ops.bn_apply_act(y1, c1.scale, c1.shift, ops.ACT_RELU, 0.0)
+            y2 = c2.fwd_train(a1)
+            ys = cs.fwd_train(a)
+            out = ops.bn_apply_act(ys, cs.scale, cs.shift, ops.ACT_RELU, 0.0, y2=y2, scale2=c2.scale, shift2=c2.shift)
+            saved = (a, y1, a1, y2, ys, out)
+        else:
+            sc, sh = c1.eval_affine()
+            a1 = ops.conv_fwd(a, c1.wpk, c1.cout, 3, 1, 2, 2, scale=sc, shift=sh, act=ops.ACT_RELU)
+            sc, sh = cs.eval_affine()
+            t = ops.conv_fwd(a, cs.wpk, cs.cout, 1, 1, 0, scale=sc, shift=sh)
+            sc, sh = c2.eval_affine()
+            out = ops.conv_fwd(a1, c2.wpk, c2.cout, 3, 1, 1, scale=sc, shift=sh, residual=t, act=ops.ACT_RELU)
+            saved = None
+        return ops.nhwc_to_nchw(out, c1.cout), saved
+
+    def backward(self, saved, d_out):
+        a_in, y1, a1, y2, ys, out = saved
+        c1, c2, cs = self.c1, self.c2, self.cs
+        dev = d_out.device
+        arena, packs = self._arena, self._packs
+        if arena.aliased_by_param_grads():
+            arena = GradArena(self.params, dev)
+            packs = ConvPackSet([(c.conv, True) for c in (c1, c2, cs)], dev, arena, split=self.split)
+        packs.zero_grads()
+        gview = arena.view_of
+        g = ops.nchw_to_nhwc(d_out, ops.channels(out))
+        count = ys.numel() // ys.shape[-1]
+        parts_s, parts_2 = ops.bn_bwd_reduce2(g, out, ys, y2, cs.mean, cs.rstd, c2.mean, c2.rstd, ops.ACT_RELU, 0.0)
+        cs.finalize_bwd(parts_s, count, gview)
+        c2.finalize_bwd(parts_2, count, gview)
+        dys, dy2 = ops.bn_bwd_apply2(g, out, ys, y2, cs.mean, cs.rstd, c2.mean, c2.rstd, cs.coef, c2.coef,
+                                     ops.ACT_RELU, 0.0)
+        g_in = cs.finish(a_in, dys, gview, packs)
+        g_a1 = c2.finish(a1, dy2, gview, packs)
+        g_in = c1.bwd(a_in, y1, g_a1, None, ops.ACT_RELU, gview, packs, dx_out=g_in)
+        packs.unpack_all()
+        allreduce_gradients(arena.flat)
+        return ops.nhwc_to_nchw(g_in, c1.cin), arena.views
+
+    def run(self, x):
+        require_cuda(x, "ResNet.forward")
+        with torch.cuda.device(x.device):
+            return _ResBlockFn.apply(self, x.float(), self.block.training, torch.is_grad_enabled(), *self.params)
+
+
+class _ResBlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine, x, train, grad_enabled, *params):
+        want_grad = grad_enabled and train and any(ctx.needs_input_grad[1:])
+        with ops.precision(engine.split):
+            out, saved = engine.forward(x, train, want_grad)
+        if not want_grad:
+            ctx.mark_non_differentiable(out)
+            return out
+        ctx.engine, ctx.saved = engine, saved
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        with torch.cuda.device(d_out.device), ops.precision(ctx.engine.split):
+            dx, views = ctx.engine.backward(ctx.saved, d_out.contiguous().float())
+        ctx.saved = None
+        return (None, dx, None, None, *views)
 
 
 # ---------------------------------------------------------------------------- CrossRatioLoss

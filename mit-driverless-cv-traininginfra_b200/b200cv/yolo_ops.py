@@ -100,6 +100,12 @@ def yolo_head_grad(z, yt: YoloTargets, num_classes, consts, gscale, out_dtype=to
     cell_ld = (5 * yt.A + 3) // 4 * 4
     dcell = torch.empty(npix, cell_ld, dtype=torch.float32, device=z.device)
     yolo_loss_cells(z, False, yt, num_classes, consts, dcell=dcell, gscale=gscale)
+    from . import ops
+
+    if ops.split_mode() and out_dtype == torch.bfloat16:  # fp32-parity mode: fp32 gradient, stored split
+        dl = torch.empty(z.shape, dtype=torch.float32, device=z.device)
+        yolo_expand_dlogits(dcell, dl, yt.A, num_classes)
+        return ops.split_from_f32(dl)
     dl = torch.empty(z.shape, dtype=out_dtype, device=z.device)
     yolo_expand_dlogits(dcell, dl, yt.A, num_classes)
     return dl

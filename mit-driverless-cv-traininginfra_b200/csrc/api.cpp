@@ -110,4 +110,6 @@ int b200cv_check_device_error(void* stream) {
   return 0;
 }
 
+int b200cv_split_pieces(void) { return b200cv::kSplitPieces; }
+
 }  // extern "C"

@@ -6,6 +6,7 @@
 #include <cstdlib>
 
 #include "internal.h"
+#include "stat_acc.cuh"
 
 namespace b200cv {
 
@@ -35,9 +36,39 @@ struct Geometry {
   int OHt, OWt;  // traversal grid (rows of D per image = OHt*OWt)
 };
 
+// fp32-parity mode: every tap becomes six k-passes over the split operands x = x0 + x1 + x2, w = w0 + w1 + w2 (bf16
+// pieces of decreasing magnitude): all products x_i * w_j with i + j <= 2, smallest first; what is dropped
+// (i + j >= 3) is below 2^-24 of the result, fp32's own rounding.  A packed row holds [w0(Cin) | w1(Cin) | w2(Cin)]
+// per tap.
+int expand_split_taps(IgemmParams& p, int cin) {
+  static const int kPassA[6] = {2, 0, 1, 1, 0, 0};
+  static const int kPassW[6] = {0, 2, 1, 0, 1, 0};
+  const int n = p.num_taps;
+  if (6 * n > kMaxTaps) return set_error(B200CV_ERR_ARG, "conv: %d taps do not fit the fp32-parity mode", n);
+  for (int t = n - 1; t >= 0; --t) {
+    const short tw = p.tap_w[t], th = p.tap_h[t];
+    const int k3 = kSplitPieces * p.tap_k[t];
+    for (int ps = 5; ps >= 0; --ps) {
+      const int i = ps * n + t;
+      p.tap_w[i] = tw;
+      p.tap_h[i] = th;
+      p.tap_c[i] = (short)(kPassA[ps] * cin);
+      p.tap_k[i] = k3 + kPassW[ps] * cin;
+    }
+  }
+  p.num_taps = 6 * n;
+  return 0;
+}
+
 int run_igemm(const Geometry& g, const void* act, const void* wpk, int64_t w_rows, int64_t w_cols,
-              IgemmParams& p, cudaStream_t stream, const void* bn_y = nullptr, int64_t bn_y_ld = 0) {
+              IgemmParams& p, cudaStream_t stream, const void* bn_y = nullptr, int64_t bn_y_ld = 0,
+              bool split_in = false) {
   const int kc = kc_for(g.C);
+  if (split_in) {
+    if (int rc = expand_split_taps(p, g.C)) return rc;
+    w_cols *= kSplitPieces;
+  }
+  const int cmul = split_in ? kSplitPieces : 1;  // channels of a stored activation row per logical channel
   p.cblocks = g.C / kc;
   p.OHW = g.OHt * g.OWt;
   p.OW = g.OWt;
@@ -55,8 +86,8 @@ int run_igemm(const Geometry& g, const void* act, const void* wpk, int64_t w_row
     p.dbg = dbg;
   }
   CUtensorMap tmA, tmB;
-  int rc = make_tmap_im2col_bf16(&tmA, act, g.N, g.H, g.W, g.C, g.C, (int64_t)g.W * g.C,
-                                 (int64_t)g.H * g.W * g.C, g.lower_w, g.lower_h, g.upper_w, g.upper_h,
+  int rc = make_tmap_im2col_bf16(&tmA, act, g.N, g.H, g.W, cmul * g.C, cmul * g.C, (int64_t)g.W * cmul * g.C,
+                                 (int64_t)g.H * g.W * cmul * g.C, g.lower_w, g.lower_h, g.upper_w, g.upper_h,
                                  g.trav_w, g.trav_h, kc, 128);
   if (rc) return rc;
   rc = make_tmap_2d_bf16(&tmB, wpk, w_rows, w_cols, w_cols, bn, kc);
@@ -67,7 +98,8 @@ int run_igemm(const Geometry& g, const void* act, const void* wpk, int64_t w_row
   const CUtensorMap* pI = nullptr;
   const CUtensorMap* pR = nullptr;
   static const bool no_res_mma = getenv("B200CV_NO_RES_MMA") != nullptr;
-  if (p.res && !no_res_mma && bn % 64 == 0 && !p.scale && p.act == 0 && p.res_vec_ok && p.r_sc == 1 &&
+  if (p.res && !no_res_mma && !split_in && !p.res_lo && !p.out_lo && bn % 64 == 0 && !p.scale && p.act == 0 &&
+      p.res_vec_ok && p.r_sc == 1 &&
       p.r_sw % 8 == 0 && p.r_sh == (long long)p.OW * p.r_sw && p.r_sn == (long long)p.OHW * p.r_sw) {
     const void* ident = device_identity128();
     if (!ident) return set_error(B200CV_ERR_DEVICE, "igemm: identity matrix allocation failed");
@@ -86,7 +118,8 @@ int run_igemm(const Geometry& g, const void* act, const void* wpk, int64_t w_row
   // stride-1 data gradients); strided (parity scatter, NCHW), fp32 or unaligned outputs take the generic one.
   const long long ld = p.o_sw;
   static const bool no_tma_store = getenv("B200CV_NO_TMA_STORE") != nullptr;
-  const bool tma_out = !no_tma_store && !p.out_fp32 && p.vec_ok && p.o_sc == 1 && ld >= p.Cout && ld % 8 == 0 &&
+  const bool tma_out = !no_tma_store && !p.out_fp32 && !p.out_lo && !p.res_lo && p.vec_ok && p.o_sc == 1 &&
+                       ld >= p.Cout && ld % 8 == 0 &&
                        p.o_sh == (long long)p.OW * ld && p.o_sn == (long long)p.OHW * ld && p.Cout % 8 == 0 &&
                        (!p.res || p.res_vec_ok);
   // 256-row tiles for 128-wide GEMMs (data gradients of the 128-channel 3x3 layers, forward 64->128): the weight
@@ -140,8 +173,10 @@ void fill_epilogue(IgemmParams& p, const b200cv_conv_args* a, int64_t out_off, i
   p.act = a->act;
   p.res_after_act = a->res_after_act;
   p.slope = a->slope;
-  p.stats = a->stats;
+  p.stats = static_cast<StatAcc*>(a->stats);
   p.stats_parts = a->stats_parts > 0 ? a->stats_parts : 1;
+  p.out_lo = a->y_lo;
+  p.res_lo = p.res ? a->r_lo : 0;
 }
 
 int validate_common(const b200cv_conv_args* a) {
@@ -155,6 +190,11 @@ int validate_common(const b200cv_conv_args* a) {
   B200CV_CHECK_ARG(aligned16(a->x) && aligned16(a->w), "conv: x/w must be 16-byte aligned");
   B200CV_CHECK_ARG(a->y_dtype == B200CV_DT_BF16 || a->y_dtype == B200CV_DT_F32, "conv: bad y_dtype");
   B200CV_CHECK_ARG(!a->stats || a->Cout <= 1024, "conv: statistics support at most 1024 output channels");
+  B200CV_CHECK_ARG(a->x_lo == 0 || a->x_lo == a->Cin, "conv: x_lo must be 0 or Cin (whole split tensors)");
+  B200CV_CHECK_ARG(a->y_lo == 0 || (a->y_dtype == B200CV_DT_BF16 && a->y_lo % 8 == 0),
+                   "conv: a split output is bf16 with a 16-byte aligned piece stride");
+  B200CV_CHECK_ARG(a->r_lo == 0 || a->r_lo % 8 == 0, "conv: r_lo must be a multiple of 8");
+  B200CV_CHECK_ARG(!(a->bn_sums && (a->x_lo || a->y_lo)), "conv: no fused BN-backward reduction in the fp32-parity mode");
   return 0;
 }
 
@@ -188,7 +228,7 @@ extern "C" int b200cv_conv_fwd(const b200cv_conv_args* a, void* stream) {
     }
   fill_epilogue(p, a, 0, 0, 1, 1);
   return run_igemm(g, a->x, a->w, a->Cout, (int64_t)a->R * a->S * a->Cin, p,
-                   static_cast<cudaStream_t>(stream));
+                   static_cast<cudaStream_t>(stream), nullptr, 0, a->x_lo != 0);
 }
 
 extern "C" int b200cv_conv_dgrad(const b200cv_conv_args* a, int out_h, int out_w, void* stream) {
@@ -242,7 +282,7 @@ extern "C" int b200cv_conv_dgrad(const b200cv_conv_args* a, int out_h, int out_w
         B200CV_CHECK_ARG(a->bn_y && a->bn_scale && a->bn_shift && a->bn_mean && a->bn_rstd && a->bn_parts > 0 &&
                              a->bn_y_ld % 8 == 0 && aligned16(a->bn_y),
                          "conv_dgrad: incomplete bn_* arguments");
-        p.bn_sums = a->bn_sums;
+        p.bn_sums = static_cast<StatAcc*>(a->bn_sums);
         p.bn_parts = a->bn_parts;
         p.bn_scale = a->bn_scale;
         p.bn_shift = a->bn_shift;
@@ -250,7 +290,8 @@ extern "C" int b200cv_conv_dgrad(const b200cv_conv_args* a, int out_h, int out_w
         p.bn_rstd = a->bn_rstd;
         p.bn_neg = a->bn_act == B200CV_ACT_LEAKY ? a->bn_slope : (a->bn_act == B200CV_ACT_RELU ? 0.f : 1.f);
       }
-      int rc = run_igemm(g, a->x, a->w, a->Cout, (int64_t)a->R * a->S * a->Cin, p, st, a->bn_y, a->bn_y_ld);
+      int rc = run_igemm(g, a->x, a->w, a->Cout, (int64_t)a->R * a->S * a->Cin, p, st, a->bn_y, a->bn_y_ld,
+                         a->x_lo != 0);
       if (rc) return rc;
     }
   }
@@ -297,25 +338,28 @@ __global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ s
   }
 }
 
+__device__ __forceinline__ void put_packed(__nv_bfloat16* dst, long long row, int col, int W, bool split, float v);
+
 __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int O,
                                     int I, int RS, int Ipad, int Opad, int transpose, long long total) {
+  const bool split = (transpose & 8) != 0;
+  transpose &= 7;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     float v = 0.f;
+    const int W = transpose ? Opad : Ipad;
+    const int col = (int)(i % W);
+    const long long r = i / W;
     if (!transpose) {  // dst[o][t][ip]
-      const int ip = (int)(i % Ipad);
-      const long long r = i / Ipad;
       const int t = (int)(r % RS);
       const int o = (int)(r / RS);
-      if (ip < I) v = w[((long long)o * I + ip) * RS + t];
+      if (col < I) v = w[((long long)o * I + col) * RS + t];
     } else {  // dst[i][t][op]
-      const int op = (int)(i % Opad);
-      const long long r = i / Opad;
       const int t = (int)(r % RS);
       const int ii = (int)(r / RS);
-      if (op < O) v = w[((long long)op * I + ii) * RS + t];
+      if (col < O) v = w[((long long)col * I + ii) * RS + t];
     }
-    dst[i] = __float2bfloat16_rn(v);
+    put_packed(dst, r, col, W, split, v);
   }
 }
 
@@ -344,9 +388,26 @@ struct PackEntry {          // mirrors b200cv_pack_entry (include/b200cv.h)
 // gathered with a stride of RS floats and ran at ~1 TB/s).
 constexpr int kPackSmemFloats = 9600;  // 37.5 KB: one [I*RS] row (I*RS <= 9600) or a 32 x (32*RS+1) tile (RS <= 9)
 
+// One packed element: row-major [row][W] bf16, or -- fp32-parity (split) pack -- [row][w0(W) | w1(W) | w2(W)].
+__device__ __forceinline__ void put_packed(__nv_bfloat16* dst, long long row, int col, int W, bool split, float v) {
+  const long long b = row * (split ? kSplitPieces * W : W) + col;
+  if (!split) {
+    dst[b] = __float2bfloat16_rn(v);
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < kSplitPieces; ++j) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    dst[b + j * W] = h;
+    v -= __bfloat162float(h);
+  }
+}
+
 __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackEntry* __restrict__ table) {
   __shared__ float sm[kPackSmemFloats];
-  const PackEntry e = table[blockIdx.y];
+  PackEntry e = table[blockIdx.y];
+  const bool split = (e.transpose & 8) != 0;  // b200cv_pack_entry: transpose | 8 = split pack
+  e.transpose &= 7;
   __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(e.dst);
   const int tid = threadIdx.x, nt = blockDim.x;
   if (e.transpose == 2) {
@@ -357,7 +418,7 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackEntry
       const int o = (int)(i / e.Ipad);
       float v = 0.f;
       if (k < e.RS * e.I) v = e.src[((long long)o * e.I + (k % e.I)) * e.RS + (k / e.I)];
-      dst[i] = __float2bfloat16_rn(v);
+      put_packed(dst, o, k, e.Ipad, split, v);
     }
   } else if (!e.transpose) {
     // dst[o][t][ip] <- src[o][i][t]: one output channel (I*RS contiguous floats) per block iteration
@@ -365,7 +426,6 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackEntry
     const bool staged = row <= kPackSmemFloats;
     for (int o = blockIdx.x; o < e.O; o += gridDim.x) {
       const float* sp = e.src + (long long)o * row;
-      __nv_bfloat16* dp = dst + (long long)o * e.RS * e.Ipad;
       if (staged) {
         for (int j = tid; j < row; j += nt) sm[j] = sp[j];
         __syncthreads();
@@ -374,7 +434,7 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackEntry
         const int t = j / e.Ipad, ip = j - t * e.Ipad;
         float v = 0.f;
         if (ip < e.I) v = staged ? sm[ip * e.RS + t] : sp[ip * e.RS + t];
-        dp[j] = __float2bfloat16_rn(v);
+        put_packed(dst, (long long)o * e.RS + t, ip, e.Ipad, split, v);
       }
       if (staged) __syncthreads();
     }
@@ -389,7 +449,7 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackEntry
         const long long r = i / e.Opad;
         const int t = (int)(r % e.RS);
         const int ii = (int)(r / e.RS);
-        dst[i] = __float2bfloat16_rn(op < e.O ? e.src[((long long)op * e.I + ii) * e.RS + t] : 0.f);
+        put_packed(dst, r, op, e.Opad, split, op < e.O ? e.src[((long long)op * e.I + ii) * e.RS + t] : 0.f);
       }
       return;
     }
@@ -405,8 +465,7 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackEntry
       __syncthreads();
       for (int j = tid; j < ni * e.RS * 32; j += nt) {
         const int ol = j & 31, k = j >> 5;  // k = il*RS + t
-        if (o0 + ol < e.Opad)
-          dst[((long long)i0 * e.RS + k) * e.Opad + o0 + ol] = __float2bfloat16_rn(sm[ol * ld + k]);
+        if (o0 + ol < e.Opad) put_packed(dst, (long long)i0 * e.RS + k, o0 + ol, e.Opad, split, sm[ol * ld + k]);
       }
       __syncthreads();
     }
@@ -540,6 +599,56 @@ __global__ void im2col_nchw_generic_kernel(const float* __restrict__ x, __nv_bfl
   }
 }
 
+// fp32-parity (split) forms of the layout kernels: plain loops, one thread per element
+__global__ void nchw_f32_to_nhwc_split_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C,
+                                              long long HW, int Cpad, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cpad);
+    const long long pix = i / Cpad;
+    const long long n = pix / HW, hw = pix - n * HW;
+    const float v = c < C ? __ldg(src + (n * C + c) * HW + hw) : 0.f;
+    put_packed(dst, pix, c, Cpad, true, v);
+  }
+}
+__global__ void nhwc_split_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int C,
+                                              long long HW, int Cpad, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long hw = i % HW;
+    const long long nc = i / HW;
+    const int c = (int)(nc % C);
+    const long long n = nc / C;
+    const __nv_bfloat16* p = src + (n * HW + hw) * kSplitPieces * Cpad + c;
+    float v = 0.f;
+#pragma unroll
+    for (int j = kSplitPieces - 1; j >= 0; --j) v += __bfloat162float(p[j * Cpad]);
+    dst[i] = v;
+  }
+}
+__global__ void im2col_nchw_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int C,
+                                         int H, int W, int R, int S, int stride, int pad, int dil, int OH, int OW,
+                                         int Kp) {
+  const long long total = (long long)N * OH * OW * Kp;
+  const int K = R * S * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % Kp);
+    const long long m = i / Kp;
+    const int ow = (int)(m % OW);
+    const long long t = m / OW;
+    const int oh = (int)(t % OH);
+    const long long n = t / OH;
+    float val = 0.f;
+    if (k < K) {
+      const int c = k % C, rs = k / C;
+      const int ih = oh * stride - pad + (rs / S) * dil, iw = ow * stride - pad + (rs % S) * dil;
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) val = __ldg(x + ((n * C + c) * H + ih) * W + iw);
+    }
+    put_packed(out, m, k, Kp, true, val);
+  }
+}
+
 int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = (long long)sm_count() * 16;
@@ -567,11 +676,43 @@ extern "C" int b200cv_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, 
   return check_launch("nhwc_bf16_to_nchw_f32");
 }
 
+extern "C" int b200cv_nchw_f32_to_nhwc_split(const float* src, void* dst, int N, int C, int H, int W, int Cpad,
+                                             void* stream) {
+  B200CV_CHECK_ARG(src && dst && N > 0 && C > 0 && H > 0 && W > 0 && Cpad >= C, "nchw->nhwc(split): bad args");
+  const long long total = (long long)N * H * W * Cpad;
+  nchw_f32_to_nhwc_split_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(dst), C, (long long)H * W, Cpad, total);
+  return check_launch("nchw_f32_to_nhwc_split");
+}
+
+extern "C" int b200cv_nhwc_split_to_nchw_f32(const void* src, float* dst, int N, int C, int H, int W, int Cpad,
+                                             void* stream) {
+  B200CV_CHECK_ARG(src && dst && N > 0 && C > 0 && H > 0 && W > 0 && Cpad >= C, "nhwc(split)->nchw: bad args");
+  const long long total = (long long)N * C * H * W;
+  nhwc_split_to_nchw_f32_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), dst, C, (long long)H * W, Cpad, total);
+  return check_launch("nhwc_split_to_nchw_f32");
+}
+
+extern "C" int b200cv_im2col_nchw_f32_split(const float* x, void* patches, int N, int C, int H, int W, int R, int S,
+                                            int stride, int pad, int dil, int Kp, void* stream) {
+  B200CV_CHECK_ARG(x && patches && N > 0 && C > 0 && H > 0 && W > 0 && R > 0 && S > 0 && stride > 0 && dil > 0,
+                   "im2col(split): bad args");
+  B200CV_CHECK_ARG(Kp >= R * S * C && Kp % 8 == 0, "im2col(split): Kp=%d must be a multiple of 8 and >= R*S*C", Kp);
+  const int OH = (H + 2 * pad - dil * (R - 1) - 1) / stride + 1;
+  const int OW = (W + 2 * pad - dil * (S - 1) - 1) / stride + 1;
+  B200CV_CHECK_ARG(OH > 0 && OW > 0, "im2col(split): empty output");
+  const long long total = (long long)N * OH * OW * Kp;
+  im2col_nchw_split_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<__nv_bfloat16*>(patches), N, C, H, W, R, S, stride, pad, dil, OH, OW, Kp);
+  return check_launch("im2col_nchw_split");
+}
+
 extern "C" int b200cv_pack_weights(const float* w, void* dst, int O, int I, int R, int S, int Ipad,
                                    int Opad, int transpose, void* stream) {
   B200CV_CHECK_ARG(w && dst && O > 0 && I > 0 && R > 0 && S > 0 && Ipad >= I && Opad >= O,
                    "pack_weights: bad args");
-  const long long total = transpose ? (long long)I * R * S * Opad : (long long)O * R * S * Ipad;
+  const long long total = (transpose & 7) ? (long long)I * R * S * Opad : (long long)O * R * S * Ipad;
   pack_weights_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       w, static_cast<__nv_bfloat16*>(dst), O, I, R * S, Ipad, Opad, transpose, total);
   return check_launch("pack_weights");

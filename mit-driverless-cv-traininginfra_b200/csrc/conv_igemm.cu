@@ -25,6 +25,7 @@
 
 #include "internal.h"
 #include "ptx.cuh"
+#include "stat_acc.cuh"
 
 namespace b200cv {
 
@@ -203,14 +204,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const uint16_t ow = static_cast<uint16_t>(p.tap_w[tap]);
           const uint16_t oh = static_cast<uint16_t>(p.tap_h[tap]);
           const int kb = p.tap_k[tap];
+          const int ca = p.tap_c[tap];  // 0, or the lo half of a split activation (fp32-parity mode)
           for (int cb = 0; cb < p.cblocks; ++cb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err, 1);
             uint8_t* sa = stage_base + stage * C::kStageBytes;
             uint8_t* sb = sa + C::kABytes;
             ptx::mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-            ptx::tma_load_im2col_4d(sa, &tmA, &full_bar[stage], cb * KC, cw, ch, n_img, ow, oh);
+            ptx::tma_load_im2col_4d(sa, &tmA, &full_bar[stage], ca + cb * KC, cw, ch, n_img, ow, oh);
             if constexpr (kM2)
-              ptx::tma_load_im2col_4d(sa + C::kASubBytes, &tmA, &full_bar[stage], cb * KC, cw1, ch1, n_img1, ow, oh);
+              ptx::tma_load_im2col_4d(sa + C::kASubBytes, &tmA, &full_bar[stage], ca + cb * KC, cw1, ch1, n_img1, ow,
+                                      oh);
             ptx::tma_load_2d(sb, &tmB, &full_bar[stage], kb + cb * KC, nt * BN);
             if (++stage == nstages) {
               stage = 0;
@@ -335,9 +338,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       float acc_s[kBPW][2], acc_t[kBPW][2];
 #pragma unroll
       for (int i = 0; i < kBPW; ++i) acc_s[i][0] = acc_s[i][1] = acc_t[i][0] = acc_t[i][1] = 0.f;
-      float* const stat_base = kBnRed ? p.bn_sums : p.stats;
+      StatAcc* const stat_base = kBnRed ? p.bn_sums : p.stats;
       const int stat_parts = kBnRed ? p.bn_parts : p.stats_parts;
-      float* stats_row =
+      StatAcc* stats_row =
           stat_base ? stat_base + static_cast<long long>(blockIdx.x % stat_parts) * 2 * p.Cout : nullptr;
       auto flush = [&](int nt_) {
 #pragma unroll
@@ -346,8 +349,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int e = 0; e < 2; ++e) {
             const int n = nt_ * BN + block_of(bi) * 64 + my_col + e;
             if (n < p.Cout) {
-              atomicAdd(stats_row + n, acc_s[bi][e]);
-              atomicAdd(stats_row + p.Cout + n, kBnRed ? acc_t[bi][e] * __ldg(p.bn_rstd + n) : acc_t[bi][e]);
+              stat_add(stats_row + n, acc_s[bi][e]);
+              stat_add(stats_row + p.Cout + n, kBnRed ? acc_t[bi][e] * __ldg(p.bn_rstd + n) : acc_t[bi][e]);
             }
             acc_s[bi][e] = acc_t[bi][e] = 0.f;
           }
@@ -612,9 +615,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
       for (int i = 0; i < C::kChunksPerWarp; ++i) acc_s[i] = acc_t[i] = 0.f;
       // statistics target: forward [sum | sumsq] (p.stats) or, fused BN backward, [sum dz | sum dz*xhat] (p.bn_sums)
-      float* const stat_base = kBnRed ? p.bn_sums : p.stats;
+      StatAcc* const stat_base = kBnRed ? p.bn_sums : p.stats;
       const int stat_parts = kBnRed ? p.bn_parts : p.stats_parts;
-      float* stats_row =
+      StatAcc* stats_row =
           stat_base ? stat_base + static_cast<long long>(blockIdx.x % stat_parts) * 2 * p.Cout : nullptr;
       // ---- fused BN backward: ring of two TMA-loaded y tiles, one chunk ahead of the one being processed
       const int yslots = p.y_slots, ylog = p.y_slots_log2;  // power of two
@@ -664,8 +667,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             for (int ci = 0; ci < C::kChunksPerWarp; ++ci) {
               const int n = stat_nt * BN + (half + 2 * ci) * C::kChunk + my_col;
               if (col_owner && (half + 2 * ci) < C::kNumChunks && n < p.Cout) {
-                atomicAdd(stats_row + n, acc_s[ci]);
-                atomicAdd(stats_row + p.Cout + n, kBnRed ? acc_t[ci] * __ldg(p.bn_rstd + n) : acc_t[ci]);
+                stat_add(stats_row + n, acc_s[ci]);
+                stat_add(stats_row + p.Cout + n, kBnRed ? acc_t[ci] * __ldg(p.bn_rstd + n) : acc_t[ci]);
               }
               acc_s[ci] = acc_t[ci] = 0.f;
             }
@@ -882,8 +885,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int ci = 0; ci < C::kChunksPerWarp; ++ci) {
           const int n = stat_nt * BN + (half + 2 * ci) * C::kChunk + my_col;
           if (col_owner && (half + 2 * ci) < C::kNumChunks && n < p.Cout) {
-            atomicAdd(stats_row + n, acc_s[ci]);
-            atomicAdd(stats_row + p.Cout + n, kBnRed ? acc_t[ci] * __ldg(p.bn_rstd + n) : acc_t[ci]);
+            stat_add(stats_row + n, acc_s[ci]);
+            stat_add(stats_row + p.Cout + n, kBnRed ? acc_t[ci] * __ldg(p.bn_rstd + n) : acc_t[ci]);
           }
         }
       }
@@ -893,7 +896,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     float* scratch = s_scratch + ew * 32 * kScratchLd;
     float* my_sum = s_stats + ew * 2 * C::kAccPerWarp;  // [kAccPerWarp sums | kAccPerWarp sums of squares]
     float* my_sq = my_sum + C::kAccPerWarp;
-    float* stats_row = p.stats ? p.stats + static_cast<long long>(blockIdx.x % p.stats_parts) * 2 * p.Cout : nullptr;
+    StatAcc* stats_row = p.stats ? p.stats + static_cast<long long>(blockIdx.x % p.stats_parts) * 2 * p.Cout : nullptr;
     int stat_nt = -1;  // n-tile the warp-private statistics belong to
     // adds the warp-private partial sums of n-tile `nt` to this CTA's row of the global partials and clears them
     auto flush_stats = [&](int nt) {
@@ -902,8 +905,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int n = nt * BN + (half + 2 * ci) * C::kChunk + (i - ci * C::kChunk);
         const float s1 = my_sum[i], s2 = my_sq[i];
         if (n < p.Cout && (s1 != 0.f || s2 != 0.f)) {
-          atomicAdd(stats_row + n, s1);
-          atomicAdd(stats_row + p.Cout + n, s2);
+          stat_add(stats_row + n, s1);
+          stat_add(stats_row + p.Cout + n, s2);
         }
         my_sum[i] = 0.f;
         my_sq[i] = 0.f;
@@ -990,6 +993,23 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 v[j + 2 * e + 1] += f.y;
               }
             }
+            if (p.res_lo) {  // split residual: add the lower pieces too
+#pragma unroll
+              for (int pc = 1; pc < kSplitPieces; ++pc) {
+                const uint4* rl = reinterpret_cast<const uint4*>(p.res + (row_ok ? r_row : 0) + pc * p.res_lo + n_base);
+#pragma unroll
+                for (int j = 0; j < C::kChunk; j += 8) {
+                  const uint4 q = __ldg(rl + (j >> 3));
+                  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(h[e]);
+                    v[j + 2 * e] += f.x;
+                    v[j + 2 * e + 1] += f.y;
+                  }
+                }
+              }
+            }
             if (!p.res_after_act && p.act != 0) {
 #pragma unroll
               for (int j = 0; j < C::kChunk; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * neg;
@@ -1008,6 +1028,31 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
               for (int j = 0; j < C::kChunk; j += 4)
                 *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+          } else if (p.out_lo) {
+            // fp32-parity mode: v = sum of kSplitPieces bf16 pieces, out_lo elements apart; statistics see that sum
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + o_row + n_base;
+#pragma unroll
+            for (int j = 0; j < C::kChunk; j += 8) {
+              float rem[8], tot[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { rem[e] = v[j + e]; tot[e] = 0.f; }
+#pragma unroll
+              for (int pc = 0; pc < kSplitPieces; ++pc) {
+                uint4 pk;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  h[e] = __floats2bfloat162_rn(rem[2 * e], rem[2 * e + 1]);
+                  const float2 f = __bfloat1622float2(h[e]);
+                  rem[2 * e] -= f.x;
+                  rem[2 * e + 1] -= f.y;
+                }
+                if (row_ok) *reinterpret_cast<uint4*>(o + pc * p.out_lo + j) = pk;
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[j + e] -= rem[e];  // = the stored value (exact: the pieces do not overlap)
+              (void)tot;
             }
           } else {
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + o_row + n_base;
@@ -1034,11 +1079,26 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (n < p.Cout && row_ok) {
               if (p.scale) x *= __ldg(p.scale + n);
               if (p.shift) x += __ldg(p.shift + n);
-              if (p.res && !p.res_after_act) x += __bfloat162float(p.res[r_row + n * p.r_sc]);
+              float rv = 0.f;
+              if (p.res) {
+                rv = __bfloat162float(p.res[r_row + n * p.r_sc]);
+                if (p.res_lo)
+                  for (int pc = 1; pc < kSplitPieces; ++pc)
+                    rv += __bfloat162float(p.res[r_row + pc * p.res_lo + n * p.r_sc]);
+              }
+              if (p.res && !p.res_after_act) x += rv;
               x = apply_act(x, p.act, p.slope);
-              if (p.res && p.res_after_act) x += __bfloat162float(p.res[r_row + n * p.r_sc]);
+              if (p.res && p.res_after_act) x += rv;
               if (p.out_fp32) {
                 reinterpret_cast<float*>(p.out)[o_row + n * p.o_sc] = x;
+              } else if (p.out_lo) {
+                float rem = x;
+                for (int pc = 0; pc < kSplitPieces; ++pc) {
+                  const __nv_bfloat16 hb = __float2bfloat16_rn(rem);
+                  reinterpret_cast<__nv_bfloat16*>(p.out)[o_row + pc * p.out_lo + n * p.o_sc] = hb;
+                  rem -= __bfloat162float(hb);
+                }
+                x -= rem;
               } else {
                 const __nv_bfloat16 hb = __float2bfloat16_rn(x);
                 reinterpret_cast<__nv_bfloat16*>(p.out)[o_row + n * p.o_sc] = hb;

@@ -41,6 +41,9 @@ struct WgradParams {
   int kb_total;  // ceil(M_pix / 64)
   float* dw;
   int* err;
+  // fp32-parity (split) mode: npass = 6 passes per k-block over the piece pairs (dY_i, X_j), i + j <= 2, smallest
+  // first; a_lo / b_lo = piece stride in dY / X rows (npass = 1, offsets 0 in the bf16 mode)
+  int npass, a_lo, b_lo;
   short tap_w[kMaxTaps];
   short tap_h[kMaxTaps];
 };
@@ -136,23 +139,28 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
         for (int kb = kb0; kb < kb1; ++kb) {
           const int cw = p.lower_w + qc * p.trav_w;
           const int ch = p.lower_h + pr * p.trav_h;
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err, 11);
-          uint8_t* sa = smem + stage * stage_bytes;
-          uint8_t* sb = sa + 2 * kASlabBytes;
-          ptx::mbar_expect_tx(&full_bar[stage], my_bytes);
-          if (pj == 0)
-            for (int sl = 0; sl < p.a_slabs; ++sl)
-              ptx::tma_load_2d(sa + sl * kASlabBytes, &tmDY, &full_bar[stage], ot * 128 + sl * 64, m0);
+          for (int ps = 0; ps < p.npass; ++ps) {
+            // piece pair of this pass: (2,0) (0,2) (1,1) (1,0) (0,1) (0,0) packed two bits each
+            const int a_off = p.npass == 1 ? 0 : ((0x052 >> (2 * ps)) & 3) * p.a_lo;
+            const int b_off = p.npass == 1 ? 0 : ((0x118 >> (2 * ps)) & 3) * p.b_lo;
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err, 11);
+            uint8_t* sa = smem + stage * stage_bytes;
+            uint8_t* sb = sa + 2 * kASlabBytes;
+            ptx::mbar_expect_tx(&full_bar[stage], my_bytes);
+            if (pj == 0)
+              for (int sl = 0; sl < p.a_slabs; ++sl)
+                ptx::tma_load_2d(sa + sl * kASlabBytes, &tmDY, &full_bar[stage], a_off + ot * 128 + sl * 64, m0);
 #pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            if (tt[k] < p.T) {
+            for (int k = 0; k < 3; ++k) {
+              if (tt[k] < p.T) {
 #pragma unroll
-              for (int sl = 0; sl < kBSlabs; ++sl)
-                ptx::tma_load_im2col_4d(sb + tt[k] * kBTapBytes + sl * kBSlabBytes, &tmX, &full_bar[stage],
-                                        it * BNW + sl * CB, cw, ch, n_img, tw[k], th[k]);
+                for (int sl = 0; sl < kBSlabs; ++sl)
+                  ptx::tma_load_im2col_4d(sb + tt[k] * kBTapBytes + sl * kBSlabBytes, &tmX, &full_bar[stage],
+                                          b_off + it * BNW + sl * CB, cw, ch, n_img, tw[k], th[k]);
+              }
             }
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
           // next k-block: 64 output pixels further in (image, row, column) order
           m0 += kKB;
           qc += kKB;
@@ -169,7 +177,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
         const int ntot = p.T * BNW;
         int stage = 0;
         uint32_t phase = 0;
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = 0; kb < nkb * p.npass; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase, p.err, 12);
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
@@ -292,7 +300,7 @@ using namespace b200cv;
 
 extern "C" int b200cv_conv_wgrad(const void* x, const void* dy, float* dw_packed, int N, int H, int W,
                                  int Cin, int Cout, int dy_ld, int R, int S, int stride, int pad, int dil,
-                                 void* stream) {
+                                 int64_t x_lo, int64_t dy_lo, void* stream) {
   B200CV_CHECK_ARG(x && dy && dw_packed, "conv_wgrad: null pointer");
   B200CV_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cout > 0, "conv_wgrad: empty shape");
   B200CV_CHECK_ARG(Cin == pad_channels(Cin), "conv_wgrad: Cin=%d is not a padded channel count", Cin);
@@ -300,6 +308,9 @@ extern "C" int b200cv_conv_wgrad(const void* x, const void* dy, float* dw_packed
                    dy_ld);
   B200CV_CHECK_ARG(R * S <= kMaxTaps && stride >= 1 && stride <= 8 && dil >= 1 && pad >= 0,
                    "conv_wgrad: unsupported filter");
+  B200CV_CHECK_ARG((x_lo == 0) == (dy_lo == 0) && (x_lo == 0 || (x_lo == Cin && dy_lo % 8 == 0 && dy_ld >= (kSplitPieces - 1) * dy_lo + Cout)),
+                   "conv_wgrad: fp32-parity mode needs both operands split (x_lo == Cin, dy_lo + Cout <= dy_ld)");
+  const int xmul = x_lo ? kSplitPieces : 1;  // stored channels per logical channel of x
   const int OH = (H + 2 * pad - dil * (R - 1) - 1) / stride + 1;
   const int OW = (W + 2 * pad - dil * (S - 1) - 1) / stride + 1;
   B200CV_CHECK_ARG(OH > 0 && OW > 0, "conv_wgrad: empty output");
@@ -319,6 +330,9 @@ extern "C" int b200cv_conv_wgrad(const void* x, const void* dy, float* dw_packed
   p.Ipad = Cin;
   p.dw = dw_packed;
   p.err = device_error_word();
+  p.npass = x_lo ? 6 : 1;
+  p.a_lo = (int)dy_lo;
+  p.b_lo = (int)x_lo;
   for (int r = 0; r < R; ++r)
     for (int s = 0; s < S; ++s) {
       p.tap_w[r * S + s] = (short)(s * dil);
@@ -328,7 +342,7 @@ extern "C" int b200cv_conv_wgrad(const void* x, const void* dy, float* dw_packed
   const int bnw = Cin < 64 ? Cin : (Cin % 128 == 0 ? 128 : 64);
   p.num_o_tiles = (Cout + 127) / 128;
   p.num_i_tiles = Cin / bnw;
-  p.a_slabs = (Cout > 64 && dy_ld > 64) ? 2 : 1;
+  p.a_slabs = (Cout > 64 && (dy_lo ? dy_lo : dy_ld) > 64) ? 2 : 1;
   // taps per CTA: the largest divisor of RS whose accumulators fit the 512 TMEM columns
   int T = 1;
   for (int t = 1; t <= p.RS; ++t)
@@ -351,8 +365,9 @@ extern "C" int b200cv_conv_wgrad(const void* x, const void* dy, float* dw_packed
   CUtensorMap tmDY, tmX;
   int rc = make_tmap_2d_bf16(&tmDY, dy, p.M_pix, dy_ld, dy_ld, kKB, 64);
   if (rc) return rc;
-  rc = make_tmap_im2col_bf16(&tmX, x, N, H, W, Cin, Cin, (int64_t)W * Cin, (int64_t)H * W * Cin, -pad, -pad,
-                             pad - (S - 1) * dil, pad - (R - 1) * dil, stride, stride, cb, kKB);
+  rc = make_tmap_im2col_bf16(&tmX, x, N, H, W, xmul * Cin, xmul * Cin, (int64_t)W * xmul * Cin,
+                             (int64_t)H * W * xmul * Cin, -pad, -pad, pad - (S - 1) * dil, pad - (R - 1) * dil, stride,
+                             stride, cb, kKB);
   if (rc) return rc;
   CUtensorMap tmDW;
   rc = make_tmap_2d_f32(&tmDW, dw_packed, Cout, (int64_t)p.RS * p.Ipad, (int64_t)p.RS * p.Ipad, 32,

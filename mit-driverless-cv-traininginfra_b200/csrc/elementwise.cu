@@ -9,6 +9,7 @@
 #include <cstdlib>
 
 #include "internal.h"
+#include "stat_acc.cuh"
 
 namespace b200cv {
 namespace {
@@ -56,29 +57,14 @@ int ew_grid(long long work_items, int block) {
 
 // ------------------------------------------------------------------ BN finalize
 __global__ void __launch_bounds__(256)
-bn_finalize_kernel(const float* __restrict__ stats, int parts, float count, const float* __restrict__ gamma,
+bn_finalize_kernel(const StatAcc* __restrict__ stats, int parts, float count, const float* __restrict__ gamma,
                    const float* __restrict__ beta, const float* __restrict__ conv_bias, float eps, float momentum,
                    float* running_mean, float* running_var, float* __restrict__ scale, float* __restrict__ shift,
                    float* __restrict__ save_mean, float* __restrict__ save_rstd, int C) {
-  __shared__ float sh1[8][33], sh2[8][33];
-  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cx;
-  float s1 = 0.f, s2 = 0.f;
-  if (c < C)
-#pragma unroll 8
-    for (int p = py; p < parts; p += 8) {  // fixed order
-      s1 += stats[(long long)p * 2 * C + c];
-      s2 += stats[(long long)p * 2 * C + C + c];
-    }
-  sh1[py][cx] = s1;
-  sh2[py][cx] = s2;
-  __syncthreads();
-  if (py != 0 || c >= C) return;
-#pragma unroll
-  for (int q = 1; q < 8; ++q) {
-    s1 += sh1[q][cx];
-    s2 += sh2[q][cx];
-  }
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float s1 = stat_fold(stats, parts, 2 * C, c);
+  const float s2 = stat_fold(stats, parts, 2 * C, C + c);
   const float mean = s1 / count;
   float var = s2 / count - mean * mean;
   var = var > 0.f ? var : 0.f;
@@ -229,7 +215,7 @@ __global__ void __launch_bounds__(kEwThreads, 4) bn_apply_kernel(const ApplyArgs
 
 // ---- fused: fold the partial statistics (bn_finalize) in the prologue of every block, then apply
 struct FusedFwdArgs {
-  const float* stats; int parts; float count;
+  const StatAcc* stats; int parts; float count;
   const float* gamma; const float* beta; const float* conv_bias; float eps, momentum;
   float* running_mean; float* running_var;
   float* scale; float* shift; float* save_mean; float* save_rstd;
@@ -241,11 +227,8 @@ __global__ void __launch_bounds__(kEwThreads, V == 8 ? 2 : 4) bn_stats_apply_ker
   extern __shared__ float s_ss[];  // [scale | shift]
   const int C = a.C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s1 = 0.f, s2 = 0.f;
-    for (int p = 0; p < f.parts; ++p) {
-      s1 += __ldg(f.stats + (long long)p * 2 * C + c);
-      s2 += __ldg(f.stats + (long long)p * 2 * C + C + c);
-    }
+    const float s1 = stat_fold(f.stats, f.parts, 2 * C, c);
+    const float s2 = stat_fold(f.stats, f.parts, 2 * C, C + c);
     const float mean = s1 / f.count;
     float var = s2 / f.count - mean * mean;
     var = var > 0.f ? var : 0.f;
@@ -328,7 +311,7 @@ struct BwdArgs {
   const __nv_bfloat16* aout; long long aout_ld;   // optional: sign source for act'
   const float* scale; const float* shift;         // of this BN (to recompute z when aout == null)
   const float* mean; const float* rstd;
-  float* sums;                                    // pass 1 out: [nparts][2C], ADDED to (caller zeroes)
+  StatAcc* sums;                                  // pass 1 out: [nparts][2C], ADDED to (caller zeroes)
   int nparts;
   const float* coef;                              // pass 2 in  [3C]: g, k1, k2
   __nv_bfloat16* dy; long long dy_ld;             // pass 2 out
@@ -339,9 +322,9 @@ template <bool kAout, int V>
 __global__ void __launch_bounds__(kEwThreads, V == 8 ? 2 : 4) bn_bwd_reduce_kernel(const BwdArgs a) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ float s_acc[];  // [2C]
+  extern __shared__ StatAcc s_acc[];  // [2C]
   const int C = a.C;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i].w1 = s_acc[i].w2 = 0;
   __syncthreads();
   const int vpr = C / V;
   const int rpp = kEwThreads / vpr;
@@ -396,43 +379,25 @@ __global__ void __launch_bounds__(kEwThreads, V == 8 ? 2 : 4) bn_bwd_reduce_kern
     loadVf<V>(a.rstd + c0, rstd);
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      atomicAdd(&s_acc[c0 + j], s1[j]);
-      atomicAdd(&s_acc[C + c0 + j], s2[j] * rstd[j]);
+      stat_add(&s_acc[c0 + j], s1[j]);
+      stat_add(&s_acc[C + c0 + j], s2[j] * rstd[j]);
     }
   }
   __syncthreads();
-  float* row = a.sums + (long long)(blockIdx.x % a.nparts) * 2 * C;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
-    const float v = s_acc[i];
-    if (v != 0.f) atomicAdd(row + i, v);
-  }
+  StatAcc* row = a.sums + (long long)(blockIdx.x % a.nparts) * 2 * C;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) stat_merge(row + i, s_acc[i]);
 }
 
 // coef[c] = gamma*rstd ; coef[C+c] = sum_dz/M ; coef[2C+c] = sum_dz_xhat/M ; also dgamma/dbeta
 // block = 32 channels x 8 part-lanes: partial rows are summed 8 at a time, then folded through shared memory
 __global__ void __launch_bounds__(256)
-bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, const float* __restrict__ gamma,
+bn_bwd_finalize_kernel(const StatAcc* __restrict__ partials, int nparts, const float* __restrict__ gamma,
                        const float* __restrict__ rstd, float count, float* __restrict__ coef, float* dgamma,
                        float* dbeta, int C) {
-  __shared__ float sh1[8][33], sh2[8][33];
-  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cx;
-  float s1 = 0.f, s2 = 0.f;
-  if (c < C)
-#pragma unroll 8
-    for (int p = py; p < nparts; p += 8) {
-      s1 += partials[(long long)p * 2 * C + c];
-      s2 += partials[(long long)p * 2 * C + C + c];
-    }
-  sh1[py][cx] = s1;
-  sh2[py][cx] = s2;
-  __syncthreads();
-  if (py == 0 && c < C) {
-#pragma unroll
-    for (int q = 1; q < 8; ++q) {
-      s1 += sh1[q][cx];
-      s2 += sh2[q][cx];
-    }
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    const float s1 = stat_fold(partials, nparts, 2 * C, c);
+    const float s2 = stat_fold(partials, nparts, 2 * C, C + c);
     coef[c] = gamma[c] * rstd[c];
     coef[C + c] = s1 / count;
     coef[2 * C + c] = s2 / count;
@@ -517,7 +482,7 @@ struct Bwd2Args {
   const __nv_bfloat16* yB; long long yB_ld;
   const float* meanA; const float* rstdA;
   const float* meanB; const float* rstdB;
-  float* sumsA; float* sumsB; int nparts;          // reduce: [nparts][2C] each, ADDED to
+  StatAcc* sumsA; StatAcc* sumsB; int nparts;      // reduce: [nparts][2C] each, ADDED to
   const float* coefA; const float* coefB;          // apply: [3C] each (g, k1, k2)
   __nv_bfloat16* dyA; long long dyA_ld;
   __nv_bfloat16* dyB; long long dyB_ld;
@@ -525,9 +490,9 @@ struct Bwd2Args {
 };
 
 __global__ void __launch_bounds__(kEwThreads, 2) bn_bwd_reduce2_kernel(const Bwd2Args a) {
-  extern __shared__ float s_acc2[];  // [3C]: sum dz | sum dz*(yA-meanA)*rstdA | sum dz*(yB-meanB)*rstdB
+  extern __shared__ StatAcc s_acc2[];  // [3C]: sum dz | sum dz*(yA-meanA)*rstdA | sum dz*(yB-meanB)*rstdB
   const int C = a.C;
-  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_acc2[i] = 0.f;
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_acc2[i].w1 = s_acc2[i].w2 = 0;
   __syncthreads();
   const int vpr = C >> 2;
   const int rpp = kEwThreads / vpr;
@@ -576,21 +541,18 @@ __global__ void __launch_bounds__(kEwThreads, 2) bn_bwd_reduce2_kernel(const Bwd
     load4f(a.rstdB + c0, rstdB);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      atomicAdd(&s_acc2[c0 + j], s1[j]);
-      atomicAdd(&s_acc2[C + c0 + j], sA[j] * rstdA[j]);
-      atomicAdd(&s_acc2[2 * C + c0 + j], sB[j] * rstdB[j]);
+      stat_add(&s_acc2[c0 + j], s1[j]);
+      stat_add(&s_acc2[C + c0 + j], sA[j] * rstdA[j]);
+      stat_add(&s_acc2[2 * C + c0 + j], sB[j] * rstdB[j]);
     }
   }
   __syncthreads();
   const long long part = (long long)(blockIdx.x % a.nparts) * 2 * C;
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    const float v1 = s_acc2[i], vA = s_acc2[C + i], vB = s_acc2[2 * C + i];
-    if (v1 != 0.f) {
-      atomicAdd(a.sumsA + part + i, v1);
-      atomicAdd(a.sumsB + part + i, v1);
-    }
-    if (vA != 0.f) atomicAdd(a.sumsA + part + C + i, vA);
-    if (vB != 0.f) atomicAdd(a.sumsB + part + C + i, vB);
+    stat_merge(a.sumsA + part + i, s_acc2[i]);
+    stat_merge(a.sumsB + part + i, s_acc2[i]);
+    stat_merge(a.sumsA + part + C + i, s_acc2[C + i]);
+    stat_merge(a.sumsB + part + C + i, s_acc2[2 * C + i]);
   }
 }
 
@@ -665,7 +627,7 @@ __global__ void __launch_bounds__(kEwThreads, 2) bn_bwd_apply2_kernel(const Bwd2
 
 // ---- fused: fold the backward partial sums (bn_bwd_finalize) in the prologue of every block, then apply
 struct FusedBwdArgs {
-  const float* partials; int nparts; float count;
+  const StatAcc* partials; int nparts; float count;
   const float* gamma; float* coef; float* dgamma; float* dbeta;
 };
 template <int V>
@@ -675,11 +637,8 @@ __global__ void __launch_bounds__(kEwThreads, V == 8 ? 2 : 4) bn_bwd_stats_apply
   extern __shared__ float s_gab[];  // [g | A | B]
   const int C = a.C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s1 = 0.f, s2 = 0.f;
-    for (int p = 0; p < f.nparts; ++p) {
-      s1 += __ldg(f.partials + (long long)p * 2 * C + c);
-      s2 += __ldg(f.partials + (long long)p * 2 * C + C + c);
-    }
+    const float s1 = stat_fold(f.partials, f.nparts, 2 * C, c);
+    const float s2 = stat_fold(f.partials, f.nparts, 2 * C, C + c);
     const float rstd = a.rstd[c], mean = a.mean[c];
     const float g = f.gamma[c] * rstd;
     const float k1 = s1 / f.count, k2 = s2 / f.count;
@@ -793,7 +752,8 @@ __global__ void copy_slice_kernel(const __nv_bfloat16* __restrict__ src, long lo
 // ------------------------------------------------------------------ column sums (conv bias gradient)
 __global__ void __launch_bounds__(256) col_sum_kernel(const __nv_bfloat16* __restrict__ x, long long ld,
                                                       long long rows, int C, float* __restrict__ out) {
-  extern __shared__ float s_acc[];
+  extern __shared__ float s_colsum[];
+  float* s_acc = s_colsum;
   for (int i = threadIdx.x; i < C; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   const int vpr = C >> 3;
@@ -964,15 +924,15 @@ bool ok_vec(const void* p, long long ld, int C) {
 using namespace b200cv;
 typedef __nv_bfloat16 bf16;
 
-extern "C" int b200cv_bn_finalize(const float* stats, int stats_parts, int64_t count, const float* gamma, const float* beta,
+extern "C" int b200cv_bn_finalize(const void* stats, int stats_parts, int64_t count, const float* gamma, const float* beta,
                                   const float* conv_bias, float eps, float momentum, float* running_mean,
                                   float* running_var, float* scale, float* shift, float* save_mean,
                                   float* save_rstd, int C, void* stream) {
   B200CV_CHECK_ARG(stats && gamma && beta && scale && shift && save_mean && save_rstd && C > 0 && count > 0 &&
                        stats_parts > 0,
                    "bn_finalize: bad args");
-  bn_finalize_kernel<<<(C + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      stats, stats_parts, (float)count, gamma, beta, conv_bias, eps, momentum, running_mean, running_var, scale, shift,
+  bn_finalize_kernel<<<(C + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const StatAcc*>(stats), stats_parts, (float)count, gamma, beta, conv_bias, eps, momentum, running_mean, running_var, scale, shift,
       save_mean, save_rstd, C);
   return check_launch("bn_finalize");
 }
@@ -1014,32 +974,32 @@ static int fill_bwd(BwdArgs& a, const void* da, int64_t da_ld, const void* y, in
 
 extern "C" int b200cv_bn_bwd_reduce(const void* da, int64_t da_ld, const void* y, int64_t y_ld, const void* aout,
                                     int64_t aout_ld, const float* scale, const float* shift, const float* mean,
-                                    const float* rstd, float* partials, int nparts, int64_t rows, int C, int act,
+                                    const float* rstd, void* partials, int nparts, int64_t rows, int C, int act,
                                     float slope, void* stream) {
   BwdArgs a;
   if (int rc = fill_bwd(a, da, da_ld, y, y_ld, aout, aout_ld, scale, shift, mean, rstd, rows, C, act, slope))
     return rc;
   B200CV_CHECK_ARG(partials != nullptr && nparts > 0, "bn_bwd_reduce: null partials");
-  a.sums = partials;  // [nparts][2C], zeroed by the caller: block b ADDS its sums to row b % nparts
+  a.sums = static_cast<StatAcc*>(partials);  // [nparts][2C], zeroed by the caller: block b ADDS its sums to row b % nparts
   a.nparts = nparts;
   const int V = ew_vec(C);
   const int grid = stream_grid(rows, C, V);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (V == 8) {
-    if (aout) launch_pdl(bn_bwd_reduce_kernel<true, 8>, dim3(grid), dim3(kEwThreads), 2 * C * sizeof(float), st, a);
-    else launch_pdl(bn_bwd_reduce_kernel<false, 8>, dim3(grid), dim3(kEwThreads), 2 * C * sizeof(float), st, a);
+    if (aout) launch_pdl(bn_bwd_reduce_kernel<true, 8>, dim3(grid), dim3(kEwThreads), 2 * C * sizeof(StatAcc), st, a);
+    else launch_pdl(bn_bwd_reduce_kernel<false, 8>, dim3(grid), dim3(kEwThreads), 2 * C * sizeof(StatAcc), st, a);
   } else {
-    if (aout) launch_pdl(bn_bwd_reduce_kernel<true, 4>, dim3(grid), dim3(kEwThreads), 2 * C * sizeof(float), st, a);
-    else launch_pdl(bn_bwd_reduce_kernel<false, 4>, dim3(grid), dim3(kEwThreads), 2 * C * sizeof(float), st, a);
+    if (aout) launch_pdl(bn_bwd_reduce_kernel<true, 4>, dim3(grid), dim3(kEwThreads), 2 * C * sizeof(StatAcc), st, a);
+    else launch_pdl(bn_bwd_reduce_kernel<false, 4>, dim3(grid), dim3(kEwThreads), 2 * C * sizeof(StatAcc), st, a);
   }
   return check_launch("bn_bwd_reduce");
 }
 
-extern "C" int b200cv_bn_bwd_finalize(const float* partials, int nparts, const float* gamma, const float* rstd,
+extern "C" int b200cv_bn_bwd_finalize(const void* partials, int nparts, const float* gamma, const float* rstd,
                                       int64_t count, float* coef, float* dgamma, float* dbeta, int C, void* stream) {
   B200CV_CHECK_ARG(partials && nparts > 0 && gamma && rstd && coef && C > 0 && count > 0, "bn_bwd_finalize: bad args");
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      partials, nparts, gamma, rstd, (float)count, coef, dgamma, dbeta, C);
+  bn_bwd_finalize_kernel<<<(C + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const StatAcc*>(partials), nparts, gamma, rstd, (float)count, coef, dgamma, dbeta, C);
   return check_launch("bn_bwd_finalize");
 }
 
@@ -1078,16 +1038,16 @@ static int fill_bwd2(Bwd2Args& a, const void* da, int64_t da_ld, const void* aou
 
 extern "C" int b200cv_bn_bwd_reduce2(const void* da, int64_t da_ld, const void* aout, int64_t aout_ld, const void* yA,
                                      int64_t yA_ld, const void* yB, int64_t yB_ld, const float* meanA,
-                                     const float* rstdA, const float* meanB, const float* rstdB, float* partialsA,
-                                     float* partialsB, int nparts, int64_t rows, int C, int act, float slope,
+                                     const float* rstdA, const float* meanB, const float* rstdB, void* partialsA,
+                                     void* partialsB, int nparts, int64_t rows, int C, int act, float slope,
                                      void* stream) {
   Bwd2Args a;
   if (int rc = fill_bwd2(a, da, da_ld, aout, aout_ld, yA, yA_ld, yB, yB_ld, meanA, rstdA, meanB, rstdB, rows, C, act,
                          slope))
     return rc;
   B200CV_CHECK_ARG(partialsA && partialsB && nparts > 0, "bn_bwd_reduce2: null partials");
-  a.sumsA = partialsA; a.sumsB = partialsB; a.nparts = nparts;
-  bn_bwd_reduce2_kernel<<<stream_grid(rows, C), kEwThreads, 3 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(a);
+  a.sumsA = static_cast<StatAcc*>(partialsA); a.sumsB = static_cast<StatAcc*>(partialsB); a.nparts = nparts;
+  bn_bwd_reduce2_kernel<<<stream_grid(rows, C), kEwThreads, 3 * C * sizeof(StatAcc), static_cast<cudaStream_t>(stream)>>>(a);
   return check_launch("bn_bwd_reduce2");
 }
 
@@ -1107,7 +1067,7 @@ extern "C" int b200cv_bn_bwd_apply2(const void* da, int64_t da_ld, const void* a
   return check_launch("bn_bwd_apply2");
 }
 
-extern "C" int b200cv_bn_stats_apply_act(const float* stats, int stats_parts, int64_t count, const float* gamma,
+extern "C" int b200cv_bn_stats_apply_act(const void* stats, int stats_parts, int64_t count, const float* gamma,
                                          const float* beta, const float* conv_bias, float eps, float momentum,
                                          float* running_mean, float* running_var, float* scale, float* shift,
                                          float* save_mean, float* save_rstd, const void* y, int64_t y_ld,
@@ -1119,7 +1079,7 @@ extern "C" int b200cv_bn_stats_apply_act(const float* stats, int stats_parts, in
   B200CV_CHECK_ARG(ok_vec(y, y_ld, C) && ok_vec(out, out_ld, C) && rows > 0, "bn_stats_apply_act: bad args");
   B200CV_CHECK_ARG(!post || ok_vec(post, post_ld, C), "bn_stats_apply_act: bad residual");
   B200CV_CHECK_ARG(C / 4 <= kEwThreads, "bn_stats_apply_act: C too large");
-  FusedFwdArgs f{stats, stats_parts, (float)count, gamma, beta, conv_bias, eps, momentum, running_mean, running_var,
+  FusedFwdArgs f{static_cast<const StatAcc*>(stats), stats_parts, (float)count, gamma, beta, conv_bias, eps, momentum, running_mean, running_var,
                  scale, shift, save_mean, save_rstd};
   ApplyArgs a{(const bf16*)y, y_ld, nullptr, nullptr, nullptr, 0, nullptr, nullptr,
               (const bf16*)post, post_ld, (bf16*)out, out_ld, rows, C, act, slope};
@@ -1137,7 +1097,7 @@ extern "C" int b200cv_bn_stats_apply_act(const float* stats, int stats_parts, in
   return check_launch("bn_stats_apply_act");
 }
 
-extern "C" int b200cv_bn_bwd_stats_apply(const float* partials, int nparts, int64_t count, const float* gamma,
+extern "C" int b200cv_bn_bwd_stats_apply(const void* partials, int nparts, int64_t count, const float* gamma,
                                          float* coef, float* dgamma, float* dbeta, const void* da, int64_t da_ld,
                                          const void* y, int64_t y_ld, const float* scale, const float* shift,
                                          const float* mean, const float* rstd, void* dy, int64_t dy_ld,
@@ -1147,7 +1107,7 @@ extern "C" int b200cv_bn_bwd_stats_apply(const float* partials, int nparts, int6
   B200CV_CHECK_ARG(partials && nparts > 0 && gamma && count > 0 && ok_vec(dy, dy_ld, C),
                    "bn_bwd_stats_apply: bad args");
   a.dy = (bf16*)dy; a.dy_ld = dy_ld;
-  FusedBwdArgs f{partials, nparts, (float)count, gamma, coef, dgamma, dbeta};
+  FusedBwdArgs f{static_cast<const StatAcc*>(partials), nparts, (float)count, gamma, coef, dgamma, dbeta};
   const int V = ew_vec(C);
   const int grid = stream_grid(rows, C, V);
   const size_t smem = 3 * (size_t)C * sizeof(float);

@@ -95,7 +95,7 @@ static void run_fwd(const Case& c) {
   CK(cudaMemcpy(dx, xb.data(), nx * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dw, wb.data(), nw * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dr, rb.data(), ny * 2, cudaMemcpyHostToDevice));
-  float *dscale = dalloc<float>(c.Cout), *dshift = dalloc<float>(c.Cout), *dstats = dalloc<float>(2 * c.Cout);
+  float *dscale = dalloc<float>(c.Cout), *dshift = dalloc<float>(c.Cout), *dstats = dalloc<float>(8 * c.Cout);  // b200cv_stat [2*Cout]
   CK(cudaMemcpy(dscale, scale.data(), c.Cout * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dshift, shift.data(), c.Cout * 4, cudaMemcpyHostToDevice));
   void* dy = c.fp32_out ? (void*)dalloc<float>(ny) : (void*)dalloc<__nv_bfloat16>(ny);
@@ -124,7 +124,12 @@ static void run_fwd(const Case& c) {
     for (size_t i = 0; i < ny; ++i) y[i] = __bfloat162float(yb[i]);
   }
   std::vector<float> hstats(2 * c.Cout, 0.f);
-  CK(cudaMemcpy(hstats.data(), dstats, 2 * c.Cout * 4, cudaMemcpyDeviceToHost));
+  {
+    std::vector<b200cv_stat> raw(2 * c.Cout);
+    CK(cudaMemcpy(raw.data(), dstats, 2 * c.Cout * sizeof(b200cv_stat), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 2 * c.Cout; ++i)
+      hstats[i] = (float)((double)raw[i].w1 / 1048576.0 + (double)raw[i].w2 * 0x1p-70);
+  }
 
   double max_err = 0, max_ref = 0;
   int nbad = 0;
@@ -284,7 +289,7 @@ static void run_wgrad(const Case& c) {
   CK(cudaMemcpy(dx, xb.data(), nx * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ddy, dyb.data(), ndy * 2, cudaMemcpyHostToDevice));
   int rc = b200cv_conv_wgrad(dx, ddy, ddw, c.N, c.H, c.W, Cin, c.Cout, Cop, c.R, c.S, c.stride, c.pad, c.dil,
-                             nullptr);
+                             0, 0, nullptr);
   int derr = b200cv_check_device_error(nullptr);
   CK(cudaDeviceSynchronize());
   std::vector<float> dw(ndw);
@@ -337,7 +342,7 @@ static void bench_case(const char* name, int N, int H, int W, int Cin_true, int 
   auto* dw = dalloc<__nv_bfloat16>(nw);
   auto* dwt = dalloc<__nv_bfloat16>((size_t)Cin * R * R * Cop);
   auto* dgw = dalloc<float>(nw);
-  auto* dstats = dalloc<float>(2 * Cout);
+  auto* dstats = dalloc<float>(8 * Cout);  // b200cv_stat [2*Cout]
   // non-trivial contents so the power draw is realistic
   {
     std::vector<__nv_bfloat16> h(std::max(nx, std::max(ny, nw)));
@@ -369,7 +374,7 @@ static void bench_case(const char* name, int N, int H, int W, int Cin_true, int 
       if (i == 3) CK(cudaEventRecord(e0));
       if (mode == 0) rc |= b200cv_conv_fwd(&f, nullptr);
       if (mode == 1) rc |= b200cv_conv_dgrad(&g, H, W, nullptr);
-      if (mode == 2) rc |= b200cv_conv_wgrad(dx, dy, dgw, N, H, W, Cin, Cout, Cop, R, R, stride, pad, dil, nullptr);
+      if (mode == 2) rc |= b200cv_conv_wgrad(dx, dy, dgw, N, H, W, Cin, Cout, Cop, R, R, stride, pad, dil, 0, 0, nullptr);
     }
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));

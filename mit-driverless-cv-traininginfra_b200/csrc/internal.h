@@ -9,6 +9,8 @@
 
 namespace b200cv {
 
+struct StatAcc;  // stat_acc.cuh: 2 x int64 fixed-point accumulator of one per-channel statistic
+
 // ---- error plumbing (api.cpp) -------------------------------------------------
 int set_error(int code, const char* fmt, ...);
 int check_launch(const char* what);  // cudaGetLastError() -> error code
@@ -36,6 +38,9 @@ int make_tmap_2d_f32(CUtensorMap* out, const void* base, int64_t rows, int64_t c
 
 // ---- implicit-GEMM convolution core (conv_igemm.cu) ----------------------------
 constexpr int kMaxTaps = 64;
+// fp32-parity (split) mode: an fp32 value is stored as kSplitPieces bf16 numbers (hi, mid, lo: 3 x 8 = 24 mantissa
+// bits, i.e. fp32's own precision), piece j of a row lying j * lo elements after the hi piece.
+constexpr int kSplitPieces = 3;
 
 struct IgemmParams {
   // GEMM view: D[m, n] = sum_{tap, c} A_tap[m, c] * B[n, tap_k[tap] + c]
@@ -59,11 +64,11 @@ struct IgemmParams {
   const float* shift;
   int act;  // 0 none, 1 leaky(slope), 2 relu
   float slope;
-  float* stats;  // [stats_parts][2*Cout]: sum, sum of squares (added), or null
+  StatAcc* stats;  // [stats_parts][2*Cout]: sum, sum of squares (added, see stat_acc.cuh), or null
   int stats_parts;
   int* err;
   // fused BN-backward reduction (dgrad, staged epilogue only): sums of dz and dz*(y-mean)*rstd, see b200cv.h
-  float* bn_sums;
+  StatAcc* bn_sums;
   int bn_parts;
   const float* bn_scale;
   const float* bn_shift;
@@ -74,8 +79,11 @@ struct IgemmParams {
   int y_slots, y_slots_log2;  // y tiles per epilogue warp of the fused BN-backward reduction (power of two)
   int res_iters;  // residual added by the tensor core: extra k-iterations D += I[:, k-slice] * R[k-slice rows, :] (0 = off)
   int dbg;  // B200CV_DBG bits (bring-up timing experiments only): 1 no stores, 2 no stats, 4 no TMEM read
+  // fp32-parity (split) mode: lo halves of the output / residual lie this many elements after the hi halves (0 = off)
+  long long out_lo, res_lo;
   short tap_w[kMaxTaps];
   short tap_h[kMaxTaps];
+  short tap_c[kMaxTaps];  // channel offset of the A operand (0, or the lo half of a split activation)
   int tap_k[kMaxTaps];
 };
 

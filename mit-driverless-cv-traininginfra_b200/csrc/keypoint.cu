@@ -283,6 +283,29 @@ __global__ void __launch_bounds__(256) kpt_head_bwd_kernel(const KptBwdArgs a) {
     for (int k = 0; k < 8; ++k) hh[k] = __floats2bfloat162_rn(o[2 * k], o[2 * k + 1]);
     *reinterpret_cast<uint4*>(d) = pk[0];
     *reinterpret_cast<uint4*>(d + 8) = pk[1];
+    if (a.ld == 16 * kSplitPieces) {  // fp32-parity (split) rows: [p0(16) | p1(16) | p2(16)]
+      float rem[16];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float2 f = __bfloat1622float2(hh[k]);
+        rem[2 * k] = o[2 * k] - f.x;
+        rem[2 * k + 1] = o[2 * k + 1] - f.y;
+      }
+#pragma unroll
+      for (int pc = 1; pc < kSplitPieces; ++pc) {
+        uint4 pl[2];
+        __nv_bfloat162* ll = reinterpret_cast<__nv_bfloat162*>(pl);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          ll[k] = __floats2bfloat162_rn(rem[2 * k], rem[2 * k + 1]);
+          const float2 f = __bfloat1622float2(ll[k]);
+          rem[2 * k] -= f.x;
+          rem[2 * k + 1] -= f.y;
+        }
+        *reinterpret_cast<uint4*>(d + 16 * pc) = pl[0];
+        *reinterpret_cast<uint4*>(d + 16 * pc + 8) = pl[1];
+      }
+    }
   }
 }
 
@@ -346,7 +369,7 @@ extern "C" int b200cv_kpt_head_bwd(const float* hm, const float* thm, const floa
                                    int ld, void* stream) {
   B200CV_CHECK_ARG(hm && pts && tpts && vx && vy && dlogits, "kpt_head_bwd: null pointer");
   B200CV_CHECK_ARG(B > 0 && K > 0 && K <= kKpt && H > 0 && W > 0 && ld >= 16 && ld % 8 == 0, "kpt_head_bwd: bad shape");
-  B200CV_CHECK_ARG(ld == 16, "kpt_head_bwd: dlogits row pitch must be 16 channels");
+  B200CV_CHECK_ARG(ld == 16 || ld == 16 * kSplitPieces, "kpt_head_bwd: dlogits rows are 16 channels (48 = split rows)");
   B200CV_CHECK_ARG(loss_type != 1 || thm, "kpt_head_bwd: l2_heatmap needs target_hm");
   B200CV_CHECK_ARG(!include_geo || (K == kKpt && ubar), "kpt_head_bwd: geometric term needs 7 keypoints and ubar");
   KptBwdArgs a{hm, thm, pts, tpts, ubar, vx, vy, g_loc, g_geo, d_hm_up, d_pts_up, B, K, H, W, loss_type, include_geo,

@@ -59,15 +59,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a broken pipeline must not hang the GPU box. On timeout the
-// error word is set and the caller carries on (results are garbage, the host
-// reports the error after the launch).
+// Bounded wait: a broken pipeline must not hang the GPU box, and it must not go unnoticed either.  On timeout the
+// error word is set (b200cv_check_device_error names the stage) and the kernel TRAPS: the launch -- and every later
+// CUDA call of the process -- fails loudly instead of feeding garbage activations to the optimizer.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 24)) {
       if (err) atomicExch(err, code);
-      return;
+      __threadfence_system();
+      asm volatile("trap;");
     }
   }
 }

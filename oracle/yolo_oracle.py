@@ -206,7 +206,10 @@ def yolo_layer(sample: torch.Tensor, targets: Optional[torch.Tensor], anchors, n
         boxes = torch.stack((x.data + gx, y.data + gy, torch.exp(w.data) * sa[:, 0].view(1, na, 1, 1),
                              torch.exp(h.data) * sa[:, 1].view(1, na, 1, 1)), dim=-1)
         return torch.cat((boxes.view(nb, -1, 4) * stride, conf.view(nb, -1, 1), cls.view(nb, -1, num_classes)), -1)
-    mask, conf_mask, tx, ty, tw, th, tconf, tcls = build_targets(targets, sa, num_classes, ngh, ngw, ignore_thres)
+    mask, conf_mask, tx, ty, tw, th, tconf, tcls = build_targets(targets.float(), sa, num_classes, ngh, ngw, ignore_thres)
+    # no-op in fp32 (the reference's arithmetic).  Tests also evaluate this restatement in fp64 -- same assignment,
+    # wider arithmetic -- as the yardstick for how far the reference's OWN fp32 rounding moves losses and gradients.
+    tx, ty, tw, th, tconf = (t.to(sample.dtype) for t in (tx, ty, tw, th, tconf))
     m = mask.bool()
     cf = (conf_mask - mask).bool()  # :196
     mse = lambda a, b: F.mse_loss(a, b, reduction="mean")

@@ -44,3 +44,15 @@ def grad_errors(named_params, gold_grads):
         scale = float(ref["val"].abs().max()) + ref["norm"] / max(1.0, p.numel() ** 0.5) + 1e-12
         errs[k] = float((mine - ref["val"]).abs().max()) / scale
     return errs
+
+
+def write_mini_cfg(directory, classes, layers_text):
+    """cfg of the two-head mini network of oracle/gen_golden_weights.py (same recipe, layer text from the golden)."""
+    os.makedirs(directory, exist_ok=True)
+    csv_path = os.path.join(directory, "train.csv")
+    if not os.path.exists(csv_path):
+        cfg_gen.write_anchor_csv(csv_path)
+    path = os.path.join(directory, f"mini_c{classes}.cfg")
+    with open(path, "w") as f:
+        f.write(cfg_gen._net(64, 64, classes, "3,4,5|0,1,2", "2,1", csv_path, "255,255") + layers_text)
+    return path

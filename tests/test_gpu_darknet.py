@@ -328,3 +328,52 @@ def test_full_size_eval_is_permutation_equivariant_and_reproducible(cfg_dir):
     assert torch.equal(d0, d1)
     assert torch.equal(dp, d0[perm])
     assert torch.equal(d2, d0[5:7])
+
+
+def test_eval_mode_loss_pass_without_no_grad(cfg_dir):
+    """Darknet.forward(x, targets) in eval mode with grad mode ON computes the 7-tuple (folded running statistics) and
+    returns it as a constant instead of raising."""
+    model, _ = helpers.make_darknet(cfg_dir, "yolo_baseline_tiny.cfg", 128, 1)
+    model = model.to(DEV).eval()
+    x, tg = YO.synth_images(2, 128, 128).to(DEV), YO.synth_targets(2, 16).to(DEV)
+    out = model(x, tg)
+    assert len(out) == 7 and not out[0].requires_grad and bool(torch.isfinite(out[0]))
+    with torch.no_grad():
+        again = model(x, tg)
+    assert float(out[0]) == float(again[0])
+
+
+def test_second_forward_before_backward_keeps_both_gradients(cfg_dir):
+    """Two same-shape training forwards whose losses are back-propagated LATER (summed micro-batches): the CUDA-graph
+    step must not let the second forward overwrite the first one's saved activations."""
+    model, _ = helpers.make_darknet(cfg_dir, "yolo_baseline_tiny.cfg", 128, 1)
+    model = model.to(DEV).train()
+    xs = [YO.synth_images(2, 128, 128, seed=s).to(DEV) for s in (0, 1)]
+    ts = [YO.synth_targets(2, 16, seed=10 + s).to(DEV) for s in (0, 1)]
+    for _ in range(4):  # get past the eager warm-up so the step is graph-replayed
+        model.zero_grad()
+        model(xs[0], ts[0])[0].backward()
+    singles = []
+    for x, t in zip(xs, ts):
+        model.zero_grad()
+        model(x, t)[0].backward()
+        singles.append({k: p.grad.clone() for k, p in model.named_parameters()})
+    model.zero_grad()
+    la = model(xs[0], ts[0])[0]
+    lb = model(xs[1], ts[1])[0]
+    (la + lb).backward()
+    for k, p in model.named_parameters():
+        want = singles[0][k] + singles[1][k]
+        cos = float((p.grad.double() * want.double()).sum() / (p.grad.double().norm() * want.double().norm() + 1e-30))
+        assert cos > 0.999, (k, cos)
+
+
+def test_dataparallel_wrap_is_refused_with_instructions(cfg_dir):
+    """train.py:193-195 wraps the model in nn.DataParallel when several GPUs are visible: replicating the B200 model
+    must fail loudly with the torchrun recipe, never train silently on stale replicas."""
+    model, _ = helpers.make_darknet(cfg_dir, "yolo_baseline_tiny.cfg", 128, 1)
+    with pytest.raises(RuntimeError, match="torchrun"):
+        model._replicate_for_data_parallel()
+    wrapped = torch.nn.DataParallel(model.to(DEV), device_ids=[0])  # one visible device: passes straight through
+    out = wrapped(YO.synth_images(2, 128, 128).to(DEV), YO.synth_targets(2, 16).to(DEV))
+    assert len(out) == 7

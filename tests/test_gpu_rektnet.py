@@ -105,3 +105,51 @@ def test_soft_argmax_delta():
     hm, pts = torch.empty_like(logits), torch.empty(1, 1, 2, device=DEV)
     lib().call("b200cv_kpt_softmax_argmax", ptr(logits), ptr(vx), ptr(vx), ptr(hm), ptr(pts), 1, 80, 80, stream_ptr())
     assert torch.allclose(pts.cpu().view(-1), torch.tensor([0.375, 0.125]), atol=1e-6)
+
+
+@pytest.mark.parametrize("cin,cout", [(16, 32), (64, 128)])
+def test_resnet_block_on_its_own(cin, cout):
+    """resnet.ResNet.forward as a callable block (RektNet/resnet.py:22-27): output, parameter gradients and the
+    gradient of its INPUT vs the oracle's res_block (pinned to the reference) on the same weights."""
+    import resnet
+
+    torch.manual_seed(3)
+    blk = resnet.ResNet(cin, cout)
+    params = {f"b.{k}": v.detach().clone().requires_grad_(True) for k, v in blk.named_parameters()}
+    buffers = {f"b.{k}": v.clone() for k, v in blk.named_buffers()}
+    g = torch.Generator().manual_seed(5)
+    xc = torch.randn(4, cin, 40, 40, generator=g).requires_grad_(True)
+    want = RO.res_block(xc, params, buffers, "b", True)
+    up = torch.randn(want.shape, generator=g)
+    want.backward(up)
+    blk = blk.to(DEV).train()
+    x = xc.detach().to(DEV).requires_grad_(True)
+    out = blk(x)
+    assert out.shape == want.shape and out.dtype == torch.float32
+    out.backward(up.to(DEV))
+    assert float((out.detach().cpu() - want.detach()).norm() / want.detach().norm()) < 1e-2
+    assert _cos(x.grad.cpu(), xc.grad) > 0.995
+    for k, p in blk.named_parameters():
+        if k.endswith("bias") and "bn" not in k:
+            continue  # conv biases: analytically zero gradient under train-mode BN
+        assert _cos(p.grad.cpu(), params[f"b.{k}"].grad) > 0.99, k
+    for k, b in blk.named_buffers():  # running statistics follow the reference (conv bias included in the mean)
+        if b.dtype.is_floating_point:
+            assert torch.allclose(b.cpu(), buffers[f"b.{k}"], rtol=2e-2, atol=2e-3), k
+    blk.eval()
+    y_eval = blk(x.detach())  # eval mode WITHOUT no_grad (RektNet/detect.py:38-39): computed, not differentiable
+    assert not y_eval.requires_grad
+    want_eval = RO.res_block(xc.detach(), {k: v.detach() for k, v in params.items()},
+                             {k: v.cpu() for k, v in (("b." + n, t) for n, t in blk.named_buffers())}, "b", False)
+    assert float((y_eval.cpu() - want_eval).norm() / want_eval.norm()) < 1e-2
+
+
+def test_eval_forward_without_no_grad():
+    """`model.eval(); out = model(x)` with grad mode ON must compute: reference RektNet/detect.py:38-39."""
+    net = _net().to(DEV).eval()
+    x, _, _ = RO.synth_batch(2, seed=0)
+    hm, pts = net(x.to(DEV))
+    assert not hm.requires_grad and not pts.requires_grad
+    with torch.no_grad():
+        hm2, pts2 = net(x.to(DEV))
+    assert torch.equal(pts, pts2)

@@ -58,6 +58,42 @@ def test_weights_file_roundtrip(cfg_dir, tmp_path):
             assert torch.equal(a, b), k
 
 
+def _state_items(model):
+    return list(model.named_parameters()) + [(k, v) for k, v in model.named_buffers() if v.dtype.is_floating_point]
+
+
+def test_weights_files_written_by_the_reference(cfg_dir, tmp_path):
+    """a-9: `.weights` bytes pinned to files the REFERENCE's save_weights wrote (oracle/gen_golden_weights.py):
+    A = 80-class model (255-filter heads), B = the 1-class model after load_weights(A, [255, 255]) kept the first 18 of
+    the 255 head filters (models.py:380-394).  Loading gives the reference's tensors; saving reproduces its bytes,
+    header included (`seen` lives in header[3], models.py:344,403)."""
+    import models
+
+    gold_dir = os.path.join(os.path.dirname(__file__), "golden")
+    g = torch.load(os.path.join(gold_dir, "weights_golden.pt"), weights_only=False)
+    a_path, b_path = os.path.join(gold_dir, "mini_c80_ref.weights"), os.path.join(gold_dir, "mini_c1_ref.weights")
+    m80 = models.Darknet(helpers.write_mini_cfg(cfg_dir, 80, g["layers"]), 2.0, 1.6, 25.0, 0.1, True)
+    m80.load_weights(a_path, m80.get_start_weight_dim())
+    assert int(m80.seen) == 777
+    helpers.assert_digest(_state_items(m80), g["digest_c80"])
+    out_a = str(tmp_path / "a.weights")
+    m80.seen = 777
+    m80.save_weights(out_a)
+    assert open(out_a, "rb").read() == open(a_path, "rb").read()
+    m1 = models.Darknet(helpers.write_mini_cfg(cfg_dir, 1, g["layers"]), 2.0, 1.6, 25.0, 0.1, True)
+    m1.load_weights(a_path, m1.get_start_weight_dim())  # truncation 255 -> 18 filters per head
+    assert int(m1.seen) == g["seen_after_load"] == 777
+    helpers.assert_digest(_state_items(m1), g["digest_c1"])
+    m1.seen = 778
+    out_b = str(tmp_path / "b.weights")
+    m1.save_weights(out_b)
+    assert open(out_b, "rb").read() == open(b_path, "rb").read()
+    # a model that never loaded a file can still save (the reference cannot: its header is a torch tensor, :277)
+    fresh = models.Darknet(helpers.write_mini_cfg(cfg_dir, 1, g["layers"]), 2.0, 1.6, 25.0, 0.1, True)
+    fresh.save_weights(str(tmp_path / "c.weights"))
+    assert os.path.getsize(str(tmp_path / "c.weights")) == os.path.getsize(b_path)
+
+
 def test_getters(cfg_dir):
     model, path = helpers.make_darknet(cfg_dir, "yolo_baseline_tiny.cfg", 416, 1)
     assert model.img_size() == (416, 416)
