@@ -49,9 +49,12 @@ def test_darknet_train_step_vs_reference(cfg_dir, golden_yolo, name):
     got = torch.stack([l.detach() for l in losses]).cpu()
     rel = ((got - g["losses"]).abs() / g["losses"].abs().clamp_min(1e-3))
     assert float(rel[0]) < LOSS_RTOL, (got, g["losses"])          # total loss
-    # parts are means over a handful of object cells; the 75-layer net at 4x4 resolution additionally amplifies the
-    # run-to-run ulp differences of the atomically accumulated BN statistics (observed: up to 3.2 % on one part)
-    part_tol = (6 if name.startswith("full") else 3) * LOSS_RTOL
+    # Parts: the north star's 1e-2 for the tiny networks (measured <= 8.7e-3; the statistics are accumulated with
+    # integer atomics now, so these numbers are reproducible).  Darknet-53 at 128x128 with B = 2 is the one case above
+    # it in the bf16 mode (x / y parts 2.3e-2 / 2.0e-2: means over ~10 object cells behind 75 bf16-stored layers with a
+    # 4x4 final grid); the fp32-parity mode meets 1e-4 on this golden (test_gpu_fp32_mode.py) and the bf16 mode meets
+    # 1e-2 on every part at the headline batch (test_gpu_headline.py).
+    part_tol = 3 * LOSS_RTOL if name.startswith("full") else LOSS_RTOL
     assert float(rel.max()) < part_tol, (got, g["losses"])
     emu, emu_losses = _emulated_oracle_grads(cfg_dir, g)
     rel_e = (got - emu_losses).abs() / emu_losses.abs().clamp_min(1e-3)
@@ -114,10 +117,14 @@ def test_darknet_loss_matches_oracle_on_device_weights(cfg_dir):
         assert abs(float(a) - float(b)) <= LOSS_RTOL * max(abs(float(b)), 1e-3)
 
 
-def test_darknet53_608_odd_grids_match_oracle(cfg_dir):
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_darknet53_608_odd_grids_match_oracle(cfg_dir, mode):
     """BASELINE config 4's shape (Darknet-53 at 608x608: grids 19/38/76, pixel counts that are not multiples of the
     128-row GEMM tile) at a batch the CPU oracle finishes in seconds: 7-tuple vs the oracle on the same weights, and a
-    backward pass whose gradients are finite and non-trivial for every parameter."""
+    backward pass whose gradients are finite and non-trivial for every parameter.  fp32-parity mode: every element of
+    the tuple within 1e-4.  bf16 mode: total within 1e-2; the w / h parts (means over ~15 object cells at B = 2, behind
+    75 bf16-stored layers) sit at 2.7e-2 / 3.5e-2 -- bounded at 5e-2 here, 1e-2 at the headline batch
+    (test_gpu_headline.py)."""
     model, path = helpers.make_darknet(cfg_dir, "yolo_baseline.cfg", 608, 80, seed=5)
     params = {k: v.detach().clone() for k, v in model.named_parameters()}
     buffers = {k: v.clone() for k, v in model.named_buffers()}
@@ -125,12 +132,16 @@ def test_darknet53_608_odd_grids_match_oracle(cfg_dir):
     with torch.no_grad():
         want = YO.darknet_forward(YO.NetSpec(path), params, buffers, x, tg)
     model = model.to(DEV).train()
+    model.engine().set_precision(mode)
     got = model(x.to(DEV), tg.to(DEV))
     g7 = torch.stack([l.detach() for l in got]).cpu()
     w7 = torch.stack([torch.as_tensor(float(v)) for v in want])
     rel = (g7 - w7).abs() / w7.abs().clamp_min(1e-3)
-    assert float(rel[0]) < LOSS_RTOL, (g7, w7)          # total loss
-    assert float(rel.max()) < 6 * LOSS_RTOL, (g7, w7)   # parts: means over a handful of object cells (B=2), see above
+    if mode == "fp32":
+        assert float(rel.max()) < 1e-4, (g7, w7)
+    else:
+        assert float(rel[0]) < LOSS_RTOL, (g7, w7)          # total loss
+        assert float(rel.max()) < 5 * LOSS_RTOL, (g7, w7)   # parts at B = 2 in the bf16 mode, see above
     got[0].sum().backward()
     for k, p in model.named_parameters():
         assert p.grad is not None and bool(torch.isfinite(p.grad).all()), k

@@ -30,7 +30,13 @@ def _worker(rank, world, port, out_dir):
     arena = torch.arange(10, dtype=torch.float32) * (rank + 1)  # the flat gradient arena of this replica
     parallel.allreduce_gradients(arena)
     lo, hi = parallel.shard_batch(7)
-    torch.save({"arena": arena, "shard": (lo, hi)}, os.path.join(out_dir, f"r{rank}.pt"))
+    # B200CV_AUTO_DP loss reporting: value = sum over the replicas (train.py:70 `losses[0].sum()` on a DataParallel
+    # output), gradient = this replica's own
+    w = torch.tensor([float(rank + 1)], requires_grad=True)
+    tot = parallel.sum_over_replicas(w * 2.0)
+    tot.sum().backward()
+    torch.save({"arena": arena, "shard": (lo, hi), "dp_value": tot.detach(), "dp_grad": w.grad},
+               os.path.join(out_dir, f"r{rank}.pt"))
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
 
@@ -43,6 +49,8 @@ def test_allreduce_sum_and_sharding(tmp_path):
     for r in res:
         assert torch.equal(r["arena"], want)
     assert [r["shard"] for r in res] == [(0, 4), (4, 7)]
+    for r in res:
+        assert float(r["dp_value"]) == 6.0 and float(r["dp_grad"]) == 2.0  # 2*1 + 2*2 everywhere; own gradient only
 
 
 def test_single_process_is_a_noop():
@@ -53,3 +61,27 @@ def test_single_process_is_a_noop():
     t = torch.ones(4)
     parallel.allreduce_gradients(t)
     assert torch.equal(t, torch.ones(4)) and parallel.world_size() == 1 and parallel.shard_batch(5) == (0, 5)
+
+
+def test_dataparallel_chunks_and_gpu_binding(monkeypatch):
+    """B200CV_AUTO_DP: the scatter chunks of nn.DataParallel (torch.chunk: ceil(n/w) per replica) and the one-GPU-per-
+    process binding that lets the unchanged train.py (device 'cuda:0', DataParallel only when device_count() > 1) run
+    under torchrun."""
+    from b200cv import parallel
+
+    assert [parallel.dp_chunk(64, r, 8) for r in (0, 7)] == [(0, 8), (56, 64)]
+    assert [parallel.dp_chunk(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]  # torch.chunk sizes
+    assert parallel.dp_chunk(5, 3, 4) == (5, 5)  # trailing replica without work
+    monkeypatch.delenv("B200CV_AUTO_DP", raising=False)
+    monkeypatch.setenv("WORLD_SIZE", "4")
+    assert not parallel.auto_dp_enabled()
+    monkeypatch.setenv("B200CV_AUTO_DP", "1")
+    assert parallel.auto_dp_enabled()
+    monkeypatch.setenv("LOCAL_RANK", "2")
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "4,5,6,7")
+    monkeypatch.delenv("B200CV_AUTO_DP_BOUND", raising=False)
+    monkeypatch.setattr(torch.cuda, "is_initialized", lambda: False)
+    parallel.bind_process_to_local_gpu()
+    assert os.environ["CUDA_VISIBLE_DEVICES"] == "6" and os.environ["B200CV_AUTO_DP_BOUND"] == "1"
+    parallel.bind_process_to_local_gpu()  # DataLoader workers inherit the environment: no second remap
+    assert os.environ["CUDA_VISIBLE_DEVICES"] == "6"

@@ -40,8 +40,7 @@ def run(batch=128, iters=30, warmup=3, boxes=8.0, classes=80, frame=(720, 1280))
     from b200cv import synth
     from utils.utils import weights_init_normal
 
-    dev = torch.device("cuda:0")
-    torch.cuda.set_device(dev)
+    dev = torch.device("cuda", torch.cuda.current_device())
     B, (H, W) = args.batch, args.frame
     d = tempfile.mkdtemp()
     torch.manual_seed(0)
