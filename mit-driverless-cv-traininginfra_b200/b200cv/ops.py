@@ -268,7 +268,7 @@ def sm_count(device=None) -> int:
 
 
 # rows of a partial-statistics matrix: CTA / block b adds into row b % STAT_PARTS (spreads the atomics)
-STAT_PARTS = int(__import__("os").environ.get("B200CV_STAT_PARTS", "4"))
+STAT_PARTS = int(__import__("os").environ.get("B200CV_STAT_PARTS", "1"))
 STAT_WORDS = 2  # int64 words of one entry (b200cv_stat: value = w1 * 2^-20 + w2 * 2^-70)
 
 

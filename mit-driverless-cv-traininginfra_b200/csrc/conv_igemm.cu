@@ -342,19 +342,49 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int stat_parts = kBnRed ? p.bn_parts : p.stats_parts;
       StatAcc* stats_row =
           stat_base ? stat_base + static_cast<long long>(blockIdx.x % stat_parts) * 2 * p.Cout : nullptr;
+      // The epilogue warps that own the same columns (the four lane quarters of one half; all eight with 256-row tiles)
+      // first add their partial sums in shared memory, in warp order, so that ONE integer add per column and CTA goes
+      // to global memory: with 148 CTAs x 4-8 warps hitting the same few addresses the atomics of the last wave
+      // showed up as a 5-8 % tail on the 3x3 data gradients.  All eight warps flush at the same tiles.
+      bool store_pending = false;
       auto flush = [&](int nt_) {
+        if (store_pending) {  // the parking area is this warp's staging tile: its last bulk store must have read it
+          if (lane == 0) ptx::tma_store_wait_read<0>();
+          __syncwarp();
+          store_pending = false;
+        }
+        float* park = reinterpret_cast<float*>(stg);
 #pragma unroll
         for (int bi = 0; bi < kBPW; ++bi) {
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const int n = nt_ * BN + block_of(bi) * 64 + my_col + e;
-            if (n < p.Cout) {
-              stat_add(stats_row + n, acc_s[bi][e]);
-              stat_add(stats_row + p.Cout + n, kBnRed ? acc_t[bi][e] * __ldg(p.bn_rstd + n) : acc_t[bi][e]);
-            }
+            park[((bi * 2 + e) * 2 + 0) * 32 + lane] = acc_s[bi][e];
+            park[((bi * 2 + e) * 2 + 1) * 32 + lane] = acc_t[bi][e];
             acc_s[bi][e] = acc_t[bi][e] = 0.f;
           }
         }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        const int g0 = kM2 ? 0 : 4 * half;
+        if (ew == g0) {
+#pragma unroll
+          for (int bi = 0; bi < kBPW; ++bi) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              float ssum = 0.f, tsum = 0.f;
+              for (int w = g0; w < g0 + (kM2 ? 8 : 4); ++w) {
+                const float* pk = reinterpret_cast<const float*>(s_extra + w * 4096);
+                ssum += pk[((bi * 2 + e) * 2 + 0) * 32 + lane];
+                tsum += pk[((bi * 2 + e) * 2 + 1) * 32 + lane];
+              }
+              const int n = nt_ * BN + block_of(bi) * 64 + my_col + e;
+              if (n < p.Cout) {
+                stat_add(stats_row + n, ssum);
+                stat_add(stats_row + p.Cout + n, kBnRed ? tsum * __ldg(p.bn_rstd + n) : tsum);
+              }
+            }
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       };
       // ---- fused BN backward: ring of TMA-loaded y tiles (4 KB each), `yslots` blocks ahead
       const int yslots = p.y_slots, ylog = p.y_slots_log2;
@@ -388,7 +418,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       }
       int stat_nt = -1;
-      bool store_pending = false;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -656,23 +685,47 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       int stat_nt = -1;
       bool store_pending = false;
+      // the four lane-quarter warps of one half own the same columns: add their partial sums in shared memory (warp
+      // order) and send ONE integer add per column and CTA to global memory (see the wide form above)
+      auto flush_narrow = [&](int nt_) {
+        if (store_pending) {
+          if (lane == 0) ptx::tma_store_wait_read<0>();
+          __syncwarp();
+          store_pending = false;
+        }
+        float* park = reinterpret_cast<float*>(stg);
+#pragma unroll
+        for (int ci = 0; ci < C::kChunksPerWarp; ++ci) {
+          park[(ci * 2 + 0) * 32 + lane] = acc_s[ci];
+          park[(ci * 2 + 1) * 32 + lane] = acc_t[ci];
+          acc_s[ci] = acc_t[ci] = 0.f;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        if (ew == 4 * half) {
+#pragma unroll
+          for (int ci = 0; ci < C::kChunksPerWarp; ++ci) {
+            float ssum = 0.f, tsum = 0.f;
+            for (int w = 4 * half; w < 4 * half + 4; ++w) {
+              const float* pk = reinterpret_cast<const float*>(s_extra + w * 2048);
+              ssum += pk[(ci * 2 + 0) * 32 + lane];
+              tsum += pk[(ci * 2 + 1) * 32 + lane];
+            }
+            const int n = nt_ * BN + (half + 2 * ci) * C::kChunk + my_col;
+            if (col_owner && (half + 2 * ci) < C::kNumChunks && n < p.Cout) {
+              stat_add(stats_row + n, ssum);
+              stat_add(stats_row + p.Cout + n, kBnRed ? tsum * __ldg(p.bn_rstd + n) : tsum);
+            }
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      };
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mt = tile / p.num_n_tiles;
         const int nt = tile - mt * p.num_n_tiles;
         if (stat_base && nt != stat_nt) {
-          if (stat_nt >= 0) {
-#pragma unroll
-            for (int ci = 0; ci < C::kChunksPerWarp; ++ci) {
-              const int n = stat_nt * BN + (half + 2 * ci) * C::kChunk + my_col;
-              if (col_owner && (half + 2 * ci) < C::kNumChunks && n < p.Cout) {
-                stat_add(stats_row + n, acc_s[ci]);
-                stat_add(stats_row + p.Cout + n, kBnRed ? acc_t[ci] * __ldg(p.bn_rstd + n) : acc_t[ci]);
-              }
-              acc_s[ci] = acc_t[ci] = 0.f;
-            }
-          }
+          if (stat_nt >= 0) flush_narrow(stat_nt);
           stat_nt = nt;
         }
         const int m_warp = mt * kBlockM + quarter * 32;  // first output row of this warp
@@ -880,16 +933,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           acc_phase ^= 1;
         }
       }
-      if (stat_base && stat_nt >= 0) {
-#pragma unroll
-        for (int ci = 0; ci < C::kChunksPerWarp; ++ci) {
-          const int n = stat_nt * BN + (half + 2 * ci) * C::kChunk + my_col;
-          if (col_owner && (half + 2 * ci) < C::kNumChunks && n < p.Cout) {
-            stat_add(stats_row + n, acc_s[ci]);
-            stat_add(stats_row + p.Cout + n, kBnRed ? acc_t[ci] * __ldg(p.bn_rstd + n) : acc_t[ci]);
-          }
-        }
-      }
+      if (stat_base && stat_nt >= 0) flush_narrow(stat_nt);
       if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
       __syncwarp();
     } else {

@@ -858,6 +858,45 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __
   }
 }
 
+// Stride-2 windows on even H, W do not overlap: one thread per WINDOW reads its four inputs and dy once and writes the
+// four dx values (dy to the first maximum, zeros elsewhere) -- the gather form above re-read three neighbours and dy
+// for every input pixel (0.55 ms of the 2.6 ms yolov3-tiny step at 416x416 bs16).
+__global__ void maxpool_bwd_s2_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                      __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int OH, int OW) {
+  const int vpr = C >> 3;
+  const long long total = (long long)N * OH * OW * vpr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % vpr) << 3;
+    long long r = i / vpr;
+    const int ow = (int)(r % OW); r /= OW;
+    const int oh = (int)(r % OH);
+    const long long n = r / OH;
+    const long long base = ((n * H + 2 * oh) * W + 2 * ow) * C + c0;
+    float v[4][8], d[8];
+    unpack8(ldg16(x + base), v[0]);
+    unpack8(ldg16(x + base + C), v[1]);
+    unpack8(ldg16(x + base + (long long)W * C), v[2]);
+    unpack8(ldg16(x + base + (long long)W * C + C), v[3]);
+    unpack8(ldg16(dy + ((n * OH + oh) * OW + ow) * C + c0), d);
+    float o[4][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int arg = 0;
+      float best = v[0][j];
+#pragma unroll
+      for (int pos = 1; pos < 4; ++pos)
+        if (v[pos][j] > best) { best = v[pos][j]; arg = pos; }  // first maximum in scan order
+#pragma unroll
+      for (int pos = 0; pos < 4; ++pos) o[pos][j] = pos == arg ? d[j] : 0.f;
+    }
+    stg16(dx + base, pack8(o[0]));
+    stg16(dx + base + C, pack8(o[1]));
+    stg16(dx + base + (long long)W * C, pack8(o[2]));
+    stg16(dx + base + (long long)W * C + C, pack8(o[3]));
+  }
+}
+
 // ------------------------------------------------------------------ nearest x2 upsample
 __global__ void upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                       long long y_ld, int N, int H, int W, int C) {
@@ -1156,6 +1195,11 @@ extern "C" int b200cv_maxpool2x2_bwd(const void* x, const void* dy, void* dx, in
   B200CV_CHECK_ARG(ok_vec(x, C, C) && ok_vec(dy, C, C) && ok_vec(dx, C, C) && (stride == 1 || stride == 2),
                    "maxpool_bwd: bad args");
   const int OH = stride == 2 ? H / 2 : H, OW = stride == 2 ? W / 2 : W;
+  if (stride == 2 && H % 2 == 0 && W % 2 == 0) {
+    maxpool_bwd_s2_kernel<<<ew_grid((long long)N * OH * OW * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        (const bf16*)x, (const bf16*)dy, (bf16*)dx, N, H, W, C, OH, OW);
+    return check_launch("maxpool_bwd");
+  }
   maxpool_bwd_kernel<<<ew_grid((long long)N * H * W * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       (const bf16*)x, (const bf16*)dy, (bf16*)dx, N, H, W, C, stride, OH, OW);
   return check_launch("maxpool_bwd");
