@@ -22,6 +22,7 @@ import torch
 from . import ops, yolo_ops
 from .lib import require_cuda
 from .packing import ConvPackSet, GradArena
+from . import parallel
 from .parallel import allreduce_gradients
 
 BN_EPS = 1e-5
@@ -227,8 +228,70 @@ class DarknetEngine:
             return self._run_forward_impl(x, targets, bn_train, want_grad, private)
 
     def _run_backward(self, state, g7, force_persistent_arena=False, do_allreduce=True):
+        """Eager backward.  With several processes the gradient arena is all-reduced (SUM) in buckets: the bucket of
+        the LAST layers is complete first and its transfer runs on the collective's stream while the earlier layers are
+        still being back-propagated."""
+        handles = []
+        gen = self._run_backward_segments(state, g7, force_persistent_arena, parallel.grad_buckets() if do_allreduce else 1)
+        while True:
+            try:
+                chunk = next(gen)
+            except StopIteration as done:
+                views = done.value
+                break
+            if do_allreduce:
+                handles.append(parallel.allreduce_gradients_async(chunk))
+        parallel.finish_allreduces(handles)
+        return views
+
+    def _run_backward_segments(self, state, g7, force_persistent_arena, nbuckets):
+        """Generator form of the backward pass: yields the slice of the flat gradient arena that has just become final
+        (all its layers back-propagated, weight gradients un-packed), `nbuckets` times, last layers first; returns the
+        per-parameter views.  The CUDA-graph step captures every segment as a graph of its own."""
         with ops.precision(self.split):
-            return self._run_backward_impl(state, g7, force_persistent_arena, do_allreduce)
+            gen = self._run_backward_impl(state, g7, force_persistent_arena, nbuckets)
+            while True:
+                try:
+                    chunk = next(gen)
+                except StopIteration as done:
+                    return done.value
+                _tls_leave = ops.split_mode()  # the consumer runs outside the precision context
+                ops._tls.split = False
+                try:
+                    yield chunk
+                finally:
+                    ops._tls.split = _tls_leave
+
+    def _bucket_plan(self, nbuckets):
+        """[(first layer index, arena lo, arena hi, conv lo, conv hi)] of the gradient buckets in BACKWARD order, cut at
+        layer boundaries.  Shares of the parameter bytes shrink geometrically (60 %, 24 %, 9.6 %, ...): most parameters
+        sit in the LAST layers, whose backward is over after a fraction of the pass, while the early high-resolution
+        layers take most of the time and own few parameters -- the bucket that is still exposed after backward is
+        the smallest one."""
+        layer_params, conv_index = [], []
+        nconv = 0
+        for L in self.layers:
+            n = 0
+            if L.type == "convolutional":
+                n = sum(p.numel() for p in L.conv.parameters()) + (sum(p.numel() for p in L.bn.parameters())
+                                                                  if L.bn is not None else 0)
+                nconv += 1
+            layer_params.append(n)
+            conv_index.append(nconv)  # convs in layers [0, i]
+        total = sum(layer_params)
+        offs = [0]
+        for n in layer_params:
+            offs.append(offs[-1] + n)
+        plan, hi_layer = [], len(self.layers)
+        for k in range(nbuckets - 1):
+            target = total * 0.4 ** (k + 1)  # arena offset where this bucket should start
+            lo_layer = min(range(hi_layer), key=lambda i: abs(offs[i] - target)) if hi_layer > 0 else 0
+            if lo_layer >= hi_layer or lo_layer <= 0:
+                continue
+            plan.append((lo_layer, offs[lo_layer], offs[hi_layer], conv_index[lo_layer - 1], conv_index[hi_layer - 1]))
+            hi_layer = lo_layer
+        plan.append((0, 0, offs[hi_layer], 0, conv_index[hi_layer - 1] if hi_layer > 0 else 0))
+        return plan
 
     def _run_forward_impl(self, x, targets, bn_train: bool, want_grad: bool, private: bool = False):
         """Returns (out7 or detections, saved-state).  `private`: the per-layer BatchNorm vectors this pass saves for
@@ -319,8 +382,10 @@ class DarknetEngine:
         return torch.cat(dets, 1), None
 
     # ------------------------------------------------------------------ backward
-    def _run_backward_impl(self, state, g7, force_persistent_arena=False, do_allreduce=True):
+    def _run_backward_impl(self, state, g7, force_persistent_arena=False, nbuckets=1):
         outs, saved, private = state
+        plan = self._bucket_plan(nbuckets)
+        cut = {first: (lo, hi, clo, chi) for first, lo, hi, clo, chi in plan}
         model = self.model
         dev = g7.device
         g = g7[0:1].contiguous().float()
@@ -374,6 +439,13 @@ class DarknetEngine:
 
         for L in reversed(self.layers):
             i = L.index
+            if (i + 1) in cut:  # every layer > i is done: that bucket of the gradient arena is final
+                if side is not None:
+                    main.wait_stream(side)
+                    keep.clear()
+                lo, hi, clo, chi = cut[i + 1]
+                packs.unpack_range(clo, chi)
+                yield arena.flat[lo:hi]
             if L.type == "yolo":
                 z, yt = saved[i]
                 dl = yolo_ops.yolo_head_grad(z, yt, L.yolo.num_classes, consts, g)
@@ -454,9 +526,9 @@ class DarknetEngine:
         if side is not None:
             main.wait_stream(side)
         keep.clear()
-        packs.unpack_all()
-        if do_allreduce:
-            allreduce_gradients(arena.flat)
+        lo, hi, clo, chi = cut[0]
+        packs.unpack_range(clo, chi)
+        yield arena.flat[lo:hi]
         return views
 
     # ------------------------------------------------------------------ public entry points
@@ -561,7 +633,7 @@ class _GraphedStep:
         self.weight_ptrs = tuple(p.data_ptr() for p in engine.params)
         torch.cuda.synchronize()
         self.pool = torch.cuda.graph_pool_handle()
-        self.fwd_graph, self.bwd_graph = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        self.fwd_graph = torch.cuda.CUDAGraph()
         from .lib import lib
 
         n0 = lib().launches
@@ -569,9 +641,21 @@ class _GraphedStep:
             with torch.cuda.graph(self.fwd_graph, pool=self.pool):
                 self.out7, self.state = engine._run_forward(self.static_x, self.static_t, bn_train=True, want_grad=True)
             n1 = lib().launches
-            with torch.cuda.graph(self.bwd_graph, pool=self.pool):
-                self.views = engine._run_backward(self.state, self.static_g, force_persistent_arena=True,
-                                                  do_allreduce=False)
+            # backward: one graph per gradient bucket (a single one without data parallelism), so that the all-reduce
+            # of a finished bucket can be started between two replays and overlap the rest of the pass
+            self.bwd_graphs, self.buckets = [], []
+            gen = engine._run_backward_segments(self.state, self.static_g, True, parallel.grad_buckets())
+            done = False
+            while not done:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=self.pool):
+                    try:
+                        self.buckets.append(next(gen))
+                    except StopIteration as fin:
+                        self.views = fin.value
+                        done = True
+                if not done:
+                    self.bwd_graphs.append(g)
         # kernel-launching ABI calls recorded in each graph: a replay launches that many of our kernels
         self.fwd_launches, self.bwd_launches = n1 - n0, lib().launches - n1
         self.generation = 0        # bumped by every replayed forward (a stale backward is refused)
@@ -607,7 +691,10 @@ class _DarknetGraphFn(torch.autograd.Function):
         step.engine._pending = None
         with torch.cuda.device(step.static_g.device):
             step.static_g.copy_(g7)
-            step.bwd_graph.replay()
+            handles = []
+            for graph, chunk in zip(step.bwd_graphs, step.buckets):
+                graph.replay()
+                handles.append(parallel.allreduce_gradients_async(chunk))  # overlaps the next segment's replay
             _count_launches(step.bwd_launches)
-            allreduce_gradients(step.engine._arena.flat)
+            parallel.finish_allreduces(handles)
         return (None, None, None, *step.views)

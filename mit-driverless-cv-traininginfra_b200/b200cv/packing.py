@@ -121,3 +121,10 @@ class ConvPackSet:
 
     def unpack_all(self):
         lib().call("b200cv_unpack_wgrad_multi", self._unpack_table.data_ptr(), self._n_unpack, stream_ptr())
+
+    def unpack_range(self, lo: int, hi: int):
+        """Un-pack the weight gradients of convs [lo, hi) (network order) only: lets the data-parallel all-reduce of a
+        finished bucket of layers start while backward is still working on the earlier layers."""
+        if hi > lo:
+            lib().call("b200cv_unpack_wgrad_multi", self._unpack_table.data_ptr() + lo * _ENTRY.itemsize, hi - lo,
+                       stream_ptr())

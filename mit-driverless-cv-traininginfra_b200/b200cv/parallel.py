@@ -97,6 +97,31 @@ def allreduce_gradients(arena: torch.Tensor) -> None:
         dist.all_reduce(arena, op=dist.ReduceOp.SUM)
 
 
+def allreduce_gradients_async(chunk: torch.Tensor):
+    """Start the SUM all-reduce of one bucket of the gradient arena on the collective's own stream (it waits for the
+    work already queued on the current stream, the current stream does NOT wait for it): backward of the earlier layers
+    overlaps the transfer.  Returns a handle for finish_allreduces, or None for a single process."""
+    if world_size() <= 1 or chunk.numel() == 0:
+        return None
+    return dist.all_reduce(chunk, op=dist.ReduceOp.SUM, async_op=True)
+
+
+def finish_allreduces(handles) -> None:
+    """Make the current stream wait for every bucket started with allreduce_gradients_async."""
+    for h in handles:
+        if h is not None:
+            h.wait()
+
+
+def grad_buckets() -> int:
+    """Number of gradient buckets of a data-parallel step (B200CV_GRAD_BUCKETS, default 4; 1 = one all-reduce after
+    backward).  A single process always uses one."""
+    forced = os.environ.get("B200CV_GRAD_BUCKETS_FORCE")  # tests: segment the backward pass in a single process too
+    if forced:
+        return max(1, int(forced))
+    return max(1, int(os.environ.get("B200CV_GRAD_BUCKETS", "4"))) if world_size() > 1 else 1
+
+
 def shard_batch(n: int, r: int | None = None, w: int | None = None):
     """[start, stop) of the contiguous shard of a global batch of n that rank r owns."""
     r = rank() if r is None else r

@@ -166,9 +166,11 @@ class RektNetEngine:
         with ops.precision(self.split):
             return self._forward_impl(x, train, want_grad)
 
-    def _backward(self, saved, hm, pts, d_hm, d_pts, handle: Optional["_HeadHandle"], logits_grad=None):
+    def _backward(self, saved, hm, pts, d_hm, d_pts, handle: Optional["_HeadHandle"], logits_grad=None,
+                  do_allreduce=True, persistent_arena=False):
         with ops.precision(self.split):
-            return self._backward_impl(saved, hm, pts, d_hm, d_pts, handle, logits_grad)
+            return self._backward_impl(saved, hm, pts, d_hm, d_pts, handle, logits_grad, do_allreduce,
+                                       persistent_arena)
 
     def _forward_impl(self, x, train: bool, want_grad: bool):
         m = self.model
@@ -216,11 +218,12 @@ class RektNetEngine:
         return hm, pts
 
     # ------------------------------------------------------------------ backward
-    def _backward_impl(self, saved, hm, pts, d_hm, d_pts, handle: Optional[_HeadHandle], logits_grad=None):
+    def _backward_impl(self, saved, hm, pts, d_hm, d_pts, handle: Optional[_HeadHandle], logits_grad=None,
+                       do_allreduce=True, persistent_arena=False):
         m = self.model
         dev = hm.device if hm is not None else logits_grad.device
         arena = self._arena
-        if arena.aliased_by_param_grads():
+        if not persistent_arena and arena.aliased_by_param_grads():
             arena = GradArena(self.params, dev)
             packs = ConvPackSet(self._conv_list(), dev, arena, flat=[self.stem.conv], split=self.split)
         else:
@@ -282,7 +285,8 @@ class RektNetEngine:
             g = c1.bwd(a_in, y1, g_a1, None, ops.ACT_RELU, gview, packs, dx_out=g_in, parts=parts1, bn_reduce=red0)
         self.stem.bwd(saved["x"], saved["y0"], g, None, ops.ACT_RELU, gview, packs, want_dx=False, parts=stem_parts)
         packs.unpack_all()
-        allreduce_gradients(arena.flat)
+        if do_allreduce:
+            allreduce_gradients(arena.flat)
         return views
 
     # ------------------------------------------------------------------ public entry point
@@ -293,10 +297,144 @@ class RektNetEngine:
             if m.onnx_mode:
                 return _KeypointLogitsFn.apply(self, x.float(), m.training, torch.is_grad_enabled(), *self.params)
             handle = _HeadHandle()
-            hm, pts = _KeypointNetFn.apply(self, x.float(), m.training, handle, torch.is_grad_enabled(), *self.params)
+            step = self._graphed_step(x)
+            if step is not None:
+                hm, pts = _KeypointGraphFn.apply(step, x, handle, *self.params)
+            else:
+                hm, pts = _KeypointNetFn.apply(self, x.float(), m.training, handle, torch.is_grad_enabled(),
+                                               *self.params)
         hm._b200cv_head = handle
         pts._b200cv_head = handle
         return hm, pts
+
+    def _graphed_step(self, x):
+        """The CUDA-graph step for this input shape, once two eager training steps have run with it (None = take the
+        eager launches).  ~100 launches per step: at the reference's batch sizes (8-32) the host cannot keep up."""
+        if not (self.model.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.params)):
+            return None
+        if os.environ.get("B200CV_CUDA_GRAPH", "1") == "0" or torch.cuda.is_current_stream_capturing():
+            return None
+        graphs = self.__dict__.setdefault("_graphs", {})
+        key = (tuple(x.shape), str(x.device), self.split)
+        entry = graphs.get(key, 0)
+        if isinstance(entry, _GraphedRektStep):
+            return entry if entry.usable() else None
+        if entry >= GRAPH_WARMUP_CALLS:
+            try:
+                graphs[key] = _GraphedRektStep(self, x)
+                return graphs[key]
+            except Exception as e:  # capture is an optimisation: fall back to the eager launches, loudly
+                import warnings
+
+                warnings.warn(f"b200cv: CUDA-graph capture of the KeypointNet step failed ({e}); staying eager")
+                graphs[key] = -(10 ** 9)
+                torch.cuda.synchronize()
+                return None
+        graphs[key] = entry + 1
+        return None
+
+
+GRAPH_WARMUP_CALLS = 2
+
+
+class _GraphedRektStep:
+    """One KeypointNet training step (fixed input shape) as CUDA graphs sharing a memory pool: the forward graph
+    (network + soft-argmax) is captured at the third step with a shape; the backward graph -- loss gradient, fused head
+    backward, the whole backbone -- at the first backward whose CrossRatioLoss configuration is known, one per
+    configuration.  The heat-maps / points handed to the caller are views of the step's static buffers: valid until
+    the next training forward with the same shape (every training loop consumes them at once)."""
+
+    def __init__(self, engine, x):
+        self.engine = engine
+        dev = x.device
+        self.static_x = x.detach().float().clone()
+        engine._setup(dev)
+        self.weight_ptrs = tuple(p.data_ptr() for p in engine.params)
+        torch.cuda.synchronize()
+        self.pool = torch.cuda.graph_pool_handle()
+        self.fwd_graph = torch.cuda.CUDAGraph()
+        n0 = lib().launches
+        with torch.no_grad():
+            with torch.cuda.graph(self.fwd_graph, pool=self.pool):
+                logits, self.saved = engine._forward(self.static_x, True, True)
+                self.hm, self.pts = engine._softmax(logits)
+        self.fwd_launches = lib().launches - n0
+        self.bwd = {}  # loss configuration -> (graph, static loss tensors, views, launches)
+        self.generation = 0
+        torch.cuda.synchronize()
+
+    def usable(self) -> bool:
+        e = self.engine
+        return (tuple(p.data_ptr() for p in e.params) == self.weight_ptrs and e._arena is not None
+                and not e._arena.aliased_by_param_grads())
+
+    def backward(self, handle, d_hm, d_pts):
+        """Replay (or first capture) the backward graph for the pending loss; None = not graphable (the caller runs the
+        eager backward on the saved static activations)."""
+        p = handle.pending if handle is not None else None
+        if p is None or d_hm is not None or not self.usable():
+            return None
+        key = (p["loss_type"], bool(p["include_geo"]), float(p["gamma_h"]), float(p["gamma_v"]), p["thm"] is None)
+        names = ("thm", "tpts", "ubar", "g_loc", "g_geo")
+        entry = self.bwd.get(key)
+        if entry is None:
+            static = {k: (p[k].detach().clone() if p[k] is not None else None) for k in names}
+            static_dpts = torch.zeros_like(self.pts) if d_pts is None else d_pts.detach().clone()
+            pend = dict(p)
+            pend.update(static)
+            h = _HeadHandle()
+            h.pending = pend
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = lib().launches
+            with torch.no_grad():
+                with torch.cuda.graph(g, pool=self.pool):
+                    views = self.engine._backward(self.saved, self.hm, self.pts, None, static_dpts, h,
+                                                  do_allreduce=False, persistent_arena=True)
+            entry = (g, static, static_dpts, views, lib().launches - n0)
+            self.bwd[key] = entry
+        g, static, static_dpts, views, launches = entry
+        for k in names:
+            if static[k] is not None:
+                static[k].copy_(p[k], non_blocking=True)
+        if d_pts is None:
+            static_dpts.zero_()
+        else:
+            static_dpts.copy_(d_pts, non_blocking=True)
+        handle.pending = None
+        g.replay()
+        lib().launches += launches
+        allreduce_gradients(self.engine._arena.flat)
+        return views
+
+
+class _KeypointGraphFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, step, x, handle, *params):
+        step.static_x.copy_(x, non_blocking=True)
+        step.fwd_graph.replay()
+        lib().launches += step.fwd_launches
+        for c in step.engine._all():  # the replay moved the running statistics: drop the folded inference affines
+            c._eval_key = None
+        step.generation += 1
+        ctx.step, ctx.handle, ctx.generation = step, handle, step.generation
+        ctx.set_materialize_grads(False)
+        return step.hm.view_as(step.hm), step.pts.view_as(step.pts)
+
+    @staticmethod
+    def backward(ctx, d_hm, d_pts):
+        step = ctx.step
+        if ctx.generation != step.generation:
+            raise RuntimeError("b200cv: this KeypointNet forward was replayed from a CUDA graph and a LATER forward of "
+                               "the same shape has overwritten its saved activations; back-propagate each forward "
+                               "before the next one, or set B200CV_CUDA_GRAPH=0")
+        d_hm = d_hm.contiguous().float() if d_hm is not None else None
+        d_pts = d_pts.contiguous().float() if d_pts is not None else None
+        with torch.cuda.device(step.static_x.device):
+            views = step.backward(ctx.handle, d_hm, d_pts)
+            if views is None:  # un-fused loss / upstream heat-map gradient: eager backward on the static activations
+                views = step.engine._backward(step.saved, step.hm, step.pts, d_hm, d_pts, ctx.handle)
+        return (None, None, None, *views)
 
 
 class _KeypointNetFn(torch.autograd.Function):
@@ -312,6 +450,7 @@ class _KeypointNetFn(torch.autograd.Function):
             return hm, pts
         ctx.engine, ctx.saved, ctx.handle = engine, saved, handle
         ctx.save_for_backward(hm, pts)
+        ctx.set_materialize_grads(False)  # an output the loss does not use arrives as None, not as a zero tensor
         return hm, pts
 
     @staticmethod

@@ -27,7 +27,6 @@ namespace {
 
 constexpr int kWThreads = 256;   // warp 0, 6, 7: TMA producers; warp 1: MMA issuer; warps 2..5: epilogue
 constexpr int kWProducers = 3;
-constexpr int kKB = 64;         // pixels per k-block
 constexpr int kMaxWStages = 8;
 
 struct WgradParams {
@@ -48,8 +47,11 @@ struct WgradParams {
   short tap_h[kMaxTaps];
 };
 
-// CB: channels per B slab (16/32/64), BNW: N tile (CB, or 128 = two 64-channel slabs)
-template <int CB, int BNW>
+// CB: channels per B slab (16/32/64), BNW: N tile (CB, or 128 = two 64-channel slabs), kKB: pixels per k-block.
+// kKB = 64 for the multi-tap (3x3) layers; the single-tap layers (1x1 convolutions, the flat image layers) were bound
+// by the ISSUE rate of their one producer thread -- one TMA instruction per ~166 ns whatever its size, 2-4 of them
+// per 64-pixel block against 130 ns of tensor work -- and take 128- or 256-pixel blocks.
+template <int CB, int BNW, int kKB>
 __global__ void __launch_bounds__(kWThreads, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
              const __grid_constant__ CUtensorMap tmDW, const __grid_constant__ WgradParams p) {
@@ -65,7 +67,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
   // align to 1024 B (128B-swizzle atom) by pointer arithmetic so the shared state space stays provable
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int a_bytes = p.a_slabs * kASlabBytes;
-  const int stage_bytes = 2 * kASlabBytes + p.T * kBTapBytes;  // A region always 2 slabs wide
+  const int stage_bytes = p.a_slabs * kASlabBytes + p.T * kBTapBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + kMaxWStages;
   uint64_t* done_bar = empty_bar + kMaxWStages;
@@ -145,7 +147,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
             const int b_off = p.npass == 1 ? 0 : ((0x118 >> (2 * ps)) & 3) * p.b_lo;
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err, 11);
             uint8_t* sa = smem + stage * stage_bytes;
-            uint8_t* sb = sa + 2 * kASlabBytes;
+            uint8_t* sb = sa + a_bytes;
             ptx::mbar_expect_tx(&full_bar[stage], my_bytes);
             if (pj == 0)
               for (int sl = 0; sl < p.a_slabs; ++sl)
@@ -181,11 +183,13 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
           ptx::mbar_wait(&full_bar[stage], phase, p.err, 12);
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
-          const uint32_t sb = sa + 2 * kASlabBytes;
+          const uint32_t sb = sa + a_bytes;
 #pragma unroll
           for (int k = 0; k < kKB / 16; ++k) {
-            // MN-major: LBO = distance between channel slabs, SBO = 8 pixel rows
-            const uint64_t adesc = ptx::make_smem_desc(sa + k * 16 * 128, kASlabBytes, 8 * 128, 2);
+            // MN-major: LBO = distance between channel slabs, SBO = 8 pixel rows.  With a single dY slab (Cout <= 64)
+            // the upper 64 rows of the M = 128 operand alias the lower ones (LBO 0): their products are never stored,
+            // and the operand must not reach past the stage (the A region is a_slabs wide).
+            const uint64_t adesc = ptx::make_smem_desc(sa + k * 16 * 128, p.a_slabs == 2 ? kASlabBytes : 0, 8 * 128, 2);
 #pragma unroll 1
             for (int n0 = 0; n0 < ntot; n0 += 256) {
               const int n = ntot - n0 < 256 ? ntot - n0 : 256;
@@ -271,16 +275,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
   }
 }
 
-template <int CB, int BNW>
+template <int CB, int BNW, int kKB>
 int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const CUtensorMap& tmDW, WgradParams& p,
                  cudaStream_t stream) {
   constexpr int kBTapBytes = (BNW / CB) * kKB * CB * 2;
-  const int stage_bytes = 2 * kKB * 128 + p.T * kBTapBytes;
+  const int stage_bytes = p.a_slabs * kKB * 128 + p.T * kBTapBytes;
   p.stages = std::min(kMaxWStages, (204 * 1024) / stage_bytes);
   if (p.stages < 2) return set_error(B200CV_ERR_ARG, "wgrad: stage too large (%d bytes)", stage_bytes);
   // align slack | stage ring | barriers + tmem slot | align slack + 4 staging tiles of 4 KB
   const int smem = 1024 + p.stages * stage_bytes + (2 * kMaxWStages + 1) * 8 + 32 + 1024 + 4 * 4096;
-  auto kern = wgrad_kernel<CB, BNW>;
+  auto kern = wgrad_kernel<CB, BNW, kKB>;
   static int configured_smem = 0;
   if (smem > configured_smem) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -350,6 +354,9 @@ extern "C" int b200cv_conv_wgrad(const void* x, const void* dy, float* dw_packed
   if (bnw == 128 && T > 3) T = 3;  // keep >= 3 pipeline stages in shared memory
   p.T = T;
   p.num_tap_groups = p.RS / T;
+  // pixels per k-block: 64 with several taps per CTA; single-tap layers take bigger blocks (see wgrad_kernel)
+  static const bool no_big_kb = getenv("B200CV_WGRAD_KB64") != nullptr;
+  const int kKB = (p.RS == 1 && !no_big_kb) ? (cb == 64 ? 128 : 256) : 64;
   p.kb_total = (p.M_pix + kKB - 1) / kKB;
   const int base_ctas = p.num_o_tiles * p.num_i_tiles * p.num_tap_groups;
   // split-K so that the grid fills (at most) two full waves of one CTA per SM: rounding the split UP left a
@@ -374,9 +381,16 @@ extern "C" int b200cv_conv_wgrad(const void* x, const void* dy, float* dw_packed
                         bnw >= 32 ? 32 : 16);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (cb == 64 && bnw == 128) return launch_wgrad<64, 128>(tmDY, tmX, tmDW, p, st);
-  if (cb == 64 && bnw == 64) return launch_wgrad<64, 64>(tmDY, tmX, tmDW, p, st);
-  if (cb == 32) return launch_wgrad<32, 32>(tmDY, tmX, tmDW, p, st);
-  if (cb == 16) return launch_wgrad<16, 16>(tmDY, tmX, tmDW, p, st);
+  if (kKB == 64) {
+    if (cb == 64 && bnw == 128) return launch_wgrad<64, 128, 64>(tmDY, tmX, tmDW, p, st);
+    if (cb == 64 && bnw == 64) return launch_wgrad<64, 64, 64>(tmDY, tmX, tmDW, p, st);
+    if (cb == 32) return launch_wgrad<32, 32, 64>(tmDY, tmX, tmDW, p, st);
+    if (cb == 16) return launch_wgrad<16, 16, 64>(tmDY, tmX, tmDW, p, st);
+  } else {
+    if (cb == 64 && bnw == 128) return launch_wgrad<64, 128, 128>(tmDY, tmX, tmDW, p, st);
+    if (cb == 64 && bnw == 64) return launch_wgrad<64, 64, 128>(tmDY, tmX, tmDW, p, st);
+    if (cb == 32) return launch_wgrad<32, 32, 256>(tmDY, tmX, tmDW, p, st);
+    if (cb == 16) return launch_wgrad<16, 16, 256>(tmDY, tmX, tmDW, p, st);
+  }
   return set_error(B200CV_ERR_ARG, "conv_wgrad: unsupported channel tile");
 }

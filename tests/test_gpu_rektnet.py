@@ -153,3 +153,41 @@ def test_eval_forward_without_no_grad():
     with torch.no_grad():
         hm2, pts2 = net(x.to(DEV))
     assert torch.equal(pts, pts2)
+
+
+def test_cuda_graph_step_matches_eager(monkeypatch):
+    """From the third step with a shape the KeypointNet step is replayed from CUDA graphs (forward; backward per loss
+    configuration).  With lr = 0 the replayed steps reproduce the eager ones on new inputs: same losses (the forward is
+    bit-reproducible), same gradients, same running statistics."""
+    import cross_ratio_loss
+
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("B200CV_CUDA_GRAPH", mode)
+        net = _net().to(DEV).train()
+        loss_fn = cross_ratio_loss.CrossRatioLoss("l2_heatmap", True, 0.055, 0.038)
+        opt = torch.optim.SGD(net.parameters(), lr=0.0)
+        hist = []
+        for it in range(5):
+            x, thm, tpts = (t.to(DEV) for t in RO.synth_batch(4, seed=it))
+            opt.zero_grad()
+            hm, pts = net(x)
+            loss = loss_fn(hm, pts, thm, tpts)
+            loss[2].backward()
+            opt.step()
+            hist.append((torch.stack([l.detach().float().to(DEV) for l in loss]).cpu(), pts.detach().cpu().clone(),
+                         {k: p.grad.detach().cpu().clone() for k, p in net.named_parameters()}))
+        res[mode] = (hist, {k: v.detach().cpu().clone() for k, v in net.state_dict().items()})
+        if mode == "1":
+            from b200cv.rektnet_engine import _GraphedRektStep
+
+            steps = [v for v in net.engine()._graphs.values() if isinstance(v, _GraphedRektStep)]
+            assert steps and len(steps[0].bwd) == 1  # one backward graph for the one loss configuration
+    for (la, pa, ga), (lb, pb, gb) in zip(res["0"][0], res["1"][0]):
+        assert torch.equal(la, lb) and torch.equal(pa, pb)
+        for k in ga:
+            if k == "out.bias":
+                continue  # analytically zero (softmax Jacobian): what is left is the rounding noise of a float reduction
+            assert torch.allclose(ga[k], gb[k], rtol=1e-4, atol=1e-6 * float(ga[k].abs().max()) + 1e-12), k
+    for k, v in res["0"][1].items():
+        assert torch.equal(v, res["1"][1][k]), k
