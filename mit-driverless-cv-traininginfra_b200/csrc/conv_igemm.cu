@@ -81,12 +81,13 @@ struct Cfg {
   static constexpr int kScratchBytes = kTma ? kEpiWarps * kStgTile : kEpiWarps * 32 * kScratchLd * 4;
   // shared memory of a launch with `y_slots` y tiles per epilogue warp (0 unless kBnRed); the pipeline gets
   // whatever is left (stages are a RUN-TIME parameter: short-K layers trade stages for a deeper y ring)
-  static constexpr int extra_bytes(int y_slots) {
-    return 1024 /*align slack*/ + 2048 /*barrier block + align*/ + kStatBytes + kScratchBytes +
+  // stg_slots: staging tiles per epilogue warp (wide staged epilogue: 1, or 2 for short-K tiles, see launch_one)
+  static constexpr int extra_bytes(int y_slots, int stg_slots = 1) {
+    return 1024 /*align slack*/ + 2048 /*barrier block + align*/ + kStatBytes + kScratchBytes * stg_slots +
            kEpiWarps * y_slots * kStgTile;
   }
-  static constexpr int stages_for(int y_slots) {
-    const int n = ((kCtasPerSm == 2 ? kSmemMax2 : kSmemMax) - extra_bytes(y_slots)) / kStageBytes;
+  static constexpr int stages_for(int y_slots, int stg_slots = 1) {
+    const int n = ((kCtasPerSm == 2 ? kSmemMax2 : kSmemMax) - extra_bytes(y_slots, stg_slots)) / kStageBytes;
     return n > kMaxStages ? kMaxStages : n;
   }
   static_assert(kBarBytes <= 1024, "barrier block");
@@ -331,7 +332,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       auto block_of = [&](int bi) { return kM2 ? bi : half + 2 * bi; };
       const int sub_m = kM2 ? half * kBlockM : 0;   // row offset of this warp's sub-tile
       const int sub_c = kM2 ? half * BN : 0;        // TMEM column offset of its accumulator
-      uint8_t* stg = s_extra + ew * 4096;
+      // staging tiles: slot s of warp ew at s_extra + (s * kEpiWarps + ew) * 4 KB.  With two slots (short-K tiles: the
+      // 1x1 layers, where the epilogue is the critical path) a block is staged while the bulk store of the previous
+      // one is still reading its tile; with one slot every block waited for that store first.
+      uint8_t* const stg0 = s_extra + ew * 4096;
+      const int stg_slots = p.stg_slots;
+      uint32_t stg_count = 0;
+      uint8_t* stg = stg0;
       const int sw_w = lane & 7;              // writer: row = lane, 16-byte piece j -> j ^ (row & 7)
       const int rq = lane & 7, rg = lane >> 3;  // reader: piece rq, rows rg + 4 i (i = 0..7)
       const int my_col = 8 * rq + 4 * ((lane >> 4) & 1) + 2 * ((lane >> 3) & 1);  // first of the 2 columns owned
@@ -353,7 +360,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           __syncwarp();
           store_pending = false;
         }
-        float* park = reinterpret_cast<float*>(stg);
+        float* park = reinterpret_cast<float*>(stg0);
 #pragma unroll
         for (int bi = 0; bi < kBPW; ++bi) {
 #pragma unroll
@@ -388,7 +395,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       };
       // ---- fused BN backward: ring of TMA-loaded y tiles (4 KB each), `yslots` blocks ahead
       const int yslots = p.y_slots, ylog = p.y_slots_log2;
-      uint8_t* const ybuf = s_extra + kEpiWarps * 4096 + ew * yslots * 4096;
+      uint8_t* const ybuf = s_extra + stg_slots * kEpiWarps * 4096 + ew * yslots * 4096;
       uint64_t* const ybar = y_bar + kMaxYSlots * ew;
       auto block_valid = [&](int tile, int bi) { return bi < kBPW && (tile % p.num_n_tiles) * BN + block_of(bi) * 64 < p.Cout; };
       auto next_block = [&](int& tile, int& bi) {
@@ -449,9 +456,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const int b0 = block_of(bi) * 64;
           const int nb_base = nt * BN + b0;
           if (nb_base >= p.Cout || (p.dbg & 4)) break;  // warp-uniform
-          // the previous bulk store of this warp must have finished READING the staging tile
+          // the bulk store that last used this staging slot must have finished READING it
+          stg = stg0 + (stg_count & (stg_slots - 1)) * (kEpiWarps * 4096);
+          ++stg_count;
           if (store_pending) {
-            if (lane == 0) ptx::tma_store_wait_read<0>();
+            if (lane == 0) {
+              if (stg_slots == 2) ptx::tma_store_wait_read<1>();
+              else ptx::tma_store_wait_read<0>();
+            }
             __syncwarp();
           }
 #pragma unroll
@@ -1223,8 +1235,25 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
     while (q.y_slots > 1 && C::stages_for(q.y_slots) < (forced ? 2 : 3)) q.y_slots >>= 1;
     q.y_slots_log2 = q.y_slots == 4 ? 2 : (q.y_slots == 2 ? 1 : 0);
   }
-  q.stages = C::stages_for(q.y_slots);
-  const int smem_bytes = C::extra_bytes(q.y_slots) + q.stages * C::kStageBytes;
+  // second staging tile per epilogue warp for short-K tiles of the wide staged epilogue (1x1 layers: the pipeline
+  // needs few stages there and the epilogue is the critical path)
+  q.stg_slots = 1;
+  {
+    static const int forced = getenv("B200CV_STG_SLOTS") ? atoi(getenv("B200CV_STG_SLOTS")) : 0;
+    const int kit = p.num_taps * p.cblocks + p.res_iters;
+    if (C::kTma && C::kWide && (forced ? forced == 2 : (kit <= 8 && !C::kBnRed))) {
+      // trade y-ring depth for the second staging tile, never below 3 pipeline stages
+      int ys = q.y_slots;
+      while (ys > 1 && C::stages_for(ys, 2) < 3) ys >>= 1;
+      if (C::stages_for(ys, 2) >= 3 && (!C::kBnRed || ys >= 2 || q.y_slots == 1)) {
+        q.stg_slots = 2;
+        q.y_slots = ys;
+        q.y_slots_log2 = ys == 4 ? 2 : (ys == 2 ? 1 : 0);
+      }
+    }
+  }
+  q.stages = C::stages_for(q.y_slots, q.stg_slots);
+  const int smem_bytes = C::extra_bytes(q.y_slots, q.stg_slots) + q.stages * C::kStageBytes;
   constexpr int kSmemAttr = C::kCtasPerSm == 2 ? kSmemMax2 : kSmemMax;
   static bool configured = false;  // benign race: attribute set is idempotent
   auto kern = igemm_kernel<KC, BN, kMode, kM2>;

@@ -77,6 +77,7 @@ struct IgemmParams {
   float bn_neg;  // act'(z) for z <= 0
   int stages;                 // pipeline stages of this launch (set by launch_igemm)
   int y_slots, y_slots_log2;  // y tiles per epilogue warp of the fused BN-backward reduction (power of two)
+  int stg_slots;              // staging tiles per epilogue warp of the wide staged epilogue (1 or 2)
   int res_iters;  // residual added by the tensor core: extra k-iterations D += I[:, k-slice] * R[k-slice rows, :] (0 = off)
   int dbg;  // B200CV_DBG bits (bring-up timing experiments only): 1 no stores, 2 no stats, 4 no TMEM read
   // fp32-parity (split) mode: lo halves of the output / residual lie this many elements after the hi halves (0 = off)
