@@ -382,6 +382,16 @@ int b200cv_letterbox_u8(const uint8_t* frames, int B, int H, int W, int pad_w, i
                         int reverse_channels, const int32_t* hx_min, const int32_t* hx_cnt, const int32_t* hx_k,
                         int ksize_h, const int32_t* vy_min, const int32_t* vy_cnt, const int32_t* vy_k, int ksize_v,
                         int out_w, int out_h, float* out, void* stream);
+/* Tile-and-scale input pipeline (CVC-YOLOv3/utils/datasets.py:143-159 + utils/utils.py:321-426):
+ * frames u8 [B][H][W][3] -> scale_image (PIL LANCZOS resize to new_w x new_h) -> pad `fill` up to the patch size ->
+ * crop one patch per frame -> to_tensor, out fp32 [B][3][out_h][out_w].  off_x / off_y int32 [B]: the patch origin in
+ * the SCALED frame (rounded left/top of get_patch minus the pad; may be negative = inside the pad).  Tables as for
+ * b200cv_letterbox_u8 but indexed by scaled-frame column / row, made for the LANCZOS filter (b200cv/tiler.py); NULL =
+ * that axis is not rescaled. */
+int b200cv_tile_scale_u8(const uint8_t* frames, int B, int H, int W, int new_w, int new_h, int fill,
+                         const int32_t* off_x, const int32_t* off_y, const int32_t* hx_min, const int32_t* hx_cnt,
+                         const int32_t* hx_k, int ksize_h, const int32_t* vy_min, const int32_t* vy_cnt,
+                         const int32_t* vy_k, int ksize_v, int out_w, int out_h, float* out, void* stream);
 /* Per-image detection metric on the NMS output: CVC-YOLOv3/validate.py:98-128 (target boxes from the
  * normalised labels, bbox_iou with the +1 convention, greedy matching in score order at iou_thres) and
  * utils/utils.py:58-119 (average_precision, compute_ap).  boxes [B][top_k][4] / counts [B] from b200cv_detect_nms;

@@ -519,10 +519,96 @@ letterbox_kernel(const unsigned char* __restrict__ frames, int H, int W, int pad
   }
 }
 
+// Tile-and-scale input pipeline (CVC-YOLOv3/utils/datasets.py:143-159): scale_image (PIL LANCZOS resize of the whole
+// frame) -> pad 127 up to the patch size -> crop patch `patch_index` -> to_tensor, for a batch of frames in one launch.
+// Output pixel (xx, yy) of image b is pixel (off_x[b] + xx, off_y[b] + yy) of the scaled frame (offsets = rounded patch
+// origin minus the pad): inside the scaled frame it is Pillow's two-pass 8-bit resample (horizontal pass rounded to u8,
+// then vertical; coefficient tables from the host, b200cv/tiler.py), outside it is the fill value.  Neither the scaled
+// frame nor the padded one is materialised.
+__global__ void __launch_bounds__(256)
+tile_scale_kernel(const unsigned char* __restrict__ frames, int H, int W, int new_w, int new_h, int fill,
+                  const int* __restrict__ off_x, const int* __restrict__ off_y, const int* __restrict__ hx_min,
+                  const int* __restrict__ hx_cnt, const int* __restrict__ hx_k, int ksh,
+                  const int* __restrict__ vy_min, const int* __restrict__ vy_cnt, const int* __restrict__ vy_k, int ksv,
+                  int out_w, int out_h, float* __restrict__ out) {
+  __shared__ float lut[256];
+  lut[threadIdx.x] = (float)threadIdx.x / 255.f;  // to_tensor
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= out_w * out_h) return;
+  const int yy = e / out_w, xx = e - yy * out_w;
+  const int sx = off_x[b] + xx, sy = off_y[b] + yy;  // position in the scaled frame
+  const size_t plane = (size_t)out_h * out_w;
+  float* o = out + (size_t)b * 3 * plane + e;
+  if (sx < 0 || sx >= new_w || sy < 0 || sy >= new_h) {
+    o[0] = o[plane] = o[2 * plane] = lut[fill];
+    return;
+  }
+  const unsigned char* f = frames + (size_t)b * H * W * 3;
+  const int x0 = hx_k ? hx_min[sx] : sx, xn = hx_k ? hx_cnt[sx] : 1;
+  const int y0 = vy_k ? vy_min[sy] : sy, yn = vy_k ? vy_cnt[sy] : 1;
+  const int* kh = hx_k ? hx_k + (size_t)sx * ksh : nullptr;
+  const int* kv = vy_k ? vy_k + (size_t)sy * ksv : nullptr;
+  int accv[3] = {1 << (kPilBits - 1), 1 << (kPilBits - 1), 1 << (kPilBits - 1)};
+  int last[3] = {0, 0, 0};
+  for (int r = 0; r < yn; ++r) {
+    const unsigned char* row = f + (size_t)(y0 + r) * W * 3;
+    int hv[3];
+    if (kh) {
+      int acc[3] = {1 << (kPilBits - 1), 1 << (kPilBits - 1), 1 << (kPilBits - 1)};
+      for (int x = 0; x < xn; ++x) {
+        const unsigned char* q = row + (size_t)(x0 + x) * 3;
+        const int k = kh[x];
+        acc[0] += q[0] * k;
+        acc[1] += q[1] * k;
+        acc[2] += q[2] * k;
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) hv[c] = min(max(acc[c] >> kPilBits, 0), 255);
+    } else {
+      const unsigned char* q = row + (size_t)x0 * 3;
+      hv[0] = q[0];
+      hv[1] = q[1];
+      hv[2] = q[2];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      last[c] = hv[c];
+      if (kv) accv[c] += hv[c] * kv[r];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int v = kv ? min(max(accv[c] >> kPilBits, 0), 255) : last[c];
+    o[(size_t)c * plane] = lut[v];
+  }
+}
+
 }  // namespace
 }  // namespace b200cv
 
 using namespace b200cv;
+
+extern "C" int b200cv_tile_scale_u8(const uint8_t* frames, int B, int H, int W, int new_w, int new_h, int fill,
+                                    const int32_t* off_x, const int32_t* off_y, const int32_t* hx_min,
+                                    const int32_t* hx_cnt, const int32_t* hx_k, int ksize_h, const int32_t* vy_min,
+                                    const int32_t* vy_cnt, const int32_t* vy_k, int ksize_v, int out_w, int out_h,
+                                    float* out, void* stream) {
+  if (B == 0) return B200CV_OK;
+  B200CV_CHECK_ARG(frames && off_x && off_y && out && B > 0 && H > 0 && W > 0 && new_w > 0 && new_h > 0 && out_w > 0 &&
+                       out_h > 0 && fill >= 0 && fill <= 255,
+                   "tile_scale_u8: bad args");
+  B200CV_CHECK_ARG(hx_k ? (hx_min && hx_cnt && ksize_h > 0) : (W == new_w),
+                   "tile_scale_u8: no horizontal tables although the frame is rescaled");
+  B200CV_CHECK_ARG(vy_k ? (vy_min && vy_cnt && ksize_v > 0) : (H == new_h),
+                   "tile_scale_u8: no vertical tables although the frame is rescaled");
+  const dim3 grid((out_w * out_h + 255) / 256, B);
+  tile_scale_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      frames, H, W, new_w, new_h, fill, off_x, off_y, hx_min, hx_cnt, hx_k, ksize_h, vy_min, vy_cnt, vy_k, ksize_v,
+      out_w, out_h, out);
+  return check_launch("tile_scale_u8");
+}
 
 extern "C" int b200cv_detect_nms(const float* det, int64_t det_batch_stride, int B, int rows, int row_len,
                                  int box_format, float conf_thres, float nms_thres, int top_k, float* boxes,

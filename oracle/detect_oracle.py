@@ -386,3 +386,147 @@ def letterbox(frame_rgb, new_w, new_h):
     out = pil_resize_bilinear_u8(padded, new_w, new_h)
     chw = torch.from_numpy(out.transpose(2, 0, 1).copy()).to(torch.float32).div(255)  # to_tensor
     return chw.numpy(), (ratio, pad_w, pad_h)
+
+
+# ------------------------------------------------------------------------------------------ tile-and-scale input pipeline
+# CVC-YOLOv3/utils/datasets.py:143-159 (ts mode): scale_image (utils/utils.py:321-326: PIL resize with ANTIALIAS =
+# LANCZOS) -> pre_tile_padding (:376-382) -> torchvision pad(fill=127) -> get_patch_spacings (:384-405) -> get_patch
+# (:411-426: PIL crop, which rounds its float box) -> to_tensor; labels: datasets.py:176-186 + utils/utils.py:456-472.
+# Pillow's LANCZOS is the same two-pass resampler as BILINEAR with the truncated-sinc filter of support 3
+# (Resample.c: lanczos_filter / sinc_filter); restated here and pinned against the installed Pillow by the tests.
+import math as _math
+
+
+def pil_lanczos_coeffs(in_size, out_size):
+    """Resample.c precompute_coeffs + normalize_coeffs_8bpc for the LANCZOS filter over the whole axis."""
+    scale = filterscale = float(in_size) / out_size
+    if filterscale < 1.0:
+        filterscale = 1.0
+    support = 3.0 * filterscale
+    ksize = int(_math.ceil(support)) * 2 + 1
+    xmin_a = np.zeros(out_size, np.int32)
+    cnt_a = np.zeros(out_size, np.int32)
+    kk = np.zeros((out_size, ksize), np.int32)
+    ss = 1.0 / filterscale
+
+    def sinc(x):
+        if x == 0.0:
+            return 1.0
+        x = x * _math.pi
+        return _math.sin(x) / x
+
+    for xx in range(out_size):
+        center = 0.0 + (xx + 0.5) * scale
+        xmin = int(center - support + 0.5)
+        if xmin < 0:
+            xmin = 0
+        xmax = int(center + support + 0.5)
+        if xmax > in_size:
+            xmax = in_size
+        xmax -= xmin
+        k = np.zeros(ksize, np.float64)
+        ww = 0.0
+        for x in range(xmax):
+            a = (x + xmin - center + 0.5) * ss
+            w = sinc(a) * sinc(a / 3) if -3.0 <= a < 3.0 else 0.0
+            k[x] = w
+            ww += w
+        for x in range(xmax):
+            if ww != 0.0:
+                k[x] /= ww
+        for x in range(ksize):
+            v = k[x] * (1 << PIL_PRECISION_BITS)
+            kk[xx, x] = int(-0.5 + v) if k[x] < 0 else int(0.5 + v)
+        xmin_a[xx] = xmin
+        cnt_a[xx] = xmax
+    return xmin_a, cnt_a, kk
+
+
+def pil_resize_lanczos_u8(img, out_w, out_h):
+    """PIL.Image.resize((out_w, out_h), LANCZOS) for an HxWxC uint8 array (horizontal pass, then vertical)."""
+    H, W, _ = img.shape
+    if W != out_w:
+        img = _pil_pass(img, *pil_lanczos_coeffs(W, out_w), axis=1)
+    if H != out_h:
+        img = _pil_pass(img, *pil_lanczos_coeffs(H, out_h), axis=0)
+    return img
+
+
+def pre_tile_padding(img_width, img_height, patch_width, patch_height):
+    """utils/utils.py:376-382."""
+    vert_pad, horiz_pad = 0, 0
+    if img_width < patch_width:
+        horiz_pad = _math.ceil((patch_width - img_width) / 2)
+    if img_height < patch_height:
+        vert_pad = _math.ceil((patch_height - img_height) / 2)
+    return vert_pad, horiz_pad
+
+
+def get_patch_spacings(img_width, img_height, patch_width, patch_height):
+    """utils/utils.py:384-405: (patches wide, patches high, total, horizontal offset, vertical offset)."""
+    assert img_width >= patch_width and img_height >= patch_height
+    hn = _math.ceil(img_width / patch_width)
+    h_over = hn * patch_width - img_width
+    h_off = 0 if hn == 1 else h_over / (hn - 1)
+    vn = _math.ceil(img_height / patch_height)
+    v_over = vn * patch_height - img_height
+    v_off = 0 if vn == 1 else v_over / (vn - 1)
+    return hn, vn, vn * hn, h_off, v_off
+
+
+def patch_boundary(padded_w, padded_h, patch_width, patch_height, patch_index):
+    """utils/utils.py:411-426 (the float boundary get_patch returns; PIL's crop rounds it)."""
+    n_wide, _, _, h_off, v_off = get_patch_spacings(padded_w, padded_h, patch_width, patch_height)
+    row_position = patch_index % n_wide
+    left = patch_width * row_position - h_off * row_position
+    col_position = _math.floor(patch_index / n_wide)
+    top = patch_height * col_position - v_off * col_position
+    return (left, top, left + patch_width, top + patch_height)
+
+
+def tile_scale(frame_rgb, scale, patch_w, patch_h, patch_index):
+    """datasets.py:143-159 on one HxWx3 uint8 RGB frame -> (fp32 [3,patch_h,patch_w] in [0,1], boundary, (horiz_pad,
+    vert_pad), n_patches)."""
+    h, w, _ = frame_rgb.shape
+    new_h, new_w = int(h * scale), int(w * scale)  # scale_image, utils/utils.py:321-326
+    scaled = pil_resize_lanczos_u8(frame_rgb, new_w, new_h)
+    vert_pad, horiz_pad = pre_tile_padding(new_w, new_h, patch_w, patch_h)
+    padded = np.full((new_h + 2 * vert_pad, new_w + 2 * horiz_pad, 3), 127, np.uint8)
+    padded[vert_pad:vert_pad + new_h, horiz_pad:horiz_pad + new_w] = scaled
+    ph, pw = padded.shape[:2]
+    n_patches = get_patch_spacings(pw, ph, patch_w, patch_h)[2]
+    boundary = patch_boundary(pw, ph, patch_w, patch_h, patch_index)
+    x0, y0 = int(round(boundary[0])), int(round(boundary[1]))  # PIL.Image.crop: map(int, map(round, box))
+    x1, y1 = int(round(boundary[2])), int(round(boundary[3]))
+    patch = np.zeros((y1 - y0, x1 - x0, 3), np.uint8)  # a crop beyond the image reads zeros (never happens: tiles fit)
+    ys, xs = max(y0, 0), max(x0, 0)
+    ye, xe = min(y1, ph), min(x1, pw)
+    patch[ys - y0:ye - y0, xs - x0:xe - x0] = padded[ys:ye, xs:xe]
+    chw = torch.from_numpy(patch.transpose(2, 0, 1).copy()).to(torch.float32).div(255)  # to_tensor
+    return chw.numpy(), boundary, (horiz_pad, vert_pad), n_patches
+
+
+def tile_labels(labels_xyhw, scale, horiz_pad, vert_pad, boundary, patch_w, patch_h, num_targets):
+    """Labels of one patch: datasets.py:176-186 (add class column, corner form, scale, pad offset,
+    filter_and_offset_labels utils/utils.py:456-472) then :300-304 (centre form, normalised) and the zero padding to
+    `num_targets` rows (:313).  labels_xyhw: rows (x, y, h, w) with (x, y) the upper-left corner, as in the CSV."""
+    left, top, right, bottom = boundary
+    rows = []
+    for x, y, hh, ww in labels_xyhw:
+        x0, y0, x1, y1 = scale * x + horiz_pad, scale * y + vert_pad, scale * (x + ww) + horiz_pad, scale * (y + hh) + vert_pad
+        box_area = float(x1 - x0) * (y1 - y0)
+        dx = min(x1, right) - max(x0, left)
+        dy = min(y1, bottom) - max(y0, top)
+        overlap = float(dx * dy) if (dx >= 0 and dy >= 0) else 0
+        if box_area > 0 and (overlap / box_area > 0.5 or overlap > 1000):
+            rows.append([0.0, max(x0, left) - left, max(y0, top) - top, min(x1, right) - left, min(y1, bottom) - top])
+    out = torch.zeros(num_targets, 5)
+    if not rows:
+        # filter_and_offset_labels returns zeros((len(labels), 5)): all-zero rows, i.e. padding
+        return out
+    t = torch.tensor(rows, dtype=torch.float32)
+    cx, cy = (t[:, 1] + t[:, 3]) / 2, (t[:, 2] + t[:, 4]) / 2
+    bw, bh = t[:, 3] - t[:, 1], t[:, 4] - t[:, 2]
+    n = min(len(rows), num_targets)
+    out[:n, 1], out[:n, 2], out[:n, 3], out[:n, 4] = cx[:n] / patch_w, cy[:n] / patch_h, bw[:n] / patch_w, bh[:n] / patch_h
+    return out
