@@ -421,3 +421,30 @@ def test_bucketed_backward_segments_match_the_single_pass(cfg_dir, monkeypatch):
         assert torch.equal(la, lb)  # the forward pass is bit-reproducible
         for k in ga:  # split-K weight gradients are reduce-added in arrival order: equal to fp32 rounding
             assert torch.allclose(ga[k], gb[k], rtol=1e-4, atol=1e-6 * float(ga[k].abs().max()) + 1e-12), k
+
+
+def test_onnx_export_of_a_trained_b200_model_matches_its_inference(cfg_dir):
+    """f-3: the graph exported from the live CUDA model (after training steps moved weights and running statistics),
+    evaluated on the CPU, decodes to the detections the B200 inference path produces (bf16 tolerance)."""
+    from b200cv import onnx_export as OX
+
+    model, path = helpers.make_darknet(cfg_dir, "yolo_baseline.cfg", 64, 2)
+    model = model.to(DEV).train()
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3)
+    x, tg = YO.synth_images(4, 64, 64).to(DEV), YO.synth_targets(4, 16).to(DEV)
+    for _ in range(3):
+        opt.zero_grad()
+        model(x, tg)[0].backward()
+        opt.step()
+    model.eval()
+    with torch.no_grad():
+        det = model(x[:1]).cpu()
+    g = OX.parse_model(OX.darknet_to_onnx(model))
+    heads = OX.run_graph(g, x[:1].cpu())
+    spec = YO.NetSpec(path)
+    yolo_layers = [L for L in spec.layers if L["type"] == "yolo"]
+    want = torch.cat([YO.yolo_layer(heads[n], None, L["anchors"], spec.num_classes, spec.height, spec.ignore_thresh, 2.0,
+                                    1.6, 0.1, 25.0) for n, L in zip(g["outputs"], yolo_layers)], 1)
+    assert det.shape == want.shape
+    assert float((det[..., 4:] - want[..., 4:]).abs().max()) < 3e-2
+    assert float(((det[..., :4] - want[..., :4]).abs() / (want[..., :4].abs() + 1.0)).max()) < 5e-2
