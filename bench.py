@@ -320,6 +320,14 @@ class Harness:
             ms = float(t)
         return ms, lib().launches - l0
 
+    def _result_landing(self, result, slot):
+        """Pinned host buffer the step result is copied into (two, alternating)."""
+        key = (tuple(result.shape), result.dtype, slot)
+        cache = self.__dict__.setdefault("_landing", {})
+        if key not in cache:
+            cache[key] = torch.empty(result.shape, dtype=result.dtype).pin_memory()
+        return cache[key]
+
     def e2e(self, host_tensors, step_fn, n):
         """Every step copies ITS inputs from pinned host memory (double-buffered on a copy stream, so the copy of step
         i+1 overlaps the compute of step i) and reads the step's result back."""
@@ -339,7 +347,7 @@ class Harness:
             for ev in freed:
                 ev.record()
             prefetch(0)
-            host = None
+            host, pending = None, None
             for i in range(count):
                 slot = i & 1
                 if i + 1 < count:
@@ -347,8 +355,19 @@ class Harness:
                 torch.cuda.current_stream().wait_event(ready[slot])
                 result = step_fn(*bufs[slot])
                 freed[slot].record()
-                host = result.cpu()  # device -> host read of the step's result
-            return host
+                # device -> host read of EVERY step's result: the copy is queued behind the step and consumed one
+                # step later (what a training loop that logs the previous step's loss does), so the host enqueues
+                # step i+1 while step i runs; the last result is read inside the timed region too
+                landing = self._result_landing(result, i & 1)
+                landing.copy_(result, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record()
+                if pending is not None:
+                    pending[1].synchronize()
+                    host = pending[0].clone()
+                pending = (landing, done)
+            pending[1].synchronize()
+            return pending[0].clone()
 
         run(2)
         ms, _ = self.timed(lambda: run(n), 1)

@@ -30,6 +30,8 @@ for _ in range(10):
     step()
 torch.cuda.synchronize()
 wall = (time.perf_counter() - t0) / 10 * 1e3
+os.environ["B200CV_CUDA_GRAPH"] = "0"  # the per-call timing needs the eager launches
+step()
 calls = lib().profile_step(step, detail=True)
 tot = sum(ms for _, _, ms in calls)
 print(f"# RektNet 80^2 bs{B}: wall {wall:.2f} ms/step, sum of per-call device times {tot:.2f} ms, {len(calls)} ABI calls")
