@@ -45,6 +45,18 @@ def _wgrad_side_stream() -> bool:
     return os.environ.get("B200CV_WGRAD_STREAM", "0") != "0"
 
 
+def _wgrad_tail_fill_hw() -> int:
+    """Layers whose feature map is at most this many pixels high launch their weight gradient on the side stream AFTER
+    their data gradient: the persistent dgrad of a 13x13 layer is 170 tiles on 148 SMs, so 126 SMs idle through its
+    second wave -- the wgrad CTAs queued behind it fill them, and they keep the tensor pipe busy under the HBM-bound
+    BatchNorm-backward passes of the next layer.  Measured on Darknet-53 416^2 bs64: 25.77 ms/step off, 25.75 / 25.61 /
+    25.20 ms with 13 / 26 / 52, no further gain at 104+ (those weight gradients are HBM-bound themselves; launching
+    wgrad BEFORE dgrad, B200CV_WGRAD_STREAM=1, was neutral).  0 = off."""
+    import os
+
+    return int(os.environ.get("B200CV_WGRAD_TAIL_FILL", "52"))
+
+
 def _graphs_enabled() -> bool:
     import os
 
@@ -411,19 +423,21 @@ class DarknetEngine:
         # until the join (no allocator reuse while the side stream may still read them).
         main = torch.cuda.current_stream()
         side = None
-        if _wgrad_side_stream():
+        tail_hw = 0 if self.split else _wgrad_tail_fill_hw()
+        if _wgrad_side_stream() or tail_hw > 0:
             if getattr(self, "_side", None) is None or self._side.device != dev:
                 self._side = torch.cuda.Stream(device=dev)
             side = self._side
             side.wait_stream(main)
         keep = []
 
-        def wgrad(x_, dy_, cout_, k_, st_, pd_, out_):
-            if side is None:
+        def wgrad(x_, dy_, cout_, k_, st_, pd_, out_, on_side=True, ev=None):
+            if side is None or not on_side:
                 ops.conv_wgrad(x_, dy_, cout_, k_, st_, pd_, out=out_)
                 return
-            ev = torch.cuda.Event()
-            ev.record(main)
+            if ev is None:
+                ev = torch.cuda.Event()
+                ev.record(main)
             side.wait_event(ev)
             with torch.cuda.stream(side):
                 ops.conv_wgrad(x_, dy_, cout_, k_, st_, pd_, out=out_)
@@ -476,10 +490,15 @@ class DarknetEngine:
                     (xin,) = saved[i]
                     dy = G
                     gview[id(L.conv.bias)].copy_(ops.bias_grad(dy, L.cout))
-                if i == 0 and self._flat_convs():
-                    wgrad(xin, dy, L.cout, 1, 1, 0, packs.dwp[id(L.conv)])  # xin = im2col patches
+                # tail-fill mode: the weight gradient of a small-map layer is queued BEHIND its data gradient
+                fill = tail_hw > 0 and i > 0 and dy.shape[1] <= tail_hw
+                if fill:
+                    dy_ready = torch.cuda.Event()
+                    dy_ready.record(main)
+                elif i == 0 and self._flat_convs():
+                    wgrad(xin, dy, L.cout, 1, 1, 0, packs.dwp[id(L.conv)], on_side=tail_hw == 0)  # xin = im2col patches
                 else:
-                    wgrad(xin, dy, L.cout, L.k, L.stride, L.pad, packs.dwp[id(L.conv)])
+                    wgrad(xin, dy, L.cout, L.k, L.stride, L.pad, packs.dwp[id(L.conv)], on_side=tail_hw == 0)
                 if i > 0:
                     prev = grads[i - 1]
                     # this dgrad completes grads[i-1]; when that is the activation gradient of a conv+BN layer the
@@ -496,6 +515,8 @@ class DarknetEngine:
                     dx = ops.conv_dgrad(dy, L.wpk_t, L.cin, L.k, L.stride, L.pad, 1, (xin.shape[1], xin.shape[2]),
                                         out=prev, residual=prev, bn_reduce=bn_red)
                     grads[i - 1] = dx
+                    if fill:
+                        wgrad(xin, dy, L.cout, L.k, L.stride, L.pad, packs.dwp[id(L.conv)], ev=dy_ready)
             elif L.type == "maxpool":
                 (xin,) = saved[i]
                 add_grad(i - 1, ops.maxpool_bwd(xin, G, L.pool_stride))

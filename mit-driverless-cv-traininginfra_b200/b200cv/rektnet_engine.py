@@ -76,7 +76,8 @@ class _ConvBN:
         parts = ops.stats_buffer(self.cout, y.device)
         return (y, self.scale, self.shift, self.mean, self.rstd, act, 0.0, parts), parts
 
-    def bwd(self, x_in, y, da, aout, act, gview, packs, dx_out=None, want_dx=True, parts=None, bn_reduce=None):
+    def bwd(self, x_in, y, da, aout, act, gview, packs, dx_out=None, want_dx=True, parts=None, bn_reduce=None,
+            side=None):
         """BN+act backward then wgrad (+ dgrad).  Returns dx (or None).  `parts`: BN-backward sums already produced by
         the dgrad that wrote `da`; `bn_reduce`: fused reduction for the layer whose dL/da this dgrad writes."""
         count = y.numel() // y.shape[-1]
@@ -85,21 +86,62 @@ class _ConvBN:
         ops.bn_bwd_finalize(parts, self.bn.weight, self.rstd, count, self.coef, gview[id(self.bn.weight)],
                             gview[id(self.bn.bias)])
         dy = ops.bn_bwd_apply(da, y, aout, self.scale, self.shift, self.mean, self.rstd, self.coef, act, 0.0)
-        return self.finish(x_in, dy, gview, packs, dx_out, want_dx, bn_reduce)
+        return self.finish(x_in, dy, gview, packs, dx_out, want_dx, bn_reduce, side)
 
     def finalize_bwd(self, parts, count, gview):
         """BN-backward sums -> d(gamma), d(beta) and the per-channel constants of the apply pass."""
         ops.bn_bwd_finalize(parts, self.bn.weight, self.rstd, count, self.coef, gview[id(self.bn.weight)],
                             gview[id(self.bn.bias)])
 
-    def finish(self, x_in, dy, gview, packs, dx_out=None, want_dx=True, bn_reduce=None):
-        """wgrad (+ dgrad) from the conv-output gradient dy."""
-        ops.conv_wgrad(x_in, dy, self.cout, self.k, 1, self.pad, self.dil, out=packs.dwp[id(self.conv)])
+    def finish(self, x_in, dy, gview, packs, dx_out=None, want_dx=True, bn_reduce=None, side=None):
+        """wgrad (+ dgrad) from the conv-output gradient dy.  With a `_SideQueue` the weight gradient is queued on the
+        side stream BEHIND the data gradient: it is off the dependency chain, so it fills the SMs the persistent dgrad
+        leaves idle in its last wave and runs under the HBM-bound BatchNorm passes that follow."""
         gview[id(self.conv.bias)].zero_()  # analytically zero under train-mode BN
-        if not want_dx:
-            return None
-        return ops.conv_dgrad(dy, self.wpk_t, self.cin, self.k, 1, self.pad, self.dil, (x_in.shape[1], x_in.shape[2]),
-                              out=dx_out, residual=dx_out, bn_reduce=bn_reduce)
+
+        def wgrad():
+            ops.conv_wgrad(x_in, dy, self.cout, self.k, 1, self.pad, self.dil, out=packs.dwp[id(self.conv)])
+
+        if side is None:
+            wgrad()
+        else:
+            ready = side.mark()
+        dx = None
+        if want_dx:
+            dx = ops.conv_dgrad(dy, self.wpk_t, self.cin, self.k, 1, self.pad, self.dil,
+                                (x_in.shape[1], x_in.shape[2]), out=dx_out, residual=dx_out, bn_reduce=bn_reduce)
+        if side is not None:
+            side.run(ready, wgrad, x_in, dy)
+        return dx
+
+
+class _SideQueue:
+    """A second stream for work that is off the critical path of the backward pass (weight gradients).  Operands are
+    kept alive until `join()` so the caching allocator cannot hand their memory out while the side stream reads it."""
+
+    def __init__(self, dev):
+        self.main = torch.cuda.current_stream(dev)
+        self.side = torch.cuda.Stream(device=dev)
+        self.keep = []
+
+    def begin(self):
+        self.main = torch.cuda.current_stream(self.side.device)
+        self.side.wait_stream(self.main)
+
+    def mark(self):
+        ev = torch.cuda.Event()
+        ev.record(self.main)
+        return ev
+
+    def run(self, ready, fn, *operands):
+        self.side.wait_event(ready)
+        with torch.cuda.stream(self.side):
+            fn()
+        self.keep.append(operands)
+
+    def join(self):
+        self.main.wait_stream(self.side)
+        self.keep.clear()
 
 
 class _HeadHandle:
@@ -229,6 +271,12 @@ class RektNetEngine:
         else:
             packs = self._packs
         packs.zero_grads()
+        side = None
+        if not self.split and os.environ.get("B200CV_WGRAD_TAIL_FILL", "52") != "0":
+            if getattr(self, "_side", None) is None or self._side.side.device != dev:
+                self._side = _SideQueue(dev)
+            side = self._side
+            side.begin()
         views, gview = arena.views, arena.view_of
         a_last = saved["a_last"]
         b, h, w = a_last.shape[0], a_last.shape[1], a_last.shape[2]
@@ -269,21 +317,24 @@ class RektNetEngine:
                 c2.finalize_bwd(parts_2, count, gview)
                 dys, dy2 = ops.bn_bwd_apply2(g, out, ys, y2, cs.mean, cs.rstd, c2.mean, c2.rstd, cs.coef, c2.coef,
                                              ops.ACT_RELU, 0.0)
-                g_in = cs.finish(a_in, dys, gview, packs)
+                g_in = cs.finish(a_in, dys, gview, packs, side=side)
             else:
-                g_in = cs.bwd(a_in, ys, g, out, ops.ACT_RELU, gview, packs)
+                g_in = cs.bwd(a_in, ys, g, out, ops.ACT_RELU, gview, packs, side=side)
             # a1 = relu(bn_1(y1)) has ONE consumer: conv2's data gradient is dL/da1, so its epilogue also forms the
             # BN-backward sums of bn_1; likewise the last data gradient into the first block's input for the stem
             red1, parts1 = c1.reduce_spec(y1, ops.ACT_RELU) if fuse else (None, None)
             if dual:
-                g_a1 = c2.finish(a1, dy2, gview, packs, bn_reduce=red1)
+                g_a1 = c2.finish(a1, dy2, gview, packs, bn_reduce=red1, side=side)
             else:
-                g_a1 = c2.bwd(a1, y2, g, out, ops.ACT_RELU, gview, packs, bn_reduce=red1)
+                g_a1 = c2.bwd(a1, y2, g, out, ops.ACT_RELU, gview, packs, bn_reduce=red1, side=side)
             red0 = None
             if fuse and bi == len(self.blocks) - 1:
                 red0, stem_parts = self.stem.reduce_spec(saved["y0"], ops.ACT_RELU)
-            g = c1.bwd(a_in, y1, g_a1, None, ops.ACT_RELU, gview, packs, dx_out=g_in, parts=parts1, bn_reduce=red0)
+            g = c1.bwd(a_in, y1, g_a1, None, ops.ACT_RELU, gview, packs, dx_out=g_in, parts=parts1, bn_reduce=red0,
+                       side=side)
         self.stem.bwd(saved["x"], saved["y0"], g, None, ops.ACT_RELU, gview, packs, want_dx=False, parts=stem_parts)
+        if side is not None:
+            side.join()
         packs.unpack_all()
         if do_allreduce:
             allreduce_gradients(arena.flat)
