@@ -293,6 +293,30 @@ def cpu_baseline(name, cpu_batch=None):
 
 
 # ----------------------------------------------------------------------------------------------- B200 arm
+CONV_ENTRY_POINTS = ("b200cv_conv_fwd", "b200cv_conv_dgrad", "b200cv_conv_wgrad", "b200cv_conv_image_fwd",
+                     "b200cv_conv_image_wgrad")
+
+
+def serial_profile(step_fn):
+    """CUDA-event time of every ABI call of ONE eager step with everything on one stream: per-launch events need the
+    eager launches (not the captured graph), and a kernel's own duration needs it to run alone (the product path
+    queues weight gradients on a side stream, which would be billed to whatever shares the SMs with them)."""
+    from b200cv.lib import lib
+
+    saved = {k: os.environ.get(k) for k in ("B200CV_CUDA_GRAPH", "B200CV_WGRAD_TAIL_FILL")}
+    os.environ["B200CV_CUDA_GRAPH"] = "0"
+    os.environ["B200CV_WGRAD_TAIL_FILL"] = "0"
+    try:
+        step_fn()  # the first eager call after graph replays may allocate
+        return lib().profile_step(step_fn)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 class Harness:
     def __init__(self, dev, rank, world, steps, warmup):
         self.dev, self.rank, self.world, self.steps, self.warmup = dev, rank, world, steps, warmup
@@ -419,14 +443,12 @@ def bench_yolo(name, H, precision, with_clocks=True, ncu_window=False):
     e2e_value = H.world * BATCH * H.steps / (ms_e2e / 1e3)
     # roofline of the dominant kernels: event-time every conv launch of one more step (every rank runs the step -- it
     # contains the gradient all-reduce -- rank 0 reports)
-    os.environ["B200CV_CUDA_GRAPH"] = "0"  # per-launch events need the eager launches, not the captured graph
-    prof = lib().profile_step(lambda: step(imgs_d, tg_d))
-    os.environ["B200CV_CUDA_GRAPH"] = "1"
+    prof = serial_profile(lambda: step(imgs_d, tg_d))
     out = None
     if H.rank == 0:
         fwd_f, tot_f = conv_flops_per_image(synth.conv_layer_table(model), IMG)
         pk = peaks()
-        conv_ms = sum(v for k, v in prof.items() if k in ("b200cv_conv_fwd", "b200cv_conv_dgrad", "b200cv_conv_wgrad"))
+        conv_ms = sum(v for k, v in prof.items() if k in CONV_ENTRY_POINTS)
         step_ms = sum(prof.values())
         achieved = tot_f * BATCH / (conv_ms / 1e3) / 1e12
         of_step = tot_f * BATCH / (ms / H.steps / 1e3) / 1e12
@@ -491,14 +513,12 @@ def bench_rektnet(H, precision, with_clocks=False):
     clocks = sampler.stop() if sampler else None
     value = H.world * B * H.steps / (ms / 1e3)
     ms_e2e, h2d = H.e2e([x_h, thm_h, tpts_h], lambda a, b, c_: step(a, b, c_).view(1), H.steps)
-    os.environ["B200CV_CUDA_GRAPH"] = "0"
-    prof = lib().profile_step(lambda: step(x, thm, tpts))
-    os.environ["B200CV_CUDA_GRAPH"] = "1"
+    prof = serial_profile(lambda: step(x, thm, tpts))
     out = None
     if H.rank == 0:
         fwd_f, tot_f = rektnet_flops_per_image()
         pk = peaks()
-        conv_ms = sum(v for k, v in prof.items() if k in ("b200cv_conv_fwd", "b200cv_conv_dgrad", "b200cv_conv_wgrad"))
+        conv_ms = sum(v for k, v in prof.items() if k in CONV_ENTRY_POINTS)
         achieved = tot_f * B / (conv_ms / 1e3) / 1e12
         of_step = tot_f * B / (ms / H.steps / 1e3) / 1e12
         out = {"metric": c["metric"], "value": value, "unit": "img/s", "n_gpus": H.world, "steps": H.steps,

@@ -78,6 +78,20 @@ int b200cv_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int N, int C, int 
  * The convolution then runs as a 1x1 conv over the patch matrix (Cin = Kp). */
 int b200cv_im2col_nchw_f32(const float* x, void* patches, int N, int C, int H, int W, int R, int S, int stride,
                            int pad, int dil, int Kp, void* stream);
+/* The image layers WITHOUT a patch matrix (bf16 mode): k x k (3 or 7), stride 1, pad (k-1)/2, 3-channel fp32 NCHW x,
+ * 16 or 32 filters.  Replaces im2col + 1x1 conv for CVC-YOLOv3/models.py:59-69 (conv_0) and RektNet/keypoint_net.py:17
+ * (the 7x7 stem): a CTA stages the halo of an 8x32-pixel tile in shared memory and the warps gather their mma.sync
+ * fragments from it.  w_flat = the FLAT pack [Cout][Kp] (k = tap*3 + c, see b200cv_pack_entry.transpose == 2).
+ *   fwd:   y[N,H,W,y_ld] bf16 = act(conv(x, w) * scale[c] + shift[c]) (scale / shift may be null); `stats` (or null) gets
+ *          the per-channel sum / sum of squares of the stored values, [stats_parts][2*Cout] b200cv_stat.
+ *   wgrad: dw_flat[Cout][Kp] fp32 += dy^T * patches (the flat gradient layout of b200cv_unpack_wgrad_multi).
+ * b200cv_conv_image_supported() tells whether a layer shape takes this path (1) or the im2col path (0). */
+int b200cv_conv_image_supported(int C, int R, int S, int stride, int pad, int dil, int Cout);
+int b200cv_conv_image_fwd(const float* x, const void* w_flat, int N, int C, int H, int W, int R, int S, int pad,
+                          int dil, int Cout, int Kp, void* y, int64_t y_ld, const float* scale, const float* shift,
+                          int act, float slope, void* stats, int stats_parts, void* stream);
+int b200cv_conv_image_wgrad(const float* x, const void* dy, int64_t dy_ld, int N, int C, int H, int W, int R, int S,
+                            int pad, int dil, int Cout, int Kp, float* dw_flat, void* stream);
 /* fp32-parity mode: split patch matrix [N*OH*OW][p0(Kp) | p1(Kp) | p2(Kp)]. */
 int b200cv_im2col_nchw_f32_split(const float* x, void* patches, int N, int C, int H, int W, int R, int S, int stride,
                                  int pad, int dil, int Kp, void* stream);

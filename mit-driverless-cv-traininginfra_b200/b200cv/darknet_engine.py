@@ -314,8 +314,14 @@ class DarknetEngine:
         self._setup(dev)
         self._pack(need_t=want_grad, frozen=not bn_train and not want_grad)
         flat0 = bool(self._flat_convs())
-        cur = ops.im2col_nchw(x, self.layers[0].k, self.layers[0].stride, self.layers[0].pad) if flat0 \
-            else ops.nchw_to_nhwc(x)
+        L0 = self.layers[0]
+        # bf16 mode: conv_0 reads the NCHW fp32 image itself (no patch matrix, csrc/conv_image.cu)
+        img0 = flat0 and L0.bn is not None and L0.post_from is None and \
+            ops.use_image_path(L0.cin, L0.k, L0.stride, L0.pad, 1, L0.cout)
+        if img0:
+            cur = x.contiguous().float()
+        else:
+            cur = ops.im2col_nchw(x, L0.k, L0.stride, L0.pad) if flat0 else ops.nchw_to_nhwc(x)
         outs: List[Optional[torch.Tensor]] = [None] * len(self.layers)
         saved = {}
         training = targets is not None
@@ -336,7 +342,10 @@ class DarknetEngine:
                 if L.bn is not None:
                     post = outs[L.post_from] if L.post_from is not None else None
                     if bn_train:
-                        y = ops.conv_fwd(xin, L.wpk, L.cout, k_, st_, pd_, stats=L.stats)
+                        if img0 and i == 0:
+                            y = ops.conv_image_fwd(xin, L.wpk, L.cout, L.k, L.pad, stats=L.stats)
+                        else:
+                            y = ops.conv_fwd(xin, L.wpk, L.cout, k_, st_, pd_, stats=L.stats)
                         count = y.numel() // y.shape[-1]
                         vec = (L.scale, L.shift, L.mean, L.rstd)
                         if private:
@@ -347,8 +356,12 @@ class DarknetEngine:
                         saved[i] = (xin, y, vec)
                     else:
                         scale, shift = self._eval_affine(L)
-                        cur = ops.conv_fwd(xin, L.wpk, L.cout, k_, st_, pd_, scale=scale, shift=shift,
-                                           residual=post, act=L.act, slope=L.slope, res_after_act=True)
+                        if img0 and i == 0:
+                            cur = ops.conv_image_fwd(xin, L.wpk, L.cout, L.k, L.pad, scale=scale, shift=shift,
+                                                     act=L.act, slope=L.slope)
+                        else:
+                            cur = ops.conv_fwd(xin, L.wpk, L.cout, k_, st_, pd_, scale=scale, shift=shift,
+                                               residual=post, act=L.act, slope=L.slope, res_after_act=True)
                 else:  # pre-YOLO conv: bias, linear, fp32 logits
                     cur = ops.conv_fwd(xin, L.wpk, L.cout, k_, st_, pd_, out_dtype=torch.float32,
                                        shift=L.conv.bias.detach())
@@ -495,6 +508,8 @@ class DarknetEngine:
                 if fill:
                     dy_ready = torch.cuda.Event()
                     dy_ready.record(main)
+                elif i == 0 and xin.dtype == torch.float32:  # xin = the NCHW image (conv_image path)
+                    ops.conv_image_wgrad(xin, dy, L.cout, L.k, L.pad, 1, packs.dwp[id(L.conv)])
                 elif i == 0 and self._flat_convs():
                     wgrad(xin, dy, L.cout, 1, 1, 0, packs.dwp[id(L.conv)], on_side=tail_hw == 0)  # xin = im2col patches
                 else:

@@ -20,7 +20,7 @@ __all__ = [
     "pack_weights", "unpack_wgrad", "conv_fwd", "conv_dgrad", "conv_wgrad", "bn_finalize", "bn_apply_act",
     "bn_bwd_reduce", "bn_bwd_finalize", "bn_bwd_apply", "bn_stats_apply_act", "bn_bwd_stats_apply", "act_bwd", "copy_slice", "col_sum", "maxpool_fwd",
     "maxpool_bwd", "upsample_fwd", "upsample_bwd", "act_code", "sm_count", "stats_buffer", "stats_value", "im2col_nchw",
-    "use_flat_path", "flat_k", "split_mode", "precision", "set_default_precision", "default_split", "channels",
+    "use_flat_path", "use_image_path", "conv_image_fwd", "conv_image_wgrad", "flat_k", "split_mode", "precision", "set_default_precision", "default_split", "channels",
     "bias_grad", "concat_channels", "slice_grad", "split_from_f32", "split_to_f32",
 ]
 
@@ -151,6 +151,38 @@ def im2col_nchw(x: torch.Tensor, k: int, stride: int, pad: int, dil: int = 1) ->
     out = torch.empty(n, oh, ow, _mul() * kp, dtype=torch.bfloat16, device=x.device)
     name = "b200cv_im2col_nchw_f32_split" if split_mode() else "b200cv_im2col_nchw_f32"
     lib().call(name, ptr(x), ptr(out), n, c, h, w, k, k, stride, pad, dil, kp, stream_ptr())
+    return out
+
+
+def use_image_path(cin: int, k: int, stride: int, pad: int, dil: int, cout: int) -> bool:
+    """The 3-channel image layers of the bf16 mode run WITHOUT a patch matrix (csrc/conv_image.cu); the fp32-parity
+    mode and other shapes keep im2col + 1x1 conv.  B200CV_IMAGE_CONV=0 restores the im2col path."""
+    if split_mode() or __import__("os").environ.get("B200CV_IMAGE_CONV", "1") == "0":
+        return False
+    return bool(lib().cdll.b200cv_conv_image_supported(cin, k, k, stride, pad, dil, cout))
+
+
+def conv_image_fwd(x: torch.Tensor, w_flat: torch.Tensor, cout: int, k: int, pad: int, dil: int = 1, scale=None,
+                   shift=None, act=ACT_NONE, slope=0.0, stats=None) -> torch.Tensor:
+    """NCHW fp32 image, flat-packed weights [Cout][1][Kp] -> NHWC bf16 [N,H,W,pad(Cout)] (stride 1, same padding)."""
+    require_cuda(x, "conv_image_fwd")
+    x = x.contiguous().float()
+    n, c, h, w = x.shape
+    out = torch.empty(n, h, w, pad_channels(cout), dtype=torch.bfloat16, device=x.device)
+    lib().call("b200cv_conv_image_fwd", ptr(x), ptr(w_flat), n, c, h, w, k, k, pad, dil, cout, w_flat.shape[-1],
+               ptr(out), out.stride(-2), ptr(scale) if scale is not None else None,
+               ptr(shift) if shift is not None else None, act, float(slope),
+               ptr(stats) if stats is not None else None, stats.shape[0] if stats is not None else 0, stream_ptr(),
+               tag=(c, cout, k, 1, n, h, w))
+    return out
+
+
+def conv_image_wgrad(x: torch.Tensor, dy: torch.Tensor, cout: int, k: int, pad: int, dil: int, out: torch.Tensor):
+    """Accumulates the flat packed fp32 gradient [Cout][1][Kp] of an image layer; `out` must be zeroed."""
+    x = x.contiguous().float()
+    n, c, h, w = x.shape
+    lib().call("b200cv_conv_image_wgrad", ptr(x), ptr(dy), dy.stride(-2), n, c, h, w, k, k, pad, dil, cout,
+               out.shape[-1], ptr(out), stream_ptr(), tag=(c, cout, k, 1, n, h, w))
     return out
 
 

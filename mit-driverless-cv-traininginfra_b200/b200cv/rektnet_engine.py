@@ -50,7 +50,11 @@ class _ConvBN:
         self.vecs(x.device)
         self._eval_key = None  # bn_finalize updates the running statistics behind torch's version counters
         self.stats.zero_()
-        y = ops.conv_fwd(x, self.wpk, self.cout, self.k, 1, self.pad, self.dil, stats=self.stats)
+        if x.dtype == torch.float32:  # the stem on the NCHW image itself (csrc/conv_image.cu)
+            y = ops.conv_image_fwd(x, self.wpk, self.cout, self.conv.kernel_size[0], self.conv.padding[0],
+                                   stats=self.stats)
+        else:
+            y = ops.conv_fwd(x, self.wpk, self.cout, self.k, 1, self.pad, self.dil, stats=self.stats)
         count = y.numel() // y.shape[-1]
         # the conv bias cancels inside a train-mode BN: it is left out of y and only enters running_mean
         ops.bn_finalize(self.stats, count, self.bn.weight, self.bn.bias, self.conv.bias, BN_EPS, BN_MOMENTUM,
@@ -100,7 +104,11 @@ class _ConvBN:
         gview[id(self.conv.bias)].zero_()  # analytically zero under train-mode BN
 
         def wgrad():
-            ops.conv_wgrad(x_in, dy, self.cout, self.k, 1, self.pad, self.dil, out=packs.dwp[id(self.conv)])
+            if x_in.dtype == torch.float32:  # the stem: x_in is the NCHW image
+                ops.conv_image_wgrad(x_in, dy, self.cout, self.conv.kernel_size[0], self.conv.padding[0], 1,
+                                     packs.dwp[id(self.conv)])
+            else:
+                ops.conv_wgrad(x_in, dy, self.cout, self.k, 1, self.pad, self.dil, out=packs.dwp[id(self.conv)])
 
         if side is None:
             wgrad()
@@ -220,7 +228,11 @@ class RektNetEngine:
         self._setup(dev)
         self._packs.pack_all(want_grad)
         out_wpk, out_wpk_t = self._packs.wpk[id(m.out)], self._packs.wpk_t[id(m.out)]
-        xin = ops.im2col_nchw(x, 7, 1, 3)  # stem runs as explicit im2col + 1x1 conv over [.., 192] patches
+        sc_ = self.stem.conv
+        if ops.use_image_path(sc_.in_channels, sc_.kernel_size[0], 1, sc_.padding[0], sc_.dilation[0], sc_.out_channels):
+            xin = x.contiguous().float()  # bf16 mode: the stem reads the image itself (no patch matrix)
+        else:
+            xin = ops.im2col_nchw(x, 7, 1, 3)  # explicit im2col + 1x1 conv over [.., 192] patches
         saved = {"x": xin, "blocks": [], "out_wpk_t": out_wpk_t}
         if train:
             y0 = self.stem.fwd_train(xin)
@@ -237,7 +249,11 @@ class RektNetEngine:
                 a = out
         else:
             sc, sh = self.stem.eval_affine()
-            a = ops.conv_fwd(xin, self.stem.wpk, self.stem.cout, 1, 1, 0, scale=sc, shift=sh, act=ops.ACT_RELU)
+            if xin.dtype == torch.float32:
+                a = ops.conv_image_fwd(xin, self.stem.wpk, self.stem.cout, sc_.kernel_size[0], sc_.padding[0],
+                                       scale=sc, shift=sh, act=ops.ACT_RELU)
+            else:
+                a = ops.conv_fwd(xin, self.stem.wpk, self.stem.cout, 1, 1, 0, scale=sc, shift=sh, act=ops.ACT_RELU)
             for c1, c2, cs in self.blocks:
                 sc, sh = c1.eval_affine()
                 a1 = ops.conv_fwd(a, c1.wpk, c1.cout, 3, 1, 2, 2, scale=sc, shift=sh, act=ops.ACT_RELU)

@@ -142,3 +142,54 @@ def test_bn_pool_upsample_against_torch():
     dxu = ops.upsample_bwd(ops.nchw_to_nhwc(gu.to(DEV)))
     want = gu.view(n, c, h, 2, w, 2).sum((3, 5))
     assert float((ops.nhwc_to_nchw(dxu, c).cpu() - want).abs().max()) < 3e-2
+
+
+IMAGE_CASES = [  # N, H, W, k, Cout  (3-channel image layers: CVC-YOLOv3 conv_0, the RektNet stem)
+    (2, 32, 64, 3, 32),
+    (3, 21, 45, 3, 32),     # ragged: partial tiles in both directions
+    (2, 80, 80, 7, 16),
+    (2, 19, 70, 7, 16),
+    (5, 8, 32, 3, 16),
+]
+
+
+@pytest.mark.parametrize("case", IMAGE_CASES)
+def test_image_conv_without_patch_matrix(case):
+    """b200cv_conv_image_fwd / _wgrad (halo tile in shared memory + mma.sync) against torch fp32 on the same
+    bf16-rounded operands: output, fused BatchNorm statistics (bit-reproducible), folded affine + activation, and the
+    flat packed weight gradient."""
+    n, h, w, k, cout = case
+    pad = (k - 1) // 2
+    assert ops.use_image_path(3, k, 1, pad, 1, cout)
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.rand(n, 3, h, w, generator=g)
+    wt = _bf(torch.randn(cout, 3, k, k, generator=g) * 0.2).requires_grad_(True)
+    y_ref = F.conv2d(_bf(x), wt, None, 1, pad)
+    dy = _bf(torch.randn(y_ref.shape, generator=g))
+    y_ref.backward(dy)
+    kp = ops.flat_k(3, k)
+    flat = torch.zeros(cout, 1, kp)
+    flat[:, 0, :3 * k * k] = wt.detach().permute(0, 2, 3, 1).reshape(cout, -1)
+    flat = flat.to(DEV).to(torch.bfloat16)
+    xd = x.to(DEV)
+    stats = ops.stats_buffer(cout, DEV)
+    y = ops.conv_image_fwd(xd, flat, cout, k, pad, stats=stats)
+    assert y.shape == (n, h, w, ops.pad_channels(cout))
+    got = ops.nhwc_to_nchw(y, cout).cpu()
+    assert float((got - y_ref.detach()).abs().max()) <= 1e-2 * float(y_ref.abs().max())
+    yf = y.float()[..., :cout]
+    tot = ops.stats_value(stats).float()
+    assert torch.allclose(tot[:cout], yf.sum((0, 1, 2)), rtol=1e-3, atol=1e-2)
+    assert torch.allclose(tot[cout:], (yf * yf).sum((0, 1, 2)), rtol=1e-3, atol=1e-2)
+    again = ops.stats_buffer(cout, DEV)
+    y2 = ops.conv_image_fwd(xd, flat, cout, k, pad, stats=again)
+    assert torch.equal(y, y2) and torch.equal(stats.sum(0), again.sum(0))
+    scale, shift = torch.rand(cout, device=DEV) + 0.5, torch.randn(cout, device=DEV)
+    out = ops.conv_image_fwd(xd, flat, cout, k, pad, scale=scale, shift=shift, act=ops.ACT_LEAKY, slope=0.1)
+    want = F.leaky_relu(y_ref.detach().to(DEV) * scale[None, :, None, None] + shift[None, :, None, None], 0.1)
+    assert float((ops.nhwc_to_nchw(out, cout) - want).abs().max()) <= 1.5e-2 * float(want.abs().max())
+    dwp = torch.zeros(cout, 1, kp, device=DEV)
+    ops.conv_image_wgrad(xd, ops.nchw_to_nhwc(dy.to(DEV)), cout, k, pad, 1, dwp)
+    want_dw = wt.grad.permute(0, 2, 3, 1).reshape(cout, -1)
+    assert float((dwp[:, 0, :3 * k * k].cpu() - want_dw).abs().max()) <= 2e-3 * float(want_dw.abs().max())
+    assert float(dwp[:, 0, 3 * k * k:].abs().max()) == 0.0 if kp > 3 * k * k else True

@@ -15,6 +15,7 @@ from utils.utils import weights_init_normal
 size = int(sys.argv[1]) if len(sys.argv) > 1 else 416
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 os.environ["B200CV_CUDA_GRAPH"] = "0"
+os.environ["B200CV_WGRAD_TAIL_FILL"] = "0"  # one stream: a kernel's own duration needs it to run alone
 dev = torch.device("cuda")
 cfg = cfg_gen.write_cfg(tempfile.mkdtemp(), "darknet53", size, size, 80)
 torch.manual_seed(0)

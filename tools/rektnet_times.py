@@ -30,7 +30,8 @@ for _ in range(10):
     step()
 torch.cuda.synchronize()
 wall = (time.perf_counter() - t0) / 10 * 1e3
-os.environ["B200CV_CUDA_GRAPH"] = "0"  # the per-call timing needs the eager launches
+os.environ["B200CV_CUDA_GRAPH"] = "0"
+os.environ["B200CV_WGRAD_TAIL_FILL"] = "0"  # one stream: a kernel's own duration needs it to run alone  # the per-call timing needs the eager launches
 step()
 calls = lib().profile_step(step, detail=True)
 tot = sum(ms for _, _, ms in calls)
