@@ -61,41 +61,61 @@ template <class C>
 struct HaloRegs {
   static constexpr int kN = (3 * C::kHH * C::kHW + kThreads - 1) / kThreads;
   float v[kN];
-  // per-thread constants (the same halo elements every tile): offset inside an image plane set, smem offset
-  int rel[kN];   // (c << 20) | (row << 10) | col, or -1 past the end of the halo
+  // per-thread constants (the same halo elements every tile)
+  int rc[kN];    // (row << 16) | col inside the halo, or -1 past its end
+  int goff[kN];  // (c*H + row)*W + col: global offset relative to the tile's top-left halo element
   int soff[kN];  // element offset in the shared-memory halo
 
-  __device__ __forceinline__ void init() {
+  __device__ __forceinline__ void init(int H, int W) {
 #pragma unroll
     for (int i = 0; i < kN; ++i) {
       const int idx = threadIdx.x + i * kThreads;
       const int col = idx % C::kHW;
-      const int rc = idx / C::kHW;
-      const int row = rc % C::kHH;
-      const int c = rc / C::kHH;
-      rel[i] = c < 3 ? ((c << 20) | (row << 10) | col) : -1;
+      const int q = idx / C::kHW;
+      const int row = q % C::kHH;
+      const int c = q / C::kHH;
+      rc[i] = c < 3 ? ((row << 16) | col) : -1;
+      goff[i] = (c * H + row) * W + col;
       soff[i] = c * C::kPlane + row * C::kHWp + col;
     }
   }
 };
 
+// Tile walk without divisions: (n, ty, tx) advanced by the grid size in mixed radix.
+struct TileWalk {
+  int n, ty, tx;
+  int dn, dty, dtx, tiles_x, tiles_y;
+  __device__ __forceinline__ void start(int first, int step, int tx_count, int ty_count) {
+    tiles_x = tx_count; tiles_y = ty_count;
+    tx = first % tiles_x; ty = (first / tiles_x) % tiles_y; n = first / (tiles_x * tiles_y);
+    dtx = step % tiles_x; dty = (step / tiles_x) % tiles_y; dn = step / (tiles_x * tiles_y);
+  }
+  __device__ __forceinline__ void advance() {
+    tx += dtx;
+    int carry = tx >= tiles_x;
+    tx -= carry ? tiles_x : 0;
+    ty += dty + carry;
+    carry = ty >= tiles_y;
+    ty -= carry ? tiles_y : 0;
+    n += dn + carry;
+  }
+};
+
+// the fp32 image values of tile `t` -> registers (32-bit offsets: the entry points check 3*H*W < 2^31)
 template <class C, int R>
-__device__ __forceinline__ void halo_fetch(HaloRegs<C>& h, const float* __restrict__ x, long long tile, long long ntiles,
-                                           int tiles_x, int tiles_y, int H, int W) {
+__device__ __forceinline__ void halo_fetch(HaloRegs<C>& h, const float* __restrict__ x, const TileWalk& t, int N, int H,
+                                           int W) {
   constexpr int pad = (R - 1) / 2;
-  if (tile >= ntiles) return;
-  const int tx = (int)(tile % tiles_x);
-  const int ty = (int)((tile / tiles_x) % tiles_y);
-  const int n = (int)(tile / ((long long)tiles_x * tiles_y));
-  const float* img = x + (long long)n * 3 * H * W;
-  const int gy0 = ty * kTileH - pad, gx0 = tx * kTileW - pad;
+  if (t.n >= N) return;
+  const int gy0 = t.ty * kTileH - pad, gx0 = t.tx * kTileW - pad;
+  const int base = t.n * 3 * H * W + gy0 * W + gx0;  // 32-bit: the entry points check N*3*H*W < 2^31
 #pragma unroll
   for (int i = 0; i < HaloRegs<C>::kN; ++i) {
-    const int r = h.rel[i];
-    const int gy = gy0 + ((r >> 10) & 1023), gx = gx0 + (r & 1023);
-    float v = 0.f;
-    if (r >= 0 && gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(img + ((long long)(r >> 20) * H + gy) * W + gx);
-    h.v[i] = v;
+    const int r = h.rc[i];
+    const int gy = gy0 + (r >> 16), gx = gx0 + (r & 0xffff);
+    const bool ok = r >= 0 && static_cast<unsigned>(gy) < static_cast<unsigned>(H) &&
+                    static_cast<unsigned>(gx) < static_cast<unsigned>(W);
+    h.v[i] = ok ? __ldg(x + (base + h.goff[i])) : 0.f;
   }
 }
 
@@ -103,7 +123,7 @@ template <class C>
 __device__ __forceinline__ void halo_commit(const HaloRegs<C>& h, __nv_bfloat16* halo) {
 #pragma unroll
   for (int i = 0; i < HaloRegs<C>::kN; ++i)
-    if (h.rel[i] >= 0) halo[h.soff[i]] = __float2bfloat16_rn(h.v[i]);
+    if (h.rc[i] >= 0) halo[h.soff[i]] = __float2bfloat16_rn(h.v[i]);
 }
 
 // offset of filter element k = tap*3 + c inside the halo, relative to the output pixel's top-left halo element
@@ -175,18 +195,18 @@ conv_image_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restri
   }
 
   const int tiles_x = (W + kTileW - 1) / kTileW, tiles_y = (H + kTileH - 1) / kTileH;
-  const long long ntiles = (long long)N * tiles_y * tiles_x;
   HaloRegs<C> pre;
-  pre.init();
-  halo_fetch<C, R>(pre, x, blockIdx.x, ntiles, tiles_x, tiles_y, H, W);
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int tx = (int)(tile % tiles_x);
-    const int ty = (int)((tile / tiles_x) % tiles_y);
-    const int n = (int)(tile / ((long long)tiles_x * tiles_y));
-    const int y0 = ty * kTileH, x0 = tx * kTileW;
+  pre.init(H, W);
+  TileWalk cur, nxt;
+  cur.start(blockIdx.x, gridDim.x, tiles_x, tiles_y);
+  halo_fetch<C, R>(pre, x, cur, N, H, W);
+  for (; cur.n < N; cur = nxt) {
+    const int n = cur.n, y0 = cur.ty * kTileH, x0 = cur.tx * kTileW;
+    nxt = cur;
+    nxt.advance();
     halo_commit<C>(pre, halo);  // every warp passed the barrier after its last halo read of the previous tile
     __syncthreads();            // halo complete; the previous tile's staged outputs have been stored
-    halo_fetch<C, R>(pre, x, tile + gridDim.x, ntiles, tiles_x, tiles_y, H, W);
+    halo_fetch<C, R>(pre, x, nxt, N, H, W);
     const bool row_ok = y0 + warp < H;
     // both 16-pixel groups of this warp's row: all fragment gathers are independent (latency, not issue, bound)
     float acc[2][C::kNT][4];
@@ -249,13 +269,17 @@ conv_image_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restri
     __syncthreads();
     // coalesced stores: a tile row is kTileW * COUT contiguous bf16 in global memory
     constexpr int kVecPerPix = COUT / 8;
-    for (int idx = threadIdx.x; idx < kTileH * kTileW * kVecPerPix; idx += kThreads) {
+    __nv_bfloat16* ytile = y + (((long long)n * H + y0) * W + x0) * y_ld;
+    const int ld32 = static_cast<int>(y_ld);  // offsets inside a tile fit 32 bits
+#pragma unroll
+    for (int i = 0; i < kTileH * kTileW * kVecPerPix / kThreads; ++i) {
+      const int idx = threadIdx.x + i * kThreads;
       const int v = idx % kVecPerPix;
       const int pix = idx / kVecPerPix;
       const int px = pix % kTileW, row = pix / kTileW;
       if (y0 + row < H && x0 + px < W) {
         const uint4 q = *reinterpret_cast<const uint4*>(outs + pix * C::kOutPitch + v * 8);
-        *reinterpret_cast<uint4*>(y + (((long long)n * H + y0 + row) * W + x0 + px) * y_ld + v * 8) = q;
+        *reinterpret_cast<uint4*>(ytile + ((row * W + px) * ld32 + v * 8)) = q;
       }
     }
   }
@@ -306,31 +330,32 @@ conv_image_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __rest
     for (int nt = 0; nt < C::kNT8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
 
   const int tiles_x = (W + kTileW - 1) / kTileW, tiles_y = (H + kTileH - 1) / kTileH;
-  const long long ntiles = (long long)N * tiles_y * tiles_x;
   constexpr int kVecPerPix = COUT / 8;
   constexpr int kDyVecs = kTileH * kTileW * kVecPerPix / kThreads;  // 16-byte dy vectors per thread and tile
   HaloRegs<C> pre;
-  pre.init();
+  pre.init(H, W);
   uint4 dpre[kDyVecs];
-  auto dy_fetch = [&](long long tile) {
-    if (tile >= ntiles) return;
-    const int tx = (int)(tile % tiles_x);
-    const int ty = (int)((tile / tiles_x) % tiles_y);
-    const int n = (int)(tile / ((long long)tiles_x * tiles_y));
+  auto dy_fetch = [&](const TileWalk& t) {
+    if (t.n >= N) return;
+    const __nv_bfloat16* dtile = dy + (((long long)t.n * H + t.ty * kTileH) * W + t.tx * kTileW) * dy_ld;
 #pragma unroll
     for (int i = 0; i < kDyVecs; ++i) {
       const int idx = threadIdx.x + i * kThreads;
       const int v = idx % kVecPerPix;
       const int pix = idx / kVecPerPix;
-      const int gx = tx * kTileW + pix % kTileW, gy = ty * kTileH + pix / kTileW;
+      const int px = pix % kTileW, row = pix / kTileW;
       dpre[i] = make_uint4(0u, 0u, 0u, 0u);  // pixels outside the image contribute nothing
-      if (gy < H && gx < W)
-        dpre[i] = __ldg(reinterpret_cast<const uint4*>(dy + (((long long)n * H + gy) * W + gx) * dy_ld + v * 8));
+      if (t.ty * kTileH + row < H && t.tx * kTileW + px < W)
+        dpre[i] = __ldg(reinterpret_cast<const uint4*>(dtile + ((row * W + px) * static_cast<int>(dy_ld) + v * 8)));
     }
   };
-  halo_fetch<C, R>(pre, x, blockIdx.x, ntiles, tiles_x, tiles_y, H, W);
-  dy_fetch(blockIdx.x);
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  TileWalk cur, nxt;
+  cur.start(blockIdx.x, gridDim.x, tiles_x, tiles_y);
+  halo_fetch<C, R>(pre, x, cur, N, H, W);
+  dy_fetch(cur);
+  for (; cur.n < N; cur = nxt) {
+    nxt = cur;
+    nxt.advance();
     __syncthreads();  // every warp is done with the previous tile's buffers
     halo_commit<C>(pre, halo);
 #pragma unroll
@@ -339,8 +364,8 @@ conv_image_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __rest
       *reinterpret_cast<uint4*>(dys + (idx / kVecPerPix) * C::kOutPitch + (idx % kVecPerPix) * 8) = dpre[i];
     }
     __syncthreads();
-    halo_fetch<C, R>(pre, x, tile + gridDim.x, ntiles, tiles_x, tiles_y, H, W);
-    dy_fetch(tile + gridDim.x);
+    halo_fetch<C, R>(pre, x, nxt, N, H, W);
+    dy_fetch(nxt);
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {  // 16 pixels of this warp's row per k-step
       // A = dy^T through ldmatrix.trans: stored rows are pixels (k), 8 channels (m) per 16-byte row
@@ -463,6 +488,8 @@ extern "C" int b200cv_conv_image_fwd(const float* x, const void* w_flat, int N, 
   B200CV_CHECK_ARG(image_shape_ok(C, R, S, pad, dil, Cout),
                    "conv_image_fwd: only 3-channel 3x3 / 7x7 stride-1 same-padding layers with 16 or 32 filters");
   B200CV_CHECK_ARG(Kp >= ((3 * R * S + 15) / 16) * 16 && Kp % 8 == 0, "conv_image_fwd: Kp=%d too small", Kp);
+  B200CV_CHECK_ARG(3LL * N * H * W < (1LL << 31) && (long long)N * ((H + 7) / 8) * ((W + 31) / 32) < (1LL << 31),
+                   "conv_image_fwd: image too large for 32-bit tile arithmetic");
   B200CV_CHECK_ARG(y_ld >= Cout && y_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
                        (reinterpret_cast<uintptr_t>(w_flat) & 3) == 0,
                    "conv_image_fwd: y must be 16-byte aligned rows of >= Cout bf16");
@@ -488,6 +515,8 @@ extern "C" int b200cv_conv_image_wgrad(const float* x, const void* dy, int64_t d
   B200CV_CHECK_ARG(image_shape_ok(C, R, S, pad, dil, Cout),
                    "conv_image_wgrad: only 3-channel 3x3 / 7x7 stride-1 same-padding layers with 16 or 32 filters");
   B200CV_CHECK_ARG(Kp >= 3 * R * S, "conv_image_wgrad: Kp=%d too small", Kp);
+  B200CV_CHECK_ARG(3LL * N * H * W < (1LL << 31) && (long long)N * ((H + 7) / 8) * ((W + 31) / 32) < (1LL << 31),
+                   "conv_image_wgrad: image too large for 32-bit tile arithmetic");
   B200CV_CHECK_ARG(dy_ld >= Cout && dy_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0,
                    "conv_image_wgrad: dy must be 16-byte aligned rows of >= Cout bf16");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
