@@ -426,20 +426,34 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackEntry
       put_packed(dst, o, k, e.Ipad, split, v);
     }
   } else if (!e.transpose) {
-    // dst[o][t][ip] <- src[o][i][t]: one output channel (I*RS contiguous floats) per block iteration
+    // dst[o][t][ip] <- src[o][i][t]: one output channel (I*RS contiguous floats) per block iteration.  No
+    // per-element division: a warp walks one tap row at a time (the first version spent most of its time in
+    // integer divisions by RS*Ipad and ran at 1 TB/s).
     const int row = e.I * e.RS;
     const bool staged = row <= kPackSmemFloats;
+    const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
     for (int o = blockIdx.x; o < e.O; o += gridDim.x) {
       const float* sp = e.src + (long long)o * row;
       if (staged) {
         for (int j = tid; j < row; j += nt) sm[j] = sp[j];
         __syncthreads();
       }
-      for (int j = tid; j < e.RS * e.Ipad; j += nt) {
-        const int t = j / e.Ipad, ip = j - t * e.Ipad;
-        float v = 0.f;
-        if (ip < e.I) v = staged ? sm[ip * e.RS + t] : sp[ip * e.RS + t];
-        put_packed(dst, (long long)o * e.RS + t, ip, e.Ipad, split, v);
+      for (int t = warp; t < e.RS; t += nw) {
+        const long long prow = (long long)o * e.RS + t;
+        if (!split && (e.Ipad & 1) == 0) {  // two channels per lane: 4-byte stores
+          __nv_bfloat162* d2 = reinterpret_cast<__nv_bfloat162*>(dst + prow * e.Ipad);
+          for (int ip = 2 * lane; ip < e.Ipad; ip += 64) {
+            const float v0 = ip < e.I ? (staged ? sm[ip * e.RS + t] : sp[ip * e.RS + t]) : 0.f;
+            const float v1 = ip + 1 < e.I ? (staged ? sm[(ip + 1) * e.RS + t] : sp[(ip + 1) * e.RS + t]) : 0.f;
+            d2[ip >> 1] = __floats2bfloat162_rn(v0, v1);
+          }
+        } else {
+          for (int ip = lane; ip < e.Ipad; ip += 32) {
+            float v = 0.f;
+            if (ip < e.I) v = staged ? sm[ip * e.RS + t] : sp[ip * e.RS + t];
+            put_packed(dst, prow, ip, e.Ipad, split, v);
+          }
+        }
       }
       if (staged) __syncthreads();
     }
@@ -458,19 +472,31 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackEntry
       }
       return;
     }
+    const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
     for (int tile = blockIdx.x; tile < tiles_i * tiles_o; tile += gridDim.x) {
       const int i0 = (tile / tiles_o) * 32, o0 = (tile % tiles_o) * 32;
       const int ni = min(32, e.I - i0);
-      for (int j = tid; j < 32 * 32 * e.RS; j += nt) {
-        const int ol = j / (32 * e.RS), k = j - ol * 32 * e.RS;  // k = il*RS + t
-        float v = 0.f;
-        if (o0 + ol < e.O && k < ni * e.RS) v = e.src[((long long)(o0 + ol) * e.I + i0) * e.RS + k];
-        sm[ol * ld + k] = v;
+      const int run = ni * e.RS;  // contiguous source floats of one output channel inside this tile
+      // load: warp w takes output channels w, w + 8, ...: `run` contiguous floats each (coalesced)
+      for (int ol = warp; ol < 32; ol += nw) {
+        const bool ok = o0 + ol < e.O;
+        const float* sp = e.src + ((long long)(o0 + ol) * e.I + i0) * e.RS;
+        for (int k = lane; k < run; k += 32) sm[ol * ld + k] = ok ? sp[k] : 0.f;
       }
       __syncthreads();
-      for (int j = tid; j < ni * e.RS * 32; j += nt) {
-        const int ol = j & 31, k = j >> 5;  // k = il*RS + t
-        if (o0 + ol < e.Opad) put_packed(dst, (long long)i0 * e.RS + k, o0 + ol, e.Opad, split, sm[ol * ld + k]);
+      // store: row k = il*RS + t of the tile is 32 consecutive output channels; two rows per warp instruction
+      // (lanes 0-15 / 16-31), two channels per lane
+      if (!split) {
+        const int half = lane >> 4, ol2 = 2 * (lane & 15);
+        for (int k = 2 * warp + half; k < run; k += 2 * nw) {
+          if (o0 + ol2 < e.Opad) {  // Opad is even: the pair is in or out together
+            const __nv_bfloat162 h = __floats2bfloat162_rn(sm[ol2 * ld + k], sm[(ol2 + 1) * ld + k]);
+            *reinterpret_cast<__nv_bfloat162*>(dst + ((long long)i0 * e.RS + k) * e.Opad + o0 + ol2) = h;
+          }
+        }
+      } else {
+        for (int k = warp; k < run; k += nw)
+          if (o0 + lane < e.Opad) put_packed(dst, (long long)i0 * e.RS + k, o0 + lane, e.Opad, split, sm[lane * ld + k]);
       }
       __syncthreads();
     }
