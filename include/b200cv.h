@@ -113,7 +113,9 @@ typedef struct b200cv_pack_entry {
   void* dst;
   int32_t O, I, RS, Ipad, Opad, transpose;
 } b200cv_pack_entry;
-/* entry.transpose == 2 selects the FLAT layout used with b200cv_im2col_nchw_f32: packed row = [Ipad] with
+/* entry.transpose == 3 (3x3 filters, bf16 mode): the depth-to-space operand of b200cv_conv_dgrad_d2s,
+ * dst[(a*2+b)*I + i][(u*2+v)*Opad + o] = w[o][i][r(a,u)][s(b,v)] or 0, r(0,0)=1, r(1,0)=2, r(1,1)=0.
+ * entry.transpose == 2 selects the FLAT layout used with b200cv_im2col_nchw_f32: packed row = [Ipad] with
  * k = tap*I + i (Ipad >= R*S*I); the matching gradient row is un-packed the same way.
  * transpose | 8 (also for b200cv_pack_weights) = fp32-parity (split) pack: every innermost run of W channels becomes
  * [w0(W) | w1(W) | w2(W)], the three bf16 pieces of the fp32 weight. */
@@ -180,6 +182,13 @@ int b200cv_conv_fwd(const b200cv_conv_args* a, void* stream);
  * spatial size of dX; stride/pad/dil are the FORWARD conv's.  residual adds an existing gradient
  * (shortcut / route fan-out).  autograd of nn.Conv2d: CVC-YOLOv3/train.py:70. */
 int b200cv_conv_dgrad(const b200cv_conv_args* a, int out_h, int out_w, void* stream);
+/* The 3x3 stride-2 pad-1 data gradient as ONE launch (instead of one per output-parity class): a GEMM over the dy
+ * grid whose 4*C output columns are the 2x2 block of input pixels each dy pixel owns, stored depth-to-space by 3-D TMA
+ * stores.  `a->w` = the `transpose == 3` pack of b200cv_pack_weights_multi ([4*Cin_fwd][4*pad(Cout_fwd)]).  Needs an
+ * even output whose width is a multiple of 8 and >= 64, C = a->Cout a padded multiple of 32, a contiguous NHWC bf16 y and no residual /
+ * fused epilogue (B200CV_ERR_ARG otherwise -- the caller then takes b200cv_conv_dgrad).  CVC-YOLOv3 down-sampling
+ * convs, models.py:59-65 with stride=2. */
+int b200cv_conv_dgrad_d2s(const b200cv_conv_args* a, int out_h, int out_w, void* stream);
 
 /* Weight gradient: dw_packed[o][tap][i] += sum_pixels dY[pix][o] * X[pix+tap][i]  (fp32, atomically
  * accumulated; zero it first).  x: NHWC bf16 [N,H,W,Cin]; dy: NHWC bf16 [N,OH,OW,dy_ld].

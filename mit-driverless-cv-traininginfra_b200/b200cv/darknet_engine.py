@@ -175,7 +175,7 @@ class DarknetEngine:
             self._nbt = [L.bn.num_batches_tracked for L in bn_layers if L.bn.num_batches_tracked is not None]
             self._arena = GradArena(self.params, dev)
             convs = [(L.conv, L.index > 0) for L in self.layers if L.type == "convolutional"]
-            self._packs = ConvPackSet(convs, dev, self._arena, flat=self._flat_convs(), split=self.split)
+            self._packs = ConvPackSet(convs, dev, self._arena, flat=self._flat_convs(), split=self.split, d2s=self._d2s_convs())
             for L in self.layers:
                 if L.type == "convolutional":
                     L.wpk, L.wpk_t = self._packs.wpk[id(L.conv)], self._packs.wpk_t[id(L.conv)]
@@ -191,6 +191,11 @@ class DarknetEngine:
         if Lj.type == "shortcut" and Lj.fused_alias:
             return j - 1
         return None
+
+    def _d2s_convs(self):
+        """3x3 stride-2 convs whose data gradient can run as one depth-to-space launch (ops.conv_dgrad_d2s)."""
+        return [L.conv for L in self.layers
+                if L.type == "convolutional" and L.index > 0 and ops.d2s_dgrad_ok(L.cin, L.k, L.stride, L.pad, 1 << 30)]
 
     def _flat_convs(self):
         L0 = self.layers[0]
@@ -420,7 +425,7 @@ class DarknetEngine:
             # backward so autograd's in-place accumulation stays correct
             arena = GradArena(self.params, dev)
             packs = ConvPackSet([(L.conv, L.index > 0) for L in self.layers if L.type == "convolutional"], dev, arena,
-                                flat=self._flat_convs(), split=self.split)
+                                flat=self._flat_convs(), split=self.split, d2s=self._d2s_convs())
         else:
             packs = self._packs
         packs.zero_grads()
@@ -527,8 +532,13 @@ class DarknetEngine:
                         T = self.layers[owner]
                         bn_red = (saved[owner][1], *saved[owner][2], T.act, T.slope, T.bstats)
                         reduced.add(owner)
-                    dx = ops.conv_dgrad(dy, L.wpk_t, L.cin, L.k, L.stride, L.pad, 1, (xin.shape[1], xin.shape[2]),
-                                        out=prev, residual=prev, bn_reduce=bn_red)
+                    wd2s = self._packs.wpk_d2s.get(id(L.conv)) if prev is None else None
+                    if wd2s is not None and ops.d2s_dgrad_ok(L.cin, L.k, L.stride, L.pad, dy.shape[2]) and \
+                            xin.shape[1] == 2 * dy.shape[1] and xin.shape[2] == 2 * dy.shape[2]:
+                        dx = ops.conv_dgrad_d2s(dy, wd2s, L.cin)  # one launch instead of four parity classes
+                    else:
+                        dx = ops.conv_dgrad(dy, L.wpk_t, L.cin, L.k, L.stride, L.pad, 1, (xin.shape[1], xin.shape[2]),
+                                            out=prev, residual=prev, bn_reduce=bn_red)
                     grads[i - 1] = dx
                     if fill:
                         wgrad(xin, dy, L.cout, L.k, L.stride, L.pad, packs.dwp[id(L.conv)], ev=dy_ready)

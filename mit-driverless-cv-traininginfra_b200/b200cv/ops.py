@@ -20,7 +20,7 @@ __all__ = [
     "pack_weights", "unpack_wgrad", "conv_fwd", "conv_dgrad", "conv_wgrad", "bn_finalize", "bn_apply_act",
     "bn_bwd_reduce", "bn_bwd_finalize", "bn_bwd_apply", "bn_stats_apply_act", "bn_bwd_stats_apply", "act_bwd", "copy_slice", "col_sum", "maxpool_fwd",
     "maxpool_bwd", "upsample_fwd", "upsample_bwd", "act_code", "sm_count", "stats_buffer", "stats_value", "im2col_nchw",
-    "use_flat_path", "use_image_path", "conv_image_fwd", "conv_image_wgrad", "flat_k", "split_mode", "precision", "set_default_precision", "default_split", "channels",
+    "use_flat_path", "d2s_dgrad_ok", "conv_dgrad_d2s", "use_image_path", "conv_image_fwd", "conv_image_wgrad", "flat_k", "split_mode", "precision", "set_default_precision", "default_split", "channels",
     "bias_grad", "concat_channels", "slice_grad", "split_from_f32", "split_to_f32",
 ]
 
@@ -279,6 +279,26 @@ def conv_dgrad(dy, wpk_t, cin_fwd, k, stride, pad, dil, out_hw, out=None, residu
         a.bn_act, a.bn_slope = bact, float(bslope)
     lib().call("b200cv_conv_dgrad", ctypes.byref(a), h, w, stream_ptr(),
                tag=(cin_fwd, channels(dy), k, stride, n, dy.shape[1], dy.shape[2]))
+    return out
+
+
+def d2s_dgrad_ok(cin_fwd: int, k: int, stride: int, pad: int, dy_w: int) -> bool:
+    """Shapes the one-launch stride-2 data gradient (b200cv_conv_dgrad_d2s) takes; the operand it needs is 16/9 of the
+    filter, so it is used for the narrow (HBM-bound) layers only."""
+    return (not split_mode() and k == 3 and stride == 2 and pad == 1 and cin_fwd == pad_channels(cin_fwd)
+            and cin_fwd % 32 == 0 and cin_fwd <= 128 and dy_w >= 32 and dy_w % 4 == 0)
+
+
+def conv_dgrad_d2s(dy, wpk_d2s, cin_fwd, out=None) -> torch.Tensor:
+    """3x3 stride-2 pad-1 data gradient in one launch: dy NHWC bf16 [N,OH,OW,pad(Cout)] -> dx [N,2*OH,2*OW,Cin_fwd]."""
+    n, oh, ow, _ = dy.shape
+    h, w = 2 * oh, 2 * ow
+    if out is None:
+        out = torch.empty(n, h, w, cin_fwd, dtype=torch.bfloat16, device=dy.device)
+    ys = (out.stride(0), out.stride(1), out.stride(2), out.stride(3))
+    a = _conv_args(dy, wpk_d2s, out, cin_fwd, 3, 2, 1, 1, ys, DT_BF16, None, None, None, None, ACT_NONE, 0.0, False, None)
+    lib().call("b200cv_conv_dgrad_d2s", ctypes.byref(a), h, w, stream_ptr(),
+               tag=(cin_fwd, channels(dy), 3, 2, n, oh, ow))
     return out
 
 

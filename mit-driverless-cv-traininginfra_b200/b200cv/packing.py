@@ -37,10 +37,11 @@ class GradArena:
 
 
 class ConvPackSet:
-    def __init__(self, convs, device, grad_arena: GradArena, flat=(), split=False):
+    def __init__(self, convs, device, grad_arena: GradArena, flat=(), split=False, d2s=()):
         """convs: list of (nn.Conv2d, need_transposed_pack); `flat`: convs that use the explicit-im2col
         layout [O][1][Kp] (k = tap*I + i) instead of [O][taps][Ipad]; `split`: fp32-parity packs, every innermost
-        channel run stored as [hi | lo] (the fp32 gradient layout is the same in both modes)."""
+        channel run stored as [hi | lo] (the fp32 gradient layout is the same in both modes); `d2s`: 3x3 stride-2
+        convs that additionally get the depth-to-space operand of the one-launch data gradient (`wpk_d2s`)."""
         self.convs = [c for c, _ in convs]
         self.device = device
         self._flat = {id(c) for c in flat}
@@ -71,6 +72,14 @@ class ConvPackSet:
                 self.wpk_t[id(conv)] = None
             self.dwp[id(conv)] = self.dwp_flat[og:og + ng].view(shape)
             og += al(ng)
+        self.wpk_d2s, self._d2s = {}, [c for c in d2s if not split]
+        if self._d2s:
+            sizes = [16 * c.weight.shape[1] * pad_channels(c.weight.shape[0]) for c in self._d2s]
+            self._wpk_d2s = torch.empty(sum(al(n) for n in sizes), dtype=torch.bfloat16, device=device)
+            od = 0
+            for c, n in zip(self._d2s, sizes):
+                self.wpk_d2s[id(c)] = self._wpk_d2s[od:od + n].view(4 * c.weight.shape[1], 4, pad_channels(c.weight.shape[0]))
+                od += al(n)
         self._need_t = [t for _, t in convs]
         self._ptrs = None
         self._pack_table = self._pack_table_fwd = None
@@ -106,6 +115,10 @@ class ConvPackSet:
             if need_t:
                 both.append((conv.weight.data_ptr(), self.wpk_t[id(conv)].data_ptr(), o, i, r * s, pad_channels(i),
                              pad_channels(o), 1 | sp))
+        for conv in self._d2s:
+            o, i, r, s = conv.weight.shape
+            both.append((conv.weight.data_ptr(), self.wpk_d2s[id(conv)].data_ptr(), o, i, r * s, pad_channels(i),
+                         pad_channels(o), 3))
         self._pack_table_fwd, self._n_fwd = self._to_device(fwd), len(fwd)
         self._pack_table, self._n_pack = self._to_device(both), len(both)
 

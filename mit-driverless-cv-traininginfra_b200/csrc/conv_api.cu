@@ -132,10 +132,19 @@ int run_igemm(const Geometry& g, const void* act, const void* wpk, int64_t w_row
   static const bool no_m2 = getenv("B200CV_NO_M2") != nullptr;
   p.tile_m = 128;
   // (not for short K loops: the HBM-bound 1x1 layers lose -- 35 -> 52 us for 256->128 @52x52)
-  if (tma_out && !no_m2 && kc == 64 && bn == 128 && p.num_taps * p.cblocks >= 8 &&
+  if (tma_out && !no_m2 && !p.d2s_c2 && kc == 64 && bn == 128 && p.num_taps * p.cblocks >= 8 &&
       (p.M_total + 255) / 256 * p.num_n_tiles >= 2 * sm_count()) {
     p.tile_m = 256;
     p.num_m_tiles = (p.M_total + 255) / 256;
+  }
+  if (p.d2s_c2) {
+    // depth-to-space output (b200cv_conv_dgrad_d2s): {2C, OW, 2*N*OH} with strides 2C (pixel pair) / out_w*C (row)
+    if (bn < 128) return set_error(B200CV_ERR_ARG, "conv_dgrad_d2s: needs the wide staged epilogue (4*C >= 128)");
+    CUtensorMap tmO;
+    rc = make_tmap_3d_bf16(&tmO, p.out, p.d2s_c2, p.OW, 2LL * g.N * g.OHt, p.d2s_c2, (long long)p.OW * p.d2s_c2, 64,
+                           p.d2s_g);
+    if (rc) return rc;
+    return launch_igemm(tmA, tmB, &tmO, nullptr, nullptr, nullptr, p, kc, bn, stream);
   }
   if (tma_out) {
     CUtensorMap tmO, tmY;
@@ -303,6 +312,46 @@ extern "C" int b200cv_conv_dgrad(const b200cv_conv_args* a, int out_h, int out_w
   return 0;
 }
 
+// Stride-2 3x3 pad-1 data gradient as ONE GEMM over the dy grid (instead of four parity-class launches with the
+// direct-store epilogue): row m = dy pixel (n, q, p); the four input pixels (2q+a, 2p+b) it "owns" are the column
+// blocks (a, b, c) of a 4*C wide output; K = the 2x2 dy neighbourhood (q+u, p+v) x Cout.  Input row 2q (a = 0) sees
+// filter row r = 1 at u = 0; input row 2q+1 (a = 1) sees r = 2 at u = 0 and r = 0 at u = 1 -- the fourth (a, u)
+// combination is a zero block of the operand written by the `transpose == 3` pack (7 of 16 blocks are zero: these
+// layers are HBM-bound, 16/9 of the FLOPs is free).  The epilogue is the staged TMA store with a 3-D map.
+extern "C" int b200cv_conv_dgrad_d2s(const b200cv_conv_args* a, int out_h, int out_w, void* stream) {
+  if (int rc = validate_common(a)) return rc;
+  const int C = a->Cout;  // channels of dx
+  B200CV_CHECK_ARG(a->R == 3 && a->S == 3 && a->stride == 2 && a->pad == 1 && a->dil == 1,
+                   "conv_dgrad_d2s: 3x3 stride-2 pad-1 layers only");
+  B200CV_CHECK_ARG(out_h == 2 * a->H && out_w == 2 * a->W && a->W >= 32 && a->W % 4 == 0,
+                   "conv_dgrad_d2s: needs an even %dx%d output whose width is a multiple of 8, at least 64", out_h, out_w);
+  B200CV_CHECK_ARG(C == pad_channels(C) && C % 32 == 0, "conv_dgrad_d2s: C=%d must be a padded multiple of 32", C);
+  B200CV_CHECK_ARG(!a->residual && !a->bn_sums && !a->scale && !a->shift && a->act == 0 && !a->stats && !a->x_lo &&
+                       !a->y_lo, "conv_dgrad_d2s: plain bf16 gradient only (no residual / fused epilogue / split)");
+  B200CV_CHECK_ARG(a->y_dtype == B200CV_DT_BF16 && a->y_sc == 1 && a->y_sw == C && a->y_sh == (int64_t)out_w * C &&
+                       a->y_sn == (int64_t)out_h * out_w * C && aligned16(a->y),
+                   "conv_dgrad_d2s: y must be a contiguous NHWC bf16 tensor");
+  Geometry g;
+  g.N = a->N; g.H = a->H; g.W = a->W; g.C = a->Cin;
+  g.lower_h = 0; g.lower_w = 0; g.upper_h = 0; g.upper_w = 0;  // taps reach one pixel past the bottom / right edge
+  g.trav_h = 1; g.trav_w = 1;
+  g.OHt = a->H; g.OWt = a->W;
+  IgemmParams p{};
+  p.Cout = 4 * C;
+  p.num_taps = 4;
+  for (int u = 0; u < 2; ++u)
+    for (int v = 0; v < 2; ++v) {
+      p.tap_h[2 * u + v] = (short)u;
+      p.tap_w[2 * u + v] = (short)v;
+      p.tap_k[2 * u + v] = (2 * u + v) * a->Cin;
+    }
+  fill_epilogue(p, a, 0, 0, 1, 1);
+  p.d2s_c2 = 2 * C;
+  p.d2s_g = 32;
+  while (a->W % p.d2s_g) p.d2s_g >>= 1;
+  return run_igemm(g, a->x, a->w, 4LL * C, 4LL * a->Cin, p, static_cast<cudaStream_t>(stream));
+}
+
 // ------------------------------------------------------------------------------------------
 // layout / packing kernels (bandwidth-trivial next to the convolutions)
 namespace b200cv {
@@ -415,7 +464,21 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackEntry
   e.transpose &= 7;
   __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(e.dst);
   const int tid = threadIdx.x, nt = blockDim.x;
-  if (e.transpose == 2) {
+  if (e.transpose == 3) {
+    // depth-to-space operand of b200cv_conv_dgrad_d2s: dst[(a*2+b)*I + i][(u*2+v)*Opad + o] (3x3 filters)
+    const long long total = 16LL * e.I * e.Opad;
+    for (long long idx = blockIdx.x * (long long)nt + tid; idx < total; idx += (long long)gridDim.x * nt) {
+      const int col = (int)(idx % (4 * e.Opad));
+      const int row = (int)(idx / (4 * e.Opad));
+      const int uv = col / e.Opad, o = col - uv * e.Opad;
+      const int ab = row / e.I, i = row - ab * e.I;
+      const int r = (ab >> 1) == 0 ? ((uv >> 1) == 0 ? 1 : -1) : ((uv >> 1) == 0 ? 2 : 0);
+      const int c = (ab & 1) == 0 ? ((uv & 1) == 0 ? 1 : -1) : ((uv & 1) == 0 ? 2 : 0);
+      float v = 0.f;
+      if (r >= 0 && c >= 0 && o < e.O) v = e.src[(((long long)o * e.I + i) * 3 + r) * 3 + c];
+      dst[idx] = __float2bfloat16_rn(v);
+    }
+  } else if (e.transpose == 2) {
     // "flat" pack [O][Ipad] with k = tap*I + i (whole filter in one padded K run); tiny (image layers only)
     const long long total = (long long)e.O * e.Ipad;
     for (long long i = blockIdx.x * (long long)nt + tid; i < total; i += (long long)gridDim.x * nt) {

@@ -542,7 +542,21 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0 && !(p.dbg & 1)) {
-            ptx::tma_store_2d(&tmO, stg, nb_base, m_warp);
+            if (p.d2s_c2) {
+              // depth-to-space: this 64-column block belongs to output rows 2q + a.  Stored in groups of d2s_g
+              // rows (d2s_g divides OW, so a group never crosses the end of a dy row -- a TMA store must not start
+              // at a negative coordinate); the swizzle is a function of the shared-memory address, so a group at
+              // any row offset of the staging tile is read back correctly
+              const int cls_a = nb_base / p.d2s_c2, col_in = nb_base - cls_a * p.d2s_c2;
+              int nq = m_warp / p.OW, p0 = m_warp - nq * p.OW;
+              for (int r0 = 0; r0 < 32; r0 += p.d2s_g) {
+                ptx::tma_store_3d(&tmO, stg + r0 * 128, col_in, p0, 2 * nq + cls_a);
+                p0 += p.d2s_g;
+                if (p0 >= p.OW) { p0 = 0; ++nq; }
+              }
+            } else {
+              ptx::tma_store_2d(&tmO, stg, nb_base, m_warp);
+            }
             ptx::tma_store_commit();
           }
           store_pending = true;

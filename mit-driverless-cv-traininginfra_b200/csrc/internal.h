@@ -32,6 +32,10 @@ int make_tmap_im2col_bf16(CUtensorMap* out, const void* base, int N, int H, int 
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld,
                       int box_rows, int box_cols);
 
+// bf16 3-D tensor [d2][d1][d0] (d0 contiguous) with element strides stride1 / stride2; box = [1][box1][box0].
+int make_tmap_3d_bf16(CUtensorMap* out, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t stride1,
+                      int64_t stride2, int box0, int box1);
+
 // fp32 row-major 2-D matrix (the packed weight gradient): box = [box_rows][box_cols], swizzle = box row bytes.
 int make_tmap_2d_f32(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
                      int box_cols);
@@ -78,6 +82,11 @@ struct IgemmParams {
   int stages;                 // pipeline stages of this launch (set by launch_igemm)
   int y_slots, y_slots_log2;  // y tiles per epilogue warp of the fused BN-backward reduction (power of two)
   int stg_slots;              // staging tiles per epilogue warp of the wide staged epilogue (1 or 2)
+  // depth-to-space output of the one-launch stride-2 data gradient (b200cv_conv_dgrad_d2s): GEMM row m = pixel
+  // (n, q, p) of the dy grid, column (a, b, c) -> dx[n, 2q+a, 2p+b, c]; d2s_c2 = 2*C columns per output row (0 = off),
+  // tmO is then the 3-D map {2C, OW, 2*N*OH} with a box of d2s_g rows
+  int d2s_c2;
+  int d2s_g;  // rows per depth-to-space store: the largest power of two <= 32 that divides OW
   int res_iters;  // residual added by the tensor core: extra k-iterations D += I[:, k-slice] * R[k-slice rows, :] (0 = off)
   int dbg;  // B200CV_DBG bits (bring-up timing experiments only): 1 no stores, 2 no stats, 4 no TMEM read
   // fp32-parity (split) mode: lo halves of the output / residual lie this many elements after the hi halves (0 = off)

@@ -96,6 +96,23 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t 
   return 0;
 }
 
+int make_tmap_3d_bf16(CUtensorMap* out, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t stride1,
+                      int64_t stride2, int box0, int box1) {
+  std::call_once(g_once, resolve);
+  if (!g_tiled) return set_error(B200CV_ERR_DRIVER, "cuTensorMapEncodeTiled not available");
+  cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t strides[2] = {(cuuint64_t)stride1 * 2, (cuuint64_t)stride2 * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box0, (cuuint32_t)box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_tiled(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(box0 * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(B200CV_ERR_DRIVER, "cuTensorMapEncodeTiled(3d) failed (%d): dims %lld %lld %lld box(%d,%d)", (int)r,
+                     (long long)d0, (long long)d1, (long long)d2, box0, box1);
+  return 0;
+}
+
 int make_tmap_2d_f32(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
                      int box_cols) {
   std::call_once(g_once, resolve);

@@ -193,3 +193,29 @@ def test_image_conv_without_patch_matrix(case):
     want_dw = wt.grad.permute(0, 2, 3, 1).reshape(cout, -1)
     assert float((dwp[:, 0, :3 * k * k].cpu() - want_dw).abs().max()) <= 2e-3 * float(want_dw.abs().max())
     assert float(dwp[:, 0, 3 * k * k:].abs().max()) == 0.0 if kp > 3 * k * k else True
+
+
+@pytest.mark.parametrize("case", [(2, 32, 64, 32, 64), (3, 20, 40, 64, 128), (1, 52, 52, 128, 256), (2, 9, 36, 32, 48), (2, 38, 76, 64, 128)])
+def test_stride2_data_gradient_as_one_depth_to_space_launch(case):
+    """b200cv_conv_dgrad_d2s (one GEMM over the dy grid + 3-D TMA stores in row groups that never cross the end of a
+    dy row) equals the four-launch parity-class data gradient and torch on the same bf16-rounded operands."""
+    from b200cv.packing import ConvPackSet, GradArena
+
+    n, oh, ow, cin, cout = case
+    g = torch.Generator().manual_seed(sum(case))
+    conv = torch.nn.Conv2d(cin, cout, 3, 2, 1, bias=False).to(DEV)
+    with torch.no_grad():
+        conv.weight.copy_(_bf(torch.randn(cout, cin, 3, 3, generator=g) * 0.1))
+    packs = ConvPackSet([(conv, True)], DEV, GradArena([conv.weight], DEV), d2s=[conv])
+    packs.pack_all(True)
+    x = torch.zeros(n, cin, 2 * oh, 2 * ow, requires_grad=True)
+    dy = _bf(torch.randn(n, cout, oh, ow, generator=g))
+    F.conv2d(x, conv.weight.detach().cpu(), None, 2, 1).backward(dy)
+    dyd = ops.nchw_to_nhwc(dy.to(DEV))
+    assert ops.d2s_dgrad_ok(cin, 3, 2, 1, ow)
+    dx = ops.conv_dgrad_d2s(dyd, packs.wpk_d2s[id(conv)], cin)
+    four = ops.conv_dgrad(dyd, packs.wpk_t[id(conv)], cin, 3, 2, 1, 1, (2 * oh, 2 * ow))
+    assert dx.shape == four.shape
+    ref = x.grad
+    assert float((ops.nhwc_to_nchw(dx, cin).cpu() - ref).abs().max()) <= 1.5e-2 * float(ref.abs().max())
+    assert float((dx.float() - four.float()).abs().max()) <= 1e-2 * float(ref.abs().max())
