@@ -293,8 +293,8 @@ def cpu_baseline(name, cpu_batch=None):
 
 
 # ----------------------------------------------------------------------------------------------- B200 arm
-CONV_ENTRY_POINTS = ("b200cv_conv_fwd", "b200cv_conv_dgrad", "b200cv_conv_wgrad", "b200cv_conv_image_fwd",
-                     "b200cv_conv_image_wgrad")
+CONV_ENTRY_POINTS = ("b200cv_conv_fwd", "b200cv_conv_dgrad", "b200cv_conv_dgrad_d2s", "b200cv_conv_wgrad",
+                     "b200cv_conv_image_fwd", "b200cv_conv_image_wgrad")
 
 
 def serial_profile(step_fn):

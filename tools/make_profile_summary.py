@@ -41,11 +41,11 @@ if os.path.exists(os.path.join(SRC, f"launches_{R}.csv")):
         f.write(f"{'kernel':58s} {'n':>5s} {'us':>10s} {'share':>7s} {'us/launch':>10s} {'dram_rd_MB':>11s} {'dram_wr_MB':>11s}\n")
         for k, (n, us, rd, wr) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{k[:58]:58s} {n:5d} {us:10.1f} {100*us/tot:6.1f}% {us/n:10.2f} {rd/1e6:11.1f} {wr/1e6:11.1f}\n")
-    conv = [a for k, a in agg.items() if k.startswith(("igemm_kernel", "wgrad_kernel"))]
+    conv = [a for k, a in agg.items() if k.startswith(("igemm_kernel", "wgrad_kernel", "conv_image_"))]
     roof = {"round": R, "conv_launches_per_step": sum(a[0] for a in conv), "conv_us_ncu": sum(a[1] for a in conv),
             "conv_share_of_step_ncu": sum(a[1] for a in conv) / tot,
             "conv_dram_bytes_per_step": sum(a[2] + a[3] for a in conv),
-            "note": "DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) summed over the igemm/wgrad launches of one "
+            "note": "DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) summed over the igemm / wgrad / conv_image launches of one "
                     "eager step, from the ncu launch-list pass"}
     json.dump(roof, open(os.path.join(DST, f"roofline_{R}.json"), "w"), indent=1)
 
