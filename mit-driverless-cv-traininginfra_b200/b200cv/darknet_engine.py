@@ -524,18 +524,25 @@ class DarknetEngine:
                     # this dgrad completes grads[i-1]; when that is the activation gradient of a conv+BN layer the
                     # first pass of its BN backward (sum dz, sum dz*xhat) is folded into the epilogue
                     # (with 32-column epilogue blocks the HBM-bound 1x1 gradients lost more than the separate pass costs:
-                    # 91 us fused vs 36 + 45 us for 256->128 @52x52; with 64-column blocks the fused form is 75 us)
-                    owner = self._bn_owner(i - 1) if (fuse and not self.split and L.stride == 1 and
+                    # 91 us fused vs 36 + 45 us for 256->128 @52x52; with 64-column blocks the fused form is 75 us).
+                    # The one-launch stride-2 gradients carry it too: +0.39 ms in the three launches for 0.54 ms of
+                    # separate reduction passes, 24.72 -> 24.52 ms per step
+                    wd2s = self._packs.wpk_d2s.get(id(L.conv)) if prev is None else None
+                    use_d2s = wd2s is not None and ops.d2s_dgrad_ok(L.cin, L.k, L.stride, L.pad, dy.shape[2]) and \
+                        xin.shape[1] == 2 * dy.shape[1] and xin.shape[2] == 2 * dy.shape[2]
+                    owner = self._bn_owner(i - 1) if (fuse and not self.split and (L.stride == 1 or use_d2s) and
                                                       (L.k > 1 or fuse >= 2)) else None
+                    if owner is not None and use_d2s:
+                        yo = saved[owner][1]  # the depth-to-space form reads y as a contiguous NHWC tensor
+                        if not (yo.is_contiguous() and yo.shape[-1] == L.cin and (L.cin & (L.cin - 1)) == 0):
+                            owner = None
                     bn_red = None
                     if owner is not None:
                         T = self.layers[owner]
                         bn_red = (saved[owner][1], *saved[owner][2], T.act, T.slope, T.bstats)
                         reduced.add(owner)
-                    wd2s = self._packs.wpk_d2s.get(id(L.conv)) if prev is None else None
-                    if wd2s is not None and ops.d2s_dgrad_ok(L.cin, L.k, L.stride, L.pad, dy.shape[2]) and \
-                            xin.shape[1] == 2 * dy.shape[1] and xin.shape[2] == 2 * dy.shape[2]:
-                        dx = ops.conv_dgrad_d2s(dy, wd2s, L.cin)  # one launch instead of four parity classes
+                    if use_d2s:
+                        dx = ops.conv_dgrad_d2s(dy, wd2s, L.cin, bn_reduce=bn_red)  # one launch, not four parity classes
                     else:
                         dx = ops.conv_dgrad(dy, L.wpk_t, L.cin, L.k, L.stride, L.pad, 1, (xin.shape[1], xin.shape[2]),
                                             out=prev, residual=prev, bn_reduce=bn_red)

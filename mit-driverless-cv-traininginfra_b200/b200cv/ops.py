@@ -254,6 +254,14 @@ def conv_fwd(x, wpk, cout, k, stride, pad, dil=1, out=None, out_dtype=torch.bflo
     return out
 
 
+def _set_bn_reduce(a: ConvArgs, bn_reduce):
+    by, bsc, bsh, bmean, brstd, bact, bslope, bsums = bn_reduce
+    a.bn_sums, a.bn_parts = ptr(bsums), bsums.shape[0]
+    a.bn_y, a.bn_y_ld = ptr(by), by.stride(-2)
+    a.bn_scale, a.bn_shift, a.bn_mean, a.bn_rstd = ptr(bsc), ptr(bsh), ptr(bmean), ptr(brstd)
+    a.bn_act, a.bn_slope = bact, float(bslope)
+
+
 def conv_dgrad(dy, wpk_t, cin_fwd, k, stride, pad, dil, out_hw, out=None, residual=None, bn_reduce=None) -> torch.Tensor:
     """dy NHWC bf16 [N,OH,OW,pad(Cout)] -> dx NHWC bf16 [N,H,W,pad(Cin_fwd)] (+ residual).
     bn_reduce = (y, scale, shift, mean, rstd, act, slope, sums): also accumulate the BN-backward sums of the layer
@@ -272,11 +280,7 @@ def conv_dgrad(dy, wpk_t, cin_fwd, k, stride, pad, dil, out_hw, out=None, residu
     a = _conv_args(dy, wpk_t, out, cin_fwd, k, stride, pad, dil, ys, DT_BF16, None, None, residual, rs, ACT_NONE, 0.0,
                    False, None)
     if bn_reduce is not None:
-        by, bsc, bsh, bmean, brstd, bact, bslope, bsums = bn_reduce
-        a.bn_sums, a.bn_parts = ptr(bsums), bsums.shape[0]
-        a.bn_y, a.bn_y_ld = ptr(by), by.stride(-2)
-        a.bn_scale, a.bn_shift, a.bn_mean, a.bn_rstd = ptr(bsc), ptr(bsh), ptr(bmean), ptr(brstd)
-        a.bn_act, a.bn_slope = bact, float(bslope)
+        _set_bn_reduce(a, bn_reduce)
     lib().call("b200cv_conv_dgrad", ctypes.byref(a), h, w, stream_ptr(),
                tag=(cin_fwd, channels(dy), k, stride, n, dy.shape[1], dy.shape[2]))
     return out
@@ -289,14 +293,17 @@ def d2s_dgrad_ok(cin_fwd: int, k: int, stride: int, pad: int, dy_w: int) -> bool
             and cin_fwd % 32 == 0 and cin_fwd <= 128 and dy_w >= 32 and dy_w % 4 == 0)
 
 
-def conv_dgrad_d2s(dy, wpk_d2s, cin_fwd, out=None) -> torch.Tensor:
-    """3x3 stride-2 pad-1 data gradient in one launch: dy NHWC bf16 [N,OH,OW,pad(Cout)] -> dx [N,2*OH,2*OW,Cin_fwd]."""
+def conv_dgrad_d2s(dy, wpk_d2s, cin_fwd, out=None, bn_reduce=None) -> torch.Tensor:
+    """3x3 stride-2 pad-1 data gradient in one launch: dy NHWC bf16 [N,OH,OW,pad(Cout)] -> dx [N,2*OH,2*OW,Cin_fwd].
+    bn_reduce: as for conv_dgrad (the BN input y must be a contiguous NHWC tensor)."""
     n, oh, ow, _ = dy.shape
     h, w = 2 * oh, 2 * ow
     if out is None:
         out = torch.empty(n, h, w, cin_fwd, dtype=torch.bfloat16, device=dy.device)
     ys = (out.stride(0), out.stride(1), out.stride(2), out.stride(3))
     a = _conv_args(dy, wpk_d2s, out, cin_fwd, 3, 2, 1, 1, ys, DT_BF16, None, None, None, None, ACT_NONE, 0.0, False, None)
+    if bn_reduce is not None:
+        _set_bn_reduce(a, bn_reduce)
     lib().call("b200cv_conv_dgrad_d2s", ctypes.byref(a), h, w, stream_ptr(),
                tag=(cin_fwd, channels(dy), 3, 2, n, oh, ow))
     return out

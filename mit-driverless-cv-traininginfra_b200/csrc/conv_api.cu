@@ -86,6 +86,10 @@ int run_igemm(const Geometry& g, const void* act, const void* wpk, int64_t w_row
   const int bn = pick_block_n(p.Cout, p.num_m_tiles, p.num_taps * p.cblocks, p.bn_sums != nullptr);
   p.num_n_tiles = (p.Cout + bn - 1) / bn;
   p.err = device_error_word();
+  if (!p.d2s_c2) {
+    p.stat_cols = p.Cout;
+    p.stat_mask = -1;
+  }
   {
     static const int dbg = getenv("B200CV_DBG") ? atoi(getenv("B200CV_DBG")) : 0;
     p.dbg = dbg;
@@ -140,11 +144,16 @@ int run_igemm(const Geometry& g, const void* act, const void* wpk, int64_t w_row
   if (p.d2s_c2) {
     // depth-to-space output (b200cv_conv_dgrad_d2s): {2C, OW, 2*N*OH} with strides 2C (pixel pair) / out_w*C (row)
     if (bn < 128) return set_error(B200CV_ERR_ARG, "conv_dgrad_d2s: needs the wide staged epilogue (4*C >= 128)");
-    CUtensorMap tmO;
+    CUtensorMap tmO, tmY;
     rc = make_tmap_3d_bf16(&tmO, p.out, p.d2s_c2, p.OW, 2LL * g.N * g.OHt, p.d2s_c2, (long long)p.OW * p.d2s_c2, 64,
                            p.d2s_g);
     if (rc) return rc;
-    return launch_igemm(tmA, tmB, &tmO, nullptr, nullptr, nullptr, p, kc, bn, stream);
+    if (p.bn_sums) {  // y of the layer whose dL/da this is: a contiguous NHWC tensor like the output
+      rc = make_tmap_3d_bf16(&tmY, bn_y, p.d2s_c2, p.OW, 2LL * g.N * g.OHt, p.d2s_c2, (long long)p.OW * p.d2s_c2, 64,
+                             p.d2s_g);
+      if (rc) return rc;
+    }
+    return launch_igemm(tmA, tmB, &tmO, nullptr, nullptr, p.bn_sums ? &tmY : nullptr, p, kc, bn, stream);
   }
   if (tma_out) {
     CUtensorMap tmO, tmY;
@@ -326,8 +335,8 @@ extern "C" int b200cv_conv_dgrad_d2s(const b200cv_conv_args* a, int out_h, int o
   B200CV_CHECK_ARG(out_h == 2 * a->H && out_w == 2 * a->W && a->W >= 32 && a->W % 4 == 0,
                    "conv_dgrad_d2s: needs an even %dx%d output whose width is a multiple of 8, at least 64", out_h, out_w);
   B200CV_CHECK_ARG(C == pad_channels(C) && C % 32 == 0, "conv_dgrad_d2s: C=%d must be a padded multiple of 32", C);
-  B200CV_CHECK_ARG(!a->residual && !a->bn_sums && !a->scale && !a->shift && a->act == 0 && !a->stats && !a->x_lo &&
-                       !a->y_lo, "conv_dgrad_d2s: plain bf16 gradient only (no residual / fused epilogue / split)");
+  B200CV_CHECK_ARG(!a->residual && !a->scale && !a->shift && a->act == 0 && !a->stats && !a->x_lo && !a->y_lo,
+                   "conv_dgrad_d2s: plain bf16 gradient only (no residual / affine epilogue / split)");
   B200CV_CHECK_ARG(a->y_dtype == B200CV_DT_BF16 && a->y_sc == 1 && a->y_sw == C && a->y_sh == (int64_t)out_w * C &&
                        a->y_sn == (int64_t)out_h * out_w * C && aligned16(a->y),
                    "conv_dgrad_d2s: y must be a contiguous NHWC bf16 tensor");
@@ -347,9 +356,24 @@ extern "C" int b200cv_conv_dgrad_d2s(const b200cv_conv_args* a, int out_h, int o
     }
   fill_epilogue(p, a, 0, 0, 1, 1);
   p.d2s_c2 = 2 * C;
+  p.stat_cols = C;
+  p.stat_mask = C - 1;
+  if (a->bn_sums) {  // fused first pass of the BatchNorm backward of the layer that produced this activation
+    B200CV_CHECK_ARG((C & (C - 1)) == 0, "conv_dgrad_d2s: the fused BN-backward reduction needs a power-of-two C");
+    B200CV_CHECK_ARG(a->bn_y && a->bn_scale && a->bn_shift && a->bn_mean && a->bn_rstd && a->bn_parts > 0 &&
+                         a->bn_y_ld == C && aligned16(a->bn_y),
+                     "conv_dgrad_d2s: incomplete bn_* arguments (bn_y must be contiguous NHWC)");
+    p.bn_sums = static_cast<StatAcc*>(a->bn_sums);
+    p.bn_parts = a->bn_parts;
+    p.bn_scale = a->bn_scale;
+    p.bn_shift = a->bn_shift;
+    p.bn_mean = a->bn_mean;
+    p.bn_rstd = a->bn_rstd;
+    p.bn_neg = a->bn_act == B200CV_ACT_LEAKY ? a->bn_slope : (a->bn_act == B200CV_ACT_RELU ? 0.f : 1.f);
+  }
   p.d2s_g = 32;
   while (a->W % p.d2s_g) p.d2s_g >>= 1;
-  return run_igemm(g, a->x, a->w, 4LL * C, 4LL * a->Cin, p, static_cast<cudaStream_t>(stream));
+  return run_igemm(g, a->x, a->w, 4LL * C, 4LL * a->Cin, p, static_cast<cudaStream_t>(stream), a->bn_y, a->bn_y_ld);
 }
 
 // ------------------------------------------------------------------------------------------

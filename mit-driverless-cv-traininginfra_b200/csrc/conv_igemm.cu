@@ -348,7 +348,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       StatAcc* const stat_base = kBnRed ? p.bn_sums : p.stats;
       const int stat_parts = kBnRed ? p.bn_parts : p.stats_parts;
       StatAcc* stats_row =
-          stat_base ? stat_base + static_cast<long long>(blockIdx.x % stat_parts) * 2 * p.Cout : nullptr;
+          stat_base ? stat_base + static_cast<long long>(blockIdx.x % stat_parts) * 2 * p.stat_cols : nullptr;
       // The epilogue warps that own the same columns (the four lane quarters of one half; all eight with 256-row tiles)
       // first add their partial sums in shared memory, in warp order, so that ONE integer add per column and CTA goes
       // to global memory: with 148 CTAs x 4-8 warps hitting the same few addresses the atomics of the last wave
@@ -385,8 +385,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               }
               const int n = nt_ * BN + block_of(bi) * 64 + my_col + e;
               if (n < p.Cout) {
-                stat_add(stats_row + n, ssum);
-                stat_add(stats_row + p.Cout + n, kBnRed ? tsum * __ldg(p.bn_rstd + n) : tsum);
+                const int ch = n & p.stat_mask;  // depth-to-space: four column groups share a channel
+                stat_add(stats_row + ch, ssum);
+                stat_add(stats_row + p.stat_cols + ch, kBnRed ? tsum * __ldg(p.bn_rstd + ch) : tsum);
               }
             }
           }
@@ -411,8 +412,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const int mt = tile / p.num_n_tiles;
           const int nt = tile - mt * p.num_n_tiles;
           ptx::mbar_expect_tx(&ybar[slot], 4096);
-          ptx::tma_load_2d(ybuf + slot * 4096, &tmY, &ybar[slot], nt * BN + block_of(bi) * 64,
-                           mt * C::kTileM + sub_m + quarter * 32);
+          const int ncol0 = nt * BN + block_of(bi) * 64, mrow0 = mt * C::kTileM + sub_m + quarter * 32;
+          if (p.d2s_c2) {  // y lies like the depth-to-space output: the same row groups as the stores
+            const int cls_a = ncol0 / p.d2s_c2, col_in = ncol0 - cls_a * p.d2s_c2;
+            int nq = mrow0 / p.OW, p0 = mrow0 - nq * p.OW;
+            for (int r0 = 0; r0 < 32; r0 += p.d2s_g) {
+              ptx::tma_load_3d(ybuf + slot * 4096 + r0 * 128, &tmY, &ybar[slot], col_in, p0, 2 * nq + cls_a);
+              p0 += p.d2s_g;
+              if (p0 >= p.OW) { p0 = 0; ++nq; }
+            }
+          } else {
+            ptx::tma_load_2d(ybuf + slot * 4096, &tmY, &ybar[slot], ncol0, mrow0);
+          }
         }
       };
       uint32_t ycount = 0;
@@ -569,9 +580,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               const int yslot = ycount & (yslots - 1);
               ptx::mbar_wait(&ybar[yslot], (ycount >> ylog) & 1, p.err, 5);
               const uint8_t* ytile = ybuf + yslot * 4096;
-              const int ncol = nb_base + 8 * rq;
+              const int ncol = (nb_base + 8 * rq) & p.stat_mask;  // channel of the first of this lane's 8 columns
               float sc[8], sh[8], mu[8];
-              if (ncol + 8 <= p.Cout) {
+              if (nb_base + 8 * rq + 8 <= p.Cout) {
 #pragma unroll
                 for (int k = 0; k < 8; k += 4) {
                   const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.bn_scale + ncol + k));

@@ -86,6 +86,9 @@ struct IgemmParams {
   // (n, q, p) of the dy grid, column (a, b, c) -> dx[n, 2q+a, 2p+b, c]; d2s_c2 = 2*C columns per output row (0 = off),
   // tmO is then the 3-D map {2C, OW, 2*N*OH} with a box of d2s_g rows
   int d2s_c2;
+  // statistics of the depth-to-space form are per CHANNEL (column & stat_mask); rows of the statistics matrices hold
+  // 2*stat_cols entries.  run_igemm sets stat_cols = Cout, stat_mask = -1 otherwise.
+  int stat_cols, stat_mask;
   int d2s_g;  // rows per depth-to-space store: the largest power of two <= 32 that divides OW
   int res_iters;  // residual added by the tensor core: extra k-iterations D += I[:, k-slice] * R[k-slice rows, :] (0 = off)
   int dbg;  // B200CV_DBG bits (bring-up timing experiments only): 1 no stores, 2 no stats, 4 no TMEM read

@@ -85,6 +85,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* m, ui
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 // im2col-mode load of `pixelsPerColumn` consecutive output pixels starting at the
 // base pixel (w,h,n); (off_w, off_h) is the filter-tap offset added to every pixel.
 __device__ __forceinline__ void tma_load_im2col_4d(void* smem, const CUtensorMap* m, uint64_t* bar,

@@ -219,3 +219,16 @@ def test_stride2_data_gradient_as_one_depth_to_space_launch(case):
     ref = x.grad
     assert float((ops.nhwc_to_nchw(dx, cin).cpu() - ref).abs().max()) <= 1.5e-2 * float(ref.abs().max())
     assert float((dx.float() - four.float()).abs().max()) <= 1e-2 * float(ref.abs().max())
+    if cin & (cin - 1) == 0:
+        # the fused first pass of the BatchNorm backward (sums of dz and dz*xhat per CHANNEL: four column groups of the
+        # depth-to-space GEMM share a channel) equals the stand-alone reduction over the stored gradient
+        y = torch.randn(n, 2 * oh, 2 * ow, cin, generator=g).to(DEV).to(torch.bfloat16)
+        scale, shift = (torch.rand(cin, generator=g) + 0.5).to(DEV), torch.randn(cin, generator=g).to(DEV) * 0.3
+        mean, rstd = torch.randn(cin, generator=g).to(DEV) * 0.1, (torch.rand(cin, generator=g) + 0.5).to(DEV)
+        sums = ops.stats_buffer(cin, DEV)
+        dx2 = ops.conv_dgrad_d2s(dyd, packs.wpk_d2s[id(conv)], cin,
+                                 bn_reduce=(y, scale, shift, mean, rstd, ops.ACT_LEAKY, 0.1, sums))
+        assert torch.equal(dx2, dx)
+        want = ops.stats_value(ops.bn_bwd_reduce(dx, y, None, scale, shift, mean, rstd, ops.ACT_LEAKY, 0.1)).float()
+        got = ops.stats_value(sums).float()
+        assert torch.allclose(got, want, rtol=2e-3, atol=2e-3 * float(want.abs().max())), (got - want).abs().max()
