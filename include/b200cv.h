@@ -92,6 +92,15 @@ int b200cv_conv_image_fwd(const float* x, const void* w_flat, int N, int C, int 
                           int act, float slope, void* stats, int stats_parts, void* stream);
 int b200cv_conv_image_wgrad(const float* x, const void* dy, int64_t dy_ld, int N, int C, int H, int W, int R, int S,
                             int pad, int dil, int Cout, int Kp, float* dw_flat, void* stream);
+/* wgrad with the BatchNorm + activation backward of the SAME layer applied on the fly: `da` = dL/da of the layer's
+ * activation, dy = BN'(da, y) is formed in registers (the constants, d(gamma), d(beta) and coef exactly as
+ * b200cv_bn_bwd_stats_apply computes them from `partials`) and never written -- an image layer has no data gradient,
+ * so nothing else reads it.  Replaces b200cv_bn_bwd_stats_apply + b200cv_conv_image_wgrad for conv_0 / the stem. */
+int b200cv_conv_image_wgrad_bn(const float* x, const void* da, int64_t da_ld, const void* y, int64_t y_ld,
+                               const void* partials, int nparts, int64_t count, const float* gamma, const float* scale,
+                               const float* shift, const float* mean, const float* rstd, int act, float slope,
+                               float* coef, float* dgamma, float* dbeta, int N, int C, int H, int W, int R, int S,
+                               int pad, int dil, int Cout, int Kp, float* dw_flat, void* stream);
 /* fp32-parity mode: split patch matrix [N*OH*OW][p0(Kp) | p1(Kp) | p2(Kp)]. */
 int b200cv_im2col_nchw_f32_split(const float* x, void* patches, int N, int C, int H, int W, int R, int S, int stride,
                                  int pad, int dil, int Kp, void* stream);

@@ -500,6 +500,14 @@ class DarknetEngine:
                     parts = L.bstats
                     if i not in reduced:
                         ops.bn_bwd_reduce(G, y, None, scale, shift, mean, rstd, L.act, L.slope, partials=parts)
+                    if i == 0 and xin.dtype == torch.float32 and L.post_from is None:
+                        # conv_0 on the image: no data gradient, so dy = BN'(G, y) has one reader -- the weight
+                        # gradient forms it in registers and the 709 MB tensor is never written
+                        ops.conv_image_wgrad_bn(xin, G, y, parts, count, L.bn.weight, L.coef, gview[id(L.bn.weight)],
+                                                gview[id(L.bn.bias)], scale, shift, mean, rstd, L.act, L.slope,
+                                                L.cout, L.k, L.pad, 1, packs.dwp[id(L.conv)])
+                        grads[i] = None
+                        continue
                     dy = ops.bn_bwd_stats_apply(parts, count, L.bn.weight, L.coef, gview[id(L.bn.weight)],
                                                 gview[id(L.bn.bias)], G, y, scale, shift, mean, rstd, L.act, L.slope)
                     if L.post_from is not None:

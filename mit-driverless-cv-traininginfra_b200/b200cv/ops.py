@@ -20,7 +20,7 @@ __all__ = [
     "pack_weights", "unpack_wgrad", "conv_fwd", "conv_dgrad", "conv_wgrad", "bn_finalize", "bn_apply_act",
     "bn_bwd_reduce", "bn_bwd_finalize", "bn_bwd_apply", "bn_stats_apply_act", "bn_bwd_stats_apply", "act_bwd", "copy_slice", "col_sum", "maxpool_fwd",
     "maxpool_bwd", "upsample_fwd", "upsample_bwd", "act_code", "sm_count", "stats_buffer", "stats_value", "im2col_nchw",
-    "use_flat_path", "d2s_dgrad_ok", "conv_dgrad_d2s", "use_image_path", "conv_image_fwd", "conv_image_wgrad", "flat_k", "split_mode", "precision", "set_default_precision", "default_split", "channels",
+    "use_flat_path", "d2s_dgrad_ok", "conv_dgrad_d2s", "use_image_path", "conv_image_fwd", "conv_image_wgrad", "conv_image_wgrad_bn", "flat_k", "split_mode", "precision", "set_default_precision", "default_split", "channels",
     "bias_grad", "concat_channels", "slice_grad", "split_from_f32", "split_to_f32",
 ]
 
@@ -183,6 +183,19 @@ def conv_image_wgrad(x: torch.Tensor, dy: torch.Tensor, cout: int, k: int, pad: 
     n, c, h, w = x.shape
     lib().call("b200cv_conv_image_wgrad", ptr(x), ptr(dy), dy.stride(-2), n, c, h, w, k, k, pad, dil, cout,
                out.shape[-1], ptr(out), stream_ptr(), tag=(c, cout, k, 1, n, h, w))
+    return out
+
+
+def conv_image_wgrad_bn(x, da, y, partials, count, gamma, coef, dgamma, dbeta, scale, shift, mean, rstd, act, slope,
+                        cout: int, k: int, pad: int, dil: int, out: torch.Tensor):
+    """conv_image_wgrad with the layer's own BatchNorm + activation backward applied on the fly (da = dL/da): replaces
+    bn_bwd_stats_apply + conv_image_wgrad; dy is never written.  Also writes coef / d(gamma) / d(beta)."""
+    x = x.contiguous().float()
+    n, c, h, w = x.shape
+    lib().call("b200cv_conv_image_wgrad_bn", ptr(x), ptr(da), da.stride(-2), ptr(y), y.stride(-2), ptr(partials),
+               partials.shape[0], int(count), ptr(gamma), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), act, float(slope),
+               ptr(coef), ptr(dgamma), ptr(dbeta), n, c, h, w, k, k, pad, dil, cout, out.shape[-1], ptr(out), stream_ptr(),
+               tag=(c, cout, k, 1, n, h, w))
     return out
 
 

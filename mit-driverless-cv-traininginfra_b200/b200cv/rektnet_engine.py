@@ -87,6 +87,14 @@ class _ConvBN:
         count = y.numel() // y.shape[-1]
         if parts is None:
             parts = ops.bn_bwd_reduce(da, y, aout, self.scale, self.shift, self.mean, self.rstd, act, 0.0)
+        if x_in.dtype == torch.float32 and not want_dx and aout is None:
+            # the stem on the image: its weight gradient applies the BatchNorm + ReLU backward itself (no dy tensor)
+            gview[id(self.conv.bias)].zero_()
+            ops.conv_image_wgrad_bn(x_in, da, y, parts, count, self.bn.weight, self.coef, gview[id(self.bn.weight)],
+                                    gview[id(self.bn.bias)], self.scale, self.shift, self.mean, self.rstd, act, 0.0,
+                                    self.cout, self.conv.kernel_size[0], self.conv.padding[0], 1,
+                                    packs.dwp[id(self.conv)])
+            return None
         ops.bn_bwd_finalize(parts, self.bn.weight, self.rstd, count, self.coef, gview[id(self.bn.weight)],
                             gview[id(self.bn.bias)])
         dy = ops.bn_bwd_apply(da, y, aout, self.scale, self.shift, self.mean, self.rstd, self.coef, act, 0.0)

@@ -311,10 +311,31 @@ conv_image_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restri
 
 // ------------------------------------------------------------------------------------------------ weight gradient
 // dW[o][k] = sum over pixels dy[pixel][o] * patch[pixel][k]: M = COUT, N = K of the filter, K = pixels.
-template <int R, int COUT>
-__global__ void __launch_bounds__(kThreads)
+// kBn: `dy` is dL/da of the layer's activation and the BatchNorm + activation backward is applied on the fly
+// (dz = da * act'(y*scale+shift), dy = g*dz + A*y + B with the per-channel constants of b200cv_bn_bwd_stats_apply,
+// rounded to bf16 like the stored dy of the two-pass form): the image layers have no data gradient, so dy has no
+// other reader and the 709 MB tensor (416^2 bs64) is never written.
+struct ImgBnBwd {
+  const __nv_bfloat16* y;   // conv output (BN input), laid out like dy
+  long long y_ld;
+  const float* scale;       // forward affine of the BN: z = y*scale + shift
+  const float* shift;
+  const float* mean;
+  const float* rstd;
+  const float* gamma;
+  const StatAcc* partials;  // [nparts][2*COUT]: sum dz | sum dz*xhat
+  int nparts;
+  float count;
+  float neg;                // act'(z) for z <= 0
+  float* coef;              // [3*COUT] g | k1 | k2 (or null), written by block 0 like bn_bwd_stats_apply
+  float* dgamma;
+  float* dbeta;
+};
+
+template <int R, int COUT, bool kBn>
+__global__ void __launch_bounds__(kThreads, R == 3 ? (kBn ? 2 : 3) : 1)
 conv_image_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy, long long dy_ld, int N,
-                        int H, int W, float* __restrict__ dw, int Kp) {
+                        int H, int W, float* __restrict__ dw, int Kp, const ImgBnBwd bn) {
   using C = ImgCfg<R, COUT>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __nv_bfloat16* halo = reinterpret_cast<__nv_bfloat16*>(smem_raw);
@@ -323,6 +344,34 @@ conv_image_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __rest
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   fill_koff<C, R>(koff);
+  // per-thread BatchNorm-backward constants of the 8 channels this thread converts (vector v of every pixel)
+  float bsc[kBn ? 8 : 1], bsh[kBn ? 8 : 1], bg[kBn ? 8 : 1], bA[kBn ? 8 : 1], bB[kBn ? 8 : 1];
+  if constexpr (kBn) {
+    const int c0 = (threadIdx.x % (COUT / 8)) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      const float s1 = stat_fold(bn.partials, bn.nparts, 2 * COUT, c);
+      const float s2 = stat_fold(bn.partials, bn.nparts, 2 * COUT, COUT + c);
+      const float rstd = __ldg(bn.rstd + c), mean = __ldg(bn.mean + c);
+      const float gg = __ldg(bn.gamma + c) * rstd;
+      const float k1 = s1 / bn.count, k2 = s2 / bn.count;
+      bg[j] = gg;
+      bA[j] = -gg * k2 * rstd;
+      bB[j] = -gg * k1 - bA[j] * mean;
+      bsc[j] = __ldg(bn.scale + c);
+      bsh[j] = __ldg(bn.shift + c);
+      if (blockIdx.x == 0 && threadIdx.x < COUT / 8) {
+        if (bn.coef) {
+          bn.coef[c] = gg;
+          bn.coef[COUT + c] = k1;
+          bn.coef[2 * COUT + c] = k2;
+        }
+        if (bn.dbeta) bn.dbeta[c] = s1;
+        if (bn.dgamma) bn.dgamma[c] = s2;
+      }
+    }
+  }
   float acc[C::kMT][C::kNT8][4];
 #pragma unroll
   for (int mt = 0; mt < C::kMT; ++mt)
@@ -334,10 +383,12 @@ conv_image_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __rest
   constexpr int kDyVecs = kTileH * kTileW * kVecPerPix / kThreads;  // 16-byte dy vectors per thread and tile
   HaloRegs<C> pre;
   pre.init(H, W);
-  uint4 dpre[kDyVecs];
+  uint4 dpre[kDyVecs], ypre[kBn ? kDyVecs : 1];
   auto dy_fetch = [&](const TileWalk& t) {
     if (t.n >= N) return;
-    const __nv_bfloat16* dtile = dy + (((long long)t.n * H + t.ty * kTileH) * W + t.tx * kTileW) * dy_ld;
+    const long long tile0 = ((long long)t.n * H + t.ty * kTileH) * W + t.tx * kTileW;
+    const __nv_bfloat16* dtile = dy + tile0 * dy_ld;
+    const __nv_bfloat16* ytile = kBn ? bn.y + tile0 * bn.y_ld : nullptr;
 #pragma unroll
     for (int i = 0; i < kDyVecs; ++i) {
       const int idx = threadIdx.x + i * kThreads;
@@ -345,8 +396,14 @@ conv_image_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __rest
       const int pix = idx / kVecPerPix;
       const int px = pix % kTileW, row = pix / kTileW;
       dpre[i] = make_uint4(0u, 0u, 0u, 0u);  // pixels outside the image contribute nothing
-      if (t.ty * kTileH + row < H && t.tx * kTileW + px < W)
+      if constexpr (kBn) ypre[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (t.ty * kTileH + row < H && t.tx * kTileW + px < W) {
         dpre[i] = __ldg(reinterpret_cast<const uint4*>(dtile + ((row * W + px) * static_cast<int>(dy_ld) + v * 8)));
+        if constexpr (kBn)
+          ypre[i] = __ldg(reinterpret_cast<const uint4*>(ytile + ((row * W + px) * static_cast<int>(bn.y_ld) + v * 8)));
+      } else if constexpr (kBn) {
+        dpre[i].x = 0x7fc07fc0u;  // marks an outside pixel (bf16 NaN pair): its dy must be exactly zero
+      }
     }
   };
   TileWalk cur, nxt;
@@ -361,7 +418,26 @@ conv_image_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __rest
 #pragma unroll
     for (int i = 0; i < kDyVecs; ++i) {
       const int idx = threadIdx.x + i * kThreads;
-      *reinterpret_cast<uint4*>(dys + (idx / kVecPerPix) * C::kOutPitch + (idx % kVecPerPix) * 8) = dpre[i];
+      uint4 q = dpre[i];
+      if constexpr (kBn) {
+        if (q.x == 0x7fc07fc0u) {
+          q = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+          const __nv_bfloat162* hg = reinterpret_cast<const __nv_bfloat162*>(&dpre[i]);
+          const __nv_bfloat162* hy = reinterpret_cast<const __nv_bfloat162*>(&ypre[i]);
+          __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 g2 = __bfloat1622float2(hg[e]);
+            const float2 y2 = __bfloat1622float2(hy[e]);
+            const float dz0 = g2.x * (fmaf(y2.x, bsc[2 * e], bsh[2 * e]) > 0.f ? 1.f : bn.neg);
+            const float dz1 = g2.y * (fmaf(y2.y, bsc[2 * e + 1], bsh[2 * e + 1]) > 0.f ? 1.f : bn.neg);
+            ho[e] = __floats2bfloat162_rn(fmaf(bg[2 * e], dz0, fmaf(bA[2 * e], y2.x, bB[2 * e])),
+                                          fmaf(bg[2 * e + 1], dz1, fmaf(bA[2 * e + 1], y2.y, bB[2 * e + 1])));
+          }
+        }
+      }
+      *reinterpret_cast<uint4*>(dys + (idx / kVecPerPix) * C::kOutPitch + (idx % kVecPerPix) * 8) = q;
     }
     __syncthreads();
     halo_fetch<C, R>(pre, x, nxt, N, H, W);
@@ -453,17 +529,17 @@ int launch_fwd(const float* x, const void* w, int Kp, int N, int H, int W, void*
   return check_launch("conv_image_fwd");
 }
 
-template <int R, int COUT>
+template <int R, int COUT, bool kBn>
 int launch_wgrad(const float* x, const void* dy, long long dy_ld, int N, int H, int W, float* dw, int Kp,
-                 cudaStream_t st) {
-  auto kern = conv_image_wgrad_kernel<R, COUT>;
+                 const ImgBnBwd& bn, cudaStream_t st) {
+  auto kern = conv_image_wgrad_kernel<R, COUT, kBn>;
   const size_t smem = image_smem_bytes<R, COUT>();
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error((int)e, "conv_image_wgrad smem attr: %s", cudaGetErrorString(e));
   }
-  kern<<<image_grid(N, H, W, 3), kThreads, smem, st>>>(x, static_cast<const __nv_bfloat16*>(dy), dy_ld, N, H, W, dw,
-                                                       Kp);
+  kern<<<image_grid(N, H, W, kBn ? 2 : 3), kThreads, smem, st>>>(x, static_cast<const __nv_bfloat16*>(dy), dy_ld, N, H,
+                                                                 W, dw, Kp, bn);
   return check_launch("conv_image_wgrad");
 }
 
@@ -508,9 +584,9 @@ extern "C" int b200cv_conv_image_fwd(const float* x, const void* w_flat, int N, 
 #undef B200CV_IMG_FWD
 }
 
-extern "C" int b200cv_conv_image_wgrad(const float* x, const void* dy, int64_t dy_ld, int N, int C, int H, int W,
-                                       int R, int S, int pad, int dil, int Cout, int Kp, float* dw_flat,
-                                       void* stream) {
+namespace {
+int image_wgrad_dispatch(const float* x, const void* dy, int64_t dy_ld, int N, int C, int H, int W, int R, int S, int pad,
+                         int dil, int Cout, int Kp, float* dw_flat, const ImgBnBwd* bn, void* stream) {
   B200CV_CHECK_ARG(x && dy && dw_flat && N > 0 && H > 0 && W > 0, "conv_image_wgrad: bad args");
   B200CV_CHECK_ARG(image_shape_ok(C, R, S, pad, dil, Cout),
                    "conv_image_wgrad: only 3-channel 3x3 / 7x7 stride-1 same-padding layers with 16 or 32 filters");
@@ -520,10 +596,42 @@ extern "C" int b200cv_conv_image_wgrad(const float* x, const void* dy, int64_t d
   B200CV_CHECK_ARG(dy_ld >= Cout && dy_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0,
                    "conv_image_wgrad: dy must be 16-byte aligned rows of >= Cout bf16");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define B200CV_IMG_WG(R_, CO_) return launch_wgrad<R_, CO_>(x, dy, dy_ld, N, H, W, dw_flat, Kp, st)
+  const ImgBnBwd none{};
+#define B200CV_IMG_WG(R_, CO_)                                                                       \
+  return bn ? launch_wgrad<R_, CO_, true>(x, dy, dy_ld, N, H, W, dw_flat, Kp, *bn, st)               \
+            : launch_wgrad<R_, CO_, false>(x, dy, dy_ld, N, H, W, dw_flat, Kp, none, st)
   if (R == 3 && Cout == 32) B200CV_IMG_WG(3, 32);
   if (R == 3 && Cout == 16) B200CV_IMG_WG(3, 16);
   if (R == 7 && Cout == 32) B200CV_IMG_WG(7, 32);
   B200CV_IMG_WG(7, 16);
 #undef B200CV_IMG_WG
+}
+}  // namespace
+
+extern "C" int b200cv_conv_image_wgrad(const float* x, const void* dy, int64_t dy_ld, int N, int C, int H, int W,
+                                       int R, int S, int pad, int dil, int Cout, int Kp, float* dw_flat,
+                                       void* stream) {
+  return image_wgrad_dispatch(x, dy, dy_ld, N, C, H, W, R, S, pad, dil, Cout, Kp, dw_flat, nullptr, stream);
+}
+
+extern "C" int b200cv_conv_image_wgrad_bn(const float* x, const void* da, int64_t da_ld, const void* y, int64_t y_ld,
+                                          const void* partials, int nparts, int64_t count, const float* gamma,
+                                          const float* scale, const float* shift, const float* mean,
+                                          const float* rstd, int act, float slope, float* coef, float* dgamma,
+                                          float* dbeta, int N, int C, int H, int W, int R, int S, int pad, int dil,
+                                          int Cout, int Kp, float* dw_flat, void* stream) {
+  B200CV_CHECK_ARG(y && partials && nparts > 0 && count > 0 && gamma && scale && shift && mean && rstd,
+                   "conv_image_wgrad_bn: incomplete BatchNorm arguments");
+  B200CV_CHECK_ARG(y_ld >= Cout && y_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+                   "conv_image_wgrad_bn: y must be 16-byte aligned rows of >= Cout bf16");
+  ImgBnBwd bn{};
+  bn.y = static_cast<const __nv_bfloat16*>(y);
+  bn.y_ld = y_ld;
+  bn.scale = scale; bn.shift = shift; bn.mean = mean; bn.rstd = rstd; bn.gamma = gamma;
+  bn.partials = static_cast<const StatAcc*>(partials);
+  bn.nparts = nparts;
+  bn.count = static_cast<float>(count);
+  bn.neg = act == B200CV_ACT_LEAKY ? slope : (act == B200CV_ACT_RELU ? 0.f : 1.f);
+  bn.coef = coef; bn.dgamma = dgamma; bn.dbeta = dbeta;
+  return image_wgrad_dispatch(x, da, da_ld, N, C, H, W, R, S, pad, dil, Cout, Kp, dw_flat, &bn, stream);
 }

@@ -193,6 +193,23 @@ def test_image_conv_without_patch_matrix(case):
     want_dw = wt.grad.permute(0, 2, 3, 1).reshape(cout, -1)
     assert float((dwp[:, 0, :3 * k * k].cpu() - want_dw).abs().max()) <= 2e-3 * float(want_dw.abs().max())
     assert float(dwp[:, 0, 3 * k * k:].abs().max()) == 0.0 if kp > 3 * k * k else True
+    # weight gradient with the layer's own BatchNorm + activation backward applied on the fly == the two-pass form
+    # (bn_bwd_stats_apply writes dy in bf16, conv_image_wgrad reads it): same rounding points, same constants
+    c = ops.pad_channels(cout)
+    da = torch.randn(n, h, w, c, generator=g).to(DEV).to(torch.bfloat16)
+    gamma = (torch.rand(cout, generator=g) + 0.5).to(DEV)
+    bscale, bshift = (torch.rand(cout, generator=g) + 0.5).to(DEV), (torch.randn(cout, generator=g) * 0.3).to(DEV)
+    mean, rstd = (torch.randn(cout, generator=g) * 0.1).to(DEV), (torch.rand(cout, generator=g) + 0.5).to(DEV)
+    parts = ops.bn_bwd_reduce(da, y, None, bscale, bshift, mean, rstd, ops.ACT_LEAKY, 0.1)
+    coef_a, coef_b = torch.zeros(3 * cout, device=DEV), torch.zeros(3 * cout, device=DEV)
+    dg_a, db_a, dg_b, db_b = (torch.zeros(cout, device=DEV) for _ in range(4))
+    dy2 = ops.bn_bwd_stats_apply(parts, n * h * w, gamma, coef_a, dg_a, db_a, da, y, bscale, bshift, mean, rstd,
+                                 ops.ACT_LEAKY, 0.1)
+    two = ops.conv_image_wgrad(xd, dy2, cout, k, pad, 1, torch.zeros(cout, 1, kp, device=DEV))
+    one = ops.conv_image_wgrad_bn(xd, da, y, parts, n * h * w, gamma, coef_b, dg_b, db_b, bscale, bshift, mean, rstd,
+                                  ops.ACT_LEAKY, 0.1, cout, k, pad, 1, torch.zeros(cout, 1, kp, device=DEV))
+    assert torch.equal(coef_a, coef_b) and torch.equal(dg_a, dg_b) and torch.equal(db_a, db_b)
+    assert float((one - two).abs().max()) <= 1e-4 * float(two.abs().max())
 
 
 @pytest.mark.parametrize("case", [(2, 32, 64, 32, 64), (3, 20, 40, 64, 128), (1, 52, 52, 128, 256), (2, 9, 36, 32, 48), (2, 38, 76, 64, 128)])
