@@ -75,9 +75,9 @@ for rep in sorted(os.listdir(SRC)):
                     i = hdr.index(k)
                     f.write(f"   {k:72s} {r[i]:>18s} {units[i]}\n")
     # SASS evidence of tcgen05 / TMA for the conv kernels
-    if rep.startswith(("igemm", "wgrad", "dgrad", "optim", "detect")):
+    if rep.startswith(("igemm", "wgrad", "dgrad", "optim", "detect", "image")):
         src = subprocess.run(["ncu", "-i", os.path.join(SRC, rep), "--page", "source", "--csv"], capture_output=True, text=True).stdout
-        ops = collections.Counter(m for m in re.findall(r"\b(UTCHMMA|UTMALDG[.\w]*|UTMASTG[.\w]*|UTMAREDG[.\w]*|UTCBAR|LDTM[.\w]*|UTCATOMSWS[.\w]*|SYNCS[.\w]*)", src))
+        ops = collections.Counter(m for m in re.findall(r"\b(UTCHMMA|HMMA[.\w]*|LDSM[.\w]*|UTMALDG[.\w]*|UTMASTG[.\w]*|UTMAREDG[.\w]*|UTCBAR|LDTM[.\w]*|UTCATOMSWS[.\w]*|SYNCS[.\w]*)", src))
         with open(os.path.join(DST, "ncu_" + rep.replace(".ncu-rep", ".txt")), "a") as f:
             f.write("# SASS mnemonics (static count over the captured kernels): " + ", ".join(f"{k} x{v}" for k, v in sorted(ops.items())) + "\n")
 
