@@ -705,18 +705,18 @@ class _GraphedStep:
             # backward: one graph per gradient bucket (a single one without data parallelism), so that the all-reduce
             # of a finished bucket can be started between two replays and overlap the rest of the pass
             self.bwd_graphs, self.buckets = [], []
-            gen = engine._run_backward_segments(self.state, self.static_g, True, parallel.grad_buckets())
-            done = False
-            while not done:
+            nbuckets = parallel.grad_buckets()
+            gen = engine._run_backward_segments(self.state, self.static_g, True, nbuckets)
+            for _ in range(len(engine._bucket_plan(nbuckets))):  # one yield per planned bucket
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, pool=self.pool):
-                    try:
-                        self.buckets.append(next(gen))
-                    except StopIteration as fin:
-                        self.views = fin.value
-                        done = True
-                if not done:
-                    self.bwd_graphs.append(g)
+                    self.buckets.append(next(gen))
+                self.bwd_graphs.append(g)
+            try:  # nothing is launched after the last yield: finish the generator outside any capture
+                next(gen)
+                raise RuntimeError("backward pass yielded more buckets than planned")
+            except StopIteration as fin:
+                self.views = fin.value
         # kernel-launching ABI calls recorded in each graph: a replay launches that many of our kernels
         self.fwd_launches, self.bwd_launches = n1 - n0, lib().launches - n1
         self.generation = 0        # bumped by every replayed forward (a stale backward is refused)
