@@ -181,7 +181,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    {  // converged warp; the elected lane issues (ptx::*_elect keep the operands in uniform registers)
+      const uint32_t leader = ptx::elect_one() ? 1u : 0u;
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -210,12 +211,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err, 1);
             uint8_t* sa = stage_base + stage * C::kStageBytes;
             uint8_t* sb = sa + C::kABytes;
-            ptx::mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-            ptx::tma_load_im2col_4d(sa, &tmA, &full_bar[stage], ca + cb * KC, cw, ch, n_img, ow, oh);
+            ptx::mbar_expect_tx_elect(leader, &full_bar[stage], C::kStageBytes);
+            ptx::tma_load_im2col_4d_elect(leader, sa, &tmA, &full_bar[stage], ca + cb * KC, cw, ch, n_img, ow, oh);
             if constexpr (kM2)
-              ptx::tma_load_im2col_4d(sa + C::kASubBytes, &tmA, &full_bar[stage], ca + cb * KC, cw1, ch1, n_img1, ow,
+              ptx::tma_load_im2col_4d_elect(leader, sa + C::kASubBytes, &tmA, &full_bar[stage], ca + cb * KC, cw1, ch1, n_img1, ow,
                                       oh);
-            ptx::tma_load_2d(sb, &tmB, &full_bar[stage], kb + cb * KC, nt * BN);
+            ptx::tma_load_2d_elect(leader, sb, &tmB, &full_bar[stage], kb + cb * KC, nt * BN);
             if (++stage == nstages) {
               stage = 0;
               phase ^= 1;
@@ -229,15 +230,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err, 1);
             uint8_t* sa = stage_base + stage * C::kStageBytes;
             uint8_t* sb = sa + C::kABytes;
-            ptx::mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-            ptx::tma_load_2d(sa, &tmI, &full_bar[stage], j * KC, 0);
+            ptx::mbar_expect_tx_elect(leader, &full_bar[stage], C::kStageBytes);
+            ptx::tma_load_2d_elect(leader, sa, &tmI, &full_bar[stage], j * KC, 0);
 #pragma unroll
             for (int sl = 0; sl < BN / 64; ++sl)
-              ptx::tma_load_2d(sb + sl * KC * 128, &tmR, &full_bar[stage], nt * BN + sl * 64, m0 + j * KC);
+              ptx::tma_load_2d_elect(leader, sb + sl * KC * 128, &tmR, &full_bar[stage], nt * BN + sl * 64, m0 + j * KC);
             if constexpr (kM2) {  // residual rows of sub-tile 1 go where its A tile would be (same size: BN == 128)
 #pragma unroll
               for (int sl = 0; sl < BN / 64; ++sl)
-                ptx::tma_load_2d(sa + C::kASubBytes + sl * KC * 128, &tmR, &full_bar[stage], nt * BN + sl * 64,
+                ptx::tma_load_2d_elect(leader, sa + C::kASubBytes + sl * KC * 128, &tmR, &full_bar[stage], nt * BN + sl * 64,
                                  m1 + j * KC);
             }
             if (++stage == nstages) {
@@ -255,8 +256,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    const uint32_t leader = ptx::elect_one() ? 1u : 0u;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      if (lane == 0) {
+      {  // the whole warp walks the loop (converged); one elected lane issues, see ptx::umma_bf16_elect
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, p.err, 2);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * C::kAccCols;
@@ -270,13 +272,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
           for (int k = 0; k < KC / 16; ++k) {
             // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the >>4 field
-            ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+            ptx::umma_bf16_elect(leader, d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
             if constexpr (kM2) {
               const uint64_t adesc1 = ptx::make_smem_desc(sa + C::kASubBytes, 16, C::kSBO, C::kLayout);
-              ptx::umma_bf16(d_tmem + BN, adesc1 + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+              ptx::umma_bf16_elect(leader, d_tmem + BN, adesc1 + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
             }
           }
-          ptx::umma_commit(&empty_bar[stage]);
+          ptx::umma_commit_elect(leader, &empty_bar[stage]);
           if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
@@ -294,21 +296,21 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             for (int k = 0; k < KC / 16; ++k) {
               // MN-major B: LBO = distance between 64-channel slabs, SBO = 8 rows of 128 bytes
               const uint64_t bdesc = ptx::make_smem_desc(sb + k * 16 * 128, KC * 128, 8 * 128, 2);
-              ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc, idesc_res, 1u);
+              ptx::umma_bf16_elect(leader, d_tmem, adesc + 2 * k, bdesc, idesc_res, 1u);
               if constexpr (kM2) {
                 const uint64_t bdesc1 =
                     ptx::make_smem_desc(sa + C::kASubBytes + k * 16 * 128, KC * 128, 8 * 128, 2);
-                ptx::umma_bf16(d_tmem + BN, adesc + 2 * k, bdesc1, idesc_res, 1u);
+                ptx::umma_bf16_elect(leader, d_tmem + BN, adesc + 2 * k, bdesc1, idesc_res, 1u);
               }
             }
-            ptx::umma_commit(&empty_bar[stage]);
+            ptx::umma_commit_elect(leader, &empty_bar[stage]);
             if (++stage == nstages) {
               stage = 0;
               phase ^= 1;
             }
           }
         }
-        ptx::umma_commit(&tfull_bar[acc]);
+        ptx::umma_commit_elect(leader, &tfull_bar[acc]);
       }
       __syncwarp();
       if (++acc == 2) {

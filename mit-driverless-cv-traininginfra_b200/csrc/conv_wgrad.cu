@@ -115,7 +115,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
       // for the pixel coordinates) took ~0.9 us per k-block and starved the tensor core (42 % active): the taps are
       // now split over up to three single-thread producers and the coordinates advance incrementally.
       const int pj = warp == 0 ? 0 : warp - 5;  // producer index 0..2: taps t with t % 3 == pj (+ dY for pj == 0)
-      if (lane == 0 && pj < p.T) {
+      if (pj < p.T) {  // converged warp; the elected lane issues (ptx::*_elect)
+        const uint32_t leader = ptx::elect_one() ? 1u : 0u;
         int my_taps = 0;
         uint16_t tw[3], th[3];
         int tt[3];
@@ -148,16 +149,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1, p.err, 11);
             uint8_t* sa = smem + stage * stage_bytes;
             uint8_t* sb = sa + a_bytes;
-            ptx::mbar_expect_tx(&full_bar[stage], my_bytes);
+            ptx::mbar_expect_tx_elect(leader, &full_bar[stage], my_bytes);
             if (pj == 0)
               for (int sl = 0; sl < p.a_slabs; ++sl)
-                ptx::tma_load_2d(sa + sl * kASlabBytes, &tmDY, &full_bar[stage], a_off + ot * 128 + sl * 64, m0);
+                ptx::tma_load_2d_elect(leader, sa + sl * kASlabBytes, &tmDY, &full_bar[stage], a_off + ot * 128 + sl * 64, m0);
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
               if (tt[k] < p.T) {
 #pragma unroll
                 for (int sl = 0; sl < kBSlabs; ++sl)
-                  ptx::tma_load_im2col_4d(sb + tt[k] * kBTapBytes + sl * kBSlabBytes, &tmX, &full_bar[stage],
+                  ptx::tma_load_im2col_4d_elect(leader, sb + tt[k] * kBTapBytes + sl * kBSlabBytes, &tmX, &full_bar[stage],
                                           b_off + it * BNW + sl * CB, cw, ch, n_img, tw[k], th[k]);
               }
             }
@@ -171,7 +172,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
+      {  // converged warp, one elected lane issues (ptx::umma_bf16_elect: keeps the operands in uniform registers)
+        const uint32_t leader = ptx::elect_one() ? 1u : 0u;
         // The T tap tiles of a stage are consecutive BNW-channel slabs of ONE MN-major B operand (slab pitch =
         // kBSlabBytes), and their accumulators are consecutive TMEM columns: a single MMA covers up to 256 columns
         // = several taps.  Issuing one N = BNW MMA per tap made the 32/64-channel layers MMA-issue-bound
@@ -195,13 +197,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
               const int n = ntot - n0 < 256 ? ntot - n0 : 256;
               const uint64_t bdesc = ptx::make_smem_desc(sb + (n0 / CB) * kBSlabBytes + k * 16 * kBRow, kBSlabBytes,
                                                          8 * kBRow, kBLayout);
-              ptx::umma_bf16(tmem_base + n0, adesc, bdesc, ptx::make_idesc_bf16(128, n, 1, 1), (kb | k) != 0);
+              ptx::umma_bf16_elect(leader, tmem_base + n0, adesc, bdesc, ptx::make_idesc_bf16(128, n, 1, 1),
+                                   (kb | k) != 0);
             }
           }
-          ptx::umma_commit(&empty_bar[stage]);
+          ptx::umma_commit_elect(leader, &empty_bar[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(done_bar);
+        ptx::umma_commit_elect(leader, done_bar);
       }
       __syncwarp();
     } else {

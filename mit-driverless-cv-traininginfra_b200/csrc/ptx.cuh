@@ -105,6 +105,36 @@ __device__ __forceinline__ void tma_load_im2col_4d(void* smem, const CUtensorMap
       "h"(off_w), "h"(off_h)
       : "memory");
 }
+// Predicated forms for a CONVERGED warp (`leader` = elect_one() taken once): the operands stay warp-uniform, so
+// ptxas keeps them in uniform registers instead of broadcasting them from the one active lane before every
+// instruction (ELECT + 4 x R2UR.BROADCAST per UTMALDG: ~150 cycles per TMA issued from a single-lane branch).
+__device__ __forceinline__ void mbar_expect_tx_elect(uint32_t leader, uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %2, 0;\n\t"
+      "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(bytes), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_elect(uint32_t leader, void* smem, const CUtensorMap* m, uint64_t* bar,
+                                                  int c0, int c1) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %5, 0;\n\t"
+      "@pe cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];\n\t}\n" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_elect(uint32_t leader, void* smem, const CUtensorMap* m,
+                                                         uint64_t* bar, int c, int w, int h, int n, uint16_t off_w,
+                                                         uint16_t off_h) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %9, 0;\n\t"
+      "@pe cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};\n\t}\n" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n),
+      "h"(off_w), "h"(off_h), "r"(leader)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),
@@ -161,6 +191,29 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// The same, executed by a CONVERGED warp: one elected lane issues.  Issuing from inside a single-lane branch makes
+// ptxas move every operand from vector to uniform registers with ELECT + R2UR.BROADCAST in front of each UTCHMMA
+// (~200 cycles per MMA measured: the 3x3 layers were bound by the issue rate of this one thread, 950 cycles per
+// k-iteration for 512 cycles of tensor work); with warp-uniform operands they stay in uniform registers.
+__device__ __forceinline__ void umma_bf16_elect(uint32_t leader, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, pe;\n\t"
+      "setp.ne.b32 pe, %5, 0;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+// (`leader` = elect_one() taken ONCE by the warp: tcgen05.commit tracks the MMAs of the thread that executes it)
+__device__ __forceinline__ void umma_commit_elect(uint32_t leader, uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "setp.ne.b32 pe, %1, 0;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(leader)
       : "memory");
 }
 // Arrive on an mbarrier once every previously issued tcgen05.mma has completed.
