@@ -409,23 +409,22 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         } while (tile < num_tiles && !block_valid(tile, bi));
       };
+      const uint32_t lead0 = lane == 0 ? 1u : 0u;  // issuing lane of this warp's TMA traffic (converged issue)
       auto issue_y = [&](int tile, int bi, int slot) {
-        if (lane == 0) {
-          const int mt = tile / p.num_n_tiles;
-          const int nt = tile - mt * p.num_n_tiles;
-          ptx::mbar_expect_tx(&ybar[slot], 4096);
-          const int ncol0 = nt * BN + block_of(bi) * 64, mrow0 = mt * C::kTileM + sub_m + quarter * 32;
-          if (p.d2s_c2) {  // y lies like the depth-to-space output: the same row groups as the stores
-            const int cls_a = ncol0 / p.d2s_c2, col_in = ncol0 - cls_a * p.d2s_c2;
-            int nq = mrow0 / p.OW, p0 = mrow0 - nq * p.OW;
-            for (int r0 = 0; r0 < 32; r0 += p.d2s_g) {
-              ptx::tma_load_3d(ybuf + slot * 4096 + r0 * 128, &tmY, &ybar[slot], col_in, p0, 2 * nq + cls_a);
-              p0 += p.d2s_g;
-              if (p0 >= p.OW) { p0 = 0; ++nq; }
-            }
-          } else {
-            ptx::tma_load_2d(ybuf + slot * 4096, &tmY, &ybar[slot], ncol0, mrow0);
+        const int mt = tile / p.num_n_tiles;
+        const int nt = tile - mt * p.num_n_tiles;
+        ptx::mbar_expect_tx_elect(lead0, &ybar[slot], 4096);
+        const int ncol0 = nt * BN + block_of(bi) * 64, mrow0 = mt * C::kTileM + sub_m + quarter * 32;
+        if (p.d2s_c2) {  // y lies like the depth-to-space output: the same row groups as the stores
+          const int cls_a = ncol0 / p.d2s_c2, col_in = ncol0 - cls_a * p.d2s_c2;
+          int nq = mrow0 / p.OW, p0 = mrow0 - nq * p.OW;
+          for (int r0 = 0; r0 < 32; r0 += p.d2s_g) {
+            ptx::tma_load_3d_elect(lead0, ybuf + slot * 4096 + r0 * 128, &tmY, &ybar[slot], col_in, p0, 2 * nq + cls_a);
+            p0 += p.d2s_g;
+            if (p0 >= p.OW) { p0 = 0; ++nq; }
           }
+        } else {
+          ptx::tma_load_2d_elect(lead0, ybuf + slot * 4096, &tmY, &ybar[slot], ncol0, mrow0);
         }
       };
       uint32_t ycount = 0;
@@ -554,7 +553,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           ptx::fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && !(p.dbg & 1)) {
+          if (!(p.dbg & 1)) {
             if (p.d2s_c2) {
               // depth-to-space: this 64-column block belongs to output rows 2q + a.  Stored in groups of d2s_g
               // rows (d2s_g divides OW, so a group never crosses the end of a dy row -- a TMA store must not start
@@ -563,14 +562,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               const int cls_a = nb_base / p.d2s_c2, col_in = nb_base - cls_a * p.d2s_c2;
               int nq = m_warp / p.OW, p0 = m_warp - nq * p.OW;
               for (int r0 = 0; r0 < 32; r0 += p.d2s_g) {
-                ptx::tma_store_3d(&tmO, stg + r0 * 128, col_in, p0, 2 * nq + cls_a);
+                ptx::tma_store_3d_elect(lead0, &tmO, stg + r0 * 128, col_in, p0, 2 * nq + cls_a);
                 p0 += p.d2s_g;
                 if (p0 >= p.OW) { p0 = 0; ++nq; }
               }
+              ptx::tma_commit_elect(lead0);
             } else {
-              ptx::tma_store_2d(&tmO, stg, nb_base, m_warp);
+              ptx::tma_store_2d_elect(lead0, &tmO, stg, nb_base, m_warp);  // store + commit
             }
-            ptx::tma_store_commit();
           }
           store_pending = true;
           if ((kBnRed || p.stats) && !(p.dbg & 2)) {
@@ -704,14 +703,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         } while (tile < num_tiles && !chunk_valid(tile, ci));
       };
+      const uint32_t lead0 = lane == 0 ? 1u : 0u;  // issuing lane of this warp's TMA traffic (converged issue)
       auto issue_y = [&](int tile, int ci, int slot) {
-        if (lane == 0) {
-          const int mt = tile / p.num_n_tiles;
-          const int nt = tile - mt * p.num_n_tiles;
-          ptx::mbar_expect_tx(&ybar[slot], 32 * RB);
-          ptx::tma_load_2d(ybuf + slot * 2048, &tmY, &ybar[slot], nt * BN + (half + 2 * ci) * C::kChunk,
-                           mt * kBlockM + quarter * 32);
-        }
+        const int mt = tile / p.num_n_tiles;
+        const int nt = tile - mt * p.num_n_tiles;
+        ptx::mbar_expect_tx_elect(lead0, &ybar[slot], 32 * RB);
+        ptx::tma_load_2d_elect(lead0, ybuf + slot * 2048, &tmY, &ybar[slot], nt * BN + (half + 2 * ci) * C::kChunk,
+                               mt * kBlockM + quarter * 32);
       };
       uint32_t ycount = 0;  // chunks processed by this warp: slot = ycount % yslots, phase = (ycount / yslots) & 1
       int pf_tile = blockIdx.x, pf_ci = 0;  // next chunk whose y tile has not been requested yet
@@ -869,10 +867,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           ptx::fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && !(p.dbg & 1)) {
-            ptx::tma_store_2d(&tmO, stg, n_base, m_warp);
-            ptx::tma_store_commit();
-          }
+          if (!(p.dbg & 1)) ptx::tma_store_2d_elect(lead0, &tmO, stg, n_base, m_warp);  // store + commit
           store_pending = true;
           if constexpr (kBnRed) {
             // fused BN-backward reduction: dz = G * act'(y*scale+shift) from the STORED gradient tile and the

@@ -256,10 +256,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
                   make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             ptx::fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
-              ptx::tma_reduce_add_2d(&tmDW, stg, tap * p.Ipad + i0, o_row);  // rows >= Cout are clipped
-              ptx::tma_store_commit();
-            }
+            // rows >= Cout are clipped; issued + committed by lane 0 of the converged warp
+            ptx::tma_reduce_add_2d_elect(lane == 0 ? 1u : 0u, &tmDW, stg, tap * p.Ipad + i0, o_row);
             pending = true;
             if (++slot == ring_slots) slot = 0;
           }

@@ -135,6 +135,47 @@ __device__ __forceinline__ void tma_load_im2col_4d_elect(uint32_t leader, void* 
       "h"(off_w), "h"(off_h), "r"(leader)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_elect(uint32_t leader, void* smem, const CUtensorMap* m, uint64_t* bar,
+                                                  int c0, int c1, int c2) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %6, 0;\n\t"
+      "@pe cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];\n\t}\n" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(leader)
+      : "memory");
+}
+// stores / reductions of the lane with leader != 0 (bulk groups are per thread: commit / wait in the same lane)
+__device__ __forceinline__ void tma_store_2d_elect(uint32_t leader, const CUtensorMap* m, const void* smem, int c0,
+                                                   int c1) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %4, 0;\n\t"
+      "@pe cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n\t"
+      "@pe cp.async.bulk.commit_group;\n\t}\n" ::"l"(reinterpret_cast<uint64_t>(m)),
+      "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d_elect(uint32_t leader, const CUtensorMap* m, const void* smem, int c0,
+                                                   int c1, int c2) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %5, 0;\n\t"
+      "@pe cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n\t}\n" ::"l"(
+          reinterpret_cast<uint64_t>(m)),
+      "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d_elect(uint32_t leader, const CUtensorMap* m, const void* smem,
+                                                        int c0, int c1) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %4, 0;\n\t"
+      "@pe cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];\n\t"
+      "@pe cp.async.bulk.commit_group;\n\t}\n" ::"l"(reinterpret_cast<uint64_t>(m)),
+      "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void tma_commit_elect(uint32_t leader) {
+  asm volatile("{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %0, 0;\n\t@pe cp.async.bulk.commit_group;\n\t}\n" ::"r"(leader)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),
